@@ -1,0 +1,80 @@
+/* include/vbz_b200.h - batch extension of the VBZ C API (not present in the reference).
+ *
+ * The reference compresses one read per call on the calling thread (vbz/vbz.h:76-130); a GPU
+ * needs many reads per launch.  These entry points take a whole batch of reads and run the same
+ * per-read semantics as vbz_compress[_sized] / vbz_decompress[_sized] (vbz/vbz.cpp:116-367) for
+ * each of them: results[i] is what the reference call would have returned for read i (a byte count
+ * or one of the VBZ_*_ERROR codes).  A bad read never poisons the batch.
+ *
+ * The single-read functions of include/vbz.h and the H5Z filter of include/vbz_plugin.h are thin
+ * wrappers over a batch of one.
+ *
+ * Two flavours:
+ *   *_batch   HOST pointers (one per read).  The library stages through pinned memory, copies to the
+ *             device, runs the kernels, copies back.  Synchronous.
+ *   *_device  DEVICE pointers: one input buffer and one output buffer in HBM plus per-read offsets
+ *             (host arrays).  Work is enqueued on `stream` and the call returns without
+ *             synchronising; results[] is a DEVICE array.  Offsets must be multiples of 16.
+ *
+ * Return value of every function: 0 = the batch ran (inspect results[]), < 0 = the batch could not
+ * run at all (no CUDA device, out of device memory, invalid arguments); vbz_b200_last_error() then
+ * describes why.  There is no CPU fallback.
+ */
+#ifndef VBZ_B200_H
+#define VBZ_B200_H
+
+#include "vbz.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+typedef struct vbz_b200_ctx vbz_b200_ctx;
+
+/* number of usable CUDA devices (0 if none / driver missing) */
+VBZ_EXPORT int vbz_b200_device_count(void);
+/* A context owns one device's stream, scratch HBM and pinned staging.  Not thread-safe: use one
+ * per thread (the single-read API keeps a pool internally).  NULL on failure. */
+VBZ_EXPORT vbz_b200_ctx* vbz_b200_create(int device);
+VBZ_EXPORT void vbz_b200_destroy(vbz_b200_ctx* ctx);
+/* thread-local description of the last failure */
+VBZ_EXPORT const char* vbz_b200_last_error(void);
+
+/* ---- host-pointer batches ------------------------------------------------------------------- */
+/* per read i: results[i] = vbz_compress[_sized](src[i], src_size[i], dst[i], dst_cap[i], options) */
+VBZ_EXPORT int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src, const vbz_size_t* src_size,
+                                       void* const* dst, const vbz_size_t* dst_cap, vbz_size_t* results,
+                                       uint32_t n_reads, const struct CompressionOptions* options, int sized);
+/* per read i: results[i] = vbz_decompress[_sized](src[i], src_size[i], dst[i], dst_size[i], options)
+ * (dst_size = exact size for the unsized form, capacity for the sized form) */
+VBZ_EXPORT int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* src, const vbz_size_t* src_size,
+                                         void* const* dst, const vbz_size_t* dst_size, vbz_size_t* results,
+                                         uint32_t n_reads, const struct CompressionOptions* options, int sized);
+
+/* ---- device-resident batches ---------------------------------------------------------------- */
+/* Size of the output slot the device-resident API needs for a read of source_size bytes: a tight
+ * bound on what the kernels can emit, rounded up to 16 (the reference's vbz_max_compressed_size,
+ * vbz/vbz.cpp:79-114, over-asks by up to 2x for int16 and would not let a 100k-read batch fit in HBM). */
+VBZ_EXPORT uint64_t vbz_b200_compress_bound(vbz_size_t source_size, const struct CompressionOptions* options, int sized);
+/* Read i occupies d_src[src_off[i] .. +src_size[i]); its output goes to d_dst[dst_off[i] ..
+ * +dst_cap[i]).  dst_cap[i] must be >= vbz_b200_compress_bound(src_size[i], options, sized).  d_results[i] (device) receives the per-read result.  `stream` is a
+ * cudaStream_t (NULL = the context's own stream). */
+VBZ_EXPORT int vbz_b200_compress_device(vbz_b200_ctx* ctx, const void* d_src, const uint64_t* src_off,
+                                        const vbz_size_t* src_size, void* d_dst, const uint64_t* dst_off,
+                                        const vbz_size_t* dst_cap, vbz_size_t* d_results, uint32_t n_reads,
+                                        const struct CompressionOptions* options, int sized, void* stream);
+/* dst_size[i] is the exact decompressed size of read i (the caller allocated it, so it knows it);
+ * with sized != 0 the 4-byte header at the start of each read is checked against it. */
+VBZ_EXPORT int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, const uint64_t* src_off,
+                                          const vbz_size_t* src_size, void* d_dst, const uint64_t* dst_off,
+                                          const vbz_size_t* dst_size, vbz_size_t* d_results, uint32_t n_reads,
+                                          const struct CompressionOptions* options, int sized, void* stream);
+/* wait for everything enqueued on the context's own stream */
+VBZ_EXPORT int vbz_b200_synchronize(vbz_b200_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
+VBZ_EXPORT uint64_t vbz_b200_kernel_launches(vbz_b200_ctx* ctx);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif

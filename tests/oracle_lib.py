@@ -26,9 +26,10 @@ def is_error(v):
     return v >= ERR_OOM
 
 
-class Options(ctypes.Structure):
-    _fields_ = [("perform_delta_zig_zag", ctypes.c_bool), ("integer_size", ctypes.c_uint),
-                ("zstd_compression_level", ctypes.c_uint), ("vbz_version", ctypes.c_uint)]
+import sys
+sys.path.insert(0, ROOT)
+# one ctypes declaration of the 16-byte options struct (ref vbz/vbz.h:29-53) for oracle and product alike
+from vbz_compression_b200._lib import CompressionOptions as Options  # noqa: E402
 
 
 assert ctypes.sizeof(Options) == 16

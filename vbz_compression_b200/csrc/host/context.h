@@ -1,0 +1,50 @@
+// csrc/host/context.h - per-device state of the host layer: a stream, grow-only scratch in HBM,
+// pinned staging.  One context is used by one thread at a time.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "runtime.h"
+
+namespace vbz {
+
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+// returns false and records "<what>: <cuda error string>" when e != cudaSuccess
+bool cuda_ok(cudaError_t e, const char* what);
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n);  // grow-only; contents are NOT preserved
+    void release();
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n);
+    void release();
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace vbz
+
+struct vbz_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t upload_done = nullptr;  // guards reuse of the pinned descriptor staging
+    uint64_t launches = 0;
+
+    // descriptors and look-back state (stage 1)
+    vbz::DevBuf d_reads, d_tiles, d_status, d_results, d_sizes;
+    vbz::PinBuf h_reads, h_results;
+    // bulk staging for the host-pointer API
+    vbz::DevBuf d_in, d_out, d_mid;
+    vbz::PinBuf h_in, h_out;
+
+    ~vbz_b200_ctx();
+};

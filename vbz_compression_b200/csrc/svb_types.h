@@ -1,0 +1,68 @@
+// csrc/svb_types.h - descriptors and geometry shared by the host layer and the stage-1 kernels
+// (csrc/svb_kernels.cuh).  Plain structs, no device code.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VBZ_HD __host__ __device__ __forceinline__
+#else
+#define VBZ_HD inline
+#endif
+
+namespace vbz {
+
+enum : uint32_t {
+    kErrZstd = 0xFFFFFFFFu,
+    kErrInputSize = 0xFFFFFFFEu,
+    kErrIntegerSize = 0xFFFFFFFDu,
+    kErrDestinationSize = 0xFFFFFFFCu,
+    kErrStream = 0xFFFFFFFBu,
+    kErrVersion = 0xFFFFFFFAu,
+    kErrOutOfMemory = 0xFFFFFFF9u,
+};
+
+// MODE of the pre-transform / value semantics
+enum : int {
+    kModeI16X86 = 0,   // int16 + zigzag exactly as the x86 reference build computes it (16-bit delta)
+    kModeGeneric = 1,  // widen to 32 bits (sign extension), 32-bit delta + zigzag or none
+};
+
+struct SvbRead {
+    uint64_t src_off;      // byte offset of this read's input from SvbParams::src (multiple of 16)
+    uint64_t dst_off;      // byte offset of this read's output slot from SvbParams::dst (multiple of 16)
+    uint32_t src_bytes;    // encode: raw bytes; decode: stage-1 bytes (unless SvbParams::src_sizes is set)
+    uint32_t n_values;     // number of integers in the read
+    uint32_t first_tile;   // index of the read's first tile
+    uint32_t rejected;     // != 0: the read was decided on the host; copy `preset` to results[], do nothing else
+    uint32_t preset;
+    uint32_t reserved;
+};
+
+struct SvbParams {
+    const uint8_t* src;
+    uint8_t* dst;
+    const SvbRead* reads;
+    const uint32_t* tile_read;  // tile -> read index
+    uint64_t* status_a;         // look-back chain A (data bytes), one word per tile, zeroed before launch
+    uint64_t* status_b;         // look-back chain B (sample value), decode only
+    uint32_t* results;          // per read: bytes produced, or a VBZ error code
+    const uint32_t* src_sizes;  // decode: optional per-read stage-1 size computed on the device (zstd stage);
+                                // a value >= kErrOutOfMemory is an upstream error and is passed through
+    uint32_t hdr_bytes;         // encode: 4 = put the "sized" header (ref vbz/vbz.cpp:316-317) before the payload
+    uint32_t n_reads;
+};
+
+constexpr int kSvbThreads = 256;
+constexpr int kSvbGroups = 2;                                    // groups of 16 raw bytes per thread
+constexpr int kSvbTileBytes = kSvbThreads * kSvbGroups * 16;     // raw bytes per tile (8 KiB)
+constexpr uint64_t kStAggregate = 1ull << 62, kStInclusive = 2ull << 62, kStValueMask = (1ull << 62) - 1;
+
+VBZ_HD uint32_t svb_tile_values(int isz) { return (uint32_t)(kSvbTileBytes / isz); }
+VBZ_HD uint32_t svb_tiles_of(uint32_t n_values, int isz)
+{
+    uint32_t tv = svb_tile_values(isz);
+    uint32_t t = (uint32_t)(((uint64_t)n_values + tv - 1) / tv);
+    return t ? t : 1;  // an empty read still owns one (empty) tile: it writes the header and the result
+}
+
+}  // namespace vbz

@@ -1,0 +1,26 @@
+// csrc/vbzk.h - the thin C-ABI shim between the C++ host layer and the CUDA kernels.
+// Plain pointers, sizes and a stream handle; no C++ types cross it.  Every function only enqueues
+// work on `stream` and returns 0, or a non-zero cudaError_t from the launch.
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct VbzkSvbRead;   /* == vbz::SvbRead   (csrc/svb_kernels.cuh) */
+struct VbzkSvbParams; /* == vbz::SvbParams (csrc/svb_kernels.cuh) */
+
+/* geometry helpers (host side needs them to size tables) */
+uint32_t vbzk_svb_tile_values(int integer_size);
+uint32_t vbzk_svb_smem_bytes(int integer_size, int mode, int decode);
+
+/* tile -> read table */
+int vbzk_svb_fill_tiles(const struct VbzkSvbRead* d_reads, uint32_t n_reads, uint32_t tile_values, uint32_t* d_tile_read, void* stream);
+/* stage 1, v0 packing: integer_size 1/2/4, zigzag 0/1, mode 0 = int16 x86 semantics, 1 = generic */
+int vbzk_svb_encode(int integer_size, int zigzag, int mode, const struct VbzkSvbParams* params, uint32_t n_tiles, void* stream);
+int vbzk_svb_decode(int integer_size, int zigzag, int mode, const struct VbzkSvbParams* params, uint32_t n_tiles, void* stream);
+
+#ifdef __cplusplus
+}
+#endif

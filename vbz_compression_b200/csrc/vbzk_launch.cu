@@ -1,0 +1,71 @@
+// csrc/vbzk_launch.cu - kernel instantiations + the C-ABI launch shim (csrc/vbzk.h).
+#include "vbzk.h"
+#include "svb_kernels.cuh"
+
+using namespace vbz;
+
+#ifdef VBZ_CPUSIM
+#define VBZK_SET_SMEM(kernel, bytes) 0
+#define VBZK_LAST_ERROR() 0
+#else
+#define VBZK_SET_SMEM(kernel, bytes) \
+    ((bytes) > 48 * 1024 ? (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)) : 0)
+#define VBZK_LAST_ERROR() ((int)cudaGetLastError())
+#endif
+
+extern "C" uint32_t vbzk_svb_tile_values(int isz) { return svb_tile_values(isz); }
+
+template <int ISZ, int MODE>
+static uint32_t smem_of(int decode) { return decode ? SvbSmem<ISZ, MODE>::kDecodeBytes : SvbSmem<ISZ, MODE>::kEncodeBytes; }
+
+extern "C" uint32_t vbzk_svb_smem_bytes(int isz, int mode, int decode)
+{
+    if (isz == 2) return mode == kModeI16X86 ? smem_of<2, kModeI16X86>(decode) : smem_of<2, kModeGeneric>(decode);
+    if (isz == 4) return smem_of<4, kModeGeneric>(decode);
+    return smem_of<1, kModeGeneric>(decode);
+}
+
+extern "C" int vbzk_svb_fill_tiles(const VbzkSvbRead* d_reads, uint32_t n_reads, uint32_t tile_values, uint32_t* d_tile_read, void* stream)
+{
+    if (n_reads == 0) return 0;
+    const uint32_t warps_per_cta = 8;
+    const uint32_t grid = (n_reads + warps_per_cta - 1) / warps_per_cta;
+    VBZ_LAUNCH(svb_fill_tiles_kernel, grid, warps_per_cta * 32, 0, (vbz_stream_t)stream,
+               reinterpret_cast<const SvbRead*>(d_reads), n_reads, tile_values, d_tile_read);
+    return VBZK_LAST_ERROR();
+}
+
+template <int ISZ, bool ZZ, int MODE>
+static int launch_encode(const SvbParams& p, uint32_t n_tiles, void* stream)
+{
+    const uint32_t smem = SvbSmem<ISZ, MODE>::kEncodeBytes;
+    if (int e = VBZK_SET_SMEM((svb_encode_kernel<ISZ, ZZ, MODE>), smem)) return e;
+    VBZ_LAUNCH((svb_encode_kernel<ISZ, ZZ, MODE>), n_tiles, kSvbThreads, smem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+template <int ISZ, bool ZZ, int MODE>
+static int launch_decode(const SvbParams& p, uint32_t n_tiles, void* stream)
+{
+    const uint32_t smem = SvbSmem<ISZ, MODE>::kDecodeBytes;
+    if (int e = VBZK_SET_SMEM((svb_decode_kernel<ISZ, ZZ, MODE>), smem)) return e;
+    VBZ_LAUNCH((svb_decode_kernel<ISZ, ZZ, MODE>), n_tiles, kSvbThreads, smem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+
+#define VBZK_DISPATCH(fn)                                                                            \
+    const SvbParams& p = *reinterpret_cast<const SvbParams*>(params);                                \
+    if (n_tiles == 0) return 0;                                                                      \
+    if (isz == 2 && zz && mode == kModeI16X86) return fn<2, true, kModeI16X86>(p, n_tiles, stream);  \
+    if (isz == 2) return zz ? fn<2, true, kModeGeneric>(p, n_tiles, stream) : fn<2, false, kModeGeneric>(p, n_tiles, stream); \
+    if (isz == 4) return zz ? fn<4, true, kModeGeneric>(p, n_tiles, stream) : fn<4, false, kModeGeneric>(p, n_tiles, stream); \
+    if (isz == 1) return zz ? fn<1, true, kModeGeneric>(p, n_tiles, stream) : fn<1, false, kModeGeneric>(p, n_tiles, stream); \
+    return -1;
+
+extern "C" int vbzk_svb_encode(int isz, int zz, int mode, const VbzkSvbParams* params, uint32_t n_tiles, void* stream)
+{
+    VBZK_DISPATCH(launch_encode)
+}
+extern "C" int vbzk_svb_decode(int isz, int zz, int mode, const VbzkSvbParams* params, uint32_t n_tiles, void* stream)
+{
+    VBZK_DISPATCH(launch_decode)
+}
