@@ -57,8 +57,9 @@ VBZ_EXPORT int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
  * vbz/vbz.cpp:79-114, over-asks by up to 2x for int16 and would not let a 100k-read batch fit in HBM). */
 VBZ_EXPORT uint64_t vbz_b200_compress_bound(vbz_size_t source_size, const struct CompressionOptions* options, int sized);
 /* Read i occupies d_src[src_off[i] .. +src_size[i]); its output goes to d_dst[dst_off[i] ..
- * +dst_cap[i]).  dst_cap[i] must be >= vbz_b200_compress_bound(src_size[i], options, sized).  d_results[i] (device) receives the per-read result.  `stream` is a
- * cudaStream_t (NULL = the context's own stream). */
+ * +dst_cap[i]).  dst_cap[i] must be >= vbz_b200_compress_bound(src_size[i], options, sized).  d_results[i] (device) receives the per-read
+ * result.  `stream` is a cudaStream_t used as is (NULL = the CUDA legacy default stream, as in a kernel
+ * launch); vbz_b200_stream() returns the context's own non-blocking stream. */
 VBZ_EXPORT int vbz_b200_compress_device(vbz_b200_ctx* ctx, const void* d_src, const uint64_t* src_off,
                                         const vbz_size_t* src_size, void* d_dst, const uint64_t* dst_off,
                                         const vbz_size_t* dst_cap, vbz_size_t* d_results, uint32_t n_reads,
@@ -69,6 +70,8 @@ VBZ_EXPORT int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
                                           const vbz_size_t* src_size, void* d_dst, const uint64_t* dst_off,
                                           const vbz_size_t* dst_size, vbz_size_t* d_results, uint32_t n_reads,
                                           const struct CompressionOptions* options, int sized, void* stream);
+/* the context's own (non-blocking) stream, as a cudaStream_t */
+VBZ_EXPORT void* vbz_b200_stream(vbz_b200_ctx* ctx);
 /* wait for everything enqueued on the context's own stream */
 VBZ_EXPORT int vbz_b200_synchronize(vbz_b200_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */

@@ -39,6 +39,7 @@ def bind(lib):
     lib.vbz_b200_destroy.restype, lib.vbz_b200_destroy.argtypes = None, [vp]
     lib.vbz_b200_last_error.restype, lib.vbz_b200_last_error.argtypes = ctypes.c_char_p, []
     lib.vbz_b200_compress_bound.restype, lib.vbz_b200_compress_bound.argtypes = ctypes.c_uint64, [u32, P, ctypes.c_int]
+    lib.vbz_b200_stream.restype, lib.vbz_b200_stream.argtypes = vp, [vp]
     lib.vbz_b200_synchronize.restype, lib.vbz_b200_synchronize.argtypes = ctypes.c_int, [vp]
     lib.vbz_b200_kernel_launches.restype, lib.vbz_b200_kernel_launches.argtypes = ctypes.c_uint64, [vp]
     for n in ("vbz_b200_compress_batch", "vbz_b200_decompress_batch"):
@@ -61,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "vbz_decompress_sized", "vbz_decompressed_size",
     "vbz_b200_device_count", "vbz_b200_create", "vbz_b200_destroy", "vbz_b200_last_error", "vbz_b200_compress_batch",
     "vbz_b200_decompress_batch", "vbz_b200_compress_device", "vbz_b200_decompress_device", "vbz_b200_synchronize",
-    "vbz_b200_kernel_launches", "vbz_b200_compress_bound",
+    "vbz_b200_kernel_launches", "vbz_b200_compress_bound", "vbz_b200_stream",
     "H5PLget_plugin_type", "H5PLget_plugin_info", "vbz_plugin_info", "vbz_b200_h5z_filter",
 ]
 

@@ -232,6 +232,7 @@ extern "C" uint64_t vbz_b200_compress_bound(vbz_size_t source_size, const Compre
     return align16(m + hdr);
 }
 extern "C" uint64_t vbz_b200_kernel_launches(vbz_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* vbz_b200_stream(vbz_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int vbz_b200_synchronize(vbz_b200_ctx* ctx)
 {
     if (!ctx) return -1;
@@ -256,7 +257,7 @@ extern "C" int vbz_b200_compress_device(vbz_b200_ctx* ctx, const void* d_src, co
         return -1;
     }
     return compress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0,
-                                stream ? (cudaStream_t)stream : ctx->stream);
+                                (cudaStream_t)stream);
 }
 
 extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, const uint64_t* src_off, const vbz_size_t* src_size,
@@ -279,7 +280,7 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
         else j.rejected = decompress_precheck(kind, src_size[i] - hdr, dst_size[i], &j.code);
     }
     return decompress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0,
-                                  stream ? (cudaStream_t)stream : ctx->stream);
+                                  (cudaStream_t)stream);
 }
 
 // ---- host-pointer batches -------------------------------------------------------------------------------------
