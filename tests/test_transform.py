@@ -36,7 +36,7 @@ def test_kat_bytes(backend, k):
 
 def _cases(rng):
     yield np.zeros(0, np.int16)
-    for n in (1, 3, 4, 5, 8, 9, 31, 33, 100, 4095, 4096, 4097, 8192, 9000):
+    for n in (1, 3, 4, 5, 8, 9, 31, 33, 100, 255, 256, 257, 511, 512, 513, 1024, 4095, 4096, 4097, 8192, 9000):
         yield data_gen.nanopore_like(n, rng)
         yield data_gen.uniform_full_range(n, np.int16, rng)
     for n in (1, 7, 2047, 2048, 2049, 5000):

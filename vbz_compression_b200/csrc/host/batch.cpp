@@ -82,7 +82,7 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     const uint32_t n_tiles = (uint32_t)tiles;
     const size_t status_words = (size_t)n_tiles * (decode ? 2 : 1);
     if (!ctx->d_reads.ensure((size_t)n * sizeof(SvbRead)) || !ctx->d_tiles.ensure((size_t)n_tiles * 4) ||
-        !ctx->d_status.ensure(status_words * 8))
+        !ctx->d_status.ensure(status_words * 8) || (decode && !ctx->d_wtoff.ensure((size_t)n_tiles * kSvbWarps * 4)))
         return -1;
     // the pinned staging may still be feeding the previous batch's upload
     if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
@@ -105,8 +105,15 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     p.results = d_results;
     p.src_sizes = d_src_sizes;
     p.hdr_bytes = hdr_bytes;
+    p.wtile_off = decode ? ctx->d_wtoff.as<uint32_t>() : nullptr;
     p.n_reads = n;
+    p.n_tiles = n_tiles;
     const VbzkSvbParams* pp = reinterpret_cast<const VbzkSvbParams*>(&p);
+    if (decode) {
+        e = vbzk_svb_key_offsets(kind.isz, kind.mode, pp, stream);
+        if (e) { cuda_ok((cudaError_t)e, "svb_key_offsets launch"); return -1; }
+        ctx->launches += 1;
+    }
     e = decode ? vbzk_svb_decode(kind.isz, kind.zz, kind.mode, pp, n_tiles, stream)
                : vbzk_svb_encode(kind.isz, kind.zz, kind.mode, pp, n_tiles, stream);
     if (e) { cuda_ok((cudaError_t)e, decode ? "svb_decode launch" : "svb_encode launch"); return -1; }
@@ -178,7 +185,7 @@ using namespace vbz;
 // ======================================================================================================
 vbz_b200_ctx::~vbz_b200_ctx()
 {
-    d_reads.release(); d_tiles.release(); d_status.release(); d_results.release(); d_sizes.release();
+    d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_results.release(); d_sizes.release();
     h_reads.release(); h_results.release();
     d_in.release(); d_out.release(); d_mid.release();
     h_in.release(); h_out.release();

@@ -10,67 +10,38 @@
 //                                                        streamvbyte_decode.c:18-136, streamvbyte_zigzag.c:20-38)
 //
 // Layout.  A batch is one byte buffer in HBM plus a descriptor per read (SvbRead): where the read
-// starts, how many values it has, where its output slot starts.  Reads are cut into TILES of
-// 256 threads x 2 groups x 16 raw bytes = 8 KiB of samples; one CTA per tile, tiles numbered
-// read-major so that blockIdx order is the order of the data.  Within a tile every thread owns two
-// "groups" of 16 raw bytes (8 int16 / 4 int32 / 16 int8 values = 2 / 1 / 4 control bytes), chosen
-// strided (group = j*256 + tid) so that every 128-bit global load and store of a warp is one
-// fully-coalesced 512-byte access.
+// starts, how many values it has, where its output slot starts.  Reads are cut into TILES of 8 KiB
+// of samples, one CTA (8 warps) per tile, tiles numbered read-major so that blockIdx order is the
+// order of the data.  Each warp owns a 1 KiB WARP TILE; a lane owns two "groups" of 16 raw bytes
+// (8 int16 / 4 int32 / 16 int8 values = 2 / 1 / 4 control bytes), strided (group = j*32 + lane) so
+// that every 128-bit global load / store of a warp is one fully-coalesced 512-byte access.
 //
 // The variable-length part: the position of a value's data bytes is the sum of the byte lengths of
-// all earlier values of the READ.  Inside the tile that is a warp-shuffle scan + one cross-warp
-// step; across the tiles of a read it is a single-pass decoupled look-back (one 64-bit status word
-// per tile: 2 flag bits + 62-bit value) - no second pass over the samples.  Packed bytes are staged
-// in shared memory at the same 16-byte phase as their global destination, so the copy-out is
-// aligned 128-bit stores whatever byte offset the tile's data starts at.  Decode runs two chained
-// look-backs: data-byte offsets (known from the control bytes alone, published early) and the
-// running sample value (the delta prefix sum).
+// all earlier values of the READ.  Three levels, no CTA-wide barrier after the prologue:
+//   lane   -> shuffle scan inside the warp;
+//   warp   -> each warp posts its total in a shared-memory slot (value + ready bit in one word) and
+//             sums the slots of the warps before it, spinning only on those;
+//   tile   -> the last warp posts the CTA total as the tile's AGGREGATE in a 64-bit global status
+//             word (2 flag bits + 62-bit value) and runs a decoupled look-back, 32 predecessors at a
+//             time, over the earlier tiles of the same read - single pass, no second read of the data.
+// The dependency is pushed to the end of the tile's work: encode stages its packed bytes in shared
+// memory at tile-local offsets BEFORE the global offset is known and only the final copy-out
+// (which re-aligns with funnel shifts to aligned 128-bit stores) waits for it; decode gets its
+// data-byte offsets from a tiny pre-pass over the control bytes alone (svb_key_offsets_kernel, 1/8
+// of the bytes) and its running sample value (the delta prefix sum) from the look-back, needed
+// only for the final add + store.
 //
 // HBM traffic per int16 sample: 2 B in + 0.25 B keys + ~1.01 B data out (encode) and the reverse
-// (decode) = the algorithmic minimum; status words add 8 B per 8 KiB tile (0.1 %).
+// (decode, + 0.25 B for the control-byte pre-pass) = the algorithmic minimum + 8 %.
 #pragma once
 #include "vbz_device.h"
 #include "svb_types.h"
 
 namespace vbz {
 
-// ---- CTA-wide exclusive scan of two independent counters per thread (shared barriers) -----------
-// scratch: 2*(NW+1) words.  Two __syncthreads.
-template <int NT>
-__device__ __forceinline__ void cta_scan_pair(uint32_t a, uint32_t b, uint32_t* scratch, uint32_t& ea, uint32_t& eb,
-                                              uint32_t& ta, uint32_t& tb)
-{
-    constexpr int NW = NT / 32;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t ia = a, ib = b;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t xa = __shfl_up_sync(0xffffffffu, ia, d);
-        uint32_t xb = __shfl_up_sync(0xffffffffu, ib, d);
-        if (lane >= d) { ia += xa; ib += xb; }
-    }
-    if (lane == 31) { scratch[wid] = ia; scratch[NW + 1 + wid] = ib; }
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t wa = lane < NW ? scratch[lane] : 0, wb = lane < NW ? scratch[NW + 1 + lane] : 0;
-        uint32_t sa = wa, sb = wb;
-#pragma unroll
-        for (int d = 1; d < NW; d <<= 1) {
-            uint32_t xa = __shfl_up_sync(0xffffffffu, sa, d);
-            uint32_t xb = __shfl_up_sync(0xffffffffu, sb, d);
-            if (lane >= d) { sa += xa; sb += xb; }
-        }
-        if (lane < NW) { scratch[lane] = sa - wa; scratch[NW + 1 + lane] = sb - wb; }
-        if (lane == NW - 1) { scratch[NW] = sa; scratch[2 * NW + 1] = sb; }
-    }
-    __syncthreads();
-    ea = ia - a + scratch[wid];
-    eb = ib - b + scratch[NW + 1 + wid];
-    ta = scratch[NW];
-    tb = scratch[2 * NW + 1];
-}
+enum : uint64_t { kSlotReady = 1ull << 63 };
 
-// ---- decoupled look-back over the earlier tiles of the same read (call with all lanes of one warp)
+// ---- decoupled look-back over the earlier tiles of the same read (all 32 lanes of a warp) ----------
 __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, uint32_t tile, uint32_t first_tile)
 {
     const int lane = threadIdx.x & 31;
@@ -100,34 +71,101 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, u
     return excl;
 }
 
-// ---- shared <-> global copies where both sides sit at the same 16-byte phase ------------------------
-template <int NT>
-__device__ __forceinline__ void copy_out_aligned(uint8_t* g, const uint8_t* s, uint32_t nbytes)
+// Level "warp -> tile -> read" of the offset computation (see the header comment).  Every warp of
+// the CTA calls it once per chain with its own total; returns the exclusive prefix of this warp
+// within the tile (*warp_excl) and posts, through `cta_slot`, the exclusive prefix of the tile
+// within the read (call chain_wait() to read it when it is finally needed).
+// slots: kSvbWarps words of shared memory, zeroed in the prologue.  mask trims the running value.
+__device__ __forceinline__ void chain_post(volatile uint64_t* slots, volatile uint64_t* cta_slot, uint64_t* status, uint32_t tile,
+                                           uint32_t first_tile, uint64_t warp_total, uint64_t mask, uint64_t* warp_excl)
 {
-    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) slots[wid] = kSlotReady | (warp_total & mask);
+    uint64_t v = 0;
+    if (wid > 0) {
+        for (;;) {
+            v = lane < wid ? slots[lane] : kSlotReady;
+            if (__all_sync(0xffffffffu, (v & kSlotReady) != 0)) break;
+            VBZ_SPIN_YIELD_SHARED();
+        }
+        v &= ~kSlotReady;
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);  // only lanes < 8 carry values
+        v = __shfl_sync(0xffffffffu, v, 0) & mask;
+    }
+    *warp_excl = v;
+    if (wid == kSvbWarps - 1) {  // the last warp knows the tile total first
+        const uint64_t aggregate = (v + warp_total) & mask;
+        uint64_t excl = 0;
+        if (tile == first_tile) {
+            if (lane == 0) vbz_st_volatile_u64(status + tile, kStInclusive | aggregate);
+        } else {
+            if (lane == 0) vbz_st_volatile_u64(status + tile, kStAggregate | aggregate);
+            excl = lookback_exclusive(status, tile, first_tile) & mask;
+            if (lane == 0) vbz_st_volatile_u64(status + tile, kStInclusive | ((excl + aggregate) & mask));
+        }
+        if (lane == 0) *cta_slot = kSlotReady | excl;
+    }
+}
+__device__ __forceinline__ uint64_t chain_wait(volatile uint64_t* cta_slot)
+{
+    uint64_t v;
+    for (;;) {
+        v = *cta_slot;
+        if (v & kSlotReady) break;
+        VBZ_SPIN_YIELD_SHARED();
+    }
+    return v & ~kSlotReady;
+}
+
+// ---- warp-wide shared -> global copy, same 16-byte phase on both sides -----------------------------------
+__device__ __forceinline__ void warp_copy_out(uint8_t* g, const uint8_t* s, uint32_t nbytes)
+{
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
     if (head > nbytes) head = nbytes;
-    if (tid < head) g[tid] = s[tid];
+    if (lane < head) g[lane] = s[lane];
     const uint32_t body = (nbytes - head) >> 4;
     const uint4* s4 = reinterpret_cast<const uint4*>(s + head);
     uint4* g4 = reinterpret_cast<uint4*>(g + head);
-    for (uint32_t i = tid; i < body; i += NT) vbz_st_stream(g4 + i, s4[i]);
+    for (uint32_t i = lane; i < body; i += 32) vbz_st_stream(g4 + i, s4[i]);
     const uint32_t done = head + (body << 4);
-    if (tid < nbytes - done) g[done + tid] = s[done + tid];
+    if (lane < nbytes - done) g[done + lane] = s[done + lane];
 }
-template <int NT>
-__device__ __forceinline__ void copy_in_aligned(uint8_t* s, const uint8_t* g, uint32_t nbytes)
+// ---- warp-wide shared -> global copy, arbitrary phase on both sides: aligned 128-bit global stores fed
+// by 32-bit shared loads re-aligned with funnel shifts (the shared buffer must be readable 8 bytes past
+// the end of the range) -------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_out_shifted(uint8_t* g, const uint8_t* s, uint32_t nbytes)
 {
-    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
     if (head > nbytes) head = nbytes;
-    if (tid < head) s[tid] = g[tid];
+    if (lane < head) g[lane] = s[lane];
+    const uint32_t body = (nbytes - head) >> 4;
+    const uint8_t* sb = s + head;
+    const uint32_t sh = 8u * (uint32_t)((uintptr_t)sb & 3u);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb - ((uintptr_t)sb & 3u));
+    uint4* g4 = reinterpret_cast<uint4*>(g + head);
+    for (uint32_t i = lane; i < body; i += 32) {
+        const uint32_t* q = sw + 4 * i;
+        const uint32_t a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
+        vbz_st_stream(g4 + i, make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, d, sh), __funnelshift_r(d, e, sh)));
+    }
+    const uint32_t done = head + (body << 4);
+    if (lane < nbytes - done) g[done + lane] = s[done + lane];
+}
+__device__ __forceinline__ void warp_copy_in(uint8_t* s, const uint8_t* g, uint32_t nbytes)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
+    if (head > nbytes) head = nbytes;
+    if (lane < head) s[lane] = g[lane];
     const uint32_t body = (nbytes - head) >> 4;
     uint4* s4 = reinterpret_cast<uint4*>(s + head);
     const uint4* g4 = reinterpret_cast<const uint4*>(g + head);
-    for (uint32_t i = tid; i < body; i += NT) s4[i] = vbz_ld_stream(g4 + i);
+    for (uint32_t i = lane; i < body; i += 32) s4[i] = vbz_ld_stream(g4 + i);
     const uint32_t done = head + (body << 4);
-    if (tid < nbytes - done) s[done + tid] = g[done + tid];
+    if (lane < nbytes - done) s[done + lane] = g[done + lane];
 }
 
 template <int ISZ>
@@ -145,21 +183,35 @@ __device__ __forceinline__ int32_t svb_load_elem(const uint8_t* p, uint64_t i)
     return *reinterpret_cast<const int8_t*>(p + i);
 }
 
+// inclusive warp scan (also used on two 16-bit counters packed in one word, each total < 65536)
+__device__ __forceinline__ uint32_t warp_scan_u32(uint32_t v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += x;
+    }
+    return v;
+}
+
 // shared memory carve-up (bytes)
-constexpr int kSvbScratchBytes = 3 * 2 * (kSvbThreads / 32 + 1) * 4;  // three scan scratch areas
+constexpr int kSvbCtrlBytes = (2 * kSvbWarps + 2) * 8;  // warp slots of both chains + the two tile slots
 template <int ISZ, int MODE>
 struct SvbSmem {
+    static constexpr int kWarpValues = kSvbWarpTileBytes / ISZ;
     static constexpr int kTileValues = kSvbTileBytes / ISZ;
     static constexpr int kMaxValueBytes = MODE == kModeI16X86 ? 2 : 4;
-    static constexpr int kKeyStage = kTileValues / 4 + 32;
-    static constexpr int kDataStage = kTileValues * kMaxValueBytes + 32;
-    static constexpr int kScratchOff = 0;
-    static constexpr int kBcastOff = (kSvbScratchBytes + 15) & ~15;  // 16 bytes of broadcast slots
-    static constexpr int kKeyOff = kBcastOff + 16;
-    static constexpr int kDataOff = (kKeyOff + kKeyStage + 15) & ~15;
-    static constexpr int kEncodeBytes = kDataOff + kDataStage;
-    // decode: a (possibly corrupt) stream may carry 4-byte codes whatever the mode; keys area unused
-    static constexpr int kDecodeBytes = kDataOff + kTileValues * 4 + 32;
+    static constexpr int kCtrlOff = 0;
+    // encode: per-warp control-byte staging, then one tile-wide data staging area at tile-local offsets
+    static constexpr int kKeyStageWarp = (kWarpValues / 4 + 16 + 15) & ~15;
+    static constexpr int kKeyOff = (kSvbCtrlBytes + 15) & ~15;
+    static constexpr int kEncDataOff = kKeyOff + kKeyStageWarp * kSvbWarps;
+    static constexpr int kEncodeBytes = kEncDataOff + kTileValues * kMaxValueBytes + 32;
+    // decode: per-warp data staging; a (possibly corrupt) stream may carry 4-byte codes whatever the mode
+    static constexpr int kDecStageWarp = (kWarpValues * 4 + 32 + 15) & ~15;
+    static constexpr int kDecDataOff = (kSvbCtrlBytes + 15) & ~15;
+    static constexpr int kDecodeBytes = kDecDataOff + kDecStageWarp * kSvbWarps;
 };
 
 // =====================================================================================================
@@ -168,25 +220,27 @@ struct SvbSmem {
 template <int ISZ, bool ZZ, int MODE>
 __global__ void __launch_bounds__(kSvbThreads) svb_encode_kernel(SvbParams p)
 {
-    constexpr int NT = kSvbThreads, G = kSvbGroups, VPG = 16 / ISZ, KB = VPG / 4;
-    constexpr uint32_t TV = kSvbTileBytes / ISZ;
+    constexpr int G = kSvbGroups, VPG = 16 / ISZ, KB = VPG / 4;
+    constexpr uint32_t TV = kSvbTileBytes / ISZ, WV = kSvbWarpTileBytes / ISZ;
     using L = SvbSmem<ISZ, MODE>;
     VBZ_DYN_SMEM(smem);
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + L::kScratchOff);
-    uint64_t* bcast = reinterpret_cast<uint64_t*>(smem + L::kBcastOff);
+    volatile uint64_t* ctrl = reinterpret_cast<volatile uint64_t*>(smem + L::kCtrlOff);
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x;
     const uint32_t r = p.tile_read[t];
     const SvbRead rd = p.reads[r];
     const uint32_t ti = t - rd.first_tile;
     if (rd.rejected) {
-        if (ti == 0 && tid == 0) p.results[r] = rd.preset;
+        if (ti == 0 && threadIdx.x == 0) p.results[r] = rd.preset;
         return;
     }
+    if (threadIdx.x < 2 * kSvbWarps + 2) ctrl[threadIdx.x] = 0;
+    __syncthreads();  // the only CTA-wide barrier: nothing is in flight yet
+
     const uint32_t n = rd.n_values;
-    const uint32_t v0 = ti * TV;
-    const uint32_t nv = n - v0 < TV ? n - v0 : TV;
+    const uint32_t v0 = ti * TV + wid * WV;                                 // first value of this warp tile
+    const uint32_t nv = v0 >= n ? 0u : (n - v0 < WV ? n - v0 : WV);         // values in this warp tile
     const uint8_t* src = p.src + rd.src_off;
 
     // ---- load 16 raw bytes per group, pre-transform, classify -------------------------------------
@@ -194,7 +248,7 @@ __global__ void __launch_bounds__(kSvbThreads) svb_encode_kernel(SvbParams p)
     uint32_t key[G], len[G], cnt[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        const uint32_t g = j * NT + tid, e0 = g * VPG;
+        const uint32_t g = j * 32 + lane, e0 = g * VPG;
         cnt[j] = e0 >= nv ? 0u : (nv - e0 < (uint32_t)VPG ? nv - e0 : (uint32_t)VPG);
         uint32_t w[4] = {0, 0, 0, 0};
         const uint8_t* gp = src + ((uint64_t)v0 + e0) * ISZ;
@@ -237,36 +291,25 @@ __global__ void __launch_bounds__(kSvbThreads) svb_encode_kernel(SvbParams p)
         }
     }
 
-    // ---- where do this tile's data bytes go? -------------------------------------------------------
-    uint32_t off0, off1, tot0, tot1;
-    cta_scan_pair<NT>(len[0], len[1], scratch, off0, off1, tot0, tot1);
-    off1 += tot0;
-    const uint32_t tile_total = tot0 + tot1;
-    if (tid < 32) {
-        uint64_t excl = 0;
-        if (ti == 0) {
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStInclusive | tile_total);
-        } else {
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStAggregate | tile_total);
-            excl = lookback_exclusive(p.status_a, t, rd.first_tile);
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStInclusive | (excl + tile_total));
-        }
-        if (lane == 0) bcast[0] = excl;
-    }
-    __syncthreads();
-    const uint64_t tile_excl = bcast[0];
+    // ---- offsets: lane -> warp -> tile (shared slots) -> read (look-back, by the last warp) --------------
+    static_assert(G == 2, "the packed scan below assumes two groups per lane");
+    const uint32_t incl = warp_scan_u32(len[0] | (len[1] << 16));
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t tot0 = tot & 0xFFFFu, warp_total = tot0 + (tot >> 16);
+    uint64_t warp_excl;
+    chain_post(ctrl, ctrl + 2 * kSvbWarps, p.status_a, t, rd.first_tile, warp_total, kStValueMask, &warp_excl);
+    const uint32_t off0 = (uint32_t)warp_excl + (incl & 0xFFFFu) - len[0];
+    const uint32_t off1 = (uint32_t)warp_excl + tot0 + (incl >> 16) - len[1];
 
+    // ---- stage control bytes (final phase known) and data bytes (tile-local offsets) ---------------------
     const uint32_t nkeys = (n + 3) / 4;
     uint8_t* out = p.dst + rd.dst_off;
     uint8_t* kdst = out + p.hdr_bytes + (v0 >> 2);
-    uint8_t* ddst = out + p.hdr_bytes + nkeys + tile_excl;
-    uint8_t* kst = smem + L::kKeyOff + ((uintptr_t)kdst & 15);
-    uint8_t* dstg = smem + L::kDataOff + ((uintptr_t)ddst & 15);
-
-    // ---- stage control bytes and data bytes in shared memory ----------------------------------------
+    uint8_t* kst = smem + L::kKeyOff + wid * L::kKeyStageWarp + ((uintptr_t)kdst & 15);
+    uint8_t* dstg = smem + L::kEncDataOff;
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        const uint32_t g = j * NT + tid;
+        const uint32_t g = j * 32 + lane;
 #pragma unroll
         for (int b = 0; b < KB; ++b) kst[g * KB + b] = (uint8_t)(key[j] >> (8 * b));
         uint32_t o = j == 0 ? off0 : off1;
@@ -283,14 +326,74 @@ __global__ void __launch_bounds__(kSvbThreads) svb_encode_kernel(SvbParams p)
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
+    warp_copy_out(kdst, kst, (nv + 3) >> 2);
 
-    // ---- coalesced copy-out ---------------------------------------------------------------------------
-    copy_out_aligned<NT>(kdst, kst, (nv + 3) >> 2);
-    copy_out_aligned<NT>(ddst, dstg, tile_total);
-    if (tid == 0) {
-        if (ti == 0 && p.hdr_bytes) *reinterpret_cast<uint32_t*>(out) = rd.src_bytes;
-        if (v0 + nv == n) p.results[r] = (uint32_t)(p.hdr_bytes + nkeys + tile_excl + tile_total);
+    // ---- the only use of the global offset: copy this warp's bytes out -------------------------------------
+    const uint64_t tile_excl = chain_wait(ctrl + 2 * kSvbWarps);
+    warp_copy_out_shifted(out + p.hdr_bytes + nkeys + tile_excl + warp_excl, dstg + warp_excl, warp_total);
+    if (lane == 0) {
+        if (ti == 0 && wid == 0 && p.hdr_bytes) *reinterpret_cast<uint32_t*>(out) = rd.src_bytes;
+        // the warp holding the read's last value (or warp 0 of an empty read) reports the size
+        if ((nv && v0 + nv == n) || (n == 0 && wid == 0)) p.results[r] = (uint32_t)(p.hdr_bytes + nkeys + tile_excl + warp_excl + warp_total);
+    }
+}
+
+// =====================================================================================================
+// decode, pre-pass: data-byte offset of every warp tile from the control bytes alone (one warp per read)
+// =====================================================================================================
+template <int ISZ, int MODE>
+__global__ void __launch_bounds__(kSvbThreads) svb_key_offsets_kernel(SvbParams p)
+{
+    constexpr uint32_t WV = kSvbWarpTileBytes / ISZ;  // values per warp tile
+    constexpr uint32_t KPW = WV / 4;                  // control bytes per warp tile (64 / 128 / 256)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= p.n_reads) return;
+    const SvbRead rd = p.reads[r];
+    if (rd.rejected) return;
+    const uint32_t n = rd.n_values;
+    const uint32_t src_bytes = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
+    const uint32_t nkeys = (n + 3) / 4;
+    if (n == 0 || src_bytes >= kErrOutOfMemory || nkeys > src_bytes) return;  // svb_decode_kernel reports these
+    const uint8_t* keys = p.src + rd.src_off;
+    uint32_t* out = p.wtile_off + (uint64_t)rd.first_tile * kSvbWarps;
+    const uint32_t n_wt = (n + WV - 1) / WV;
+    uint32_t running = 0;
+    constexpr int U = 4;  // warp tiles per iteration: independent loads in flight, interleaved reductions
+    for (uint32_t wt0 = 0; wt0 < n_wt; wt0 += U) {
+        uint32_t extra[U];  // sum of the 2-bit codes of each warp tile
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            extra[q] = 0;
+            const uint32_t kb0 = (wt0 + q) * KPW;
+            for (uint32_t wq = lane; wq < KPW / 4; wq += 32) {
+                const uint32_t b0 = kb0 + 4 * wq;  // first control byte of this word; covers values 4*b0 .. 4*b0+15
+                if (b0 >= nkeys) continue;
+                uint32_t word;
+                if (b0 + 4 <= nkeys) word = *reinterpret_cast<const uint32_t*>(keys + b0);
+                else {
+                    word = 0;
+                    for (uint32_t b = b0; b < nkeys; ++b) word |= (uint32_t)keys[b] << (8 * (b - b0));
+                }
+                const uint32_t vleft = n - 4 * b0;  // values covered from this word on (>= 1)
+                if (vleft < 16) word &= (1u << (2 * vleft)) - 1u;
+                extra[q] += __popc(word & 0x55555555u) + 2 * __popc(word & 0xAAAAAAAAu);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+            for (int q = 0; q < U; ++q) extra[q] += __shfl_xor_sync(0xffffffffu, extra[q], d);
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            const uint32_t wt = wt0 + q;
+            if (wt < n_wt) {
+                if (lane == 0) out[wt] = running;
+                running += (n - wt * WV < WV ? n - wt * WV : WV) + extra[q];
+            }
+        }
     }
 }
 
@@ -300,16 +403,13 @@ __global__ void __launch_bounds__(kSvbThreads) svb_encode_kernel(SvbParams p)
 template <int ISZ, bool ZZ, int MODE>
 __global__ void __launch_bounds__(kSvbThreads) svb_decode_kernel(SvbParams p)
 {
-    constexpr int NT = kSvbThreads, G = kSvbGroups, VPG = 16 / ISZ, KB = VPG / 4;
-    constexpr uint32_t TV = kSvbTileBytes / ISZ;
-    constexpr int NW = NT / 32;
+    constexpr int G = kSvbGroups, VPG = 16 / ISZ, KB = VPG / 4;
+    constexpr uint32_t TV = kSvbTileBytes / ISZ, WV = kSvbWarpTileBytes / ISZ;
     using L = SvbSmem<ISZ, MODE>;
     VBZ_DYN_SMEM(smem);
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + L::kScratchOff);
-    uint32_t* scratch2 = scratch + 2 * (NW + 1);
-    uint64_t* bcast = reinterpret_cast<uint64_t*>(smem + L::kBcastOff);
+    volatile uint64_t* ctrl = reinterpret_cast<volatile uint64_t*>(smem + L::kCtrlOff);
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x;
     const uint32_t r = p.tile_read[t];
     const SvbRead rd = p.reads[r];
@@ -331,21 +431,26 @@ __global__ void __launch_bounds__(kSvbThreads) svb_decode_kernel(SvbParams p)
             stop = true;
         }
         if (stop) {
-            if (ti == 0 && tid == 0) p.results[r] = early;
+            if (ti == 0 && threadIdx.x == 0) p.results[r] = early;
             return;
         }
     }
+    if (ZZ) {
+        if (threadIdx.x < 2 * kSvbWarps + 2) ctrl[threadIdx.x] = 0;
+        __syncthreads();  // the only CTA-wide barrier: nothing is in flight yet
+    }
     const uint32_t ndata = src_bytes - nkeys;
-    const uint32_t v0 = ti * TV;
-    const uint32_t nv = n - v0 < TV ? n - v0 : TV;
+    const uint32_t v0 = ti * TV + wid * WV;
+    const uint32_t nv = v0 >= n ? 0u : (n - v0 < WV ? n - v0 : WV);
     const uint8_t* keys = p.src + rd.src_off + (v0 >> 2);
     const uint8_t* data = p.src + rd.src_off + nkeys;
+    const uint32_t tile_excl = nv ? p.wtile_off[(uint64_t)t * kSvbWarps + wid] : 0u;  // data bytes before this warp tile
 
     // ---- control bytes -> per-group byte counts ------------------------------------------------------------
     uint32_t key[G], len[G], cnt[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        const uint32_t g = j * NT + tid, e0 = g * VPG;
+        const uint32_t g = j * 32 + lane, e0 = g * VPG;
         cnt[j] = e0 >= nv ? 0u : (nv - e0 < (uint32_t)VPG ? nv - e0 : (uint32_t)VPG);
         uint32_t kbits = 0;
         if (cnt[j] == (uint32_t)VPG) {
@@ -359,43 +464,32 @@ __global__ void __launch_bounds__(kSvbThreads) svb_decode_kernel(SvbParams p)
         key[j] = kbits;
         len[j] = cnt[j] + __popc(kbits & 0x55555555u) + 2 * __popc(kbits & 0xAAAAAAAAu);
     }
-    uint32_t off0, off1, tot0, tot1;
-    cta_scan_pair<NT>(len[0], len[1], scratch, off0, off1, tot0, tot1);
-    off1 += tot0;
-    const uint32_t tile_total = tot0 + tot1;
-    if (tid < 32) {
-        uint64_t excl = 0;
-        if (ti == 0) {
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStInclusive | tile_total);
-        } else {
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStAggregate | tile_total);
-            excl = lookback_exclusive(p.status_a, t, rd.first_tile);
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStInclusive | (excl + tile_total));
-        }
-        if (lane == 0) bcast[0] = excl;
-    }
-    __syncthreads();
-    const uint64_t tile_excl = bcast[0];
+    static_assert(G == 2, "the packed scan below assumes two groups per lane");
+    const uint32_t incl = warp_scan_u32(len[0] | (len[1] << 16));
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t tot0 = tot & 0xFFFFu, warp_total = tot0 + (tot >> 16);
+    const uint32_t off0 = (incl & 0xFFFFu) - len[0];
+    const uint32_t off1 = tot0 + (incl >> 16) - len[1];
 
-    // ---- stage this tile's data bytes (clipped to the read's data region; the rest reads as zero) -------
+    // ---- stage this warp tile's data bytes (clipped to the read's data region; the rest reads as zero) -------
     const uint8_t* gsrc = data + tile_excl;
-    uint8_t* stg = smem + L::kDataOff + ((uintptr_t)gsrc & 15);
-    const uint32_t avail = tile_excl >= ndata ? 0u : (ndata - tile_excl < tile_total ? (uint32_t)(ndata - tile_excl) : tile_total);
-    copy_in_aligned<NT>(stg, gsrc, avail);
-    for (uint32_t i = avail + tid; i < tile_total; i += NT) stg[i] = 0;
-    __syncthreads();
+    uint8_t* stg = smem + L::kDecDataOff + wid * L::kDecStageWarp + ((uintptr_t)gsrc & 15);
+    const uint32_t avail = tile_excl >= ndata ? 0u : (ndata - tile_excl < warp_total ? ndata - tile_excl : warp_total);
+    warp_copy_in(stg, gsrc, avail);
+    for (uint32_t i = avail + lane; i < warp_total; i += 32) stg[i] = 0;
+    __syncwarp();
 
     // ---- unpack, un-zigzag, prefix-sum ---------------------------------------------------------------------
     uint32_t val[G][VPG];
     uint32_t gsum[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        const uint32_t e0 = (j * NT + tid) * VPG;
+        const uint32_t e0 = (j * 32 + lane) * VPG;
         uint32_t o = j == 0 ? off0 : off1;
         // x86 build: a group of 8 goes through the SIMD body (16-bit un-zigzag of the low 16 bits) while it is
         // one of the count/8 full groups and at least 32 data bytes remain; otherwise the scalar tail
         // (32-bit un-zigzag, truncated on store) - impl_sse3.h:494-500,505-520,542-572.
-        const bool simd16 = MODE == kModeI16X86 && ((v0 + e0) >> 3) < (n >> 3) && tile_excl + o + 32 <= (uint64_t)ndata;
+        const bool simd16 = MODE == kModeI16X86 && ((v0 + e0) >> 3) < (n >> 3) && (uint64_t)tile_excl + o + 32 <= (uint64_t)ndata;
         uint32_t run = 0;
 #pragma unroll
         for (int k = 0; k < VPG; ++k) {
@@ -420,32 +514,20 @@ __global__ void __launch_bounds__(kSvbThreads) svb_decode_kernel(SvbParams p)
     }
     uint32_t carry0 = 0, carry1 = 0;
     if (ZZ) {
-        uint32_t e0s, e1s, t0s, t1s;
-        cta_scan_pair<NT>(gsum[0], gsum[1], scratch2, e0s, e1s, t0s, t1s);
-        e1s += t0s;
-        const uint32_t tile_sum = t0s + t1s;
-        if (tid < 32) {
-            uint64_t excl = 0;
-            if (ti == 0) {
-                if (lane == 0) vbz_st_volatile_u64(p.status_b + t, kStInclusive | tile_sum);
-            } else {
-                if (lane == 0) vbz_st_volatile_u64(p.status_b + t, kStAggregate | tile_sum);
-                excl = lookback_exclusive(p.status_b, t, rd.first_tile) & 0xFFFFFFFFull;
-                if (lane == 0) vbz_st_volatile_u64(p.status_b + t, kStInclusive | ((excl + tile_sum) & 0xFFFFFFFFull));
-            }
-            if (lane == 0) bcast[1] = excl;
-        }
-        __syncthreads();
-        const uint32_t base = (uint32_t)bcast[1];
-        carry0 = base + e0s;
-        carry1 = base + e1s;
+        const uint32_t i0 = warp_scan_u32(gsum[0]), i1 = warp_scan_u32(gsum[1]);
+        const uint32_t t0s = __shfl_sync(0xffffffffu, i0, 31), t1s = __shfl_sync(0xffffffffu, i1, 31);
+        uint64_t warp_excl;
+        chain_post(ctrl + kSvbWarps, ctrl + 2 * kSvbWarps + 1, p.status_b, t, rd.first_tile, (uint64_t)(t0s + t1s), 0xFFFFFFFFull, &warp_excl);
+        const uint32_t base = (uint32_t)chain_wait(ctrl + 2 * kSvbWarps + 1) + (uint32_t)warp_excl;
+        carry0 = base + i0 - gsum[0];
+        carry1 = base + t0s + i1 - gsum[1];
     }
 
     // ---- store samples ----------------------------------------------------------------------------------------
     uint8_t* out = p.dst + rd.dst_off;
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        const uint32_t e0 = (j * NT + tid) * VPG;
+        const uint32_t e0 = (j * 32 + lane) * VPG;
         const uint32_t c = j == 0 ? carry0 : carry1;
         uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -462,9 +544,9 @@ __global__ void __launch_bounds__(kSvbThreads) svb_decode_kernel(SvbParams p)
             for (uint32_t b = 0; b < cnt[j] * ISZ; ++b) gp[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
         }
     }
-    if (tid == 0 && v0 + nv == n) {
+    if (lane == 0 && nv && v0 + nv == n) {
         // all data bytes must be consumed exactly: impl_sse3.h:574-577,638-642 / streamvbyte_decode.c:135
-        p.results[r] = (tile_excl + tile_total == (uint64_t)ndata) ? n * (uint32_t)ISZ : (uint32_t)kErrStream;
+        p.results[r] = ((uint64_t)tile_excl + warp_total == (uint64_t)ndata) ? n * (uint32_t)ISZ : (uint32_t)kErrStream;
     }
 }
 

@@ -48,13 +48,18 @@ struct SvbParams {
     uint32_t* results;          // per read: bytes produced, or a VBZ error code
     const uint32_t* src_sizes;  // decode: optional per-read stage-1 size computed on the device (zstd stage);
                                 // a value >= kErrOutOfMemory is an upstream error and is passed through
+    uint32_t* wtile_off;        // decode: data-byte offset of every warp tile (8 per tile), written by
+                                // svb_key_offsets_kernel from the control bytes, read by svb_decode_kernel
     uint32_t hdr_bytes;         // encode: 4 = put the "sized" header (ref vbz/vbz.cpp:316-317) before the payload
     uint32_t n_reads;
+    uint32_t n_tiles;
 };
 
 constexpr int kSvbThreads = 256;
-constexpr int kSvbGroups = 2;                                    // groups of 16 raw bytes per thread
-constexpr int kSvbTileBytes = kSvbThreads * kSvbGroups * 16;     // raw bytes per tile (8 KiB)
+constexpr int kSvbWarps = kSvbThreads / 32;
+constexpr int kSvbGroups = 2;                                    // groups of 16 raw bytes per lane
+constexpr int kSvbWarpTileBytes = 32 * kSvbGroups * 16;          // raw bytes per warp tile (1 KiB)
+constexpr int kSvbTileBytes = kSvbWarps * kSvbWarpTileBytes;     // raw bytes per (CTA) tile (8 KiB)
 constexpr uint64_t kStAggregate = 1ull << 62, kStInclusive = 2ull << 62, kStValueMask = (1ull << 62) - 1;
 
 VBZ_HD uint32_t svb_tile_values(int isz) { return (uint32_t)(kSvbTileBytes / isz); }

@@ -15,6 +15,7 @@
 #include "cpusim.h"
 #define VBZ_DYN_SMEM(name) unsigned char* name = (unsigned char*)cpusim::g_cur->cta->smem
 #define VBZ_SPIN_YIELD() cpusim::yield()
+#define VBZ_SPIN_YIELD_SHARED() cpusim::yield()
 #define VBZ_LAUNCH(kernel, grid, block, smem, stream, ...) \
     cpusim::launch(cpusim::Dim3(grid), cpusim::Dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
 typedef void* vbz_stream_t;
@@ -29,6 +30,7 @@ static inline uint32_t vbz_ld_volatile_u32(const uint32_t* p) { return *(const v
 #include <cuda_runtime.h>
 #define VBZ_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define VBZ_SPIN_YIELD() __nanosleep(20)
+#define VBZ_SPIN_YIELD_SHARED() asm volatile("" ::: "memory")
 #define VBZ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 typedef cudaStream_t vbz_stream_t;
 

@@ -19,6 +19,8 @@ uint32_t vbzk_svb_smem_bytes(int integer_size, int mode, int decode);
 int vbzk_svb_fill_tiles(const struct VbzkSvbRead* d_reads, uint32_t n_reads, uint32_t tile_values, uint32_t* d_tile_read, void* stream);
 /* stage 1, v0 packing: integer_size 1/2/4, zigzag 0/1, mode 0 = int16 x86 semantics, 1 = generic */
 int vbzk_svb_encode(int integer_size, int zigzag, int mode, const struct VbzkSvbParams* params, uint32_t n_tiles, void* stream);
+/* decode pre-pass: fills SvbParams::wtile_off from the control bytes (must precede vbzk_svb_decode) */
+int vbzk_svb_key_offsets(int integer_size, int mode, const struct VbzkSvbParams* params, void* stream);
 int vbzk_svb_decode(int integer_size, int zigzag, int mode, const struct VbzkSvbParams* params, uint32_t n_tiles, void* stream);
 
 #ifdef __cplusplus

@@ -52,6 +52,23 @@ static int launch_decode(const SvbParams& p, uint32_t n_tiles, void* stream)
     return VBZK_LAST_ERROR();
 }
 
+template <int ISZ, int MODE>
+static int launch_key_offsets(const SvbParams& p, void* stream)
+{
+    const uint32_t grid = (p.n_reads + kSvbWarps - 1) / kSvbWarps;
+    VBZ_LAUNCH((svb_key_offsets_kernel<ISZ, MODE>), grid, kSvbThreads, 0, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+extern "C" int vbzk_svb_key_offsets(int isz, int mode, const VbzkSvbParams* params, void* stream)
+{
+    const SvbParams& p = *reinterpret_cast<const SvbParams*>(params);
+    if (p.n_reads == 0) return 0;
+    if (isz == 2) return mode == kModeI16X86 ? launch_key_offsets<2, kModeI16X86>(p, stream) : launch_key_offsets<2, kModeGeneric>(p, stream);
+    if (isz == 4) return launch_key_offsets<4, kModeGeneric>(p, stream);
+    if (isz == 1) return launch_key_offsets<1, kModeGeneric>(p, stream);
+    return -1;
+}
+
 #define VBZK_DISPATCH(fn)                                                                            \
     const SvbParams& p = *reinterpret_cast<const SvbParams*>(params);                                \
     if (n_tiles == 0) return 0;                                                                      \
