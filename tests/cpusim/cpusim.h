@@ -154,6 +154,7 @@ static inline unsigned __brev(unsigned v)
     v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
     return __builtin_bswap32(v);
 }
+// like the CUDA intrinsic, only 3 bits per selector nibble are honoured (no sign replication)
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
 {
     uint64_t ab = ((uint64_t)b << 32) | a;
@@ -161,7 +162,6 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
     for (int i = 0; i < 4; ++i) {
         unsigned sel = (s >> (4 * i)) & 0xF;
         unsigned byte = (unsigned)(ab >> (8 * (sel & 7))) & 0xFF;
-        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0;
         r |= byte << (8 * i);
     }
     return r;

@@ -104,6 +104,32 @@ def test_batch_matches_single_and_isolates_bad_reads(backend):
     assert ol.is_error(out[2][0])
 
 
+def test_int16_decoder_on_foreign_and_damaged_streams(backend):
+    """The int16 path's scalar branch: streams with 3-byte codes (what a non-x86 build of the reference emits for
+    |delta| > 32767), streams cut short and streams with trailing bytes, over several
+    tiles so that offsets and the running sample value cross tile borders.  Checked against the oracle in x86 mode."""
+    capi = backend[0]
+    rng = np.random.default_rng(11)
+    o = Options(True, 2, 0, 0)
+    for n in (37, 9000, 20011):
+        arr = data_gen.uniform_full_range(n, np.int16, rng)
+        arr[n // 2:] = data_gen.nanopore_like(n - n // 2, rng)  # wide codes in the first half only
+        port.lib.vbzo_set_int16_x86_semantics(0)
+        try:
+            r, wide = port.compress(arr, o, sized=False)  # generic template: 32-bit deltas
+        finally:
+            port.lib.vbzo_set_int16_x86_semantics(1)
+        assert not ol.is_error(r)
+        _, narrow = port.compress(arr, o, sized=False)
+        assert len(wide) > len(narrow)
+        for blob in (wide, wide[:-1], wide + b"\x01", narrow[:-5], narrow[:len(narrow) // 2], narrow + b"\0\0"):
+            a = capi.decompress(blob, o, arr.nbytes, sized=False)
+            b = port.decompress(blob, o, arr.nbytes, sized=False)
+            assert a[0] == b[0], (n, len(blob), a[0], b[0])
+            if not ol.is_error(b[0]):
+                assert a[1] == b[1], (n, len(blob))
+
+
 def test_error_paths_match_oracle(backend):
     capi = backend[0]
     arr = np.arange(100, dtype=np.int16)

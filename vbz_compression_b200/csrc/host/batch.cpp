@@ -74,9 +74,10 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     const uint32_t n = (uint32_t)reads.size();
     if (n == 0) return 0;
     uint64_t tiles = 0;
+    const uint32_t tile_values = vbzk_svb_tile_values(kind.isz, kind.mode);
     for (uint32_t i = 0; i < n; ++i) {
         reads[i].first_tile = (uint32_t)tiles;
-        tiles += svb_tiles_of(reads[i].n_values, kind.isz);
+        tiles += svb_tiles_of(reads[i].n_values, tile_values);
     }
     if (tiles > 0x7FFFFFFFull) { set_last_error("batch too large: more than 2^31 tiles"); return -1; }
     const uint32_t n_tiles = (uint32_t)tiles;
@@ -93,7 +94,7 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     if (!cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord")) return -1;
     if (!cuda_ok(cudaMemsetAsync(ctx->d_status.p, 0, status_words * 8, stream), "reset look-back state")) return -1;
 
-    int e = vbzk_svb_fill_tiles(ctx->d_reads.as<VbzkSvbRead>(), n, vbzk_svb_tile_values(kind.isz), ctx->d_tiles.as<uint32_t>(), stream);
+    int e = vbzk_svb_fill_tiles(ctx->d_reads.as<VbzkSvbRead>(), n, tile_values, ctx->d_tiles.as<uint32_t>(), stream);
     if (e) { cuda_ok((cudaError_t)e, "svb_fill_tiles launch"); return -1; }
     SvbParams p;
     p.src = d_src;

@@ -48,8 +48,8 @@ struct SvbParams {
     uint32_t* results;          // per read: bytes produced, or a VBZ error code
     const uint32_t* src_sizes;  // decode: optional per-read stage-1 size computed on the device (zstd stage);
                                 // a value >= kErrOutOfMemory is an upstream error and is passed through
-    uint32_t* wtile_off;        // decode: data-byte offset of every warp tile (8 per tile), written by
-                                // svb_key_offsets_kernel from the control bytes, read by svb_decode_kernel
+    uint32_t* wtile_off;        // decode: data-byte offsets from the control-byte pre-pass (8 * n_tiles words).  Generic
+                                // kernels: one per warp tile; int16 path: [0, n_tiles) tile offsets, [n_tiles, 2 n_tiles) tile sums
     uint32_t hdr_bytes;         // encode: 4 = put the "sized" header (ref vbz/vbz.cpp:316-317) before the payload
     uint32_t n_reads;
     uint32_t n_tiles;
@@ -62,11 +62,11 @@ constexpr int kSvbWarpTileBytes = 32 * kSvbGroups * 16;          // raw bytes pe
 constexpr int kSvbTileBytes = kSvbWarps * kSvbWarpTileBytes;     // raw bytes per (CTA) tile (8 KiB)
 constexpr uint64_t kStAggregate = 1ull << 62, kStInclusive = 2ull << 62, kStValueMask = (1ull << 62) - 1;
 
-VBZ_HD uint32_t svb_tile_values(int isz) { return (uint32_t)(kSvbTileBytes / isz); }
-VBZ_HD uint32_t svb_tiles_of(uint32_t n_values, int isz)
+// values per tile: the int16 x86-semantics path (csrc/svb16_kernels.cuh) uses 16 KiB tiles, the generic kernels 8 KiB
+VBZ_HD uint32_t svb_tile_values(int isz, int mode) { return (isz == 2 && mode == kModeI16X86) ? 8192u : (uint32_t)(kSvbTileBytes / isz); }
+VBZ_HD uint32_t svb_tiles_of(uint32_t n_values, uint32_t tile_values)
 {
-    uint32_t tv = svb_tile_values(isz);
-    uint32_t t = (uint32_t)(((uint64_t)n_values + tv - 1) / tv);
+    uint32_t t = (uint32_t)(((uint64_t)n_values + tile_values - 1) / tile_values);
     return t ? t : 1;  // an empty read still owns one (empty) tile: it writes the header and the result
 }
 

@@ -13,6 +13,7 @@
 
 #ifdef VBZ_CPUSIM
 #include "cpusim.h"
+#include <string.h>
 #define VBZ_DYN_SMEM(name) unsigned char* name = (unsigned char*)cpusim::g_cur->cta->smem
 #define VBZ_SPIN_YIELD() cpusim::yield()
 #define VBZ_SPIN_YIELD_SHARED() cpusim::yield()
@@ -25,6 +26,33 @@ template <class T> static inline void vbz_st_stream(T* p, T v) { *p = v; }
 static inline uint64_t vbz_ld_volatile_u64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 static inline void vbz_st_volatile_u64(uint64_t* p, uint64_t v) { *(volatile uint64_t*)p = v; }
 static inline uint32_t vbz_ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+
+// packed 16-bit SIMD-in-a-word arithmetic (VIADD.16x2 on sm_100a)
+static inline uint32_t vbz_add16x2(uint32_t a, uint32_t b) { return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16); }
+static inline uint32_t vbz_sub16x2(uint32_t a, uint32_t b) { return ((a - b) & 0xFFFFu) | (((a >> 16) - (b >> 16)) << 16); }
+// full PRMT (selector bit 3 of a nibble replicates the sign of the selected byte; __byte_perm ignores that bit)
+static inline uint32_t vbz_prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    const uint64_t ab = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sel = (s >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(ab >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned s) { s = s > 32 ? 32 : s; return s == 32 ? lo : (unsigned)(((((uint64_t)hi << 32) | lo) << s) >> 32); }
+// TMA 1-D bulk copies and their mbarrier: the emulator copies synchronously
+static inline void vbz_mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+static inline void vbz_mbar_expect_tx(uint64_t*, uint32_t) {}
+static inline void vbz_bulk_load(void* s, const void* g, uint32_t n, uint64_t* bar) { memcpy(s, g, n); *bar += 1; }
+static inline void vbz_mbar_arrive_only(uint64_t* bar) { *bar += 1; }
+static inline void vbz_mbar_wait(uint64_t* bar, uint32_t) { while (*(volatile uint64_t*)bar == 0) cpusim::yield(); }
+static inline void vbz_fence_async_smem() {}
+static inline void vbz_bulk_store(void* g, const void* s, uint32_t n) { memcpy(g, s, n); }
+static inline void vbz_bulk_store_commit_wait() {}
 
 #else  // ---------------------------------------------------------------- real CUDA
 #include <cuda_runtime.h>
@@ -52,5 +80,64 @@ __device__ __forceinline__ uint32_t vbz_ld_volatile_u32(const uint32_t* p)
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// packed 16-bit SIMD-in-a-word arithmetic (VIADD.16x2 on sm_100a)
+__device__ __forceinline__ uint32_t vbz_add16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+__device__ __forceinline__ uint32_t vbz_sub16x2(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+// full PRMT (selector bit 3 of a nibble replicates the sign of the selected byte; __byte_perm ignores that bit)
+__device__ __forceinline__ uint32_t vbz_prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
+
+// ---- TMA 1-D bulk copies (cp.async.bulk) and the mbarrier that tracks a load ------------------------
+// Addresses and sizes must be multiples of 16 bytes.
+__device__ __forceinline__ uint32_t vbz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vbz_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vbz_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void vbz_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vbz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vbz_mbar_arrive_only(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(vbz_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void vbz_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vbz_smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(vbz_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void vbz_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "VBZ_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra VBZ_DONE;\n\t"
+        "bra VBZ_WAIT;\n\t"
+        "VBZ_DONE:\n\t"
+        "}" ::"r"(vbz_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// make this thread's shared-memory writes visible to the async (TMA) proxy
+__device__ __forceinline__ void vbz_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void vbz_bulk_store(void* gdst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(vbz_smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+// the issuing thread: close the group and wait until shared memory has been read
+__device__ __forceinline__ void vbz_bulk_store_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 #endif

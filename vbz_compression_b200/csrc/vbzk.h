@@ -12,7 +12,7 @@ struct VbzkSvbRead;   /* == vbz::SvbRead   (csrc/svb_kernels.cuh) */
 struct VbzkSvbParams; /* == vbz::SvbParams (csrc/svb_kernels.cuh) */
 
 /* geometry helpers (host side needs them to size tables) */
-uint32_t vbzk_svb_tile_values(int integer_size);
+uint32_t vbzk_svb_tile_values(int integer_size, int mode);
 uint32_t vbzk_svb_smem_bytes(int integer_size, int mode, int decode);
 
 /* tile -> read table */

@@ -1,6 +1,7 @@
 // csrc/vbzk_launch.cu - kernel instantiations + the C-ABI launch shim (csrc/vbzk.h).
 #include "vbzk.h"
 #include "svb_kernels.cuh"
+#include "svb16_kernels.cuh"
 
 using namespace vbz;
 
@@ -13,14 +14,15 @@ using namespace vbz;
 #define VBZK_LAST_ERROR() ((int)cudaGetLastError())
 #endif
 
-extern "C" uint32_t vbzk_svb_tile_values(int isz) { return svb_tile_values(isz); }
+extern "C" uint32_t vbzk_svb_tile_values(int isz, int mode) { return svb_tile_values(isz, mode); }
 
 template <int ISZ, int MODE>
 static uint32_t smem_of(int decode) { return decode ? SvbSmem<ISZ, MODE>::kDecodeBytes : SvbSmem<ISZ, MODE>::kEncodeBytes; }
 
 extern "C" uint32_t vbzk_svb_smem_bytes(int isz, int mode, int decode)
 {
-    if (isz == 2) return mode == kModeI16X86 ? smem_of<2, kModeI16X86>(decode) : smem_of<2, kModeGeneric>(decode);
+    if (isz == 2 && mode == kModeI16X86) return S16Smem::kBytes;
+    if (isz == 2) return smem_of<2, kModeGeneric>(decode);
     if (isz == 4) return smem_of<4, kModeGeneric>(decode);
     return smem_of<1, kModeGeneric>(decode);
 }
@@ -59,11 +61,33 @@ static int launch_key_offsets(const SvbParams& p, void* stream)
     VBZ_LAUNCH((svb_key_offsets_kernel<ISZ, MODE>), grid, kSvbThreads, 0, (vbz_stream_t)stream, p);
     return VBZK_LAST_ERROR();
 }
+// ---- int16 x86-semantics path (csrc/svb16_kernels.cuh) ---------------------------------------------------
+static int launch_s16_encode(const SvbParams& p, uint32_t n_tiles, void* stream)
+{
+    if (int e = VBZK_SET_SMEM(svb16_encode_kernel, S16Smem::kBytes)) return e;
+    VBZ_LAUNCH(svb16_encode_kernel, n_tiles, kS16Threads, S16Smem::kBytes, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+static int launch_s16_decode(const SvbParams& p, uint32_t n_tiles, void* stream)
+{
+    if (int e = VBZK_SET_SMEM(svb16_decode_kernel, S16Smem::kBytes)) return e;
+    VBZ_LAUNCH(svb16_decode_kernel, n_tiles, kS16Threads, S16Smem::kBytes, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+static int launch_s16_offsets(const SvbParams& p, void* stream)
+{
+    VBZ_LAUNCH(svb16_tile_sums_kernel, (p.n_tiles + kS16Warps - 1) / kS16Warps, kS16Threads, 0, (vbz_stream_t)stream, p);
+    if (int e = VBZK_LAST_ERROR()) return e;
+    VBZ_LAUNCH(svb16_tile_offsets_kernel, (p.n_reads + kS16Warps - 1) / kS16Warps, kS16Threads, 0, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+
 extern "C" int vbzk_svb_key_offsets(int isz, int mode, const VbzkSvbParams* params, void* stream)
 {
     const SvbParams& p = *reinterpret_cast<const SvbParams*>(params);
     if (p.n_reads == 0) return 0;
-    if (isz == 2) return mode == kModeI16X86 ? launch_key_offsets<2, kModeI16X86>(p, stream) : launch_key_offsets<2, kModeGeneric>(p, stream);
+    if (isz == 2 && mode == kModeI16X86) return launch_s16_offsets(p, stream);
+    if (isz == 2) return launch_key_offsets<2, kModeGeneric>(p, stream);
     if (isz == 4) return launch_key_offsets<4, kModeGeneric>(p, stream);
     if (isz == 1) return launch_key_offsets<1, kModeGeneric>(p, stream);
     return -1;
@@ -72,7 +96,6 @@ extern "C" int vbzk_svb_key_offsets(int isz, int mode, const VbzkSvbParams* para
 #define VBZK_DISPATCH(fn)                                                                            \
     const SvbParams& p = *reinterpret_cast<const SvbParams*>(params);                                \
     if (n_tiles == 0) return 0;                                                                      \
-    if (isz == 2 && zz && mode == kModeI16X86) return fn<2, true, kModeI16X86>(p, n_tiles, stream);  \
     if (isz == 2) return zz ? fn<2, true, kModeGeneric>(p, n_tiles, stream) : fn<2, false, kModeGeneric>(p, n_tiles, stream); \
     if (isz == 4) return zz ? fn<4, true, kModeGeneric>(p, n_tiles, stream) : fn<4, false, kModeGeneric>(p, n_tiles, stream); \
     if (isz == 1) return zz ? fn<1, true, kModeGeneric>(p, n_tiles, stream) : fn<1, false, kModeGeneric>(p, n_tiles, stream); \
@@ -80,9 +103,11 @@ extern "C" int vbzk_svb_key_offsets(int isz, int mode, const VbzkSvbParams* para
 
 extern "C" int vbzk_svb_encode(int isz, int zz, int mode, const VbzkSvbParams* params, uint32_t n_tiles, void* stream)
 {
+    if (isz == 2 && zz && mode == kModeI16X86 && n_tiles) return launch_s16_encode(*reinterpret_cast<const SvbParams*>(params), n_tiles, stream);
     VBZK_DISPATCH(launch_encode)
 }
 extern "C" int vbzk_svb_decode(int isz, int zz, int mode, const VbzkSvbParams* params, uint32_t n_tiles, void* stream)
 {
+    if (isz == 2 && zz && mode == kModeI16X86 && n_tiles) return launch_s16_decode(*reinterpret_cast<const SvbParams*>(params), n_tiles, stream);
     VBZK_DISPATCH(launch_decode)
 }
