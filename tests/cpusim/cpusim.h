@@ -140,6 +140,12 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 3
 static inline unsigned __ballot_sync(unsigned, int p) { return cpusim::warp_ballot(p != 0); }
 static inline int __any_sync(unsigned, int p) { return cpusim::warp_ballot(p != 0) != 0; }
 static inline int __all_sync(unsigned, int p) { return cpusim::warp_ballot(p == 0) == 0; }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v)
+{
+    unsigned s = 0;
+    for (unsigned i = 0; i < cpusim::g_cur->warp->nlanes; ++i) s += cpusim::warp_exchange(v, i);
+    return s;
+}
 static inline unsigned __activemask() { return cpusim::g_cur->warp->nlanes == 32 ? 0xffffffffu : ((1u << cpusim::g_cur->warp->nlanes) - 1); }
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -83,7 +83,7 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     const uint32_t n_tiles = (uint32_t)tiles;
     const size_t status_words = (size_t)n_tiles * (decode ? 2 : 1);
     if (!ctx->d_reads.ensure((size_t)n * sizeof(SvbRead)) || !ctx->d_tiles.ensure((size_t)n_tiles * 4) ||
-        !ctx->d_status.ensure(status_words * 8) || (decode && !ctx->d_wtoff.ensure((size_t)n_tiles * kSvbWarps * 4)))
+        !ctx->d_status.ensure((status_words + 1) * 8) || (decode && !ctx->d_wtoff.ensure((size_t)n_tiles * kSvbWarps * 4)))
         return -1;
     // the pinned staging may still be feeding the previous batch's upload
     if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
@@ -92,7 +92,7 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     if (!cuda_ok(cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.p, (size_t)n * sizeof(SvbRead), cudaMemcpyHostToDevice, stream), "upload descriptors"))
         return -1;
     if (!cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord")) return -1;
-    if (!cuda_ok(cudaMemsetAsync(ctx->d_status.p, 0, status_words * 8, stream), "reset look-back state")) return -1;
+    if (!cuda_ok(cudaMemsetAsync(ctx->d_status.p, 0, (status_words + 1) * 8, stream), "reset look-back state")) return -1;
 
     int e = vbzk_svb_fill_tiles(ctx->d_reads.as<VbzkSvbRead>(), n, tile_values, ctx->d_tiles.as<uint32_t>(), stream);
     if (e) { cuda_ok((cudaError_t)e, "svb_fill_tiles launch"); return -1; }
@@ -103,12 +103,14 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     p.tile_read = ctx->d_tiles.as<uint32_t>();
     p.status_a = ctx->d_status.as<uint64_t>();
     p.status_b = ctx->d_status.as<uint64_t>() + n_tiles;
+    p.ticket = reinterpret_cast<uint32_t*>(ctx->d_status.as<uint64_t>() + status_words);
     p.results = d_results;
     p.src_sizes = d_src_sizes;
     p.hdr_bytes = hdr_bytes;
     p.wtile_off = decode ? ctx->d_wtoff.as<uint32_t>() : nullptr;
     p.n_reads = n;
     p.n_tiles = n_tiles;
+    { const char* dbg = getenv("VBZ_B200_DEBUG"); p.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
     const VbzkSvbParams* pp = reinterpret_cast<const VbzkSvbParams*>(&p);
     if (decode) {
         e = vbzk_svb_key_offsets(kind.isz, kind.mode, pp, stream);

@@ -17,17 +17,25 @@
 //                        its byte offset in the shared-memory staging tile (word stores + edge bytes)
 //   decode  the inverse: 5-word window at the group's byte offset, selector table, packed un-zigzag,
 //           packed in-register prefix sum, VIADD.16x2 warp scan.
-// Geometry: a CTA (8 warps) owns a TILE of 8192 samples (16 KiB raw); a warp owns 1024 of them as
-// 4 rows of 32 groups (group = row * 32 + lane) so that every global 128-bit access of a warp is one
-// contiguous 512-byte segment.  Tiles are numbered read-major; blockIdx order is data order.
-// Offsets: lane -> warp by shuffle scan, warp -> tile through shared memory, tile -> read by a
-// decoupled look-back over 64-bit status words (csrc/svb_kernels.cuh: lookback_exclusive).
-// Data movement: encode reads samples with coalesced streaming 128-bit loads and writes BOTH output
-// streams (control bytes, data bytes) from shared-memory staging with TMA bulk stores
-// (cp.async.bulk.global.shared::cta), staged at the same 16-byte phase as the destination; decode pulls
-// its variable-length slice of data bytes and its control bytes into shared memory with TMA bulk loads
-// (cp.async.bulk.shared::cluster.global + mbarrier) issued before anything else, and stores samples with
-// coalesced streaming 128-bit stores.
+// Geometry: a TILE is 8192 samples (16 KiB raw) of one read; tiles are numbered read-major.  A warp owns
+// 1024 samples of the tile as 4 rows of 32 groups (group = row * 32 + lane): conflict-free 128-bit
+// shared-memory reads, contiguous 512-byte global stores.
+// Scheduling: PERSISTENT CTAs (8 warps; as many as are co-resident on the 148 SMs, launched cooperatively so that
+// they ARE co-resident) walk the tiles round-robin (tile = blockIdx + k * gridDim): the tiles being worked on at
+// any time are consecutive, which keeps the look-back between them short.
+// Input: the TMA engine fills the input stage of tile k+1 (cp.async.bulk.shared::cluster.global + mbarrier, one
+// instruction for 16 KiB) as soon as tile k's rows are in registers, so HBM latency is off the critical path and
+// the compute warps issue no global load instruction at all.
+// Offsets: lane -> warp by shuffle scan, warp -> tile through shared memory, tile -> read by a decoupled
+// look-back over 64-bit status words (csrc/svb_kernels.cuh: lookback_exclusive).  The look-back is DEFERRED by
+// one tile: a CTA posts the aggregate of tile k, and only then resolves tile k-1, whose predecessors posted theirs a
+// whole tile time ago - the wait for a predecessor, which bounded the first version of these kernels, is gone.
+// To make that possible encode packs tile k into shared memory at tile-local offsets (double buffered) and the
+// whole CTA copies tile k-1 out once its offset is known (aligned 128-bit streaming stores fed by funnel-shifted
+// 128-bit shared loads); the control bytes, whose position is known up front, leave through a TMA bulk store
+// (cp.async.bulk.global.shared::cta).  Decode parks the samples of tile k - complete except for the carry of the
+// tile - in a thread-private shared-memory slot and adds the carry when it stores tile k-1's samples with coalesced
+// 128-bit streaming stores.
 //
 // HBM traffic per sample: encode 2 B in + 0.25 B + ~1.01 B out; decode the reverse + 0.25 B (the control
 // bytes are read twice: once by svb16_tile_sums_kernel, which turns them into per-tile data offsets).
@@ -42,18 +50,47 @@ constexpr int kS16Rows = 4;                                         // groups pe
 constexpr uint32_t kS16WarpValues = 32 * kS16Rows * 8;              // 1024
 constexpr uint32_t kS16TileValues = kS16Warps * kS16WarpValues;     // 8192
 constexpr uint32_t kS16TileKeys = kS16TileValues / 4;               // 2048
+constexpr uint32_t kS16TileBytes = kS16TileValues * 2;              // 16384
 constexpr uint32_t kS16LutWords = 96;                               // indexed by the sparse 4-code key (bits 0,2,4,6)
 
-// shared memory carve-up (bytes)
-struct S16Smem {
-    static constexpr int kLut = 0;                                  // encode: 96 x u32, decode: 96 x uint2
-    static constexpr int kWtot = kLut + kS16LutWords * 8;           // 8 warp totals (chain A) + 8 (chain B)
-    static constexpr int kSlots = kWtot + 16 * 4;                   // two u64 look-back results, one mbarrier, flags
-    static constexpr int kKeys = kSlots + 48;                       // control bytes (+16 phase)
-    static constexpr int kData = kKeys + kS16TileKeys + 16;         // data bytes (+16 phase, +32 window over-read)
-    static constexpr int kBytes = kData + kS16TileValues * 2 + 64;
+struct S16Ctl {           // control block in shared memory
+    uint32_t wtot[8];     // per-warp data-byte totals of the current tile
+    uint32_t wsum[8];     // decode: per-warp sample sums of the current tile
+    uint32_t base[2][8];  // decode: sample value before each warp, tile-relative, for the two tiles in flight
+    uint32_t flag;        // decode: the current tile holds 3/4-byte codes
+    uint32_t carry;       // decode: look-back result (sample value before the pending tile)
+    uint64_t excl;        // encode: look-back result (data bytes before the pending tile)
+    uint64_t bar[3];      // mbarriers of the TMA loads
 };
-static_assert(S16Smem::kKeys % 16 == 0 && S16Smem::kData % 16 == 0, "staging areas must be 16-byte aligned");
+// shared memory carve-up (bytes)
+struct S16EncSmem {
+    static constexpr int kLut = 0;                                   // 96 x u32
+    static constexpr int kCtl = 384;
+    static constexpr int kIn = 576;                                  // 16 B left margin + tile + 16 B slack
+    static constexpr int kInBytes = 16 + kS16TileBytes + 16;
+    static constexpr int kKeys = kIn + kInBytes;                     // control bytes (+16 phase)
+    static constexpr int kData = kKeys + kS16TileKeys + 16;          // 2 x data bytes at tile-local offsets (+64 slack)
+    static constexpr int kDataStride = kS16TileBytes + 64;
+    static constexpr int kBytes = kData + 2 * kDataStride;
+};
+struct S16DecSmem {
+    static constexpr int kLut = 0;                                   // 96 x uint2
+    static constexpr int kCtl = 768;
+    static constexpr int kKeys = 960;                                // 2 x control bytes (+16 phase)
+    static constexpr int kKeysStride = kS16TileKeys + 16;
+    static constexpr int kData = kKeys + 2 * kKeysStride;            // data-byte slice (+16 phase, +48 slack)
+    static constexpr int kOut = kData + kS16TileBytes + 64;          // 2 x parked samples, thread-private slots
+    static constexpr int kBytes = kOut + 2 * kS16TileBytes;
+};
+static_assert(sizeof(S16Ctl) <= 192 && S16EncSmem::kKeys % 16 == 0 && S16EncSmem::kData % 16 == 0 && S16EncSmem::kDataStride % 16 == 0 &&
+                  S16DecSmem::kData % 16 == 0 && S16DecSmem::kOut % 16 == 0,
+              "smem layout");
+
+// a tile whose offset (encode) / carry (decode) is resolved one tile later; CTA-uniform, lives in registers
+struct S16Pending {
+    uint32_t valid = 0, t = 0, r = 0, first_tile = 0, n = 0, src_bytes = 0, total = 0, tile_off = 0, tile_len = 0, ndata = 0;
+    uint64_t dst_off = 0;
+};
 
 VBZ_HD uint32_t s16_tiles_of(uint32_t n_values)
 {
@@ -96,7 +133,7 @@ __device__ __forceinline__ uint32_t s16_nonzero_bytes(uint32_t w) { return (((w 
 __device__ __forceinline__ uint32_t s16_flags_to_codes(uint32_t f) { return ((f >> 7) * 0x01041040u) >> 24; }
 
 // Place `len` bytes (little-endian in r0..r3, zero above) at byte offset P of the staging area: whole words
-// where the group owns them, single bytes at the two edges it shares with its neighbours.
+// where the group owns them, single bytes at the two edges it shares with its neighbours.  Any len (ragged tiles).
 __device__ __forceinline__ void s16_place(uint8_t* stage, uint32_t P, uint32_t len, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
 {
     const uint32_t a = P & 3u, sh = a * 8u, end = a + len;
@@ -124,162 +161,296 @@ __device__ __forceinline__ void s16_place(uint8_t* stage, uint32_t P, uint32_t l
     }
 }
 
-// Copy `n` staged bytes to global memory: TMA bulk store for the 16-byte aligned body, byte stores for the
-// (< 16 byte) head and tail.  stage + (g & 15) is where byte 0 sits, so both sides share their phase.
-// Called by all threads of the CTA after the staging area has been fenced and barriered.
-__device__ __forceinline__ void s16_copy_out(uint8_t* g, const uint8_t* stage_at_g, uint32_t n, uint32_t tid, uint32_t issuer)
+// One warp copies `n` staged bytes to global memory: a TMA bulk store for the 16-byte aligned body (lane 0),
+// byte stores for the (< 16 byte) head (lanes 1..15) and tail (lanes 16..30).  stage_at_g sits at the same
+// 16-byte phase as g.  The staging area must have been fenced (fence.proxy.async) and barriered.
+__device__ __forceinline__ void s16_copy_out_warp(uint8_t* g, const uint8_t* stage_at_g, uint32_t n, uint32_t lane)
 {
     uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
     if (head > n) head = n;
     const uint32_t body = (n - head) & ~15u, tail = n - head - body;
-    if (tid == issuer && body) vbz_bulk_store(g + head, stage_at_g + head, body);
-    const uint32_t i = tid - issuer - 1;  // the threads after the issuer take the edges
-    if (i < head) g[i] = stage_at_g[i];
-    else if (i - 16u < tail) g[head + body + (i - 16u)] = stage_at_g[head + body + (i - 16u)];
+    if (lane == 0) {
+        if (body) {
+            vbz_bulk_store(g + head, stage_at_g + head, body);
+            vbz_bulk_store_commit();
+        }
+    } else if (lane < 16) {
+        if (lane - 1 < head) g[lane - 1] = stage_at_g[lane - 1];
+    } else if (lane - 16 < tail) {
+        g[head + body + (lane - 16)] = stage_at_g[head + body + (lane - 16)];
+    }
+}
+// The whole CTA copies `n` bytes from a 16-byte aligned staging area to an arbitrarily aligned global address:
+// aligned 128-bit streaming stores, each fed by two aligned 128-bit shared loads re-aligned with funnel shifts
+// (the staging area must be readable 32 bytes past the end).
+__device__ __forceinline__ void s16_copy_out_shifted(uint8_t* g, const uint8_t* stage, uint32_t n, uint32_t tid)
+{
+    uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
+    if (head > n) head = n;
+    const uint32_t nchunks = (n - head) >> 4, done = head + (nchunks << 4);
+    if (tid < head) g[tid] = stage[tid];
+    else if (tid >= 32 && tid - 32 < n - done) g[done + tid - 32] = stage[done + tid - 32];
+    const uint4* s4 = reinterpret_cast<const uint4*>(stage);  // chunk c starts at staging byte head + 16 c
+    uint4* g4 = reinterpret_cast<uint4*>(g + head);
+    const uint32_t wsel = head >> 2, sh = 8u * (head & 3u);   // CTA-uniform: which words of the 32-byte window, which byte phase
+    for (uint32_t c = tid; c < nchunks; c += kS16Threads) {
+        const uint4 A = s4[c], B = s4[c + 1];
+        uint32_t w0, w1, w2, w3, w4;
+        if (wsel == 0) { w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; }
+        else if (wsel == 1) { w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; }
+        else if (wsel == 2) { w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; }
+        else { w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; }
+        vbz_st_stream(g4 + c, make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)));
+    }
+}
+
+// ---- the packed arithmetic of one group of 8 samples -----------------------------------------------------------
+// x[0..3]: 8 samples; prevw: the sample before them in the high half.  -> zigzag words z, control bits key.
+__device__ __forceinline__ void s16_transform_group(const uint4 q, uint32_t prevw, uint32_t (&z)[4])
+{
+    const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+    const uint32_t pw[4] = {__byte_perm(prevw, x[0], 0x5432), __byte_perm(x[0], x[1], 0x5432), __byte_perm(x[1], x[2], 0x5432),
+                            __byte_perm(x[2], x[3], 0x5432)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t d = vbz_sub16x2(x[i], pw[i]);                 // 16-bit wrapping delta (impl_sse3.h:434-436)
+        z[i] = vbz_add16x2(d, d) ^ vbz_prmt(d, 0u, 0xBB99);          // (d << 1) ^ (d >> 15)  (impl_sse3.h:438-440)
+    }
+}
+__device__ __forceinline__ uint32_t s16_group_key(const uint32_t (&z)[4])
+{
+    const uint32_t k0 = s16_flags_to_codes(s16_nonzero_bytes(__byte_perm(z[0], z[1], 0x7531)));
+    const uint32_t k1 = s16_flags_to_codes(s16_nonzero_bytes(__byte_perm(z[2], z[3], 0x7531)));
+    return k0 | (k1 << 8);
+}
+// compact the group's 8..16 data bytes into r[0..3] (zero above)
+__device__ __forceinline__ void s16_compact_group(const uint32_t (&z)[4], uint32_t key, const uint32_t* s_lut, uint32_t (&r)[4])
+{
+    const uint32_t k0 = key & 0x55u, k1 = key >> 8;
+    const uint32_t sel0 = s_lut[k0], sel1 = s_lut[k1];
+    const uint32_t c0 = __byte_perm(z[0], z[1], sel0), c1 = __byte_perm(z[0], z[1], sel0 >> 16);
+    const uint32_t c2 = __byte_perm(z[2], z[3], sel1), c3 = __byte_perm(z[2], z[3], sel1 >> 16);
+    const uint32_t sh = 8u * __popc(k0);  // the second half starts at byte 4 + popc(k0)
+    r[0] = c0;
+    r[1] = c1 | __funnelshift_lc(0u, c2, sh);
+    r[2] = __funnelshift_lc(c2, c3, sh);
+    r[3] = __funnelshift_lc(c3, 0u, sh);
 }
 
 // =====================================================================================================
 // encode
 // =====================================================================================================
-__global__ void __launch_bounds__(kS16Threads, 4) svb16_encode_kernel(SvbParams p)
+// one thread: start the TMA load of `tile`'s samples (plus the 16 bytes before them, which hold the previous sample)
+__device__ __forceinline__ void s16_enc_issue(const SvbParams& p, uint32_t tile, uint8_t* in_stage, uint64_t* bar)
 {
-    VBZ_DYN_SMEM(smem);
-    uint32_t* s_lut = reinterpret_cast<uint32_t*>(smem + S16Smem::kLut);
-    uint32_t* s_wtot = reinterpret_cast<uint32_t*>(smem + S16Smem::kWtot);
-    uint64_t* s_excl = reinterpret_cast<uint64_t*>(smem + S16Smem::kSlots);
-    uint8_t* s_keys = smem + S16Smem::kKeys;
-    uint8_t* s_data = smem + S16Smem::kData;
+    if (tile >= p.n_tiles) return;
+    const uint32_t r = p.tile_read[tile];
+    const SvbRead* rd = p.reads + r;
+    const uint32_t n = rd->n_values;
+    if (rd->rejected || n == 0) return;
+    const uint32_t ti = tile - rd->first_tile;
+    const uint64_t b0 = (uint64_t)ti * kS16TileBytes, total = 2ull * n;
+    uint32_t bytes = total - b0 < kS16TileBytes ? (uint32_t)(total - b0) : kS16TileBytes;
+    bytes = (bytes + 15u) & ~15u;  // the slot of a read is padded to 16 bytes
+    const uint32_t margin = ti ? 16u : 0u;
+    vbz_mbar_expect_tx(bar, bytes + margin);
+    vbz_bulk_load(in_stage + 16 - margin, p.src + rd->src_off + b0 - margin, bytes + margin, bar);
+}
 
+// the part of a tile that waits for its offset: copy the packed data bytes out, report the size
+__device__ __forceinline__ void s16_encode_finish(const SvbParams& p, const S16Pending& pend, uint64_t excl, const uint8_t* stage, uint32_t tid)
+{
+    const uint32_t nkeys = (pend.n + 3) / 4;
+    uint8_t* out = p.dst + pend.dst_off;
+    s16_copy_out_shifted(out + p.hdr_bytes + nkeys + excl, stage, pend.total, tid);
+    const uint32_t ti = pend.t - pend.first_tile;
+    if (tid == 96 && (uint64_t)ti * kS16TileValues + kS16TileValues >= (uint64_t)pend.n)  // the read's last tile reports
+        p.results[pend.r] = (uint32_t)(p.hdr_bytes + nkeys + excl + pend.total);
+}
+// warp 0: resolve the pending tile's offset (its predecessors posted their aggregates a tile time ago)
+__device__ __forceinline__ uint64_t s16_resolve(uint64_t* status, const S16Pending& pend, uint64_t mask, uint32_t lane)
+{
+    if (pend.t == pend.first_tile) return 0;  // posted as inclusive right away
+    const uint64_t excl = lookback_exclusive(status, pend.t, pend.first_tile) & mask;
+    if (lane == 0) vbz_st_volatile_u64(status + pend.t, kStInclusive | ((excl + pend.total) & mask));
+    return excl;
+}
+
+template <bool FULL>
+__device__ __forceinline__ void s16_encode_tile(const SvbParams& p, const SvbRead& rd, uint32_t r, uint32_t t, uint32_t ti, unsigned char* smem,
+                                                 S16Pending& pend, uint32_t sbuf)
+{
+    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(smem + S16EncSmem::kLut);
+    S16Ctl* ctl = reinterpret_cast<S16Ctl*>(smem + S16EncSmem::kCtl);
+    const uint8_t* in = smem + S16EncSmem::kIn + 16;
+    uint8_t* s_keys = smem + S16EncSmem::kKeys;
+    uint8_t* s_data = smem + S16EncSmem::kData + sbuf * S16EncSmem::kDataStride;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t t = blockIdx.x;
-    const uint32_t r = p.tile_read[t];
-    const SvbRead rd = p.reads[r];
-    const uint32_t ti = t - rd.first_tile;
-    if (rd.rejected) {
-        if (ti == 0 && tid == 0) p.results[r] = rd.preset;
-        return;
-    }
-    const uint32_t n = rd.n_values;
-    uint8_t* out = p.dst + rd.dst_off;
-    const uint32_t nkeys = (n + 3) / 4;
-    if (n == 0) {  // an empty read owns one empty tile
-        if (tid == 0) {
-            if (p.hdr_bytes) *reinterpret_cast<uint32_t*>(out) = rd.src_bytes;
-            p.results[r] = p.hdr_bytes;
-        }
-        return;
-    }
-    if (tid < 86 && !(tid & 0xAAu)) s_lut[tid] = s16_make_enc_sel(tid);
+    const uint32_t n = rd.n_values, tv0 = ti * kS16TileValues;
+    const uint32_t tile_values = FULL ? kS16TileValues : n - tv0;
+    const uint32_t local0 = wid * kS16WarpValues + lane * 8;  // this lane's first value in row 0, tile-relative
 
-    // ---- load: 4 rows of 32 groups per warp, 16 bytes per lane and row -----------------------------------
-    const uint8_t* src = p.src + rd.src_off;
-    const uint32_t tv0 = ti * kS16TileValues, wv0 = tv0 + wid * kS16WarpValues;
-    uint4 q[kS16Rows];
-    uint32_t cnt[kS16Rows];
+    // ---- rows: shared -> registers, delta, zigzag, codes -------------------------------------------------------
+    uint32_t z[kS16Rows][4], key[kS16Rows], len[kS16Rows], cnt[kS16Rows];
+    {
+        uint32_t prev_row_w = 0;
+        // lane 0 of row 0 continues from the sample before the warp's first one (zero at the start of a read)
+        const uint32_t carry_w = (wid == 0 && ti == 0) ? 0u : (uint32_t)(*reinterpret_cast<const uint16_t*>(in + 2 * wid * kS16WarpValues - 2)) << 16;
 #pragma unroll
-    for (int j = 0; j < kS16Rows; ++j) {
-        const uint32_t s0 = wv0 + j * 256 + lane * 8;
-        cnt[j] = s0 >= n ? 0u : (n - s0 < 8u ? n - s0 : 8u);
-        // the slot of a read is padded to 16 bytes, so the last (partial) group can be loaded whole
-        q[j] = cnt[j] ? vbz_ld_stream(reinterpret_cast<const uint4*>(src + 2ull * s0)) : make_uint4(0, 0, 0, 0);
-    }
-    uint32_t carry_w = 0;  // lane 0: the sample before this warp's first one, in the high half
-    if (lane == 0 && wv0 > 0 && wv0 < n) carry_w = (uint32_t)(*reinterpret_cast<const uint16_t*>(src + 2ull * (wv0 - 1))) << 16;
-
-    // ---- delta, zigzag, codes --------------------------------------------------------------------------------
-    uint32_t z[kS16Rows][4], key[kS16Rows], len[kS16Rows];
+        for (int j = 0; j < kS16Rows; ++j) {
+            const uint32_t l0 = local0 + j * 256;
+            cnt[j] = FULL ? 8u : (l0 >= tile_values ? 0u : (tile_values - l0 < 8u ? tile_values - l0 : 8u));
+            const uint4 q = *reinterpret_cast<const uint4*>(in + 2 * l0);
+            const uint32_t send = lane == 31 ? prev_row_w : q.w;  // lane 31 hands its previous row's last word to lane 0
+            const uint32_t recv = __shfl_sync(0xffffffffu, send, (lane + 31) & 31);
+            prev_row_w = q.w;
+            s16_transform_group(q, (lane == 0 && j == 0) ? carry_w : recv, z[j]);
+            if (!FULL && cnt[j] < 8) {  // the read's last, partial group: samples past the end contribute nothing
 #pragma unroll
-    for (int j = 0; j < kS16Rows; ++j) {
-        const uint32_t send = (lane == 31 && j > 0) ? q[j > 0 ? j - 1 : 0].w : q[j].w;
-        const uint32_t recv = __shfl_sync(0xffffffffu, send, (lane + 31) & 31);
-        const uint32_t prevw = (lane == 0 && j == 0) ? carry_w : recv;
-        const uint32_t x[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-        const uint32_t pw[4] = {__byte_perm(prevw, x[0], 0x5432), __byte_perm(x[0], x[1], 0x5432), __byte_perm(x[1], x[2], 0x5432),
-                                __byte_perm(x[2], x[3], 0x5432)};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t d = vbz_sub16x2(x[i], pw[i]);                                  // 16-bit wrapping delta (impl_sse3.h:434-436)
-            z[j][i] = vbz_add16x2(d, d) ^ vbz_prmt(d, 0u, 0xBB99);                     // (d << 1) ^ (d >> 15)  (impl_sse3.h:438-440)
+                for (int i = 0; i < 4; ++i) z[j][i] &= cnt[j] > 2u * i + 1 ? 0xFFFFFFFFu : (cnt[j] > 2u * i ? 0x0000FFFFu : 0u);
+            }
+            key[j] = s16_group_key(z[j]);
+            len[j] = cnt[j] + __popc(key[j]);
         }
-        if (cnt[j] < 8) {  // the read's last, partial group: samples past the end contribute nothing
-#pragma unroll
-            for (int i = 0; i < 4; ++i) z[j][i] &= cnt[j] > 2u * i + 1 ? 0xFFFFFFFFu : (cnt[j] > 2u * i ? 0x0000FFFFu : 0u);
-        }
-        const uint32_t k0 = s16_flags_to_codes(s16_nonzero_bytes(__byte_perm(z[j][0], z[j][1], 0x7531)));
-        const uint32_t k1 = s16_flags_to_codes(s16_nonzero_bytes(__byte_perm(z[j][2], z[j][3], 0x7531)));
-        key[j] = k0 | (k1 << 8);
-        len[j] = cnt[j] + __popc(key[j]);
     }
 
-    // ---- offsets: lane -> warp (packed shuffle scan) -> tile (shared) -> read (look-back) -----------------------
+    // ---- offsets inside the tile: lane -> warp (packed shuffle scan) -> tile (shared) --------------------------------
     const uint32_t ia = warp_scan_u32(len[0] | (len[1] << 16)), ib = warp_scan_u32(len[2] | (len[3] << 16));
     const uint32_t ta = __shfl_sync(0xffffffffu, ia, 31), tb = __shfl_sync(0xffffffffu, ib, 31);
     const uint32_t t0 = ta & 0xFFFFu, t1 = ta >> 16, t2 = tb & 0xFFFFu, t3 = tb >> 16;
-    const uint32_t warp_total = t0 + t1 + t2 + t3;
     uint32_t off[kS16Rows];
     off[0] = (ia & 0xFFFFu) - len[0];
     off[1] = t0 + (ia >> 16) - len[1];
     off[2] = t0 + t1 + (ib & 0xFFFFu) - len[2];
     off[3] = t0 + t1 + t2 + (ib >> 16) - len[3];
-    if (lane == 0) s_wtot[wid] = warp_total;
-    __syncthreads();
-    uint32_t warp_excl = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < kS16Warps; ++w) {
-        const uint32_t v = s_wtot[w];
-        if ((uint32_t)w < wid) warp_excl += v;
-        tile_total += v;
+    if (lane == 0) {
+        ctl->wtot[wid] = t0 + t1 + t2 + t3;
+        if (wid == 0) vbz_bulk_store_wait_read();  // the previous tile's control bytes must have left their staging area
     }
+    __syncthreads();  // (1) warp totals posted, input stage consumed
+    if (tid == 64) s16_enc_issue(p, t + gridDim.x, smem + S16EncSmem::kIn, &ctl->bar[0]);
+    const uint32_t wt = ctl->wtot[lane & 7];
+    const uint32_t warp_excl = __reduce_add_sync(0xffffffffu, lane < wid ? wt : 0u);
+    const uint32_t tile_total = __reduce_add_sync(0xffffffffu, lane < kS16Warps ? wt : 0u);
     if (wid == 0) {
-        uint64_t excl = 0;
-        if (ti == 0) {
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStInclusive | tile_total);
-        } else {
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStAggregate | tile_total);
-            excl = lookback_exclusive(p.status_a, t, rd.first_tile);
-            if (lane == 0) vbz_st_volatile_u64(p.status_a + t, kStInclusive | ((excl + tile_total) & kStValueMask));
+        // post this tile's aggregate FIRST, then resolve the tile before it
+        if (lane == 0) vbz_st_volatile_u64(p.status_a + t, (ti == 0 ? kStInclusive : kStAggregate) | tile_total);
+        if (pend.valid) {
+            const uint64_t excl = s16_resolve(p.status_a, pend, kStValueMask, lane);
+            if (lane == 0) ctl->excl = excl;
         }
-        if (lane == 0) *s_excl = excl;
     }
-    __syncthreads();
-    const uint64_t tile_excl = *s_excl;
 
-    // ---- stage both streams at the 16-byte phase of their destination ---------------------------------------------
+    // ---- pack: control bytes at the phase of their destination, data bytes at tile-local offsets --------------------
+    uint8_t* out = p.dst + rd.dst_off;
     uint8_t* kg = out + p.hdr_bytes + (tv0 >> 2);
-    uint8_t* dg = out + p.hdr_bytes + nkeys + tile_excl;
-    const uint32_t dphase = (uint32_t)((uintptr_t)dg & 15u);
-    uint8_t* kstage = s_keys + ((uintptr_t)kg & 15u);
-    uint8_t* dstage = s_data + dphase;
+    uint8_t* kstage = s_keys + ((uintptr_t)kg & 15u);  // kg is even: header of 0 or 4 bytes, 16-byte aligned slots
+    uint32_t tail_prev = 0;
 #pragma unroll
     for (int j = 0; j < kS16Rows; ++j) {
-        if (cnt[j]) {
-            *reinterpret_cast<uint16_t*>(kstage + wid * 256 + j * 64 + lane * 2) = (uint16_t)key[j];  // kg is even: hdr 0 or 4, 16-byte slots
-            const uint32_t k0 = key[j] & 0x55u, k1 = key[j] >> 8;
-            const uint32_t sel0 = s_lut[k0], sel1 = s_lut[k1];
-            const uint32_t c0 = __byte_perm(z[j][0], z[j][1], sel0), c1 = __byte_perm(z[j][0], z[j][1], sel0 >> 16);
-            const uint32_t c2 = __byte_perm(z[j][2], z[j][3], sel1), c3 = __byte_perm(z[j][2], z[j][3], sel1 >> 16);
-            const uint32_t sh = 8u * __popc(k0);  // the second half starts at byte 4 + popc(k0)
-            s16_place(s_data, dphase + warp_excl + off[j], len[j], c0, c1 | __funnelshift_lc(0u, c2, sh), __funnelshift_lc(c2, c3, sh),
-                      __funnelshift_lc(c3, 0u, sh));
+        if (!FULL && cnt[j] == 0) continue;
+        *reinterpret_cast<uint16_t*>(kstage + wid * 256 + j * 64 + lane * 2) = (uint16_t)key[j];
+        uint32_t rr[4];
+        s16_compact_group(z[j], key[j], s_lut, rr);
+        const uint32_t P = warp_excl + off[j];
+        if (!FULL) {
+            s16_place(s_data, P, len[j], rr[0], rr[1], rr[2], rr[3]);
+        } else {
+            // every group has 8..16 bytes: the word that holds its last bytes also holds the first bytes of the next
+            // group, which receives them by shuffle and stores the merged word - whole-word stores only
+            const uint32_t a = P & 3u, sh = a * 8u, end = a + len[j], qe = end >> 2;
+            const uint32_t s0 = rr[0] << sh;
+            const uint32_t s1 = __funnelshift_l(rr[0], rr[1], sh), s2 = __funnelshift_l(rr[1], rr[2], sh), s3 = __funnelshift_l(rr[2], rr[3], sh);
+            const uint32_t s4 = __funnelshift_l(rr[3], 0u, sh);
+            const uint32_t tailw = qe == 2 ? s2 : (qe == 3 ? s3 : s4);  // zero if the group ends on a word boundary
+            const uint32_t recv = __shfl_sync(0xffffffffu, lane == 31 ? tail_prev : tailw, (lane + 31) & 31);
+            tail_prev = tailw;
+            uint32_t* w = reinterpret_cast<uint32_t*>(s_data + (P & ~3u));
+            if (j == 0 && lane == 0) {  // first group of the warp: the bytes before it belong to another warp
+                if (a == 0) w[0] = s0;
+                else {
+                    uint8_t* b = reinterpret_cast<uint8_t*>(w);
+                    if (a <= 1) b[1] = (uint8_t)(s0 >> 8);
+                    if (a <= 2) b[2] = (uint8_t)(s0 >> 16);
+                    b[3] = (uint8_t)(s0 >> 24);
+                }
+            } else {
+                w[0] = s0 | recv;
+            }
+            w[1] = s1;
+            if (end >= 12) w[2] = s2;
+            if (end >= 16) w[3] = s3;
+            if (j == kS16Rows - 1 && lane == 31) {  // last group of the warp: nobody merges its trailing bytes
+                uint8_t* b = reinterpret_cast<uint8_t*>(w + qe);
+                const uint32_t re = end & 3u;
+                if (re > 0) b[0] = (uint8_t)tailw;
+                if (re > 1) b[1] = (uint8_t)(tailw >> 8);
+                if (re > 2) b[2] = (uint8_t)(tailw >> 16);
+            }
         }
     }
     vbz_fence_async_smem();
-    __syncthreads();
+    __syncthreads();  // (2) both staging areas complete, the pending tile's offset known
 
-    // ---- out: TMA bulk stores for the aligned bodies, byte stores for the edges -------------------------------------
-    const uint32_t tile_values = n - tv0 < kS16TileValues ? n - tv0 : kS16TileValues;
-    s16_copy_out(kg, kstage, (tile_values + 3) >> 2, tid, 0);
-    s16_copy_out(dg, dstage, tile_total, tid, 64);
-    if (tid == 0 || tid == 64) vbz_bulk_store_commit_wait();
-    if (tid == 128) {
-        if (ti == 0 && p.hdr_bytes) *reinterpret_cast<uint32_t*>(out) = rd.src_bytes;
-        if (tv0 + tile_values == n) p.results[r] = (uint32_t)(p.hdr_bytes + nkeys + tile_excl + tile_total);
+    // ---- out: this tile's control bytes (TMA bulk store), the PENDING tile's data bytes (whole CTA) ------------------
+    if (wid == 0) s16_copy_out_warp(kg, kstage, (tile_values + 3) >> 2, lane);
+    if (tid == 96 && ti == 0 && p.hdr_bytes) *reinterpret_cast<uint32_t*>(out) = rd.src_bytes;
+    if (pend.valid) s16_encode_finish(p, pend, ctl->excl, smem + S16EncSmem::kData + (sbuf ^ 1u) * S16EncSmem::kDataStride, tid);
+    pend.valid = 1; pend.t = t; pend.r = r; pend.first_tile = rd.first_tile; pend.n = n; pend.src_bytes = rd.src_bytes;
+    pend.total = tile_total; pend.dst_off = rd.dst_off;
+}
+
+__global__ void __launch_bounds__(kS16Threads, 4) svb16_encode_kernel(SvbParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(smem + S16EncSmem::kLut);
+    S16Ctl* ctl = reinterpret_cast<S16Ctl*>(smem + S16EncSmem::kCtl);
+    const uint32_t tid = threadIdx.x;
+    if (tid < 86 && !(tid & 0xAAu)) s_lut[tid] = s16_make_enc_sel(tid);
+    if (tid == 0) {
+        vbz_mbar_init(&ctl->bar[0], 1);
+        s16_enc_issue(p, blockIdx.x, smem + S16EncSmem::kIn, &ctl->bar[0]);
     }
+    __syncthreads();
+    S16Pending pend;
+    uint32_t phase = 0, sbuf = 0;
+    for (uint32_t cur = blockIdx.x; cur < p.n_tiles; cur += gridDim.x) {
+        const uint32_t r = p.tile_read[cur];
+        const SvbRead rd = p.reads[r];
+        const uint32_t ti = cur - rd.first_tile;
+        if (rd.rejected || rd.n_values == 0) {  // decided on the host, or an empty read (one empty tile): nothing was loaded
+            if (tid == 0) {
+                if (rd.rejected) p.results[r] = rd.preset;
+                else {
+                    if (p.hdr_bytes) *reinterpret_cast<uint32_t*>(p.dst + rd.dst_off) = rd.src_bytes;
+                    p.results[r] = p.hdr_bytes;
+                }
+            }
+            __syncthreads();  // nobody is still reading the input stage
+            if (tid == 0) s16_enc_issue(p, cur + gridDim.x, smem + S16EncSmem::kIn, &ctl->bar[0]);
+            continue;
+        }
+        vbz_mbar_wait(&ctl->bar[0], phase);
+        phase ^= 1u;
+        if ((uint64_t)ti * kS16TileValues + kS16TileValues <= (uint64_t)rd.n_values) s16_encode_tile<true>(p, rd, r, cur, ti, smem, pend, sbuf);
+        else s16_encode_tile<false>(p, rd, r, cur, ti, smem, pend, sbuf);
+        sbuf ^= 1u;
+    }
+    if (pend.valid) {  // flush the last tile
+        __syncthreads();
+        if (tid < 32) {
+            const uint64_t excl = s16_resolve(p.status_a, pend, kStValueMask, tid);
+            if (tid == 0) ctl->excl = excl;
+        }
+        __syncthreads();
+        s16_encode_finish(p, pend, ctl->excl, smem + S16EncSmem::kData + (sbuf ^ 1u) * S16EncSmem::kDataStride, tid);
+    }
+    if (tid == 0) vbz_bulk_store_wait_read();  // shared memory must outlive the last bulk store
 }
 
 // =====================================================================================================
 // decode, pre-pass 1: sum of the data-byte lengths of every tile, from the control bytes alone.
-// One warp per tile (2 KiB of control bytes = 4 x 128-bit loads per lane).
+// One warp per tile (2 KiB of control bytes).
 // =====================================================================================================
 __global__ void __launch_bounds__(kS16Threads) svb16_tile_sums_kernel(SvbParams p)
 {
@@ -337,76 +508,123 @@ __global__ void __launch_bounds__(kS16Threads) svb16_tile_offsets_kernel(SvbPara
 // =====================================================================================================
 // decode
 // =====================================================================================================
-__global__ void __launch_bounds__(kS16Threads, 4) svb16_decode_kernel(SvbParams p)
+struct S16DecTile {
+    uint32_t n, nkeys, ndata, ti, tv0, tile_values, tile_off, tile_len, kphase, dphase;
+    const uint8_t* kg;     // the tile's control bytes
+    const uint8_t* dbase;  // the read's data bytes
+    bool active, short_data;
+    uint32_t early;        // result of an inactive read
+};
+// what every tile of a read agrees on, and this tile's slices (the same function tells the TMA issuer what to
+// load and the consumers what to expect)
+__device__ __forceinline__ S16DecTile s16_dec_describe(const SvbParams& p, const SvbRead* rd, uint32_t r, uint32_t t)
 {
-    VBZ_DYN_SMEM(smem);
-    uint2* s_lut = reinterpret_cast<uint2*>(smem + S16Smem::kLut);
-    uint32_t* s_wtot = reinterpret_cast<uint32_t*>(smem + S16Smem::kWtot);
-    uint64_t* s_excl = reinterpret_cast<uint64_t*>(smem + S16Smem::kSlots);
-    uint64_t* s_bar = s_excl + 2;
-    uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_excl + 3);
-    uint8_t* s_keys = smem + S16Smem::kKeys;
-    uint8_t* s_data = smem + S16Smem::kData;
+    S16DecTile d;
+    d.n = rd->n_values;
+    const uint32_t src_bytes = p.src_sizes ? p.src_sizes[r] : rd->src_bytes;
+    d.nkeys = (d.n + 3) / 4;
+    d.ti = t - rd->first_tile;
+    d.active = true;
+    d.early = 0;
+    if (rd->rejected) { d.early = rd->preset; d.active = false; }
+    else if (p.src_sizes && src_bytes >= kErrOutOfMemory) { d.early = src_bytes; d.active = false; }
+    else if (d.n == 0) { d.early = 0; d.active = false; }                               // impl_sse3.h:473-476
+    else if (d.nkeys > src_bytes) { d.early = kErrInputSize; d.active = false; }         // impl_sse3.h:479-482
+    if (!d.active) return d;
+    d.ndata = src_bytes - d.nkeys;
+    d.tv0 = d.ti * kS16TileValues;
+    d.tile_values = d.n - d.tv0 < kS16TileValues ? d.n - d.tv0 : kS16TileValues;
+    d.tile_off = p.wtile_off[t];                        // data bytes of this read before the tile
+    d.tile_len = p.wtile_off[(uint64_t)p.n_tiles + t];  // data bytes the tile's control bytes ask for
+    d.kg = p.src + rd->src_off + (d.tv0 >> 2);
+    d.dbase = p.src + rd->src_off + d.nkeys;
+    // the packed path needs the tile's data bytes in shared memory: all present, at most 2 per sample
+    d.short_data = (uint64_t)d.tile_off + d.tile_len > (uint64_t)d.ndata || d.tile_len > 2u * d.tile_values;
+    d.kphase = (uint32_t)((uintptr_t)d.kg & 15u);
+    d.dphase = (uint32_t)((uintptr_t)(d.dbase + d.tile_off) & 15u);
+    return d;
+}
+// one thread: start the TMA load of `tile`'s control bytes / of its slice of the data bytes
+__device__ __forceinline__ void s16_dec_issue_keys(const SvbParams& p, uint32_t tile, uint8_t* stage, uint64_t* bar)
+{
+    if (tile >= p.n_tiles) return;
+    const uint32_t r = p.tile_read[tile];
+    const S16DecTile d = s16_dec_describe(p, p.reads + r, r, tile);
+    if (!d.active) return;
+    const uint32_t kbytes = (d.kphase + ((d.tile_values + 3) >> 2) + 15u) & ~15u;
+    vbz_mbar_expect_tx(bar, kbytes);
+    vbz_bulk_load(stage, d.kg - d.kphase, kbytes, bar);
+}
+__device__ __forceinline__ void s16_dec_issue_data(const SvbParams& p, uint32_t tile, uint8_t* stage, uint64_t* bar)
+{
+    if (tile >= p.n_tiles) return;
+    const uint32_t r = p.tile_read[tile];
+    const S16DecTile d = s16_dec_describe(p, p.reads + r, r, tile);
+    if (!d.active || d.short_data) return;
+    const uint32_t dbytes = (d.dphase + d.tile_len + 15u) & ~15u;
+    vbz_mbar_expect_tx(bar, dbytes);
+    vbz_bulk_load(stage, d.dbase + d.tile_off - d.dphase, dbytes, bar);
+}
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t t = blockIdx.x;
-    const uint32_t r = p.tile_read[t];
-    const SvbRead rd = p.reads[r];
-    const uint32_t ti = t - rd.first_tile;
-    const uint32_t n = rd.n_values;
-    const uint32_t src_bytes = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
-    const uint32_t nkeys = (n + 3) / 4;
-    {   // whole-read rejections: every tile of the read takes the same branch
-        uint32_t early = 0;
-        bool stop = false;
-        if (rd.rejected) { early = rd.preset; stop = true; }
-        else if (p.src_sizes && src_bytes >= kErrOutOfMemory) { early = src_bytes; stop = true; }
-        else if (n == 0) { early = 0; stop = true; }                              // impl_sse3.h:473-476
-        else if (nkeys > src_bytes) { early = kErrInputSize; stop = true; }       // impl_sse3.h:479-482
-        if (stop) {
-            if (ti == 0 && tid == 0) p.results[r] = early;
-            return;
+// the part of a tile that waits for its carry: add it to the parked samples and store them
+__device__ __forceinline__ void s16_decode_finish(const SvbParams& p, const S16Pending& pend, uint32_t carry, const uint8_t* park, uint32_t tid)
+{
+    const uint32_t lane = tid & 31, wid = tid >> 5;
+    const uint32_t ti = pend.t - pend.first_tile, tv0 = ti * kS16TileValues;
+    const uint32_t tile_values = pend.n - tv0 < kS16TileValues ? pend.n - tv0 : kS16TileValues;
+    const uint32_t c = __byte_perm(carry, 0u, 0x1010);
+    const uint32_t local0 = wid * kS16WarpValues + lane * 8;
+    uint8_t* outp = p.dst + pend.dst_off + 2ull * tv0;
+#pragma unroll
+    for (int j = 0; j < kS16Rows; ++j) {
+        const uint32_t l0 = local0 + j * 256;
+        if (l0 >= tile_values) continue;
+        const uint32_t cnt = tile_values - l0 < 8u ? tile_values - l0 : 8u;
+        uint4 v = *reinterpret_cast<const uint4*>(park + 2 * l0);
+        v = make_uint4(vbz_add16x2(v.x, c), vbz_add16x2(v.y, c), vbz_add16x2(v.z, c), vbz_add16x2(v.w, c));
+        uint8_t* gp = outp + 2 * l0;
+        if (cnt == 8) vbz_st_stream(reinterpret_cast<uint4*>(gp), v);
+        else {
+            uint16_t* g16 = reinterpret_cast<uint16_t*>(gp);
+            g16[0] = (uint16_t)v.x;
+            if (cnt > 1) g16[1] = (uint16_t)(v.x >> 16);
+            if (cnt > 2) g16[2] = (uint16_t)v.y;
+            if (cnt > 3) g16[3] = (uint16_t)(v.y >> 16);
+            if (cnt > 4) g16[4] = (uint16_t)v.z;
+            if (cnt > 5) g16[5] = (uint16_t)(v.z >> 16);
+            if (cnt > 6) g16[6] = (uint16_t)v.w;
         }
     }
-    const uint32_t ndata = src_bytes - nkeys;
-    const uint32_t tv0 = ti * kS16TileValues;
-    const uint32_t tile_values = n - tv0 < kS16TileValues ? n - tv0 : kS16TileValues;
-    const uint32_t tile_keys = (tile_values + 3) >> 2;
-    const uint32_t tile_off = p.wtile_off[t];                       // data bytes of this read before the tile
-    const uint32_t tile_len = p.wtile_off[(uint64_t)p.n_tiles + t];  // data bytes the tile's control bytes ask for
-    const uint8_t* kg = p.src + rd.src_off + (tv0 >> 2);
-    const uint8_t* dbase = p.src + rd.src_off + nkeys;
-    const uint8_t* dg = dbase + tile_off;
-    // the packed path needs the tile's data bytes in shared memory: all present, at most 2 per sample
-    const bool short_data = (uint64_t)tile_off + tile_len > (uint64_t)ndata || tile_len > 2u * tile_values;
-    const uint32_t kphase = (uint32_t)((uintptr_t)kg & 15u), dphase = (uint32_t)((uintptr_t)dg & 15u);
-
-    // ---- TMA: control bytes and this tile's slice of the data bytes -> shared memory ---------------------------
-    if (tid == 0) {
-        vbz_mbar_init(s_bar, 1);
-        *s_flag = 0;
-        const uint32_t kbytes = (kphase + tile_keys + 15u) & ~15u;
-        const uint32_t dbytes = short_data ? 0u : (dphase + tile_len + 15u) & ~15u;
-        vbz_mbar_expect_tx(s_bar, kbytes + dbytes);
-        vbz_bulk_load(s_keys, kg - kphase, kbytes, s_bar);
-        if (dbytes) vbz_bulk_load(s_data, dg - dphase, dbytes, s_bar);
+    if (tid == 0 && tv0 + tile_values == pend.n) {
+        // all data bytes must be consumed exactly: impl_sse3.h:574-577, 638-642
+        p.results[pend.r] = ((uint64_t)pend.tile_off + pend.tile_len == (uint64_t)pend.ndata) ? pend.n * 2u : (uint32_t)kErrStream;
     }
-    if (tid >= 32 && tid < 32 + 86 && !((tid - 32) & 0xAAu)) s_lut[tid - 32] = s16_make_dec_sel(tid - 32);
-    __syncthreads();  // mbarrier initialised, table ready
-    vbz_mbar_wait(s_bar, 0);
+}
+
+template <bool FULL>
+__device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRead& rd, const S16DecTile& d, uint32_t r, uint32_t t, unsigned char* smem,
+                                                 S16Pending& pend, uint32_t sbuf, uint32_t data_phase)
+{
+    const uint2* s_lut = reinterpret_cast<const uint2*>(smem + S16DecSmem::kLut);
+    S16Ctl* ctl = reinterpret_cast<S16Ctl*>(smem + S16DecSmem::kCtl);
+    const uint8_t* s_keys = smem + S16DecSmem::kKeys + sbuf * S16DecSmem::kKeysStride;
+    const uint8_t* s_data = smem + S16DecSmem::kData;
+    uint8_t* park = smem + S16DecSmem::kOut + sbuf * kS16TileBytes;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n = d.n, ndata = d.ndata;
+    const uint32_t local0 = wid * kS16WarpValues + lane * 8;
 
     // ---- control bytes -> lengths -> offsets ------------------------------------------------------------------
-    const uint32_t wv0 = tv0 + wid * kS16WarpValues;
     uint32_t key[kS16Rows], len[kS16Rows], cnt[kS16Rows];
     uint32_t wide = 0;
 #pragma unroll
     for (int j = 0; j < kS16Rows; ++j) {
-        const uint32_t s0 = wv0 + j * 256 + lane * 8;
-        cnt[j] = s0 >= n ? 0u : (n - s0 < 8u ? n - s0 : 8u);
-        uint32_t kb = cnt[j] ? *reinterpret_cast<const uint16_t*>(s_keys + kphase + wid * 256 + j * 64 + lane * 2) : 0u;
-        if (cnt[j] < 8) kb &= (1u << (2 * cnt[j])) - 1u;  // bits of values past the end are ignored by the reference
+        const uint32_t l0 = local0 + j * 256;
+        cnt[j] = FULL ? 8u : (l0 >= d.tile_values ? 0u : (d.tile_values - l0 < 8u ? d.tile_values - l0 : 8u));
+        uint32_t kb = *reinterpret_cast<const uint16_t*>(s_keys + d.kphase + wid * 256 + j * 64 + lane * 2);
+        if (!FULL && cnt[j] < 8) kb &= (1u << (2 * cnt[j])) - 1u;  // bits of values past the end are ignored by the reference
         key[j] = kb;
-        wide |= kb & 0xAAAAu;
+        wide |= kb;
         len[j] = cnt[j] + __popc(kb & 0x5555u) + 2 * __popc(kb & 0xAAAAu);
     }
     const uint32_t ia = warp_scan_u32(len[0] | (len[1] << 16)), ib = warp_scan_u32(len[2] | (len[3] << 16));
@@ -417,21 +635,23 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_decode_kernel(SvbParams 
     off[1] = t0 + (ia >> 16) - len[1];
     off[2] = t0 + t1 + (ib & 0xFFFFu) - len[2];
     off[3] = t0 + t1 + t2 + (ib >> 16) - len[3];
-    if (lane == 0) s_wtot[wid] = t0 + t1 + t2 + t3;
-    if (__any_sync(0xffffffffu, wide != 0) && lane == 0) *s_flag = 1;  // 3- or 4-byte codes: not an x86-int16 stream
-    __syncthreads();
-    uint32_t warp_excl = 0;
-#pragma unroll
-    for (int w = 0; w < kS16Warps; ++w)
-        if ((uint32_t)w < wid) warp_excl += s_wtot[w];
-    const bool slow = short_data || *s_flag != 0;
+    const bool any_wide = __any_sync(0xffffffffu, (wide & 0xAAAAu) != 0);  // 3- or 4-byte codes: not an x86-int16 stream
+    if (lane == 0) {
+        ctl->wtot[wid] = t0 + t1 + t2 + t3;
+        if (any_wide) ctl->flag = 1;
+    }
+    __syncthreads();  // (1) warp totals, flag; this tile's control-byte stage is consumed
+    if (tid == 64) s16_dec_issue_keys(p, t + gridDim.x, smem + S16DecSmem::kKeys + (sbuf ^ 1u) * S16DecSmem::kKeysStride, &ctl->bar[sbuf ^ 1u]);
+    const bool slow = d.short_data || ctl->flag != 0;
+    const uint32_t warp_excl = __reduce_add_sync(0xffffffffu, lane < wid ? ctl->wtot[lane & 7] : 0u);
 
     // ---- unpack + un-zigzag + prefix sum inside the group (two samples per 32-bit word) ---------------------------
     uint32_t y[kS16Rows][4];
     if (!slow) {
+        vbz_mbar_wait(&ctl->bar[2], data_phase);
 #pragma unroll
         for (int j = 0; j < kS16Rows; ++j) {
-            const uint32_t P = dphase + warp_excl + off[j];
+            const uint32_t P = d.dphase + warp_excl + off[j];
             const uint32_t* w = reinterpret_cast<const uint32_t*>(s_data + (P & ~3u));
             const uint32_t sh = 8u * (P & 3u);
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
@@ -447,9 +667,8 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_decode_kernel(SvbParams 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 // (z >> 1) ^ -(z & 1) in both halves (impl_sse3.h:516-520), then x_lo, x_lo + x_hi, plus the running sum
-                const uint32_t d = ((zz[i] >> 1) & 0x7FFF7FFFu) ^ vbz_prmt(zz[i] << 7, 0u, 0xAA88);
-                const uint32_t pre = vbz_add16x2(d, d << 16);
-                y[j][i] = vbz_add16x2(pre, run);
+                const uint32_t dd = ((zz[i] >> 1) & 0x7FFF7FFFu) ^ vbz_prmt(zz[i] << 7, 0u, 0xAA88);
+                y[j][i] = vbz_add16x2(vbz_add16x2(dd, dd << 16), run);
                 run = __byte_perm(y[j][i], 0u, 0x3232);
             }
         }
@@ -457,86 +676,122 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_decode_kernel(SvbParams 
         // exact scalar semantics for tiles the packed path cannot express: codes 2/3 in the stream (the x86
         // build then decodes 8-value groups 16 bits wide while 32 data bytes remain and 32 bits wide in its
         // scalar tail, impl_sse3.h:494-572) or a stream that ends early (bytes past the end read as zero)
-#pragma unroll
+        if (!d.short_data) vbz_mbar_wait(&ctl->bar[2], data_phase);  // consume the phase of the load that was issued
+#pragma unroll 1
         for (int j = 0; j < kS16Rows; ++j) {
-            const uint32_t s0 = wv0 + j * 256 + lane * 8;
-            uint64_t o = (uint64_t)tile_off + warp_excl + off[j];
+            const uint32_t s0 = d.tv0 + local0 + j * 256;
+            uint64_t o = (uint64_t)d.tile_off + warp_excl + off[j];
             const bool simd16 = (s0 >> 3) < (n >> 3) && o + 32 <= (uint64_t)ndata;
-            uint32_t run = 0, prevv = 0;
+            uint32_t run = 0, prevv = 0, yy[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 uint32_t v = 0;
                 if ((uint32_t)k < cnt[j]) {
                     const uint32_t code = (key[j] >> (2 * k)) & 3u;
-                    for (uint32_t b = 0; b <= code; ++b, ++o) v |= (o < ndata ? (uint32_t)dbase[o] : 0u) << (8 * b);
+                    for (uint32_t b = 0; b <= code; ++b, ++o) v |= (o < ndata ? (uint32_t)d.dbase[o] : 0u) << (8 * b);
                 }
                 if (simd16) v &= 0xFFFFu;
                 run += (v >> 1) ^ (0u - (v & 1u));
-                if (k & 1) y[j][k >> 1] = (prevv & 0xFFFFu) | (run << 16);
+                if (k & 1) yy[k >> 1] = (prevv & 0xFFFFu) | (run << 16);
                 prevv = run;
             }
+            if (j == 0) { y[0][0] = yy[0]; y[0][1] = yy[1]; y[0][2] = yy[2]; y[0][3] = yy[3]; }
+            else if (j == 1) { y[1][0] = yy[0]; y[1][1] = yy[1]; y[1][2] = yy[2]; y[1][3] = yy[3]; }
+            else if (j == 2) { y[2][0] = yy[0]; y[2][1] = yy[1]; y[2][2] = yy[2]; y[2][3] = yy[3]; }
+            else { y[3][0] = yy[0]; y[3][1] = yy[1]; y[3][2] = yy[2]; y[3][3] = yy[3]; }
         }
     }
 
-    // ---- running sample value: lane -> warp (packed 16-bit scan) -> tile -> read (look-back) -----------------------
+    // ---- running sample value inside the warp (packed 16-bit scan); park the samples ---------------------------------
     const uint32_t la = __byte_perm(y[0][3], y[1][3], 0x7632), lb = __byte_perm(y[2][3], y[3][3], 0x7632);  // row totals, two per word
     uint32_t sa = la, sb = lb;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t xa = __shfl_up_sync(0xffffffffu, sa, d), xb = __shfl_up_sync(0xffffffffu, sb, d);
-        if (lane >= (uint32_t)d) { sa = vbz_add16x2(sa, xa); sb = vbz_add16x2(sb, xb); }
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t xa = __shfl_up_sync(0xffffffffu, sa, dd), xb = __shfl_up_sync(0xffffffffu, sb, dd);
+        if (lane >= (uint32_t)dd) { sa = vbz_add16x2(sa, xa); sb = vbz_add16x2(sb, xb); }
     }
     const uint32_t wa = __shfl_sync(0xffffffffu, sa, 31), wb = __shfl_sync(0xffffffffu, sb, 31);
     const uint32_t r0t = wa & 0xFFFFu, r1t = wa >> 16, r2t = wb & 0xFFFFu, r3t = wb >> 16;
-    const uint32_t warp_sum = (r0t + r1t + r2t + r3t) & 0xFFFFu;
-    if (lane == 0) s_wtot[8 + wid] = warp_sum;
-    __syncthreads();
-    uint32_t wsum_excl = 0, tile_sum = 0;
+    if (lane == 0) ctl->wsum[wid] = (r0t + r1t + r2t + r3t) & 0xFFFFu;
+    {   // exclusive carry of each row inside the warp: the rows before it, the lanes before it
+        const uint32_t ea = vbz_sub16x2(sa, la), eb = vbz_sub16x2(sb, lb);
+        const uint32_t carry[kS16Rows] = {ea & 0xFFFFu, r0t + (ea >> 16), r0t + r1t + (eb & 0xFFFFu), r0t + r1t + r2t + (eb >> 16)};
 #pragma unroll
-    for (int w = 0; w < kS16Warps; ++w) {
-        const uint32_t v = s_wtot[8 + w];
-        if ((uint32_t)w < wid) wsum_excl += v;
-        tile_sum += v;
+        for (int j = 0; j < kS16Rows; ++j) {
+            const uint32_t c = __byte_perm(carry[j], 0u, 0x1010);
+            *reinterpret_cast<uint4*>(park + 2 * (local0 + j * 256)) =
+                make_uint4(vbz_add16x2(y[j][0], c), vbz_add16x2(y[j][1], c), vbz_add16x2(y[j][2], c), vbz_add16x2(y[j][3], c));
+        }
     }
-    tile_sum &= 0xFFFFu;
+    __syncthreads();  // (2) warp sums; the data-byte stage is consumed
+    if (tid == 64) s16_dec_issue_data(p, t + gridDim.x, smem + S16DecSmem::kData, &ctl->bar[2]);
     if (wid == 0) {
-        uint64_t excl = 0;
-        if (ti == 0) {
-            if (lane == 0) vbz_st_volatile_u64(p.status_b + t, kStInclusive | tile_sum);
-        } else {
-            if (lane == 0) vbz_st_volatile_u64(p.status_b + t, kStAggregate | tile_sum);
-            excl = lookback_exclusive(p.status_b, t, rd.first_tile) & 0xFFFFu;
-            if (lane == 0) vbz_st_volatile_u64(p.status_b + t, kStInclusive | ((excl + tile_sum) & 0xFFFFu));
+        const uint32_t v = lane < kS16Warps ? ctl->wsum[lane] : 0u;
+        const uint32_t incl = warp_scan_u32(v);
+        const uint32_t tile_sum = __shfl_sync(0xffffffffu, incl, 31) & 0xFFFFu;
+        if (lane < kS16Warps) ctl->base[sbuf][lane] = incl - v;  // sample value before the warp's first sample, tile-relative
+        // post this tile's aggregate FIRST, then resolve the tile before it
+        if (lane == 0) vbz_st_volatile_u64(p.status_b + t, (d.ti == 0 ? kStInclusive : kStAggregate) | tile_sum);
+        if (pend.valid) {
+            const uint32_t carry = (uint32_t)s16_resolve(p.status_b, pend, 0xFFFFull, lane);
+            if (lane == 0) ctl->carry = carry;
         }
-        if (lane == 0) s_excl[1] = excl;
+        if (lane == 0) ctl->flag = 0;
+        pend.total = tile_sum;  // (warp 0's copy is the one s16_resolve uses)
+    }
+    __syncthreads();  // (3) the pending tile's carry is known
+    if (pend.valid) s16_decode_finish(p, pend, ctl->carry + ctl->base[sbuf ^ 1u][wid], smem + S16DecSmem::kOut + (sbuf ^ 1u) * kS16TileBytes, tid);
+    const uint32_t keep_total = pend.total;
+    pend.valid = 1; pend.t = t; pend.r = r; pend.first_tile = rd.first_tile; pend.n = n; pend.src_bytes = rd.src_bytes;
+    pend.total = keep_total; pend.dst_off = rd.dst_off; pend.tile_off = d.tile_off; pend.tile_len = d.tile_len; pend.ndata = ndata;
+}
+
+__global__ void __launch_bounds__(kS16Threads, 4) svb16_decode_kernel(SvbParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    uint2* s_lut = reinterpret_cast<uint2*>(smem + S16DecSmem::kLut);
+    S16Ctl* ctl = reinterpret_cast<S16Ctl*>(smem + S16DecSmem::kCtl);
+    const uint32_t tid = threadIdx.x;
+    if (tid < 86 && !(tid & 0xAAu)) s_lut[tid] = s16_make_dec_sel(tid);
+    if (tid == 0) {
+        vbz_mbar_init(&ctl->bar[0], 1);
+        vbz_mbar_init(&ctl->bar[1], 1);
+        vbz_mbar_init(&ctl->bar[2], 1);
+        ctl->flag = 0;
+        s16_dec_issue_keys(p, blockIdx.x, smem + S16DecSmem::kKeys, &ctl->bar[0]);
+        s16_dec_issue_data(p, blockIdx.x, smem + S16DecSmem::kData, &ctl->bar[2]);
     }
     __syncthreads();
-    const uint32_t base = (uint32_t)s_excl[1] + wsum_excl;
-    // exclusive carry of each row: everything before the warp, the rows before it, the lanes before it
-    const uint32_t ea = vbz_sub16x2(sa, la), eb = vbz_sub16x2(sb, lb);
-    uint32_t carry[kS16Rows];
-    carry[0] = base + (ea & 0xFFFFu);
-    carry[1] = base + r0t + (ea >> 16);
-    carry[2] = base + r0t + r1t + (eb & 0xFFFFu);
-    carry[3] = base + r0t + r1t + r2t + (eb >> 16);
-
-    // ---- store samples -------------------------------------------------------------------------------------------
-    uint8_t* outp = p.dst + rd.dst_off;
-#pragma unroll
-    for (int j = 0; j < kS16Rows; ++j) {
-        const uint32_t s0 = wv0 + j * 256 + lane * 8;
-        const uint32_t c = __byte_perm(carry[j], 0u, 0x1010);
-        const uint4 v = make_uint4(vbz_add16x2(y[j][0], c), vbz_add16x2(y[j][1], c), vbz_add16x2(y[j][2], c), vbz_add16x2(y[j][3], c));
-        uint8_t* gp = outp + 2ull * s0;
-        if (cnt[j] == 8) vbz_st_stream(reinterpret_cast<uint4*>(gp), v);
-        else if (cnt[j]) {
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-            for (uint32_t b = 0; b < cnt[j] * 2; ++b) gp[b] = (uint8_t)(wv[b >> 2] >> (8 * (b & 3)));
+    S16Pending pend;
+    uint32_t sbuf = 0, key_phases = 0, data_phase = 0;
+    for (uint32_t cur = blockIdx.x; cur < p.n_tiles; cur += gridDim.x) {
+        const uint32_t r = p.tile_read[cur];
+        const SvbRead rd = p.reads[r];
+        const S16DecTile d = s16_dec_describe(p, &rd, r, cur);
+        if (!d.active) {  // whole-read rejections (every tile of the read takes this branch): nothing was loaded
+            if (tid == 0 && d.ti == 0) p.results[r] = d.early;
+            __syncthreads();  // nobody is still reading the stages
+            if (tid == 0) {
+                s16_dec_issue_keys(p, cur + gridDim.x, smem + S16DecSmem::kKeys + sbuf * S16DecSmem::kKeysStride, &ctl->bar[sbuf]);
+                s16_dec_issue_data(p, cur + gridDim.x, smem + S16DecSmem::kData, &ctl->bar[2]);
+            }
+            continue;
         }
+        vbz_mbar_wait(&ctl->bar[sbuf], (key_phases >> sbuf) & 1u);
+        key_phases ^= 1u << sbuf;
+        if (d.tile_values == kS16TileValues) s16_decode_tile<true>(p, rd, d, r, cur, smem, pend, sbuf, data_phase);
+        else s16_decode_tile<false>(p, rd, d, r, cur, smem, pend, sbuf, data_phase);
+        if (!d.short_data) data_phase ^= 1u;
+        sbuf ^= 1u;
     }
-    if (tid == 0 && tv0 + tile_values == n) {
-        // all data bytes must be consumed exactly: impl_sse3.h:574-577, 638-642
-        p.results[r] = ((uint64_t)tile_off + tile_len == (uint64_t)ndata) ? n * 2u : (uint32_t)kErrStream;
+    if (pend.valid) {  // flush the last tile
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t carry = (uint32_t)s16_resolve(p.status_b, pend, 0xFFFFull, tid);
+            if (tid == 0) ctl->carry = carry;
+        }
+        __syncthreads();
+        s16_decode_finish(p, pend, ctl->carry + ctl->base[sbuf ^ 1u][tid >> 5], smem + S16DecSmem::kOut + (sbuf ^ 1u) * kS16TileBytes, tid);
     }
 }
 

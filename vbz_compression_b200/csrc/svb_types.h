@@ -50,9 +50,11 @@ struct SvbParams {
                                 // a value >= kErrOutOfMemory is an upstream error and is passed through
     uint32_t* wtile_off;        // decode: data-byte offsets from the control-byte pre-pass (8 * n_tiles words).  Generic
                                 // kernels: one per warp tile; int16 path: [0, n_tiles) tile offsets, [n_tiles, 2 n_tiles) tile sums
+    uint32_t* ticket;           // int16 path: tile ticket counter of the persistent CTAs, zeroed before launch
     uint32_t hdr_bytes;         // encode: 4 = put the "sized" header (ref vbz/vbz.cpp:316-317) before the payload
     uint32_t n_reads;
     uint32_t n_tiles;
+    uint32_t debug;             // experiments only (VBZ_B200_DEBUG); 0 in production
 };
 
 constexpr int kSvbThreads = 256;

@@ -44,15 +44,28 @@ static inline uint32_t vbz_prmt(uint32_t a, uint32_t b, uint32_t s)
     return r;
 }
 static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned s) { s = s > 32 ? 32 : s; return s == 32 ? lo : (unsigned)(((((uint64_t)hi << 32) | lo) << s) >> 32); }
-// TMA 1-D bulk copies and their mbarrier: the emulator copies synchronously
+// TMA 1-D bulk copies and their mbarrier: the emulator copies synchronously.  The 64-bit barrier word keeps
+// the number of completed phases (low half) and the bytes still expected in the current one (high half).
 static inline void vbz_mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
-static inline void vbz_mbar_expect_tx(uint64_t*, uint32_t) {}
-static inline void vbz_bulk_load(void* s, const void* g, uint32_t n, uint64_t* bar) { memcpy(s, g, n); *bar += 1; }
-static inline void vbz_mbar_arrive_only(uint64_t* bar) { *bar += 1; }
-static inline void vbz_mbar_wait(uint64_t* bar, uint32_t) { while (*(volatile uint64_t*)bar == 0) cpusim::yield(); }
+static inline void vbz_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    if (bytes) *bar += (uint64_t)bytes << 32;
+    else *bar += 1;
+}
+static inline void vbz_bulk_load(void* s, const void* g, uint32_t n, uint64_t* bar)
+{
+    memcpy(s, g, n);
+    *bar -= (uint64_t)n << 32;
+    if ((*bar >> 32) == 0) *bar += 1;
+}
+static inline void vbz_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while ((*(volatile uint64_t*)bar >> 32) != 0 || ((uint32_t)*(volatile uint64_t*)bar & 1u) == parity) cpusim::yield();
+}
 static inline void vbz_fence_async_smem() {}
 static inline void vbz_bulk_store(void* g, const void* s, uint32_t n) { memcpy(g, s, n); }
-static inline void vbz_bulk_store_commit_wait() {}
+static inline void vbz_bulk_store_commit() {}
+static inline void vbz_bulk_store_wait_read() {}
 
 #else  // ---------------------------------------------------------------- real CUDA
 #include <cuda_runtime.h>
@@ -104,10 +117,6 @@ __device__ __forceinline__ void vbz_mbar_expect_tx(uint64_t* bar, uint32_t bytes
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vbz_smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void vbz_mbar_arrive_only(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(vbz_smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void vbz_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vbz_smem_u32(smem_dst)),
@@ -134,10 +143,7 @@ __device__ __forceinline__ void vbz_bulk_store(void* gdst, const void* smem_src,
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(vbz_smem_u32(smem_src)), "r"(bytes) : "memory");
 }
-// the issuing thread: close the group and wait until shared memory has been read
-__device__ __forceinline__ void vbz_bulk_store_commit_wait()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+// the issuing thread: close the group / wait until every group's shared-memory source has been read
+__device__ __forceinline__ void vbz_bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void vbz_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 #endif

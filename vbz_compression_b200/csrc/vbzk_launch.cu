@@ -21,7 +21,7 @@ static uint32_t smem_of(int decode) { return decode ? SvbSmem<ISZ, MODE>::kDecod
 
 extern "C" uint32_t vbzk_svb_smem_bytes(int isz, int mode, int decode)
 {
-    if (isz == 2 && mode == kModeI16X86) return S16Smem::kBytes;
+    if (isz == 2 && mode == kModeI16X86) return decode ? S16DecSmem::kBytes : S16EncSmem::kBytes;
     if (isz == 2) return smem_of<2, kModeGeneric>(decode);
     if (isz == 4) return smem_of<4, kModeGeneric>(decode);
     return smem_of<1, kModeGeneric>(decode);
@@ -61,18 +61,44 @@ static int launch_key_offsets(const SvbParams& p, void* stream)
     VBZ_LAUNCH((svb_key_offsets_kernel<ISZ, MODE>), grid, kSvbThreads, 0, (vbz_stream_t)stream, p);
     return VBZK_LAST_ERROR();
 }
-// ---- int16 x86-semantics path (csrc/svb16_kernels.cuh) ---------------------------------------------------
+// ---- int16 x86-semantics path (csrc/svb16_kernels.cuh): persistent CTAs, as many as are co-resident -----------
+template <class K>
+static uint32_t persistent_grid(K kernel, int threads, uint32_t smem, uint32_t n_tiles)
+{
+#ifdef VBZ_CPUSIM
+    (void)kernel; (void)threads; (void)smem;
+    return n_tiles < 3 ? n_tiles : 3;
+#else
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || sms <= 0 || per_sm <= 0)
+        return n_tiles < 148 ? n_tiles : 148;
+    const uint32_t g = (uint32_t)sms * (uint32_t)per_sm;
+    return n_tiles < g ? n_tiles : g;
+#endif
+}
+// Cooperative launch: the persistent CTAs wait for each other's tiles (look-back), so all of them must be resident.
+template <class K>
+static int launch_persistent(K kernel, uint32_t smem, const SvbParams& p, uint32_t n_tiles, void* stream)
+{
+    if (int e = VBZK_SET_SMEM(kernel, smem)) return e;
+    const uint32_t grid = persistent_grid(kernel, kS16Threads, smem, n_tiles);
+#ifdef VBZ_CPUSIM
+    VBZ_LAUNCH(kernel, grid, kS16Threads, smem, (vbz_stream_t)stream, p);
+    return 0;
+#else
+    SvbParams copy = p;
+    void* args[] = {&copy};
+    return (int)cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(kS16Threads), args, smem, (cudaStream_t)stream);
+#endif
+}
 static int launch_s16_encode(const SvbParams& p, uint32_t n_tiles, void* stream)
 {
-    if (int e = VBZK_SET_SMEM(svb16_encode_kernel, S16Smem::kBytes)) return e;
-    VBZ_LAUNCH(svb16_encode_kernel, n_tiles, kS16Threads, S16Smem::kBytes, (vbz_stream_t)stream, p);
-    return VBZK_LAST_ERROR();
+    return launch_persistent(svb16_encode_kernel, S16EncSmem::kBytes, p, n_tiles, stream);
 }
 static int launch_s16_decode(const SvbParams& p, uint32_t n_tiles, void* stream)
 {
-    if (int e = VBZK_SET_SMEM(svb16_decode_kernel, S16Smem::kBytes)) return e;
-    VBZ_LAUNCH(svb16_decode_kernel, n_tiles, kS16Threads, S16Smem::kBytes, (vbz_stream_t)stream, p);
-    return VBZK_LAST_ERROR();
+    return launch_persistent(svb16_decode_kernel, S16DecSmem::kBytes, p, n_tiles, stream);
 }
 static int launch_s16_offsets(const SvbParams& p, void* stream)
 {
