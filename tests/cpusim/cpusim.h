@@ -95,6 +95,7 @@ inline unsigned warp_ballot(bool pred)
 #define __device__ inline
 #define __host__
 #define __forceinline__
+#define __noinline__
 #define __launch_bounds__(...)
 #define __constant__ static const
 #ifndef __restrict__

@@ -83,7 +83,8 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     const uint32_t n_tiles = (uint32_t)tiles;
     const size_t status_words = (size_t)n_tiles * (decode ? 2 : 1);
     if (!ctx->d_reads.ensure((size_t)n * sizeof(SvbRead)) || !ctx->d_tiles.ensure((size_t)n_tiles * 4) ||
-        !ctx->d_status.ensure((status_words + 1) * 8) || (decode && !ctx->d_wtoff.ensure((size_t)n_tiles * kSvbWarps * 4)))
+        !ctx->d_status.ensure((status_words + 1) * 8) || (decode && !ctx->d_wtoff.ensure((size_t)n_tiles * kSvbWarps * 4)) ||
+        (kind.mode == kModeI16X86 && !ctx->d_issue.ensure((size_t)n_tiles * 32)))
         return -1;
     // the pinned staging may still be feeding the previous batch's upload
     if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
@@ -103,6 +104,8 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     p.tile_read = ctx->d_tiles.as<uint32_t>();
     p.status_a = ctx->d_status.as<uint64_t>();
     p.status_b = ctx->d_status.as<uint64_t>() + n_tiles;
+    p.issue_a = reinterpret_cast<SvbLoad*>(ctx->d_issue.p);
+    p.issue_b = p.issue_a ? reinterpret_cast<SvbLoad*>(ctx->d_issue.p) + n_tiles : nullptr;
     p.ticket = reinterpret_cast<uint32_t*>(ctx->d_status.as<uint64_t>() + status_words);
     p.results = d_results;
     p.src_sizes = d_src_sizes;
@@ -120,7 +123,7 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     e = decode ? vbzk_svb_decode(kind.isz, kind.zz, kind.mode, pp, n_tiles, stream)
                : vbzk_svb_encode(kind.isz, kind.zz, kind.mode, pp, n_tiles, stream);
     if (e) { cuda_ok((cudaError_t)e, decode ? "svb_decode launch" : "svb_encode launch"); return -1; }
-    ctx->launches += 2;
+    ctx->launches += kind.mode == kModeI16X86 ? 3 : 2;  // tile table, (int16: load descriptors / second pre-pass kernel,) the codec kernel
     return 0;
 }
 
@@ -188,7 +191,7 @@ using namespace vbz;
 // ======================================================================================================
 vbz_b200_ctx::~vbz_b200_ctx()
 {
-    d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_results.release(); d_sizes.release();
+    d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
     h_reads.release(); h_results.release();
     d_in.release(); d_out.release(); d_mid.release();
     h_in.release(); h_out.release();

@@ -40,7 +40,7 @@ struct vbz_b200_ctx {
     uint64_t launches = 0;
 
     // descriptors and look-back state (stage 1)
-    vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_results, d_sizes;
+    vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
     vbz::PinBuf h_reads, h_results;
     // bulk staging for the host-pointer API
     vbz::DevBuf d_in, d_out, d_mid;

@@ -240,21 +240,36 @@ __device__ __forceinline__ void s16_compact_group(const uint32_t (&z)[4], uint32
 // =====================================================================================================
 // encode
 // =====================================================================================================
-// one thread: start the TMA load of `tile`'s samples (plus the 16 bytes before them, which hold the previous sample)
-__device__ __forceinline__ void s16_enc_issue(const SvbParams& p, uint32_t tile, uint8_t* in_stage, uint64_t* bar)
+// The TMA load of a tile's samples (plus the 16 bytes before them, which hold the previous sample), as a
+// descriptor: svb16_enc_prepare_kernel writes one per tile so that the issuing thread needs a single load.
+__device__ __forceinline__ uint4 s16_enc_describe_load(const uint8_t* src, const SvbRead& rd, uint32_t tile)
 {
-    if (tile >= p.n_tiles) return;
-    const uint32_t r = p.tile_read[tile];
-    const SvbRead* rd = p.reads + r;
-    const uint32_t n = rd->n_values;
-    if (rd->rejected || n == 0) return;
-    const uint32_t ti = tile - rd->first_tile;
+    const uint32_t n = rd.n_values;
+    if (rd.rejected || n == 0) return make_uint4(0, 0, 0, 0);
+    const uint32_t ti = tile - rd.first_tile;
     const uint64_t b0 = (uint64_t)ti * kS16TileBytes, total = 2ull * n;
     uint32_t bytes = total - b0 < kS16TileBytes ? (uint32_t)(total - b0) : kS16TileBytes;
     bytes = (bytes + 15u) & ~15u;  // the slot of a read is padded to 16 bytes
     const uint32_t margin = ti ? 16u : 0u;
-    vbz_mbar_expect_tx(bar, bytes + margin);
-    vbz_bulk_load(in_stage + 16 - margin, p.src + rd->src_off + b0 - margin, bytes + margin, bar);
+    const uint64_t g = (uint64_t)(uintptr_t)(src + rd.src_off + b0 - margin);
+    return make_uint4((uint32_t)g, (uint32_t)(g >> 32), bytes + margin, 16u - margin);
+}
+__device__ __forceinline__ uint4 s16_fetch_load(const SvbLoad* d) { return *reinterpret_cast<const uint4*>(d); }
+__device__ __forceinline__ void s16_store_load(SvbLoad* d, const uint4 v) { *reinterpret_cast<uint4*>(d) = v; }
+__device__ __forceinline__ void s16_issue(const uint4 d, uint8_t* stage, uint64_t* bar)
+{
+    if (d.z == 0) return;
+    vbz_mbar_expect_tx(bar, d.z);
+    vbz_bulk_load(stage + d.w, reinterpret_cast<const void*>((uintptr_t)(((uint64_t)d.y << 32) | d.x)), d.z, bar);
+}
+// tile -> read table and the encode-side load descriptors (one warp per read)
+__global__ void svb16_enc_prepare_kernel(SvbParams p)
+{
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= p.n_reads) return;
+    const SvbRead rd = p.reads[r];
+    const uint32_t nt = s16_tiles_of(rd.n_values);
+    for (uint32_t i = lane; i < nt; i += 32) s16_store_load(p.issue_a + rd.first_tile + i, s16_enc_describe_load(p.src, rd, rd.first_tile + i));
 }
 
 // the part of a tile that waits for its offset: copy the packed data bytes out, report the size
@@ -268,10 +283,15 @@ __device__ __forceinline__ void s16_encode_finish(const SvbParams& p, const S16P
         p.results[pend.r] = (uint32_t)(p.hdr_bytes + nkeys + excl + pend.total);
 }
 // warp 0: resolve the pending tile's offset (its predecessors posted their aggregates a tile time ago)
-__device__ __forceinline__ uint64_t s16_resolve(uint64_t* status, const S16Pending& pend, uint64_t mask, uint32_t lane)
+__device__ __forceinline__ uint64_t s16_prefetch_status(const uint64_t* status, const S16Pending& pend, uint32_t lane)
+{
+    const long long idx = (long long)pend.t - 1 - lane;
+    return (pend.valid && idx >= (long long)pend.first_tile) ? vbz_ld_volatile_u64(status + idx) : 0ull;
+}
+__device__ __forceinline__ uint64_t s16_resolve(uint64_t* status, const S16Pending& pend, uint64_t mask, uint32_t lane, uint64_t pf = 0, bool have_pf = false)
 {
     if (pend.t == pend.first_tile) return 0;  // posted as inclusive right away
-    const uint64_t excl = lookback_exclusive(status, pend.t, pend.first_tile) & mask;
+    const uint64_t excl = lookback_exclusive_pf(status, pend.t, pend.first_tile, pf, have_pf) & mask;
     if (lane == 0) vbz_st_volatile_u64(status + pend.t, kStInclusive | ((excl + pend.total) & mask));
     return excl;
 }
@@ -289,6 +309,12 @@ __device__ __forceinline__ void s16_encode_tile(const SvbParams& p, const SvbRea
     const uint32_t n = rd.n_values, tv0 = ti * kS16TileValues;
     const uint32_t tile_values = FULL ? kS16TileValues : n - tv0;
     const uint32_t local0 = wid * kS16WarpValues + lane * 8;  // this lane's first value in row 0, tile-relative
+    // warp 2 fetches the next tile's load descriptor now and issues the load once this tile's rows are in registers
+    uint4 next_load = make_uint4(0, 0, 0, 0);
+    if (wid == 2 && t + gridDim.x < p.n_tiles) next_load = s16_fetch_load(p.issue_a + (t + gridDim.x));
+    // warp 0 reads the status words the pending tile's look-back starts from; they are consumed after barrier (1)
+    uint64_t pf = 0;
+    if (wid == 0) pf = s16_prefetch_status(p.status_a, pend, lane);
 
     // ---- rows: shared -> registers, delta, zigzag, codes -------------------------------------------------------
     uint32_t z[kS16Rows][4], key[kS16Rows], len[kS16Rows], cnt[kS16Rows];
@@ -328,7 +354,7 @@ __device__ __forceinline__ void s16_encode_tile(const SvbParams& p, const SvbRea
         if (wid == 0) vbz_bulk_store_wait_read();  // the previous tile's control bytes must have left their staging area
     }
     __syncthreads();  // (1) warp totals posted, input stage consumed
-    if (tid == 64) s16_enc_issue(p, t + gridDim.x, smem + S16EncSmem::kIn, &ctl->bar[0]);
+    if (tid == 64) s16_issue(next_load, smem + S16EncSmem::kIn, &ctl->bar[0]);
     const uint32_t wt = ctl->wtot[lane & 7];
     const uint32_t warp_excl = __reduce_add_sync(0xffffffffu, lane < wid ? wt : 0u);
     const uint32_t tile_total = __reduce_add_sync(0xffffffffu, lane < kS16Warps ? wt : 0u);
@@ -336,7 +362,7 @@ __device__ __forceinline__ void s16_encode_tile(const SvbParams& p, const SvbRea
         // post this tile's aggregate FIRST, then resolve the tile before it
         if (lane == 0) vbz_st_volatile_u64(p.status_a + t, (ti == 0 ? kStInclusive : kStAggregate) | tile_total);
         if (pend.valid) {
-            const uint64_t excl = s16_resolve(p.status_a, pend, kStValueMask, lane);
+            const uint64_t excl = s16_resolve(p.status_a, pend, kStValueMask, lane, pf, true);
             if (lane == 0) ctl->excl = excl;
         }
     }
@@ -409,7 +435,7 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_encode_kernel(SvbParams 
     if (tid < 86 && !(tid & 0xAAu)) s_lut[tid] = s16_make_enc_sel(tid);
     if (tid == 0) {
         vbz_mbar_init(&ctl->bar[0], 1);
-        s16_enc_issue(p, blockIdx.x, smem + S16EncSmem::kIn, &ctl->bar[0]);
+        s16_issue(s16_fetch_load(p.issue_a + (blockIdx.x)), smem + S16EncSmem::kIn, &ctl->bar[0]);
     }
     __syncthreads();
     S16Pending pend;
@@ -427,7 +453,7 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_encode_kernel(SvbParams 
                 }
             }
             __syncthreads();  // nobody is still reading the input stage
-            if (tid == 0) s16_enc_issue(p, cur + gridDim.x, smem + S16EncSmem::kIn, &ctl->bar[0]);
+            if (tid == 0 && cur + gridDim.x < p.n_tiles) s16_issue(s16_fetch_load(p.issue_a + (cur + gridDim.x)), smem + S16EncSmem::kIn, &ctl->bar[0]);
             continue;
         }
         vbz_mbar_wait(&ctl->bar[0], phase);
@@ -448,6 +474,42 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_encode_kernel(SvbParams 
     if (tid == 0) vbz_bulk_store_wait_read();  // shared memory must outlive the last bulk store
 }
 
+struct S16DecTile {
+    uint32_t n, nkeys, ndata, ti, tv0, tile_values, tile_off, tile_len, kphase, dphase;
+    const uint8_t* kg;     // the tile's control bytes
+    const uint8_t* dbase;  // the read's data bytes
+    bool active, short_data;
+    uint32_t early;        // result of an inactive read
+};
+// what every tile of a read agrees on, and this tile's slices (the same function tells the TMA issuer what to
+// load and the consumers what to expect)
+__device__ __forceinline__ S16DecTile s16_dec_describe(const SvbParams& p, const SvbRead* rd, uint32_t r, uint32_t t)
+{
+    S16DecTile d;
+    d.n = rd->n_values;
+    const uint32_t src_bytes = p.src_sizes ? p.src_sizes[r] : rd->src_bytes;
+    d.nkeys = (d.n + 3) / 4;
+    d.ti = t - rd->first_tile;
+    d.active = true;
+    d.early = 0;
+    if (rd->rejected) { d.early = rd->preset; d.active = false; }
+    else if (p.src_sizes && src_bytes >= kErrOutOfMemory) { d.early = src_bytes; d.active = false; }
+    else if (d.n == 0) { d.early = 0; d.active = false; }                               // impl_sse3.h:473-476
+    else if (d.nkeys > src_bytes) { d.early = kErrInputSize; d.active = false; }         // impl_sse3.h:479-482
+    if (!d.active) return d;
+    d.ndata = src_bytes - d.nkeys;
+    d.tv0 = d.ti * kS16TileValues;
+    d.tile_values = d.n - d.tv0 < kS16TileValues ? d.n - d.tv0 : kS16TileValues;
+    d.tile_off = p.wtile_off[t];                        // data bytes of this read before the tile
+    d.tile_len = p.wtile_off[(uint64_t)p.n_tiles + t];  // data bytes the tile's control bytes ask for
+    d.kg = p.src + rd->src_off + (d.tv0 >> 2);
+    d.dbase = p.src + rd->src_off + d.nkeys;
+    // the packed path needs the tile's data bytes in shared memory: all present, at most 2 per sample
+    d.short_data = (uint64_t)d.tile_off + d.tile_len > (uint64_t)d.ndata || d.tile_len > 2u * d.tile_values;
+    d.kphase = (uint32_t)((uintptr_t)d.kg & 15u);
+    d.dphase = (uint32_t)((uintptr_t)(d.dbase + d.tile_off) & 15u);
+    return d;
+}
 // =====================================================================================================
 // decode, pre-pass 1: sum of the data-byte lengths of every tile, from the control bytes alone.
 // One warp per tile (2 KiB of control bytes).
@@ -503,69 +565,28 @@ __global__ void __launch_bounds__(kS16Threads) svb16_tile_offsets_kernel(SvbPara
         if (i0 + lane < nt) offs[i0 + lane] = running + incl - v;
         running += __shfl_sync(0xffffffffu, incl, 31);
     }
+    __syncwarp();
+    // the decode-side TMA load descriptors of every tile: control bytes (issue_a), data-byte slice (issue_b)
+    for (uint32_t i = lane; i < nt; i += 32) {
+        const uint32_t t = rd.first_tile + i;
+        const S16DecTile d = s16_dec_describe(p, &rd, r, t);
+        uint4 ka = make_uint4(0, 0, 0, 0), da = make_uint4(0, 0, 0, 0);
+        if (d.active) {
+            const uint64_t kgp = (uint64_t)(uintptr_t)(d.kg - d.kphase);
+            ka = make_uint4((uint32_t)kgp, (uint32_t)(kgp >> 32), (d.kphase + ((d.tile_values + 3) >> 2) + 15u) & ~15u, 0u);
+            if (!d.short_data) {
+                const uint64_t dgp = (uint64_t)(uintptr_t)(d.dbase + d.tile_off - d.dphase);
+                da = make_uint4((uint32_t)dgp, (uint32_t)(dgp >> 32), (d.dphase + d.tile_len + 15u) & ~15u, 0u);
+            }
+        }
+        s16_store_load(p.issue_a + t, ka);
+        s16_store_load(p.issue_b + t, da);
+    }
 }
 
 // =====================================================================================================
 // decode
 // =====================================================================================================
-struct S16DecTile {
-    uint32_t n, nkeys, ndata, ti, tv0, tile_values, tile_off, tile_len, kphase, dphase;
-    const uint8_t* kg;     // the tile's control bytes
-    const uint8_t* dbase;  // the read's data bytes
-    bool active, short_data;
-    uint32_t early;        // result of an inactive read
-};
-// what every tile of a read agrees on, and this tile's slices (the same function tells the TMA issuer what to
-// load and the consumers what to expect)
-__device__ __forceinline__ S16DecTile s16_dec_describe(const SvbParams& p, const SvbRead* rd, uint32_t r, uint32_t t)
-{
-    S16DecTile d;
-    d.n = rd->n_values;
-    const uint32_t src_bytes = p.src_sizes ? p.src_sizes[r] : rd->src_bytes;
-    d.nkeys = (d.n + 3) / 4;
-    d.ti = t - rd->first_tile;
-    d.active = true;
-    d.early = 0;
-    if (rd->rejected) { d.early = rd->preset; d.active = false; }
-    else if (p.src_sizes && src_bytes >= kErrOutOfMemory) { d.early = src_bytes; d.active = false; }
-    else if (d.n == 0) { d.early = 0; d.active = false; }                               // impl_sse3.h:473-476
-    else if (d.nkeys > src_bytes) { d.early = kErrInputSize; d.active = false; }         // impl_sse3.h:479-482
-    if (!d.active) return d;
-    d.ndata = src_bytes - d.nkeys;
-    d.tv0 = d.ti * kS16TileValues;
-    d.tile_values = d.n - d.tv0 < kS16TileValues ? d.n - d.tv0 : kS16TileValues;
-    d.tile_off = p.wtile_off[t];                        // data bytes of this read before the tile
-    d.tile_len = p.wtile_off[(uint64_t)p.n_tiles + t];  // data bytes the tile's control bytes ask for
-    d.kg = p.src + rd->src_off + (d.tv0 >> 2);
-    d.dbase = p.src + rd->src_off + d.nkeys;
-    // the packed path needs the tile's data bytes in shared memory: all present, at most 2 per sample
-    d.short_data = (uint64_t)d.tile_off + d.tile_len > (uint64_t)d.ndata || d.tile_len > 2u * d.tile_values;
-    d.kphase = (uint32_t)((uintptr_t)d.kg & 15u);
-    d.dphase = (uint32_t)((uintptr_t)(d.dbase + d.tile_off) & 15u);
-    return d;
-}
-// one thread: start the TMA load of `tile`'s control bytes / of its slice of the data bytes
-__device__ __forceinline__ void s16_dec_issue_keys(const SvbParams& p, uint32_t tile, uint8_t* stage, uint64_t* bar)
-{
-    if (tile >= p.n_tiles) return;
-    const uint32_t r = p.tile_read[tile];
-    const S16DecTile d = s16_dec_describe(p, p.reads + r, r, tile);
-    if (!d.active) return;
-    const uint32_t kbytes = (d.kphase + ((d.tile_values + 3) >> 2) + 15u) & ~15u;
-    vbz_mbar_expect_tx(bar, kbytes);
-    vbz_bulk_load(stage, d.kg - d.kphase, kbytes, bar);
-}
-__device__ __forceinline__ void s16_dec_issue_data(const SvbParams& p, uint32_t tile, uint8_t* stage, uint64_t* bar)
-{
-    if (tile >= p.n_tiles) return;
-    const uint32_t r = p.tile_read[tile];
-    const S16DecTile d = s16_dec_describe(p, p.reads + r, r, tile);
-    if (!d.active || d.short_data) return;
-    const uint32_t dbytes = (d.dphase + d.tile_len + 15u) & ~15u;
-    vbz_mbar_expect_tx(bar, dbytes);
-    vbz_bulk_load(stage, d.dbase + d.tile_off - d.dphase, dbytes, bar);
-}
-
 // the part of a tile that waits for its carry: add it to the parked samples and store them
 __device__ __forceinline__ void s16_decode_finish(const SvbParams& p, const S16Pending& pend, uint32_t carry, const uint8_t* park, uint32_t tid)
 {
@@ -601,6 +622,38 @@ __device__ __forceinline__ void s16_decode_finish(const SvbParams& p, const S16P
     }
 }
 
+// Exact scalar semantics for tiles the packed path cannot express: codes 2/3 in the stream (the x86 build then
+// decodes 8-value groups 16 bits wide while 32 data bytes remain and 32 bits wide in its scalar tail,
+// impl_sse3.h:494-572) or a stream that ends early (bytes past the end read as zero).  One lane's 4 groups;
+// the in-group running sums go to slot[row * 512 ..] (two samples per word, as the packed path leaves them).
+__device__ __noinline__ void s16_decode_rows_scalar(const uint8_t* dbase, uint32_t ndata, uint32_t n, uint32_t s_first, uint64_t o_base, uint32_t k0,
+                                                    uint32_t k1, uint32_t k2, uint32_t k3, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t o0,
+                                                    uint32_t o1, uint32_t o2, uint32_t o3, uint8_t* slot)
+{
+#pragma unroll 1
+    for (int j = 0; j < kS16Rows; ++j) {
+        const uint32_t key = j == 0 ? k0 : j == 1 ? k1 : j == 2 ? k2 : k3;
+        const uint32_t cnt = j == 0 ? c0 : j == 1 ? c1 : j == 2 ? c2 : c3;
+        const uint32_t s0 = s_first + j * 256;
+        uint64_t o = o_base + (j == 0 ? o0 : j == 1 ? o1 : j == 2 ? o2 : o3);
+        const bool simd16 = (s0 >> 3) < (n >> 3) && o + 32 <= (uint64_t)ndata;
+        uint32_t run = 0, prevv = 0;
+        uint32_t* out = reinterpret_cast<uint32_t*>(slot + j * 512);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 8; ++k) {
+            uint32_t v = 0;
+            if (k < cnt) {
+                const uint32_t code = (key >> (2 * k)) & 3u;
+                for (uint32_t b = 0; b <= code; ++b, ++o) v |= (o < ndata ? (uint32_t)dbase[o] : 0u) << (8 * b);
+            }
+            if (simd16) v &= 0xFFFFu;
+            run += (v >> 1) ^ (0u - (v & 1u));
+            if (k & 1) out[k >> 1] = (prevv & 0xFFFFu) | (run << 16);
+            prevv = run;
+        }
+    }
+}
+
 template <bool FULL>
 __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRead& rd, const S16DecTile& d, uint32_t r, uint32_t t, unsigned char* smem,
                                                  S16Pending& pend, uint32_t sbuf, uint32_t data_phase)
@@ -613,6 +666,12 @@ __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRea
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t n = d.n, ndata = d.ndata;
     const uint32_t local0 = wid * kS16WarpValues + lane * 8;
+    // warp 2 fetches the next tile's load descriptors now; the loads are issued as the stages become free
+    uint4 next_keys = make_uint4(0, 0, 0, 0), next_data = make_uint4(0, 0, 0, 0);
+    if (wid == 2 && t + gridDim.x < p.n_tiles) { next_keys = s16_fetch_load(p.issue_a + (t + gridDim.x)); next_data = s16_fetch_load(p.issue_b + (t + gridDim.x)); }
+    // warp 0 reads the status words the pending tile's look-back starts from; they are consumed after barrier (2)
+    uint64_t pf = 0;
+    if (wid == 0) pf = s16_prefetch_status(p.status_b, pend, lane);
 
     // ---- control bytes -> lengths -> offsets ------------------------------------------------------------------
     uint32_t key[kS16Rows], len[kS16Rows], cnt[kS16Rows];
@@ -641,7 +700,7 @@ __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRea
         if (any_wide) ctl->flag = 1;
     }
     __syncthreads();  // (1) warp totals, flag; this tile's control-byte stage is consumed
-    if (tid == 64) s16_dec_issue_keys(p, t + gridDim.x, smem + S16DecSmem::kKeys + (sbuf ^ 1u) * S16DecSmem::kKeysStride, &ctl->bar[sbuf ^ 1u]);
+    if (tid == 64) s16_issue(next_keys, smem + S16DecSmem::kKeys + (sbuf ^ 1u) * S16DecSmem::kKeysStride, &ctl->bar[sbuf ^ 1u]);
     const bool slow = d.short_data || ctl->flag != 0;
     const uint32_t warp_excl = __reduce_add_sync(0xffffffffu, lane < wid ? ctl->wtot[lane & 7] : 0u);
 
@@ -673,32 +732,14 @@ __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRea
             }
         }
     } else {
-        // exact scalar semantics for tiles the packed path cannot express: codes 2/3 in the stream (the x86
-        // build then decodes 8-value groups 16 bits wide while 32 data bytes remain and 32 bits wide in its
-        // scalar tail, impl_sse3.h:494-572) or a stream that ends early (bytes past the end read as zero)
         if (!d.short_data) vbz_mbar_wait(&ctl->bar[2], data_phase);  // consume the phase of the load that was issued
-#pragma unroll 1
-        for (int j = 0; j < kS16Rows; ++j) {
-            const uint32_t s0 = d.tv0 + local0 + j * 256;
-            uint64_t o = (uint64_t)d.tile_off + warp_excl + off[j];
-            const bool simd16 = (s0 >> 3) < (n >> 3) && o + 32 <= (uint64_t)ndata;
-            uint32_t run = 0, prevv = 0, yy[4] = {0, 0, 0, 0};
+        // rare: through a call, via the thread's slot of the park area, to keep it out of the packed path's registers
+        s16_decode_rows_scalar(d.dbase, ndata, n, d.tv0 + local0, (uint64_t)d.tile_off + warp_excl, key[0], key[1], key[2], key[3], cnt[0], cnt[1],
+                               cnt[2], cnt[3], off[0], off[1], off[2], off[3], park + 2 * local0);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint32_t v = 0;
-                if ((uint32_t)k < cnt[j]) {
-                    const uint32_t code = (key[j] >> (2 * k)) & 3u;
-                    for (uint32_t b = 0; b <= code; ++b, ++o) v |= (o < ndata ? (uint32_t)d.dbase[o] : 0u) << (8 * b);
-                }
-                if (simd16) v &= 0xFFFFu;
-                run += (v >> 1) ^ (0u - (v & 1u));
-                if (k & 1) yy[k >> 1] = (prevv & 0xFFFFu) | (run << 16);
-                prevv = run;
-            }
-            if (j == 0) { y[0][0] = yy[0]; y[0][1] = yy[1]; y[0][2] = yy[2]; y[0][3] = yy[3]; }
-            else if (j == 1) { y[1][0] = yy[0]; y[1][1] = yy[1]; y[1][2] = yy[2]; y[1][3] = yy[3]; }
-            else if (j == 2) { y[2][0] = yy[0]; y[2][1] = yy[1]; y[2][2] = yy[2]; y[2][3] = yy[3]; }
-            else { y[3][0] = yy[0]; y[3][1] = yy[1]; y[3][2] = yy[2]; y[3][3] = yy[3]; }
+        for (int j = 0; j < kS16Rows; ++j) {
+            const uint4 v = *reinterpret_cast<const uint4*>(park + 2 * (local0 + j * 256));
+            y[j][0] = v.x; y[j][1] = v.y; y[j][2] = v.z; y[j][3] = v.w;
         }
     }
 
@@ -724,7 +765,7 @@ __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRea
         }
     }
     __syncthreads();  // (2) warp sums; the data-byte stage is consumed
-    if (tid == 64) s16_dec_issue_data(p, t + gridDim.x, smem + S16DecSmem::kData, &ctl->bar[2]);
+    if (tid == 64) s16_issue(next_data, smem + S16DecSmem::kData, &ctl->bar[2]);
     if (wid == 0) {
         const uint32_t v = lane < kS16Warps ? ctl->wsum[lane] : 0u;
         const uint32_t incl = warp_scan_u32(v);
@@ -733,7 +774,7 @@ __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRea
         // post this tile's aggregate FIRST, then resolve the tile before it
         if (lane == 0) vbz_st_volatile_u64(p.status_b + t, (d.ti == 0 ? kStInclusive : kStAggregate) | tile_sum);
         if (pend.valid) {
-            const uint32_t carry = (uint32_t)s16_resolve(p.status_b, pend, 0xFFFFull, lane);
+            const uint32_t carry = (uint32_t)s16_resolve(p.status_b, pend, 0xFFFFull, lane, pf, true);
             if (lane == 0) ctl->carry = carry;
         }
         if (lane == 0) ctl->flag = 0;
@@ -758,8 +799,8 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_decode_kernel(SvbParams 
         vbz_mbar_init(&ctl->bar[1], 1);
         vbz_mbar_init(&ctl->bar[2], 1);
         ctl->flag = 0;
-        s16_dec_issue_keys(p, blockIdx.x, smem + S16DecSmem::kKeys, &ctl->bar[0]);
-        s16_dec_issue_data(p, blockIdx.x, smem + S16DecSmem::kData, &ctl->bar[2]);
+        s16_issue(s16_fetch_load(p.issue_a + (blockIdx.x)), smem + S16DecSmem::kKeys, &ctl->bar[0]);
+        s16_issue(s16_fetch_load(p.issue_b + (blockIdx.x)), smem + S16DecSmem::kData, &ctl->bar[2]);
     }
     __syncthreads();
     S16Pending pend;
@@ -771,9 +812,9 @@ __global__ void __launch_bounds__(kS16Threads, 4) svb16_decode_kernel(SvbParams 
         if (!d.active) {  // whole-read rejections (every tile of the read takes this branch): nothing was loaded
             if (tid == 0 && d.ti == 0) p.results[r] = d.early;
             __syncthreads();  // nobody is still reading the stages
-            if (tid == 0) {
-                s16_dec_issue_keys(p, cur + gridDim.x, smem + S16DecSmem::kKeys + sbuf * S16DecSmem::kKeysStride, &ctl->bar[sbuf]);
-                s16_dec_issue_data(p, cur + gridDim.x, smem + S16DecSmem::kData, &ctl->bar[2]);
+            if (tid == 0 && cur + gridDim.x < p.n_tiles) {
+                s16_issue(s16_fetch_load(p.issue_a + (cur + gridDim.x)), smem + S16DecSmem::kKeys + sbuf * S16DecSmem::kKeysStride, &ctl->bar[sbuf]);
+                s16_issue(s16_fetch_load(p.issue_b + (cur + gridDim.x)), smem + S16DecSmem::kData, &ctl->bar[2]);
             }
             continue;
         }

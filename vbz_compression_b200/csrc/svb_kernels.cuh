@@ -42,7 +42,9 @@ namespace vbz {
 enum : uint64_t { kSlotReady = 1ull << 63 };
 
 // ---- decoupled look-back over the earlier tiles of the same read (all 32 lanes of a warp) ----------
-__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, uint32_t tile, uint32_t first_tile)
+// `pf`: this lane's status word of the first window (status[tile - 1 - lane]) if the caller loaded it earlier
+// (have_pf); any valid status, however old, gives the right answer because aggregates only turn into inclusives.
+__device__ __forceinline__ uint64_t lookback_exclusive_pf(const uint64_t* status, uint32_t tile, uint32_t first_tile, uint64_t pf, bool have_pf)
 {
     const int lane = threadIdx.x & 31;
     uint64_t excl = 0;
@@ -53,7 +55,8 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, u
         uint64_t s;
         unsigned inc, upto;
         for (;;) {
-            s = valid ? vbz_ld_volatile_u64(status + idx) : kStInclusive;
+            s = valid ? (have_pf ? pf : vbz_ld_volatile_u64(status + idx)) : kStInclusive;
+            have_pf = false;
             const unsigned st = (unsigned)(s >> 62);
             const unsigned inv = __ballot_sync(0xffffffffu, st == 0);
             inc = __ballot_sync(0xffffffffu, st == 2);
@@ -69,6 +72,10 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, u
         j -= 32;
     }
     return excl;
+}
+__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, uint32_t tile, uint32_t first_tile)
+{
+    return lookback_exclusive_pf(status, tile, first_tile, 0ull, false);
 }
 
 // Level "warp -> tile -> read" of the offset computation (see the header comment).  Every warp of

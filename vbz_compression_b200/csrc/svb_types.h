@@ -38,6 +38,9 @@ struct SvbRead {
     uint32_t reserved;
 };
 
+// one TMA bulk load: global address, byte count (0 = nothing to load), offset inside the shared-memory stage
+struct alignas(16) SvbLoad { uint32_t addr_lo, addr_hi, bytes, stage_off; };
+
 struct SvbParams {
     const uint8_t* src;
     uint8_t* dst;
@@ -50,6 +53,8 @@ struct SvbParams {
                                 // a value >= kErrOutOfMemory is an upstream error and is passed through
     uint32_t* wtile_off;        // decode: data-byte offsets from the control-byte pre-pass (8 * n_tiles words).  Generic
                                 // kernels: one per warp tile; int16 path: [0, n_tiles) tile offsets, [n_tiles, 2 n_tiles) tile sums
+    SvbLoad* issue_a;             // int16 path: per-tile TMA descriptor {address lo, hi, bytes (0 = nothing to load), stage offset}
+    SvbLoad* issue_b;             //   encode: samples (issue_a); decode: control bytes (issue_a), data-byte slice (issue_b)
     uint32_t* ticket;           // int16 path: tile ticket counter of the persistent CTAs, zeroed before launch
     uint32_t hdr_bytes;         // encode: 4 = put the "sized" header (ref vbz/vbz.cpp:316-317) before the payload
     uint32_t n_reads;

@@ -94,6 +94,8 @@ static int launch_persistent(K kernel, uint32_t smem, const SvbParams& p, uint32
 }
 static int launch_s16_encode(const SvbParams& p, uint32_t n_tiles, void* stream)
 {
+    VBZ_LAUNCH(svb16_enc_prepare_kernel, (p.n_reads + kS16Warps - 1) / kS16Warps, kS16Threads, 0, (vbz_stream_t)stream, p);
+    if (int e = VBZK_LAST_ERROR()) return e;
     return launch_persistent(svb16_encode_kernel, S16EncSmem::kBytes, p, n_tiles, stream);
 }
 static int launch_s16_decode(const SvbParams& p, uint32_t n_tiles, void* stream)
