@@ -1,0 +1,117 @@
+"""Stage 2, decode direction: the product's zstd frame decoder (csrc/zstd_dec_kernels.cuh) against frames written by
+the reference (fast5 fixtures) and by libzstd at many levels, through the vbz C API (zstd_compression_level != 0).
+Runs on the CUDA emulator build (CPU suite) and on the real library (-m gpu)."""
+import numpy as np
+import pytest
+
+import data_gen
+import golden_data
+import oracle_lib as ol
+import product
+from oracle_lib import Options
+
+port = ol.port()
+
+
+@pytest.fixture(params=product.BACKENDS)
+def backend(request):
+    return product.get(request.param)
+
+
+def test_reference_written_chunks_decode(backend):
+    """The reference's own compressed files must decode bit-exactly: v0 and v1 fixtures."""
+    capi = backend[0]
+    reads = golden_data.fast5_reads()
+    take = reads if not capi.path.endswith("cpusim.so") else reads[:4]
+    for rd in take:
+        want = rd["samples"]
+        assert rd["v1_identical"]  # multi_fast5_vbz_v1.fast5 stores byte-identical chunk payloads (make_golden.py checks it)
+        for ver in (0, 1):
+            r, got = capi.decompress(rd["vbz_chunk"], Options(True, 2, 1, ver), want.nbytes, sized=True)
+            assert r == want.nbytes, (ver, r)
+            assert got == want.tobytes(), ver
+
+
+def _payloads(rng):
+    yield b""
+    yield b"a"
+    yield bytes(1000)
+    yield bytes(rng.integers(0, 256, 5000, dtype=np.uint8))                  # incompressible -> raw blocks
+    yield bytes(rng.integers(0, 4, 40000, dtype=np.uint8))                   # small alphabet -> direct Huffman weights
+    yield bytes(np.repeat(rng.integers(0, 256, 300, dtype=np.uint8), 50))    # runs -> matches with small offsets
+    yield (b"the quick brown fox jumps over the lazy dog. " * 900)           # long-range repeats, repeat offsets
+    yield ol.stage1_encode(data_gen.nanopore_like(60000, rng), 2, True)      # what VBZ feeds zstd
+    yield bytes(np.arange(200000, dtype=np.uint32).view(np.uint8))           # several blocks, structured
+    yield bytes(rng.integers(0, 256, 140000, dtype=np.uint8)) + bytes(140000)  # raw block then RLE-ish block
+
+
+@pytest.mark.parametrize("level", [1, 3, 9, 19])
+def test_libzstd_frames_decode(backend, level):
+    capi = backend[0]
+    rng = np.random.default_rng(level)
+    o = Options(False, 0, level, 0)  # zstd only: vbz_decompress == ZSTD_decompress into the destination
+    for data in _payloads(rng):
+        if capi.path.endswith("cpusim.so") and len(data) > 150000 and level > 3:
+            continue
+        frame = ol.zstd_compress_lib(data, level)
+        r, got = capi.decompress(frame, o, len(data), sized=False)
+        assert r == len(data), (level, len(data), r)
+        assert got == data
+        # capacity smaller than the content size (vbz.cpp:256-259) and larger
+        if len(data) > 1:
+            assert capi.decompress(frame, o, len(data) - 1, sized=False)[0] == ol.ERR_DEST_SIZE
+        r2, got2 = capi.decompress(frame, o, len(data) + 7, sized=False)
+        assert r2 == len(data) and got2 == data
+
+
+def test_full_vbz_decode_matches_oracle(backend):
+    capi = backend[0]
+    rng = np.random.default_rng(9)
+    for dtype, o in ((np.int16, Options(True, 2, 1, 0)), (np.int16, Options(True, 2, 3, 1)), (np.int32, Options(True, 4, 1, 0)),
+                     (np.uint32, Options(False, 4, 3, 0)), (np.int8, Options(True, 1, 1, 0))):
+        for n in (0, 1, 100, 5000, 30000):
+            arr = data_gen.nanopore_like(n, rng).astype(dtype) if dtype != np.uint32 else rng.integers(0, 1 << 20, n).astype(np.uint32)
+            for sized in (True, False):
+                rc, blob = port.compress(arr, o, sized=sized)
+                assert not ol.is_error(rc)
+                a = capi.decompress(blob, o, arr.nbytes, sized=sized)
+                b = port.decompress(blob, o, arr.nbytes, sized=sized)
+                assert a == b and a[1] == arr.tobytes(), (dtype, n, sized, a[0], b[0])
+
+
+def test_damaged_frames_report_like_the_oracle(backend):
+    capi = backend[0]
+    rng = np.random.default_rng(4)
+    arr = data_gen.nanopore_like(20000, rng)
+    o = Options(True, 2, 1, 0)
+    _, good = port.compress(arr, o, sized=True)
+    cases = [good[:10], good[:-1], good[:len(good) // 2], good + b"\\0", good[:4] + b"\\0\\0\\0\\0" + good[8:]]
+    for pos in (4, 5, 8, 9, 12, 20, 200, len(good) - 2):
+        bad = bytearray(good)
+        bad[pos] ^= 0x55
+        cases.append(bytes(bad))
+    for blob in cases:
+        for oo, ds in ((o, arr.nbytes), (Options(True, 2, 1, 2), arr.nbytes), (o, arr.nbytes - 1), (Options(False, 0, 1, 0), arr.nbytes)):
+            a = capi.decompress(blob, oo, ds, sized=True)
+            b = port.decompress(blob, oo, ds, sized=True)
+            assert a[0] == b[0], (len(blob), oo.vbz_version, oo.integer_size, ds, a[0], b[0])
+            if not ol.is_error(b[0]):
+                assert a[1] == b[1]
+
+
+def test_fuzz_corpus_level1_decode(backend):
+    """Restates the decode half of vbz/fuzzing/vbz_fuzz.cpp:138-161 at zstd level 1: arbitrary bytes must be rejected
+    (or decoded) exactly as the oracle does."""
+    capi = backend[0]
+    corpus = golden_data.fuzz_corpus()
+    step = 1 if not capi.path.endswith("cpusim.so") else 5
+    for blob in corpus[::step]:
+        n = len(blob)
+        for o in (Options(True, 2, 1, 0), Options(False, 4, 1, 0), Options(True, 1, 1, 0), Options(False, 0, 1, 0)):
+            for sized in (True, False):
+                for ds in sorted(set([0, 4, 64, n, 4 * n])):
+                    a = capi.decompress(blob, o, ds, sized=sized)
+                    b = port.decompress(blob, o, ds, sized=sized)
+                    assert a[0] == b[0], (n, ds, sized, o.integer_size, a[0], b[0])
+                    if not ol.is_error(b[0]):
+                        assert a[1] == b[1]

@@ -63,6 +63,8 @@ struct ReadJob {
     uint32_t dst_size = 0;   // compress: capacity of the slot; decompress: exact decompressed size
     bool rejected = false;   // decided on the host; `code` is the result
     uint32_t code = 0;
+    uint32_t post_code = 0;  // decompress with a zstd stage: what the read returns once its frame has decoded (0 = go on to stage 1)
+    uint64_t mid_cap = 0;    // decompress with a zstd stage: content size of the frame if the host could read it (0 = use the bound)
 };
 
 // ---- stage 1 on the device -----------------------------------------------------------------------------
@@ -127,8 +129,38 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     return 0;
 }
 
-static bool device_path_available(const Stage1Kind& kind)
+// ---- stage 2 (zstd), decode: frames -> content --------------------------------------------------------------------
+static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ZstdRead>& reads, uint32_t* d_results,
+                               cudaStream_t stream)
 {
+    const uint32_t n = (uint32_t)reads.size();
+    if (n == 0) return 0;
+    const size_t bytes = (size_t)n * sizeof(ZstdRead);
+    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes())) return -1;
+    if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
+    if (!ctx->h_zreads.ensure(bytes)) return -1;
+    memcpy(ctx->h_zreads.p, reads.data(), bytes);
+    if (!cuda_ok(cudaMemcpyAsync(ctx->d_zreads.p, ctx->h_zreads.p, bytes, cudaMemcpyHostToDevice, stream), "upload frame descriptors") ||
+        !cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord") ||
+        !cuda_ok(cudaMemsetAsync(ctx->d_zcounter.p, 0, 256, stream), "reset work counter"))
+        return -1;
+    ZstdDecParams p;
+    p.src = d_src;
+    p.dst = d_dst;
+    p.reads = ctx->d_zreads.as<ZstdRead>();
+    p.results = d_results;
+    p.lit_scratch = ctx->d_zlit.as<uint8_t>();
+    p.counter = ctx->d_zcounter.as<uint32_t>();
+    p.n_reads = n;
+    const int e = vbzk_zstd_decode(reinterpret_cast<const VbzkZstdDecParams*>(&p), stream);
+    if (e) { cuda_ok((cudaError_t)e, "zstd_decode launch"); return -1; }
+    ctx->launches += 1;
+    return 0;
+}
+
+static bool device_path_available(const Stage1Kind& kind, bool decode = false)
+{
+    if (decode && !kind.half) return true;
     if (kind.zstd_level != 0 || kind.half || kind.isz == 0) {
         set_last_error("this option combination is not implemented on the device yet");
         return false;
@@ -162,24 +194,73 @@ static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t
 static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ReadJob>& jobs,
                                   uint32_t* d_results, const Stage1Kind& kind, bool sized, cudaStream_t stream)
 {
-    if (!device_path_available(kind)) return -1;
+    if (!device_path_available(kind, true)) return -1;
     const uint32_t hdr = sized ? 4u : 0u;
-    std::vector<SvbRead> reads(jobs.size());
-    for (size_t i = 0; i < jobs.size(); ++i) {
+    const uint32_t n = (uint32_t)jobs.size();
+    const uint8_t* s1_src = d_src;
+    const uint32_t* s1_sizes = nullptr;
+    std::vector<uint64_t> mid_off;
+    if (kind.zstd_level != 0) {
+        // stage 2 first (ref vbz/vbz.cpp:234-273): each frame decodes into its slot of the intermediate buffer - or
+        // straight into the destination when there is no stage 1
+        std::vector<ZstdRead> zr(n);
+        mid_off.resize(n);
+        uint64_t mid_total = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const ReadJob& j = jobs[i];
+            ZstdRead& z = zr[i];
+            memset(&z, 0, sizeof(z));
+            z.rejected = j.rejected;
+            z.preset = j.code;
+            if (j.rejected) continue;
+            z.src_off = j.src_off + hdr;
+            z.src_bytes = j.src_size - hdr;
+            if (kind.isz == 0) {
+                z.dst_off = j.dst_off;
+                z.dst_cap = j.dst_size;
+            } else {
+                uint64_t cap = j.mid_cap;
+                if (cap == 0) cap = stage1_tight_bound(j.dst_size / (unsigned)kind.isz, kind) + 16;  // device-resident frames: the host cannot read the header
+                cap = std::min<uint64_t>(cap, 0xFFFFFFF0u);
+                mid_off[i] = mid_total;
+                z.dst_off = mid_total;
+                z.dst_cap = (uint32_t)cap;
+                mid_total += align16(cap) + 16;
+            }
+        }
+        uint32_t* zres = d_results;
+        uint8_t* zdst = d_dst;
+        if (kind.isz != 0) {
+            if (!ctx->d_mid.ensure(mid_total + 16) || !ctx->d_sizes.ensure((size_t)n * 4)) return -1;
+            zres = ctx->d_sizes.as<uint32_t>();
+            zdst = ctx->d_mid.as<uint8_t>();
+        }
+        if (enqueue_zstd_decode(ctx, d_src, zdst, zr, zres, stream) != 0) return -1;
+        if (kind.isz == 0) return 0;
+        s1_src = ctx->d_mid.as<uint8_t>();
+        s1_sizes = ctx->d_sizes.as<uint32_t>();
+    }
+    std::vector<SvbRead> reads(n);
+    for (uint32_t i = 0; i < n; ++i) {
         const ReadJob& j = jobs[i];
         SvbRead& r = reads[i];
         memset(&r, 0, sizeof(r));
-        r.src_off = j.src_off + hdr;
         r.dst_off = j.dst_off;
-        r.src_bytes = j.src_size - (j.rejected ? 0 : hdr);
-        r.rejected = j.rejected;
-        r.preset = j.code;
-        if (!j.rejected) {
+        r.rejected = j.rejected || j.post_code != 0;
+        r.preset = j.rejected ? j.code : j.post_code;
+        if (kind.zstd_level != 0) {
+            r.src_off = j.rejected ? 0 : mid_off[i];
+            r.src_bytes = 0;  // taken from the zstd stage's result
+        } else {
+            r.src_off = j.src_off + hdr;
+            r.src_bytes = j.src_size - (j.rejected ? 0 : hdr);
+        }
+        if (!r.rejected) {
             if ((j.src_off & 3) || (j.dst_off & 15)) { set_last_error("device batch offsets must be multiples of 16"); return -1; }
             r.n_values = j.dst_size / (unsigned)kind.isz;
         }
     }
-    return enqueue_stage1(ctx, true, kind, d_src, d_dst, reads, 0, d_results, nullptr, stream);
+    return enqueue_stage1(ctx, true, kind, s1_src, d_dst, reads, 0, d_results, s1_sizes, stream);
 }
 
 }  // namespace vbz
@@ -280,7 +361,7 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
     if (!ctx || !options) { set_last_error("null context or options"); return -1; }
     if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
     const Stage1Kind kind = classify_options(options);
-    if (kind.bad_isz || (kind.isz != 0 && kind.bad_version)) {
+    if (kind.bad_isz || (kind.isz != 0 && kind.bad_version && kind.zstd_level == 0)) {
         set_last_error("invalid options: every read of the batch would be rejected");
         return -1;
     }
@@ -291,6 +372,10 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
         j.src_off = src_off[i]; j.dst_off = dst_off[i]; j.src_size = src_size[i]; j.dst_size = dst_size[i];
         if (src_size[i] < hdr) { j.rejected = true; j.code = kErrInputSize; }
         else j.rejected = decompress_precheck(kind, src_size[i] - hdr, dst_size[i], &j.code);
+        if (!j.rejected && kind.zstd_level != 0 && kind.isz != 0) {  // checked by the reference after the zstd stage (vbz.cpp:282-299)
+            if (kind.bad_version) j.post_code = kErrVersion;
+            else if (dst_size[i] % (unsigned)kind.isz != 0) j.post_code = kErrDestinationSize;
+        }
     }
     return decompress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0,
                                   (cudaStream_t)stream);
@@ -400,6 +485,18 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
             continue;
         }
         ReadJob j;
+        if (kind.zstd_level != 0) {  // ref vbz/vbz.cpp:234-262: the frame must announce its content size
+            const uint64_t fcs = zstd_frame_content_size((const uint8_t*)src[i] + hdr, src_size[i] - hdr);
+            if (fcs == kZstdContentSizeUnknown || fcs == kZstdContentSizeError) { results[i] = kErrZstd; continue; }
+            if (kind.isz == 0) {
+                if (fcs > exact) { results[i] = kErrDestinationSize; continue; }
+            } else {
+                if (fcs > (1ull << 31)) { results[i] = kErrOutOfMemory; continue; }  // the reference mallocs the content size here
+                j.mid_cap = fcs ? fcs : 1;
+                if (kind.bad_version) j.post_code = kErrVersion;
+                else if (exact % (unsigned)kind.isz != 0) j.post_code = kErrDestinationSize;
+            }
+        }
         j.src_off = in_total;
         j.dst_off = out_total;
         j.src_size = src_size[i];
@@ -410,7 +507,7 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
         job_read.push_back(i);
     }
     if (jobs.empty()) return 0;
-    if (!device_path_available(kind)) return -1;
+    if (!device_path_available(kind, true)) return -1;
     const uint32_t m = (uint32_t)jobs.size();
 
     if (!ctx->h_in.ensure(in_total + 16) || !ctx->d_in.ensure(in_total + 16) || !ctx->d_out.ensure(out_total + 16) ||

@@ -42,6 +42,9 @@ struct vbz_b200_ctx {
     // descriptors and look-back state (stage 1)
     vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
     vbz::PinBuf h_reads, h_results;
+    // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
+    vbz::DevBuf d_zreads, d_zcounter, d_zlit;
+    vbz::PinBuf h_zreads;
     // bulk staging for the host-pointer API
     vbz::DevBuf d_in, d_out, d_mid;
     vbz::PinBuf h_in, h_out;

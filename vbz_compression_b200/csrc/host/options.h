@@ -111,6 +111,30 @@ inline bool compress_precheck(const Stage1Kind& k, uint32_t src_size, uint32_t d
     return true;
 }
 
+// ZSTD_getFrameContentSize of the first frame in [p, p + n) (ref call site vbz/vbz.cpp:236): the content size, or
+// kZstdContentSizeUnknown / kZstdContentSizeError (both count as errors at vbz.cpp:237).  Header parsing only.
+constexpr uint64_t kZstdContentSizeUnknown = ~0ull, kZstdContentSizeError = ~0ull - 1;
+inline uint64_t zstd_frame_content_size(const uint8_t* p, uint64_t n)
+{
+    auto le32 = [&](uint64_t o) { return (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8) | ((uint32_t)p[o + 2] << 16) | ((uint32_t)p[o + 3] << 24); };
+    if (n >= 8 && (le32(0) & 0xFFFFFFF0u) == 0x184D2A50u) return 0;  // skippable frame
+    if (n < 5 || le32(0) != 0xFD2FB528u) return kZstdContentSizeError;
+    const int fhd = p[4], fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
+    if (fhd & 0x08) return kZstdContentSizeError;
+    uint64_t h = 5;
+    if (!single) {
+        if (h + 1 > n || 10 + (p[h] >> 3) > 31) return kZstdContentSizeError;
+        h++;
+    }
+    h += did == 3 ? 4 : did;
+    const uint64_t fb = fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+    if (h + fb > n) return kZstdContentSizeError;
+    if (fb == 0) return kZstdContentSizeUnknown;
+    uint64_t v = 0;
+    for (uint64_t i = 0; i < fb; ++i) v |= (uint64_t)p[h + i] << (8 * i);
+    return fb == 2 ? v + 256 : v;
+}
+
 // What vbz_decompress returns before touching the payload when there is no zstd stage
 // (ref vbz/vbz.cpp:210-299, vbz/v0/vbz_streamvbyte.cpp:73-76).  payload_size excludes the sized header.
 inline bool decompress_precheck(const Stage1Kind& k, uint32_t payload_size, uint32_t dst_size, uint32_t* code)

@@ -492,8 +492,8 @@ __device__ __forceinline__ S16DecTile s16_dec_describe(const SvbParams& p, const
     d.ti = t - rd->first_tile;
     d.active = true;
     d.early = 0;
-    if (rd->rejected) { d.early = rd->preset; d.active = false; }
-    else if (p.src_sizes && src_bytes >= kErrOutOfMemory) { d.early = src_bytes; d.active = false; }
+    if (p.src_sizes && src_bytes >= kErrOutOfMemory) { d.early = src_bytes; d.active = false; }  // the zstd stage failed first
+    else if (rd->rejected) { d.early = rd->preset; d.active = false; }
     else if (d.n == 0) { d.early = 0; d.active = false; }                               // impl_sse3.h:473-476
     else if (d.nkeys > src_bytes) { d.early = kErrInputSize; d.active = false; }         // impl_sse3.h:479-482
     if (!d.active) return d;

@@ -427,8 +427,8 @@ __global__ void __launch_bounds__(kSvbThreads) svb_decode_kernel(SvbParams p)
     {   // whole-read rejections: every tile of the read takes the same branch
         uint32_t early = 0;
         bool stop = false;
-        if (rd.rejected) { early = rd.preset; stop = true; }
-        else if (p.src_sizes && src_bytes >= kErrOutOfMemory) { early = src_bytes; stop = true; }
+        if (p.src_sizes && src_bytes >= kErrOutOfMemory) { early = src_bytes; stop = true; }  // the zstd stage failed first
+        else if (rd.rejected) { early = rd.preset; stop = true; }
         else if (n == 0) {  // x86 int16 path returns 0 before looking at the input (impl_sse3.h:473-476);
                             // streamvbyte_validate_stream wants both counts to be zero (streamvbyte_decode.c:91-92)
             early = (MODE == kModeI16X86 || src_bytes == 0) ? 0u : (uint32_t)kErrStream;

@@ -62,6 +62,29 @@ struct SvbParams {
     uint32_t debug;             // experiments only (VBZ_B200_DEBUG); 0 in production
 };
 
+// ---- stage 2 (zstd) ----------------------------------------------------------------------------------------
+struct ZstdRead {
+    uint64_t src_off;    // the frame(s): bytes [src_off, src_off + src_bytes) of ZstdDecParams::src
+    uint64_t dst_off;    // where the content goes, offset into ZstdDecParams::dst
+    uint32_t src_bytes;
+    uint32_t dst_cap;    // capacity of the destination slot
+    uint32_t rejected;   // != 0: decided on the host; copy `preset` to results[]
+    uint32_t preset;
+};
+struct ZstdDecParams {
+    const uint8_t* src;
+    uint8_t* dst;
+    const ZstdRead* reads;
+    uint32_t* results;   // per read: content bytes, or kErrZstd
+    uint8_t* lit_scratch;  // 128 KiB + 32 per warp of the grid
+    uint32_t* counter;   // work counter, zeroed before launch
+    uint32_t n_reads;
+};
+
+constexpr uint32_t kZBlockMax = 128u * 1024u;
+constexpr int kZdecWarps = 4;
+constexpr uint32_t kZLitStride = kZBlockMax + 32;  // literal scratch per decoding warp
+
 constexpr int kSvbThreads = 256;
 constexpr int kSvbWarps = kSvbThreads / 32;
 constexpr int kSvbGroups = 2;                                    // groups of 16 raw bytes per lane

@@ -23,6 +23,13 @@ int vbzk_svb_encode(int integer_size, int zigzag, int mode, const struct VbzkSvb
 int vbzk_svb_key_offsets(int integer_size, int mode, const struct VbzkSvbParams* params, void* stream);
 int vbzk_svb_decode(int integer_size, int zigzag, int mode, const struct VbzkSvbParams* params, uint32_t n_tiles, void* stream);
 
+/* stage 2, decode: one zstd frame per read (csrc/zstd_dec_kernels.cuh).  The launch uses vbzk_zstd_decode_grid() CTAs
+ * whatever the batch size; lit_scratch must hold vbzk_zstd_decode_scratch_bytes() bytes and *counter must be 0. */
+struct VbzkZstdDecParams; /* == vbz::ZstdDecParams (csrc/svb_types.h) */
+uint32_t vbzk_zstd_decode_grid(void);
+uint64_t vbzk_zstd_decode_scratch_bytes(void);
+int vbzk_zstd_decode(const struct VbzkZstdDecParams* params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 #include "vbzk.h"
 #include "svb_kernels.cuh"
 #include "svb16_kernels.cuh"
+#include "zstd_dec_kernels.cuh"
 
 using namespace vbz;
 
@@ -138,4 +139,24 @@ extern "C" int vbzk_svb_decode(int isz, int zz, int mode, const VbzkSvbParams* p
 {
     if (isz == 2 && zz && mode == kModeI16X86 && n_tiles) return launch_s16_decode(*reinterpret_cast<const SvbParams*>(params), n_tiles, stream);
     VBZK_DISPATCH(launch_decode)
+}
+
+// ---- stage 2 (zstd) ---------------------------------------------------------------------------------------------
+extern "C" uint32_t vbzk_zstd_decode_grid(void)
+{
+    static const uint32_t g = persistent_grid(zstd_decode_kernel, kZdecWarps * 32, (uint32_t)(sizeof(ZWarp) * kZdecWarps), 0xFFFFFFFFu);
+    return g;
+}
+extern "C" uint64_t vbzk_zstd_decode_scratch_bytes(void) { return (uint64_t)vbzk_zstd_decode_grid() * kZdecWarps * kZLitStride; }
+extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
+{
+    const ZstdDecParams& p = *reinterpret_cast<const ZstdDecParams*>(params);
+    if (p.n_reads == 0) return 0;
+    const uint32_t smem = (uint32_t)(sizeof(ZWarp) * kZdecWarps);
+    if (int e = VBZK_SET_SMEM(zstd_decode_kernel, smem)) return e;
+    uint32_t grid = vbzk_zstd_decode_grid();
+    const uint32_t need = (p.n_reads + kZdecWarps - 1) / kZdecWarps;
+    if (need < grid) grid = need;
+    VBZ_LAUNCH(zstd_decode_kernel, grid, kZdecWarps * 32, smem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
 }

@@ -1,0 +1,709 @@
+// csrc/zstd_dec_kernels.cuh - stage 2 of VBZ decode on the GPU: Zstandard frame decoder (RFC 8878).
+//
+// Replaces the reference's calls into libzstd on the decode path: ZSTD_getFrameContentSize + ZSTD_decompress
+// (ref vbz/vbz.cpp:236-240, 263-272; libzstd itself is an un-vendored dependency, pinned zstd/1.4.8 by
+// CMakeLists.txt:93).  Written from the format specification; accepts everything ZSTD_compress emits at any
+// level: Raw / RLE / Compressed blocks, Raw / RLE / Huffman / Treeless literals with 1 or 4 streams, direct and
+// FSE-compressed Huffman weights, Predefined / RLE / FSE / Repeat sequence tables, repeat offsets, windowed and
+// single-segment frames, concatenated and skippable frames, the optional XXH64 content checksum.
+//
+// Parallelism: one WARP per frame (one frame = one read), frames taken from an atomic counter by persistent
+// warps - a batch holds 10^4..10^6 frames, far more than the 148 SMs have warp slots.  Inside a frame:
+//   * the four Huffman literal streams of a block are decoded by four lanes at once, table in shared memory;
+//     a block without sequences (all but the first block of a signal frame) decodes straight into its final
+//     position in the output;
+//   * sequences are decoded 32 at a time by one lane into shared memory and then executed by the whole warp:
+//     literal runs and matches are warp-wide copies (a match with offset < 32 is a periodic fill, computed
+//     without waiting on the bytes it produces);
+//   * Raw / RLE blocks, table builds are warp-wide loops.
+// Per-warp tables: Huffman 2048 x u16, three FSE tables 512/512/256 x u32 -> 10.5 KiB of shared memory.
+#pragma once
+#include "vbz_device.h"
+#include "svb_types.h"
+
+namespace vbz {
+
+
+struct ZWarp {  // per-warp shared state
+    uint16_t huf[2048];   // sym | nbBits << 8
+    uint32_t ll[512], ml[512], of[256];  // sym | nbBits << 8 | base << 16
+    uint32_t seq_ll[32], seq_ml[32], seq_of[32];
+    uint32_t wtab[64];    // FSE table of the Huffman weights (accuracy log <= 6)
+    uint8_t weights[256];
+    int16_t norm[256];
+    uint16_t next[256];
+};
+
+// ---- small readers over global memory ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t z_le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t z_le24(const uint8_t* p) { return z_le16(p) | ((uint32_t)p[2] << 16); }
+__device__ __forceinline__ uint32_t z_le32(const uint8_t* p) { return z_le24(p) | ((uint32_t)p[3] << 24); }
+__device__ __forceinline__ uint64_t z_le64(const uint8_t* p) { return (uint64_t)z_le32(p) | ((uint64_t)z_le32(p + 4) << 32); }
+__device__ __forceinline__ int z_highbit(uint32_t v) { return 31 - __clz((int)v); }
+
+// backward bit reader: the stream is a little-endian big integer whose highest set bit is a padding marker;
+// bits are consumed from the top.  `pos` = number of unread bits; reading below bit 0 yields zeros.
+struct ZBack {
+    const uint8_t* p;
+    long long pos;
+};
+__device__ __forceinline__ bool zb_init(ZBack& b, const uint8_t* p, uint32_t n)
+{
+    if (n == 0 || p[n - 1] == 0) return false;
+    b.p = p;
+    b.pos = (long long)(n - 1) * 8 + z_highbit(p[n - 1]);
+    return true;
+}
+// the 32 bits ending just below bit `pos` (bit 31 of the result = bit pos-1); bits below 0 read as zero
+__device__ __forceinline__ uint32_t zb_window(const ZBack& b)
+{
+    const long long lo = b.pos - 32;  // bit index of result bit 0
+    if (lo >= 0) {
+        const uint8_t* q = b.p + (lo >> 3);
+        const uint32_t sh = (uint32_t)(lo & 7);
+        const uint64_t v = (uint64_t)z_le32(q) | ((uint64_t)(sh ? q[4] : 0) << 32);
+        return (uint32_t)(v >> sh);
+    }
+    if (b.pos <= 0) return 0;
+    // fewer than 32 bits left: assemble from the first bytes
+    uint64_t v = 0;
+    const uint32_t nbytes = (uint32_t)((b.pos + 7) >> 3);
+    for (uint32_t i = 0; i < nbytes && i < 5; ++i) v |= (uint64_t)b.p[i] << (8 * i);
+    v &= (b.pos >= 64) ? ~0ull : ((1ull << b.pos) - 1ull);
+    return (uint32_t)(v << (uint32_t)(32 - b.pos));
+}
+__device__ __forceinline__ uint32_t zb_peek(const ZBack& b, uint32_t nb) { return nb ? zb_window(b) >> (32 - nb) : 0u; }
+__device__ __forceinline__ uint32_t zb_read(ZBack& b, uint32_t nb)
+{
+    const uint32_t v = zb_peek(b, nb);
+    b.pos -= nb;
+    return v;
+}
+
+// forward, LSB-first bit reader (FSE table descriptions)
+struct ZFwd {
+    const uint8_t* p;
+    uint32_t n, bit;
+};
+__device__ __forceinline__ uint32_t zf_peek(const ZFwd& f, uint32_t nb)
+{
+    uint64_t v = 0;
+    const uint32_t byte = f.bit >> 3;
+    for (uint32_t i = 0; i < 4; ++i)
+        if (byte + i < f.n) v |= (uint64_t)f.p[byte + i] << (8 * i);
+    return (uint32_t)(v >> (f.bit & 7)) & ((1u << nb) - 1u);
+}
+
+// ---- FSE (one lane) -----------------------------------------------------------------------------------------
+// table description -> normalised counts.  Returns bytes consumed or 0 on error.
+__device__ uint32_t z_fse_read_ncount(const uint8_t* p, uint32_t n, int max_al, int max_sym, int16_t* norm, int* nsym, int* al_out)
+{
+    ZFwd b = {p, n, 0};
+    if (n == 0) return 0;
+    const int al = (int)zf_peek(b, 4) + 5;
+    b.bit += 4;
+    if (al > max_al) return 0;
+    int remaining = (1 << al) + 1, thr = 1 << al, nb = al + 1, sym = 0, prev0 = 0;
+    while (remaining > 1 && sym <= max_sym) {
+        if (prev0) {
+            for (;;) {
+                const uint32_t r = zf_peek(b, 2);
+                b.bit += 2;
+                for (uint32_t k = 0; k < r; ++k) {
+                    if (sym > max_sym) return 0;
+                    norm[sym++] = 0;
+                }
+                if (r != 3) break;
+            }
+            if (sym > max_sym) return 0;
+        }
+        const int max = (2 * thr - 1) - remaining;
+        int c;
+        const uint32_t low = zf_peek(b, (uint32_t)(nb - 1));
+        if ((int)low < max) { c = (int)low; b.bit += (uint32_t)(nb - 1); }
+        else {
+            c = (int)zf_peek(b, (uint32_t)nb);
+            if (c >= thr) c -= max;
+            b.bit += (uint32_t)nb;
+        }
+        c -= 1;
+        remaining -= c < 0 ? -c : c;
+        norm[sym++] = (int16_t)c;
+        prev0 = (c == 0);
+        while (remaining < thr) { nb--; thr >>= 1; }
+    }
+    if (remaining != 1) return 0;
+    const uint32_t used = (b.bit + 7) / 8;
+    if (used > n) return 0;
+    *nsym = sym;
+    *al_out = al;
+    return used;
+}
+// normalised counts -> decoding table (cells: sym | nb << 8 | base << 16)
+__device__ bool z_fse_build(uint32_t* cell, uint16_t* next, const int16_t* norm, int nsym, int al)
+{
+    const int T = 1 << al;
+    int high = T - 1;
+    for (int s = 0; s < nsym; ++s) {
+        if (norm[s] == -1) { cell[high--] = (uint32_t)s; next[s] = 1; }
+        else next[s] = (uint16_t)norm[s];
+    }
+    const int step = (T >> 1) + (T >> 3) + 3;
+    int pos = 0;
+    for (int s = 0; s < nsym; ++s)
+        for (int i = 0; i < norm[s]; ++i) {
+            cell[pos] = (uint32_t)s;
+            do { pos = (pos + step) & (T - 1); } while (pos > high);
+        }
+    if (pos != 0) return false;
+    for (int u = 0; u < T; ++u) {
+        const uint32_t s = cell[u] & 0xFFu;
+        const uint32_t x = next[s]++;
+        const uint32_t nb = (uint32_t)(al - z_highbit(x));
+        cell[u] = s | (nb << 8) | ((((x << nb) - (uint32_t)T) & 0xFFFFu) << 16);
+    }
+    return true;
+}
+
+// ---- Huffman ------------------------------------------------------------------------------------------------
+// tree description -> weights[0..nw) (one lane).  Returns bytes consumed or 0 on error.
+__device__ uint32_t z_huf_read_weights(ZWarp* zw, const uint8_t* p, uint32_t n, int* nw_out)
+{
+    uint8_t* w = zw->weights;
+    int nw = 0;
+    uint32_t used;
+    if (n < 1) return 0;
+    const int hb = p[0];
+    if (hb >= 128) {
+        nw = hb - 127;
+        used = 1 + (uint32_t)(nw + 1) / 2;
+        if (used > n) return 0;
+        for (int i = 0; i < nw; ++i) w[i] = (i & 1) ? (p[1 + i / 2] & 0xF) : (p[1 + i / 2] >> 4);
+    } else {
+        used = 1 + (uint32_t)hb;
+        if (used > n || hb == 0) return 0;
+        int nsym, al;
+        const uint32_t hdr = z_fse_read_ncount(p + 1, (uint32_t)hb, 6, 255, zw->norm, &nsym, &al);
+        if (!hdr) return 0;
+        uint32_t* cell = zw->wtab;
+        if (!z_fse_build(cell, zw->next, zw->norm, nsym, al)) return 0;
+        ZBack b;
+        if (!zb_init(b, p + 1 + hdr, (uint32_t)hb - hdr)) return 0;
+        uint32_t s1 = zb_read(b, (uint32_t)al), s2 = zb_read(b, (uint32_t)al);
+        for (;;) {  // two interleaved states; stop one symbol after the stream overruns
+            if (nw > 253) return 0;
+            w[nw++] = (uint8_t)cell[s1];
+            s1 = (cell[s1] >> 16) + zb_read(b, (cell[s1] >> 8) & 0xFF);
+            if (b.pos < 0) { w[nw++] = (uint8_t)cell[s2]; break; }
+            if (nw > 253) return 0;
+            w[nw++] = (uint8_t)cell[s2];
+            s2 = (cell[s2] >> 16) + zb_read(b, (cell[s2] >> 8) & 0xFF);
+            if (b.pos < 0) { w[nw++] = (uint8_t)cell[s1]; break; }
+        }
+    }
+    *nw_out = nw;
+    return used;
+}
+// weights -> decode table zw->huf (one lane).  Returns max_bits or 0 on error.
+__device__ int z_huf_build(ZWarp* zw, int nw)
+{
+    uint8_t* w = zw->weights;
+    uint32_t total = 0, rank[16];
+    for (int i = 0; i < 16; ++i) rank[i] = 0;
+    for (int i = 0; i < nw; ++i) {
+        if (w[i] > 12) return 0;
+        rank[w[i]]++;
+        total += (1u << w[i]) >> 1;
+    }
+    if (total == 0) return 0;
+    const int max_bits = z_highbit(total) + 1;
+    if (max_bits > 11) return 0;  // HUF_TABLELOG_MAX of the format (larger tables are rejected by libzstd too)
+    const uint32_t rest = (1u << max_bits) - total;
+    if ((rest & (rest - 1)) != 0) return 0;
+    w[nw] = (uint8_t)(z_highbit(rest) + 1);
+    rank[w[nw]]++;
+    nw++;
+    if (rank[1] < 2 || (rank[1] & 1)) return 0;
+    // cells: weight 1 (longest codes) first, symbols ascending within a weight
+    uint32_t start[16], acc = 0;
+    for (int r = 1; r <= max_bits; ++r) { start[r] = acc; acc += rank[r] << (r - 1); }
+    for (int s = 0; s < nw; ++s) {
+        const int r = w[s];
+        if (!r) continue;
+        const uint32_t len = (1u << r) >> 1;
+        const uint16_t e = (uint16_t)((uint32_t)s | ((uint32_t)(max_bits + 1 - r) << 8));
+        for (uint32_t k = 0; k < len; ++k) zw->huf[start[r] + k] = e;
+        start[r] += len;
+    }
+    return max_bits;
+}
+// one Huffman stream (one lane): `count` symbols to out.  Returns true if the stream ends exactly.
+__device__ bool z_huf_decode_stream(const uint16_t* huf, int max_bits, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t count)
+{
+    ZBack b;
+    if (!zb_init(b, p, n)) return false;
+    const uint32_t mb = (uint32_t)max_bits;
+    uint32_t i = 0;
+    // fast part: a 32-bit window holds at least two symbols (max_bits <= 11) after a refill
+    while (i + 2 <= count && b.pos >= 32) {
+        const uint32_t win = zb_window(b);
+        const uint32_t e0 = huf[win >> (32 - mb)];
+        const uint32_t n0 = e0 >> 8;
+        const uint32_t e1 = huf[(win << n0) >> (32 - mb)];
+        out[i] = (uint8_t)e0;
+        out[i + 1] = (uint8_t)e1;
+        b.pos -= n0 + (e1 >> 8);
+        i += 2;
+    }
+    for (; i < count; ++i) {
+        const uint32_t e = huf[zb_peek(b, mb)];
+        out[i] = (uint8_t)e;
+        b.pos -= e >> 8;
+    }
+    return b.pos == 0;
+}
+
+// ---- warp-wide copies -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void z_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
+{
+    for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+}
+__device__ __forceinline__ void z_warp_fill(uint8_t* dst, uint8_t v, uint32_t n, uint32_t lane)
+{
+    for (uint32_t k = lane; k < n; k += 32) dst[k] = v;
+}
+// out[op .. op + mlen) = the mlen bytes starting `offset` back, overlap allowed
+__device__ __forceinline__ void z_warp_match(uint8_t* out, uint64_t op, uint32_t offset, uint32_t mlen, uint32_t lane)
+{
+    const uint8_t* base = out + op - offset;
+    if (offset >= 32) {
+        for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            if (k < mlen) out[op + k] = base[k];
+            __syncwarp();
+        }
+    } else {  // periodic fill: every source byte precedes op
+        for (uint32_t k = lane; k < mlen; k += 32) out[op + k] = base[k % offset];
+    }
+}
+
+__constant__ int16_t kZ_LL_DEF[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
+__constant__ int16_t kZ_ML_DEF[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                      1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+__constant__ int16_t kZ_OF_DEF[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+__constant__ uint32_t kZ_LL_BASE[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
+__constant__ uint8_t kZ_LL_BITS[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+__constant__ uint32_t kZ_ML_BASE[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+                                        30, 31, 32, 33, 34, 35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
+__constant__ uint8_t kZ_ML_BITS[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                       0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+
+// XXH64 with seed 0 (one lane): only the optional frame checksum needs it
+__device__ __forceinline__ uint64_t z_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ uint64_t z_xxh64(const uint8_t* p, uint64_t n)
+{
+    const uint64_t P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL, P3 = 1609587929392839161ULL, P4 = 9650029242287828579ULL,
+                   P5 = 2870177450012600261ULL;
+    const uint8_t* e = p + n;
+    uint64_t h;
+    if (n >= 32) {
+        uint64_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+        do {
+            v1 = z_rotl64(v1 + z_le64(p) * P2, 31) * P1; p += 8;
+            v2 = z_rotl64(v2 + z_le64(p) * P2, 31) * P1; p += 8;
+            v3 = z_rotl64(v3 + z_le64(p) * P2, 31) * P1; p += 8;
+            v4 = z_rotl64(v4 + z_le64(p) * P2, 31) * P1; p += 8;
+        } while (p + 32 <= e);
+        h = z_rotl64(v1, 1) + z_rotl64(v2, 7) + z_rotl64(v3, 12) + z_rotl64(v4, 18);
+        h = (h ^ (z_rotl64(v1 * P2, 31) * P1)) * P1 + P4;
+        h = (h ^ (z_rotl64(v2 * P2, 31) * P1)) * P1 + P4;
+        h = (h ^ (z_rotl64(v3 * P2, 31) * P1)) * P1 + P4;
+        h = (h ^ (z_rotl64(v4 * P2, 31) * P1)) * P1 + P4;
+    } else h = P5;
+    h += n;
+    while (p + 8 <= e) { h ^= z_rotl64(z_le64(p) * P2, 31) * P1; h = z_rotl64(h, 27) * P1 + P4; p += 8; }
+    if (p + 4 <= e) { h ^= (uint64_t)z_le32(p) * P1; h = z_rotl64(h, 23) * P2 + P3; p += 4; }
+    while (p < e) { h ^= (*p++) * P5; h = z_rotl64(h, 11) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+// per-frame decoder state that lives in registers (warp-uniform)
+struct ZFrame {
+    int huf_bits;      // 0 = no Huffman table yet
+    int al_ll, al_of, al_ml;
+    bool seq_valid;
+    uint32_t rep0, rep1, rep2;
+};
+
+// One of the three sequence tables, by mode (one lane).  Returns bytes consumed, 0xFFFFFFFF on error.
+__device__ uint32_t z_seq_table(ZWarp* zw, uint32_t* cell, int* al, int mode, const uint8_t* p, uint32_t n, int max_al, int max_sym,
+                                       const int16_t* def, int def_n, int def_al, bool have_prev)
+{
+    if (mode == 0) {
+        for (int i = 0; i < def_n; ++i) zw->norm[i] = def[i];
+        if (!z_fse_build(cell, zw->next, zw->norm, def_n, def_al)) return 0xFFFFFFFFu;
+        *al = def_al;
+        return 0;
+    }
+    if (mode == 1) {
+        if (n < 1 || p[0] > max_sym) return 0xFFFFFFFFu;
+        cell[0] = p[0];
+        *al = 0;
+        return 1;
+    }
+    if (mode == 3) return have_prev ? 0u : 0xFFFFFFFFu;
+    int nsym, a;
+    const uint32_t used = z_fse_read_ncount(p, n, max_al, max_sym, zw->norm, &nsym, &a);
+    if (!used) return 0xFFFFFFFFu;
+    if (!z_fse_build(cell, zw->next, zw->norm, nsym, a)) return 0xFFFFFFFFu;
+    *al = a;
+    return used;
+}
+
+// literals section of a compressed block -> lit_dst[0 .. *lit_n).  Whole warp.  Returns bytes consumed, 0 on error.
+__device__ uint32_t z_decode_literals(ZWarp* zw, ZFrame& f, const uint8_t* p, uint32_t n, uint8_t* lit_dst, uint32_t lit_cap, uint32_t* lit_n,
+                                             uint32_t lane)
+{
+    if (n < 1) return 0;
+    const int type = p[0] & 3, sf = (p[0] >> 2) & 3;
+    uint32_t hdr, regen, comp = 0;
+    int streams = 4;
+    if (type < 2) {
+        if (sf == 0 || sf == 2) { hdr = 1; regen = p[0] >> 3; }
+        else if (sf == 1) { if (n < 2) return 0; hdr = 2; regen = z_le16(p) >> 4; }
+        else { if (n < 3) return 0; hdr = 3; regen = z_le24(p) >> 4; }
+        if (regen > kZBlockMax || regen > lit_cap) return 0;
+        if (type == 0) {
+            if (hdr + regen > n) return 0;
+            z_warp_copy(lit_dst, p + hdr, regen, lane);
+            *lit_n = regen;
+            return hdr + regen;
+        }
+        if (hdr + 1 > n) return 0;
+        z_warp_fill(lit_dst, p[hdr], regen, lane);
+        *lit_n = regen;
+        return hdr + 1;
+    }
+    if (n < 3) return 0;
+    if (sf <= 1) { hdr = 3; const uint32_t v = z_le24(p); regen = (v >> 4) & 0x3FF; comp = (v >> 14) & 0x3FF; if (sf == 0) streams = 1; }
+    else if (sf == 2) { if (n < 4) return 0; hdr = 4; const uint32_t v = z_le32(p); regen = (v >> 4) & 0x3FFF; comp = (v >> 18) & 0x3FFF; }
+    else { if (n < 5) return 0; hdr = 5; const uint64_t v = (uint64_t)z_le32(p) | ((uint64_t)p[4] << 32); regen = (uint32_t)((v >> 4) & 0x3FFFF); comp = (uint32_t)((v >> 22) & 0x3FFFF); }
+    if (regen > kZBlockMax || regen > lit_cap || hdr + comp > n) return 0;
+    if (streams == 4 && regen < 6) return 0;  // libzstd >= 1.5.4: MIN_LITERALS_FOR_4_STREAMS
+    const uint8_t* q = p + hdr;
+    uint32_t left = comp;
+    if (type == 2) {
+        int bits = 0;
+        uint32_t t = 0;
+        if (lane == 0) {
+            int nw = 0;
+            t = z_huf_read_weights(zw, q, left, &nw);
+            if (t) bits = z_huf_build(zw, nw);
+            if (!bits) t = 0;
+        }
+        t = __shfl_sync(0xffffffffu, t, 0);
+        bits = __shfl_sync(0xffffffffu, bits, 0);
+        if (!t) return 0;
+        f.huf_bits = bits;
+        q += t;
+        left -= t;
+    } else if (!f.huf_bits) return 0;
+    __syncwarp();
+    bool ok = true;
+    if (streams == 1) {
+        if (lane == 0) ok = z_huf_decode_stream(zw->huf, f.huf_bits, q, left, lit_dst, regen);
+    } else {
+        if (left < 10) return 0;
+        const uint32_t s1 = z_le16(q), s2 = z_le16(q + 2), s3 = z_le16(q + 4);
+        if (6 + s1 + s2 + s3 > left) return 0;
+        const uint32_t s4 = left - 6 - s1 - s2 - s3;
+        const uint32_t seg = (regen + 3) / 4;
+        if (3 * seg > regen) return 0;
+        const uint8_t* d = q + 6;
+        if (lane < 4) {
+            const uint32_t so = lane == 0 ? 0u : lane == 1 ? s1 : lane == 2 ? s1 + s2 : s1 + s2 + s3;
+            const uint32_t sn = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : s4;
+            ok = z_huf_decode_stream(zw->huf, f.huf_bits, d + so, sn, lit_dst + lane * seg, lane == 3 ? regen - 3 * seg : seg);
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok)) return 0;
+    *lit_n = regen;
+    return hdr + comp;
+}
+
+// one compressed block: literals + sequences -> out[*op ..].  Whole warp.
+__device__ bool z_decode_compressed_block(ZWarp* zw, ZFrame& f, const uint8_t* p, uint32_t n, uint8_t* out, uint64_t cap, uint64_t* op_io,
+                                                 uint8_t* lit_scratch, uint32_t lane)
+{
+    uint64_t op = *op_io;
+    // does the block carry sequences?  Peek past the literals section: cheaper to decode the literals header twice
+    // than to stage every literal.  Literals go straight to the output when there are none.
+    uint32_t lit_n = 0;
+    bool direct = false;
+    {
+        // size of the literals section from its header alone
+        if (n < 1) return false;
+        const int type = p[0] & 3, sf = (p[0] >> 2) & 3;
+        uint32_t sec = 0;
+        bool known = true;
+        if (type < 2) {
+            uint32_t hdr, regen;
+            if (sf == 0 || sf == 2) { hdr = 1; regen = p[0] >> 3; }
+            else if (sf == 1) { if (n < 2) return false; hdr = 2; regen = z_le16(p) >> 4; }
+            else { if (n < 3) return false; hdr = 3; regen = z_le24(p) >> 4; }
+            sec = type == 0 ? hdr + regen : hdr + 1;
+        } else {
+            if (n < 3) return false;
+            if (sf <= 1) sec = 3 + ((z_le24(p) >> 14) & 0x3FF);
+            else if (sf == 2) { if (n < 4) return false; sec = 4 + ((z_le32(p) >> 18) & 0x3FFF); }
+            else { if (n < 5) return false; sec = 5 + (uint32_t)((((uint64_t)z_le32(p) | ((uint64_t)p[4] << 32)) >> 22) & 0x3FFFF); }
+        }
+        if (known && sec < n && p[sec] == 0 && sec + 1 == n) direct = true;
+    }
+    uint8_t* lit = direct ? out + op : lit_scratch;
+    const uint64_t room = cap - op;
+    const uint32_t lit_cap = direct ? (uint32_t)(room < kZBlockMax ? room : kZBlockMax) : kZBlockMax;
+    const uint32_t used = z_decode_literals(zw, f, p, n, lit, lit_cap, &lit_n, lane);
+    if (!used) return false;
+    p += used;
+    n -= used;
+    if (n < 1) return false;
+    uint32_t nseq = p[0];
+    uint32_t h = 1;
+    if (nseq == 0) {
+        if (n != 1) return false;
+        if (!direct) {  // (cannot happen: direct was derived from the same bytes)
+            if (op + lit_n > cap) return false;
+            z_warp_copy(out + op, lit, lit_n, lane);
+        }
+        *op_io = op + lit_n;
+        __syncwarp();
+        return true;
+    }
+    if (direct) return false;
+    if (nseq > 0x7F) {
+        if (nseq == 0xFF) { if (n < 3) return false; nseq = z_le16(p + 1) + 0x7F00; h = 3; }
+        else { if (n < 2) return false; nseq = ((nseq - 0x80) << 8) + p[1]; h = 2; }
+    }
+    if (h + 1 > n) return false;
+    const int modes = p[h++];
+    if (modes & 3) return false;  // reserved bits (checked by libzstd 1.5.x)
+    // tables (one lane), then broadcast
+    uint32_t ok = 1;
+    int al_ll = f.al_ll, al_of = f.al_of, al_ml = f.al_ml;
+    if (lane == 0) {
+        uint32_t r;
+        r = z_seq_table(zw, zw->ll, &al_ll, modes >> 6, p + h, n - h, 9, 35, kZ_LL_DEF, 36, 6, f.seq_valid);
+        if (r == 0xFFFFFFFFu) ok = 0; else h += r;
+        if (ok) { r = z_seq_table(zw, zw->of, &al_of, (modes >> 4) & 3, p + h, n - h, 8, 31, kZ_OF_DEF, 29, 5, f.seq_valid); if (r == 0xFFFFFFFFu) ok = 0; else h += r; }
+        if (ok) { r = z_seq_table(zw, zw->ml, &al_ml, (modes >> 2) & 3, p + h, n - h, 9, 52, kZ_ML_DEF, 53, 6, f.seq_valid); if (r == 0xFFFFFFFFu) ok = 0; else h += r; }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return false;
+    h = __shfl_sync(0xffffffffu, h, 0);
+    f.al_ll = __shfl_sync(0xffffffffu, al_ll, 0);
+    f.al_of = __shfl_sync(0xffffffffu, al_of, 0);
+    f.al_ml = __shfl_sync(0xffffffffu, al_ml, 0);
+    f.seq_valid = true;
+    __syncwarp();
+
+    // sequences: lane 0 decodes up to 32 into shared memory, the warp executes them
+    ZBack b;
+    b.p = p + h;
+    b.pos = 0;
+    uint32_t sl = 0, so = 0, sm = 0;
+    if (lane == 0) {
+        if (!zb_init(b, p + h, n - h)) ok = 0;
+        else {
+            sl = zb_read(b, (uint32_t)f.al_ll);
+            so = zb_read(b, (uint32_t)f.al_of);
+            sm = zb_read(b, (uint32_t)f.al_ml);
+            if (b.pos < 0) ok = 0;
+        }
+    }
+    if (!__shfl_sync(0xffffffffu, ok, 0)) return false;
+    uint32_t lp = 0;
+    uint32_t rep0 = f.rep0, rep1 = f.rep1, rep2 = f.rep2;
+    for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
+        const uint32_t cnt = nseq - i0 < 32 ? nseq - i0 : 32;
+        if (lane == 0) {
+            for (uint32_t k = 0; k < cnt && ok; ++k) {
+                const uint32_t cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
+                const uint32_t llc = cl & 0xFF, ofc = co & 0xFF, mlc = cm & 0xFF;
+                if (llc > 35 || mlc > 52 || ofc > 31) { ok = 0; break; }
+                const uint32_t ofv = (ofc ? (1u << ofc) : 1u) + (ofc ? zb_read(b, ofc) : 0u);
+                const uint32_t mlen = kZ_ML_BASE[mlc] + zb_read(b, kZ_ML_BITS[mlc]);
+                const uint32_t llen = kZ_LL_BASE[llc] + zb_read(b, kZ_LL_BITS[llc]);
+                uint32_t offset;
+                if (ofv > 3) {
+                    offset = ofv - 3;
+                    rep2 = rep1; rep1 = rep0; rep0 = offset;
+                } else {
+                    const uint32_t kk = ofv + (llen == 0 ? 1u : 0u);
+                    if (kk == 1) offset = rep0;
+                    else {
+                        offset = (kk == 4) ? rep0 - 1 : (kk == 2 ? rep1 : rep2);
+                        if (offset == 0) offset = 1;  // libzstd: "0 is not valid; input is corrupted; force offset to 1"
+                        if (kk != 2) rep2 = rep1;
+                        rep1 = rep0;
+                        rep0 = offset;
+                    }
+                }
+                if (i0 + k + 1 < nseq) {
+                    sl = (cl >> 16) + zb_read(b, (cl >> 8) & 0xFF);
+                    sm = (cm >> 16) + zb_read(b, (cm >> 8) & 0xFF);
+                    so = (co >> 16) + zb_read(b, (co >> 8) & 0xFF);
+                }
+                if (b.pos < 0) { ok = 0; break; }
+                zw->seq_ll[k] = llen;
+                zw->seq_ml[k] = mlen;
+                zw->seq_of[k] = offset;
+            }
+        }
+        __syncwarp();
+        if (!__shfl_sync(0xffffffffu, ok, 0)) return false;
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint32_t llen = zw->seq_ll[k], mlen = zw->seq_ml[k], offset = zw->seq_of[k];
+            if ((uint64_t)lp + llen > lit_n) return false;
+            if (op + llen + mlen > cap) return false;
+            z_warp_copy(out + op, lit + lp, llen, lane);
+            lp += llen;
+            op += llen;
+            if ((uint64_t)offset > op) return false;
+            __syncwarp();
+            z_warp_match(out, op, offset, mlen, lane);
+            op += mlen;
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && b.pos != 0) ok = 0;
+    if (!__shfl_sync(0xffffffffu, ok, 0)) return false;
+    f.rep0 = __shfl_sync(0xffffffffu, rep0, 0);
+    f.rep1 = __shfl_sync(0xffffffffu, rep1, 0);
+    f.rep2 = __shfl_sync(0xffffffffu, rep2, 0);
+    const uint32_t rest = lit_n - lp;
+    if (op + rest > cap) return false;
+    z_warp_copy(out + op, lit + lp, rest, lane);
+    op += rest;
+    __syncwarp();
+    *op_io = op;
+    return true;
+}
+
+// frame header.  Returns header length, 0 on error / truncated input.
+__device__ uint32_t z_frame_header(const uint8_t* p, uint64_t n, uint64_t* fcs, bool* has_fcs, bool* checksum)
+{
+    if (n < 5 || z_le32(p) != 0xFD2FB528u) return 0;
+    const int fhd = p[4], fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
+    if (fhd & 0x08) return 0;  // reserved bit
+    uint32_t h = 5;
+    if (!single) {
+        if (h + 1 > n) return 0;
+        const int wl = 10 + (p[h] >> 3);
+        if (wl > 31) return 0;
+        h++;
+    }
+    const uint32_t did_bytes = did == 3 ? 4u : (uint32_t)did;
+    if (h + did_bytes > n) return 0;
+    uint32_t dict_id = 0;
+    for (uint32_t i = 0; i < did_bytes; ++i) dict_id |= (uint32_t)p[h + i] << (8 * i);
+    h += did_bytes;
+    if (dict_id != 0) return 0;  // no dictionary is ever supplied on this path
+    const uint32_t fb = fcs_flag == 0 ? (single ? 1u : 0u) : (fcs_flag == 1 ? 2u : (fcs_flag == 2 ? 4u : 8u));
+    if (h + fb > n) return 0;
+    *has_fcs = fb != 0;
+    *fcs = 0;
+    if (fb == 1) *fcs = p[h];
+    else if (fb == 2) *fcs = z_le16(p + h) + 256;
+    else if (fb == 4) *fcs = z_le32(p + h);
+    else if (fb == 8) *fcs = z_le64(p + h);
+    *checksum = ((fhd >> 2) & 1) != 0;
+    return h + fb;
+}
+
+// ZSTD_decompress for one read: every frame in src, back to back.  Whole warp.  Returns content bytes or kErrZstd.
+__device__ uint32_t z_decompress(ZWarp* zw, const uint8_t* p, uint64_t n, uint8_t* out, uint64_t cap, uint8_t* lit_scratch, uint32_t lane)
+{
+    uint64_t total = 0;
+    while (n > 0) {
+        if (n >= 8 && (z_le32(p) & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
+            const uint64_t sk = (uint64_t)z_le32(p + 4) + 8;
+            if (sk > n) return kErrZstd;
+            p += sk;
+            n -= sk;
+            continue;
+        }
+        uint64_t fcs;
+        bool has, ck;
+        const uint32_t h = z_frame_header(p, n, &fcs, &has, &ck);
+        if (!h) return kErrZstd;
+        p += h;
+        n -= h;
+        ZFrame f;
+        f.huf_bits = 0;
+        f.al_ll = f.al_of = f.al_ml = 0;
+        f.seq_valid = false;
+        f.rep0 = 1; f.rep1 = 4; f.rep2 = 8;
+        uint8_t* fout = out + total;
+        const uint64_t fcap = cap - total;
+        uint64_t op = 0;
+        for (;;) {
+            if (n < 3) return kErrZstd;
+            const uint32_t bh = z_le24(p);
+            const int last = bh & 1, type = (bh >> 1) & 3;
+            const uint32_t bs = bh >> 3;
+            p += 3;
+            n -= 3;
+            if (type == 0) {
+                if (bs > n || op + bs > fcap) return kErrZstd;
+                z_warp_copy(fout + op, p, bs, lane);
+                op += bs; p += bs; n -= bs;
+            } else if (type == 1) {
+                if (n < 1 || op + bs > fcap) return kErrZstd;
+                z_warp_fill(fout + op, p[0], bs, lane);
+                op += bs; p += 1; n -= 1;
+            } else if (type == 2) {
+                if (bs > n || bs >= kZBlockMax) return kErrZstd;
+                if (!z_decode_compressed_block(zw, f, p, bs, fout, fcap, &op, lit_scratch, lane)) return kErrZstd;
+                p += bs; n -= bs;
+            } else return kErrZstd;
+            __syncwarp();
+            if (last) break;
+        }
+        if (has && op != fcs) return kErrZstd;
+        if (ck) {
+            if (n < 4) return kErrZstd;
+            uint32_t good = 1;
+            if (lane == 0) good = (uint32_t)z_xxh64(fout, op) == z_le32(p);
+            if (!__shfl_sync(0xffffffffu, good, 0)) return kErrZstd;
+            p += 4; n -= 4;
+        }
+        total += op;
+    }
+    if (total > 0xFFFFFFF0ull) return kErrZstd;
+    return (uint32_t)total;
+}
+
+__global__ void __launch_bounds__(kZdecWarps * 32) zstd_decode_kernel(ZstdDecParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ZWarp* zw = reinterpret_cast<ZWarp*>(smem) + wid;
+    uint8_t* lit_scratch = p.lit_scratch + (uint64_t)(blockIdx.x * kZdecWarps + wid) * kZLitStride;
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(p.counter, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= p.n_reads) break;
+        const ZstdRead rd = p.reads[r];
+        uint32_t res;
+        if (rd.rejected) res = rd.preset;
+        else res = z_decompress(zw, p.src + rd.src_off, rd.src_bytes, p.dst + rd.dst_off, rd.dst_cap, lit_scratch, lane);
+        __syncwarp();
+        if (lane == 0) p.results[r] = res;
+    }
+}
+
+}  // namespace vbz
