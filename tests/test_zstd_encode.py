@@ -1,0 +1,124 @@
+"""Stage 2, encode direction: every frame the product writes (csrc/zstd_enc_kernels.cuh) must decode with stock
+libzstd and with the reference / oracle to the original bytes, must carry its content size, and should be about as
+small as what libzstd level 1 writes for nanopore-like signal (the ratio is reported by bench.py; here only a loose
+bound is asserted).  Runs on the CUDA emulator build (CPU suite) and on the real library (-m gpu)."""
+import numpy as np
+import pytest
+
+import data_gen
+import golden_data
+import oracle_lib as ol
+import product
+from oracle_lib import Options
+
+port = ol.port()
+
+
+@pytest.fixture(params=product.BACKENDS)
+def backend(request):
+    return product.get(request.param)
+
+
+def _check_frame(frame, content):
+    assert ol.frame_content_size(frame) == len(content)          # vbz.cpp:236-240 needs it
+    assert ol.zstd_decompress_lib(frame, len(content)) == content  # stock libzstd
+    assert ol.zstd_decompress_port(frame, len(content)) == content  # the restated decoder
+
+
+def _payloads(rng, small):
+    yield b""
+    yield b"\\x07"
+    yield bytes([5, 4, 3, 2, 1, 9, 8])
+    yield bytes(100)
+    yield bytes(rng.integers(0, 256, 1000, dtype=np.uint8))
+    yield bytes(rng.integers(0, 3, 5000, dtype=np.uint8))
+    yield bytes(rng.integers(0, 200, 40000, dtype=np.uint8) // 3)
+    yield ol.stage1_encode(data_gen.nanopore_like(20000, rng), 2, True)
+    yield bytes((rng.normal(128, 4, 70000)).astype(np.uint8))              # a few very frequent and many very rare symbols: long codes
+    if not small:
+        yield ol.stage1_encode(data_gen.nanopore_like(300000, rng), 2, True)
+        yield bytes(rng.integers(0, 256, 100000, dtype=np.uint8))
+
+
+def test_zstd_only_frames_are_valid(backend):
+    capi = backend[0]
+    rng = np.random.default_rng(2)
+    small = capi.path.endswith("cpusim.so")
+    for data in _payloads(rng, small):
+        for level in (1, 3, 100):
+            o = Options(False, 0, level, 0)
+            r, frame = capi.compress(np.frombuffer(data, np.uint8), o, sized=False)
+            assert not ol.is_error(r), (len(data), level, r)
+            _check_frame(frame, data)
+            r2, back = capi.decompress(frame, o, len(data), sized=False)   # and our own decoder
+            assert r2 == len(data) and back == data
+        # a destination that is too small is a zstd error (vbz.cpp:201-204)
+        if len(data) > 2000:
+            assert capi.compress(np.frombuffer(data, np.uint8), Options(False, 0, 1, 0), sized=False, cap=64)[0] == ol.ERR_ZSTD
+
+
+def test_kat_tiny_input_is_a_raw_block(backend):
+    """vbz_test.cpp:238: {5,4,3,2,1} int32 zigzag level 100 -> a frame holding one raw block."""
+    capi = backend[0]
+    k = [k for k in golden_data.kats() if k["lvl"] != 0 and k["isz"] == 4][0]
+    arr = np.array(k["values"], dtype=k["dtype"])
+    r, out = capi.compress(arr, Options(k["zz"], k["isz"], k["lvl"], k["ver"]), sized=k["sized"])
+    assert list(out) == k["bytes"], k["source"]
+
+
+@pytest.mark.parametrize("dtype,o", [(np.int16, Options(True, 2, 1, 0)), (np.int16, Options(True, 2, 1, 1)), (np.int16, Options(False, 2, 3, 0)),
+                                     (np.int32, Options(True, 4, 1, 0)), (np.uint32, Options(False, 4, 3, 0)), (np.int8, Options(True, 1, 1, 0))])
+def test_full_vbz_roundtrip_and_reference_decodes(backend, dtype, o):
+    capi = backend[0]
+    ref = ol.ref()
+    rng = np.random.default_rng(7)
+    small = capi.path.endswith("cpusim.so")
+    for n in (0, 1, 7, 100, 4096, 20000) + (() if small else (150000,)):
+        if dtype == np.uint32:
+            arr = rng.integers(0, 1 << 20, n).astype(np.uint32)
+        else:
+            arr = data_gen.nanopore_like(n, rng).astype(dtype)
+        for sized in (True, False):
+            r, blob = capi.compress(arr, o, sized=sized)
+            assert not ol.is_error(r), (n, sized, r)
+            # the oracle (and the reference itself, where it was built) decode it to the original samples
+            rp, back = port.decompress(blob, o, arr.nbytes, sized=sized)
+            assert rp == arr.nbytes and back == arr.tobytes(), (n, sized, rp)
+            if ref is not None:
+                rr, back2 = ref.decompress(blob, o, arr.nbytes, sized=sized)
+                assert rr == arr.nbytes and back2 == arr.tobytes()
+            # stage-1 bytes inside the frame are the oracle's stage-1 bytes
+            frame = blob[4:] if sized else blob
+            s1 = ol.stage1_encode(arr, o.integer_size, o.perform_delta_zig_zag, o.vbz_version)
+            assert ol.zstd_decompress_lib(frame, len(s1)) == s1
+            # our decoder
+            r3, back3 = capi.decompress(blob, o, arr.nbytes, sized=sized)
+            assert r3 == arr.nbytes and back3 == arr.tobytes()
+
+
+def test_ratio_close_to_libzstd_on_signal(backend):
+    capi = backend[0]
+    rng = np.random.default_rng(12)
+    arr = data_gen.nanopore_like(120000, rng)
+    o = Options(True, 2, 1, 1)
+    r, blob = capi.compress(arr, o, sized=True)
+    rp, blob_ref = port.compress(arr, o, sized=True)
+    assert not ol.is_error(r)
+    assert r <= 1.05 * rp, (r, rp)   # Huffman-only blocks: within a few percent of libzstd level 1 on signal
+
+
+def test_fast5_fixture_reencode(backend):
+    """BASELINE config 1 on the product: re-encode the fixture reads, decode with the oracle, compare sizes."""
+    capi = backend[0]
+    o = Options(True, 2, 1, 1)
+    tot, tot_ref = 0, 0
+    reads = golden_data.fast5_reads()
+    for rd in (reads[:3] if capi.path.endswith("cpusim.so") else reads):
+        want = rd["samples"]
+        r, blob = capi.compress(want, o, sized=True)
+        assert not ol.is_error(r)
+        rp, back = port.decompress(blob, o, want.nbytes, sized=True)
+        assert rp == want.nbytes and back == want.tobytes()
+        tot += r
+        tot_ref += len(rd["vbz_chunk"])
+    assert tot <= 1.04 * tot_ref, (tot, tot_ref)

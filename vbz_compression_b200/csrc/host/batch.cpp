@@ -158,10 +158,53 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     return 0;
 }
 
+// ---- stage 2 (zstd), encode: content -> frames ----------------------------------------------------------------------
+// reads[i].first_block is set here.
+static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, std::vector<ZstdEncRead>& reads, const uint32_t* d_src_sizes,
+                               uint32_t* d_results, bool sized, cudaStream_t stream)
+{
+    const uint32_t n = (uint32_t)reads.size();
+    if (n == 0) return 0;
+    uint64_t blocks = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        reads[i].first_block = (uint32_t)blocks;
+        blocks += reads[i].n_blocks;
+    }
+    if (blocks > 0x7FFFFFFFull) { set_last_error("batch too large: more than 2^31 zstd blocks"); return -1; }
+    const uint32_t n_blocks = (uint32_t)blocks;
+    const size_t bytes = (size_t)n * sizeof(ZstdEncRead);
+    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zblocks.ensure((size_t)n_blocks * 4) || !ctx->d_zstatus.ensure((size_t)n_blocks * 8)) return -1;
+    if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
+    if (!ctx->h_zreads.ensure(bytes)) return -1;
+    memcpy(ctx->h_zreads.p, reads.data(), bytes);
+    if (!cuda_ok(cudaMemcpyAsync(ctx->d_zreads.p, ctx->h_zreads.p, bytes, cudaMemcpyHostToDevice, stream), "upload frame descriptors") ||
+        !cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord") ||
+        !cuda_ok(cudaMemsetAsync(ctx->d_zstatus.p, 0, (size_t)n_blocks * 8, stream), "reset look-back state"))
+        return -1;
+    int e = vbzk_zstd_enc_fill_blocks(ctx->d_zreads.as<VbzkZstdEncRead>(), n, ctx->d_zblocks.as<uint32_t>(), stream);
+    if (e) { cuda_ok((cudaError_t)e, "zstd_enc_fill_blocks launch"); return -1; }
+    ZstdEncParams p;
+    p.src = d_src;
+    p.dst = d_dst;
+    p.reads = ctx->d_zreads.as<ZstdEncRead>();
+    p.block_read = ctx->d_zblocks.as<uint32_t>();
+    p.src_sizes = d_src_sizes;
+    p.status = ctx->d_zstatus.as<uint64_t>();
+    p.results = d_results;
+    p.hdr_bytes = sized ? 4u : 0u;
+    p.err_add = sized ? 4u : 0u;
+    p.n_reads = n;
+    p.n_blocks = n_blocks;
+    e = vbzk_zstd_encode(reinterpret_cast<const VbzkZstdEncParams*>(&p), stream);
+    if (e) { cuda_ok((cudaError_t)e, "zstd_encode launch"); return -1; }
+    ctx->launches += 2;
+    return 0;
+}
+
 static bool device_path_available(const Stage1Kind& kind, bool decode = false)
 {
-    if (decode && !kind.half) return true;
-    if (kind.zstd_level != 0 || kind.half || kind.isz == 0) {
+    (void)decode;
+    if (kind.half) {
         set_last_error("this option combination is not implemented on the device yet");
         return false;
     }
@@ -173,28 +216,74 @@ static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t
                                 uint32_t* d_results, const Stage1Kind& kind, bool sized, cudaStream_t stream)
 {
     if (!device_path_available(kind)) return -1;
-    std::vector<SvbRead> reads(jobs.size());
-    for (size_t i = 0; i < jobs.size(); ++i) {
-        const ReadJob& j = jobs[i];
-        SvbRead& r = reads[i];
-        memset(&r, 0, sizeof(r));
-        r.src_off = j.src_off;
-        r.dst_off = j.dst_off;
-        r.src_bytes = j.src_size;
-        r.rejected = j.rejected;
-        r.preset = j.code;
-        if (!j.rejected) {
-            if ((j.src_off | j.dst_off) & 15) { set_last_error("device batch offsets must be multiples of 16"); return -1; }
-            r.n_values = j.src_size / (unsigned)kind.isz;
+    const uint32_t n = (uint32_t)jobs.size();
+    const bool zstd = kind.zstd_level != 0;
+    if (!zstd && kind.isz == 0) { set_last_error("plain copies (integer_size 0, level 0) are not a device operation"); return -1; }
+    const uint32_t blk = vbzk_zstd_enc_block_bytes();
+    std::vector<uint64_t> mid_off(zstd ? n : 0);
+    uint64_t mid_total = 0;
+    if (kind.isz != 0) {
+        // stage 1: straight into the destination (with the sized header) when there is no zstd stage, else into the
+        // intermediate buffer (ref vbz/vbz.cpp:163-186)
+        std::vector<SvbRead> reads(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const ReadJob& j = jobs[i];
+            SvbRead& r = reads[i];
+            memset(&r, 0, sizeof(r));
+            r.src_off = j.src_off;
+            r.dst_off = j.dst_off;
+            r.src_bytes = j.src_size;
+            r.rejected = j.rejected;
+            r.preset = j.code;
+            if (!j.rejected) {
+                if ((j.src_off | j.dst_off) & 15) { set_last_error("device batch offsets must be multiples of 16"); return -1; }
+                r.n_values = j.src_size / (unsigned)kind.isz;
+                if (zstd) {
+                    mid_off[i] = mid_total;
+                    r.dst_off = mid_total;
+                    mid_total += align16(stage1_tight_bound(r.n_values, kind)) + 16;
+                }
+            }
         }
+        if (!zstd) return enqueue_stage1(ctx, false, kind, d_src, d_dst, reads, sized ? 4u : 0u, d_results, nullptr, stream);
+        if (!ctx->d_mid.ensure(mid_total + 16) || !ctx->d_sizes.ensure((size_t)n * 4)) return -1;
+        if (enqueue_stage1(ctx, false, kind, d_src, ctx->d_mid.as<uint8_t>(), reads, 0, ctx->d_sizes.as<uint32_t>(), nullptr, stream) != 0) return -1;
     }
-    return enqueue_stage1(ctx, false, kind, d_src, d_dst, reads, sized ? 4u : 0u, d_results, nullptr, stream);
+    // stage 2: one zstd frame per read (ref vbz/vbz.cpp:194-204)
+    std::vector<ZstdEncRead> zr(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const ReadJob& j = jobs[i];
+        ZstdEncRead& z = zr[i];
+        memset(&z, 0, sizeof(z));
+        z.rejected = j.rejected;
+        z.preset = j.code;
+        z.n_blocks = 1;
+        if (j.rejected) continue;
+        z.dst_off = j.dst_off;
+        z.dst_cap = j.dst_size;
+        z.hdr_value = j.src_size;
+        uint64_t largest = j.src_size;
+        if (kind.isz != 0) {
+            const uint32_t nv = j.src_size / (unsigned)kind.isz;
+            z.src_off = mid_off[i];
+            z.split = (uint32_t)(((uint64_t)nv + 3) / 4);  // control bytes | data bytes
+            if (z.split < 512) z.split = 0;                 // too small to be worth a block (and a table) of its own
+            largest = stage1_tight_bound(nv, kind);
+        } else {
+            z.src_off = j.src_off;
+            z.src_bytes = j.src_size;
+        }
+        z.n_blocks = (uint32_t)std::max<uint64_t>(1, (z.split + blk - 1) / blk + (largest - z.split + blk - 1) / blk);
+    }
+    return enqueue_zstd_encode(ctx, kind.isz != 0 ? ctx->d_mid.as<uint8_t>() : d_src, d_dst, zr, kind.isz != 0 ? ctx->d_sizes.as<uint32_t>() : nullptr,
+                               d_results, sized, stream);
 }
 
 static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ReadJob>& jobs,
                                   uint32_t* d_results, const Stage1Kind& kind, bool sized, cudaStream_t stream)
 {
     if (!device_path_available(kind, true)) return -1;
+    if (kind.zstd_level == 0 && kind.isz == 0) { set_last_error("plain copies (integer_size 0, level 0) are not a device operation"); return -1; }
     const uint32_t hdr = sized ? 4u : 0u;
     const uint32_t n = (uint32_t)jobs.size();
     const uint8_t* s1_src = d_src;
@@ -410,8 +499,11 @@ extern "C" int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src
         j.dst_off = out_total;
         j.src_size = src_size[i];
         in_total += align16(src_size[i]);
-        const uint64_t slot = align16(hdr + stage1_tight_bound(src_size[i] / (unsigned)std::max(kind.isz, 1), kind));
-        j.dst_size = (uint32_t)std::min<uint64_t>(slot, 0xFFFFFFF0u);
+        uint64_t produced = kind.isz != 0 ? stage1_tight_bound(src_size[i] / (unsigned)kind.isz, kind) : src_size[i];
+        if (kind.zstd_level != 0) produced = zstd_enc_worst_case(produced);
+        const uint64_t slot = align16(hdr + produced);
+        // with a zstd stage the caller's capacity decides between a frame and VBZ_ZSTD_ERROR (vbz.cpp:194-204)
+        j.dst_size = (uint32_t)std::min<uint64_t>(kind.zstd_level != 0 ? std::min<uint64_t>(slot, dst_cap[i]) : slot, 0xFFFFFFF0u);
         out_total += slot;
         jobs.push_back(j);
         job_read.push_back(i);

@@ -81,6 +81,31 @@ struct ZstdDecParams {
     uint32_t n_reads;
 };
 
+struct ZstdEncRead {
+    uint64_t src_off;     // the content: bytes [src_off, src_off + size) of ZstdEncParams::src
+    uint64_t dst_off;     // the output slot, offset into ZstdEncParams::dst
+    uint32_t src_bytes;   // content size, unless ZstdEncParams::src_sizes says otherwise
+    uint32_t dst_cap;     // capacity of the output slot (sized header included)
+    uint32_t first_block; // index of the frame's first block
+    uint32_t n_blocks;    // blocks reserved for the frame (enough for the largest content stage 1 could produce)
+    uint32_t hdr_value;   // value of the 4-byte "sized" header: the original byte count (ref vbz/vbz.cpp:316-317)
+    uint32_t rejected;    // != 0: decided on the host; copy `preset` to results[]
+    uint32_t preset;
+    uint32_t split;       // blocks never straddle this content offset (the control-byte / data-byte boundary of stage 1); 0 = none
+};
+struct ZstdEncParams {
+    const uint8_t* src;
+    uint8_t* dst;
+    const ZstdEncRead* reads;
+    const uint32_t* block_read;  // block -> read
+    const uint32_t* src_sizes;   // optional per-read content size written by stage 1; >= kErrOutOfMemory is passed through
+    uint64_t* status;            // look-back chain over the blocks of a frame, zeroed before launch
+    uint32_t* results;           // per read: bytes written (headers included) or an error code
+    uint32_t hdr_bytes;          // 4 = put the "sized" header before the frame
+    uint32_t err_add;            // what the sized entry point adds to error codes (ref vbz/vbz.cpp:329)
+    uint32_t n_reads, n_blocks;
+};
+constexpr uint32_t kZEncBlock = 32u * 1024u;   // content bytes per block written by the encoder
 constexpr uint32_t kZBlockMax = 128u * 1024u;
 constexpr int kZdecWarps = 4;
 constexpr uint32_t kZLitStride = kZBlockMax + 32;  // literal scratch per decoding warp

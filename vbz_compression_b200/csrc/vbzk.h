@@ -30,6 +30,13 @@ uint32_t vbzk_zstd_decode_grid(void);
 uint64_t vbzk_zstd_decode_scratch_bytes(void);
 int vbzk_zstd_decode(const struct VbzkZstdDecParams* params, void* stream);
 
+/* stage 2, encode: one zstd frame per read (csrc/zstd_enc_kernels.cuh); one CTA per 32 KiB block */
+struct VbzkZstdEncRead;   /* == vbz::ZstdEncRead */
+struct VbzkZstdEncParams; /* == vbz::ZstdEncParams */
+uint32_t vbzk_zstd_enc_block_bytes(void);
+int vbzk_zstd_enc_fill_blocks(const struct VbzkZstdEncRead* d_reads, uint32_t n_reads, uint32_t* d_block_read, void* stream);
+int vbzk_zstd_encode(const struct VbzkZstdEncParams* params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

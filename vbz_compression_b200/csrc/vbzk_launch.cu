@@ -3,6 +3,7 @@
 #include "svb_kernels.cuh"
 #include "svb16_kernels.cuh"
 #include "zstd_dec_kernels.cuh"
+#include "zstd_enc_kernels.cuh"
 
 using namespace vbz;
 
@@ -158,5 +159,22 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     const uint32_t need = (p.n_reads + kZdecWarps - 1) / kZdecWarps;
     if (need < grid) grid = need;
     VBZ_LAUNCH(zstd_decode_kernel, grid, kZdecWarps * 32, smem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+
+extern "C" uint32_t vbzk_zstd_enc_block_bytes(void) { return kZEncBlock; }
+extern "C" int vbzk_zstd_enc_fill_blocks(const VbzkZstdEncRead* d_reads, uint32_t n_reads, uint32_t* d_block_read, void* stream)
+{
+    if (n_reads == 0) return 0;
+    VBZ_LAUNCH(zstd_enc_fill_blocks_kernel, (n_reads + 7) / 8, 256, 0, (vbz_stream_t)stream, reinterpret_cast<const ZstdEncRead*>(d_reads), n_reads, d_block_read);
+    return VBZK_LAST_ERROR();
+}
+extern "C" int vbzk_zstd_encode(const VbzkZstdEncParams* params, void* stream)
+{
+    const ZstdEncParams& p = *reinterpret_cast<const ZstdEncParams*>(params);
+    if (p.n_blocks == 0) return 0;
+    const uint32_t smem = (uint32_t)sizeof(ZEncSmem);
+    if (int e = VBZK_SET_SMEM(zstd_encode_kernel, smem)) return e;
+    VBZ_LAUNCH(zstd_encode_kernel, p.n_blocks, kZencThreads, smem, (vbz_stream_t)stream, p);
     return VBZK_LAST_ERROR();
 }
