@@ -1,0 +1,112 @@
+"""The host-pointer batch entry points (include/vbz_b200.h) run a batch as pipelined waves
+(csrc/host/batch.cpp: run_host_batch).  Every read must come back exactly as the oracle's per-read call
+returns it, whatever the wave size, the path (staged through pinned memory / direct DMA from page-locked
+caller buffers) and the mix of good and rejected reads."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import data_gen
+import oracle_lib as ol
+import product
+from oracle_lib import Options
+from vbz_compression_b200 import CompressionOptions
+
+port = ol.port()
+
+
+@pytest.fixture(params=product.BACKENDS)
+def backend(request):
+    return product.get(request.param)
+
+
+def _reads(rng, n_reads, lo, hi):
+    return [data_gen.nanopore_like(int(n), rng) for n in rng.integers(lo, hi, n_reads)]
+
+
+@pytest.mark.parametrize("level", [0, 1])
+@pytest.mark.parametrize("wave_mib", ["1", "0"])
+def test_waves_match_oracle(backend, level, wave_mib, monkeypatch):
+    _, batch, _ = backend
+    if wave_mib != "0":
+        monkeypatch.setenv("VBZ_B200_WAVE_MIB", wave_mib)
+    else:
+        monkeypatch.delenv("VBZ_B200_WAVE_MIB", raising=False)
+    rng = np.random.default_rng(11 + level)
+    reads = _reads(rng, 40, 1, 120_000)
+    reads[5] = np.zeros(0, np.int16)
+    reads[17] = reads[17].view(np.uint8)[:-1].copy()  # odd byte count: VBZ_INPUT_SIZE_ERROR for this read only
+    o = Options(True, 2, level, 1)
+    opts = CompressionOptions(True, 2, level, 1)
+    res = batch.compress(reads, opts, sized=True)
+    blobs = []
+    for arr, (code, blob) in zip(reads, res):
+        cap = port.max_compressed_size(arr.nbytes, o)
+        if ol.is_error(cap):  # api.Batch hands such a read a 4-byte slot; the sized entry point adds 4 to the error (vbz.cpp:329)
+            rp, _ = port.compress(arr, o, sized=True, cap=4)
+            assert code == rp == (ol.ERR_INPUT_SIZE + 4) & 0xFFFFFFFF
+            blobs.append(b"\x00" * 8)
+            continue
+        rp, bp = port.compress(arr, o, sized=True)
+        assert not ol.is_error(code) and not ol.is_error(rp)
+        if level == 0:
+            assert code == rp and blob == bp
+        else:  # zstd bytes are the encoder's own; the oracle must decode them
+            r2, back = port.decompress(blob, o, arr.nbytes, sized=True)
+            assert r2 == arr.nbytes and back == arr.tobytes()
+        blobs.append(blob)
+    blobs[9] = blobs[9][:len(blobs[9]) // 2]  # a truncated chunk: fails alone
+    back = batch.decompress(blobs, [a.nbytes for a in reads], opts, sized=True)
+    for i, (arr, (code, blob)) in enumerate(zip(reads, back)):
+        rp, bp = port.decompress(blobs[i], o, arr.nbytes, sized=True)
+        assert code == rp, i
+        if not ol.is_error(rp):
+            assert blob == bp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [0, 1])
+def test_direct_dma_from_pinned_buffers(level):
+    """Page-locked caller buffers are read and written in place by the DMA engine (no staging copy)."""
+    import torch
+    _, batch, lib = product.get("gpu")
+    rng = np.random.default_rng(5)
+    lens = rng.integers(40_000, 400_000, 64)
+    opts = CompressionOptions(True, 2, level, 0)
+    tot = int(lens.sum()) * 2
+    host_in = torch.empty(tot, dtype=torch.uint8).pin_memory()
+    arr = data_gen.nanopore_like(int(lens.sum()), rng)
+    host_in.numpy()[:] = arr.view(np.uint8)
+    caps = [int(lib.vbz_max_compressed_size(int(n) * 2, ctypes.byref(opts))) for n in lens]
+    host_c = torch.zeros(int(sum(caps)), dtype=torch.uint8).pin_memory()
+    host_back = torch.zeros(tot, dtype=torch.uint8).pin_memory()
+    n = len(lens)
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    offs = np.concatenate([[0], np.cumsum(lens * 2)[:-1]])
+    coffs = np.concatenate([[0], np.cumsum(caps)[:-1]])
+    srcp = (vp * n)(*[host_in.data_ptr() + int(o) for o in offs])
+    cp = (vp * n)(*[host_c.data_ptr() + int(o) for o in coffs])
+    bp = (vp * n)(*[host_back.data_ptr() + int(o) for o in offs])
+    ssz = (u32 * n)(*[int(x) * 2 for x in lens])
+    ccap = (u32 * n)(*caps)
+    res_c, res_d = (u32 * n)(), (u32 * n)()
+    for path in ("direct", "staged"):
+        os.environ["VBZ_B200_HOST_PATH"] = path
+        os.environ["VBZ_B200_WAVE_MIB"] = "8"
+        try:
+            host_c.zero_(); host_back.zero_()
+            assert lib.vbz_b200_compress_batch(batch.ctx, srcp, ssz, cp, ccap, res_c, n, ctypes.byref(opts), 1) == 0, lib.vbz_b200_last_error()
+            assert lib.vbz_b200_decompress_batch(batch.ctx, cp, res_c, bp, ssz, res_d, n, ctypes.byref(opts), 1) == 0, lib.vbz_b200_last_error()
+        finally:
+            del os.environ["VBZ_B200_HOST_PATH"], os.environ["VBZ_B200_WAVE_MIB"]
+        assert list(res_d) == [int(x) * 2 for x in lens]
+        assert torch.equal(host_in, host_back), path
+        if level == 0:
+            o = Options(True, 2, 0, 0)
+            for i in (0, n // 2, n - 1):
+                a = arr[int(offs[i]) // 2: int(offs[i]) // 2 + int(lens[i])]
+                rp, bpo = port.compress(a, o, sized=True)
+                got = host_c.numpy()[int(coffs[i]): int(coffs[i]) + res_c[i]].tobytes()
+                assert res_c[i] == rp and got == bpo

@@ -16,6 +16,7 @@
 #include "../svb_types.h"
 #include "../vbzk.h"
 #include "context.h"
+#include "copy_pool.h"
 #include "options.h"
 
 namespace vbz {
@@ -363,9 +364,18 @@ vbz_b200_ctx::~vbz_b200_ctx()
 {
     d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
     h_reads.release(); h_results.release();
-    d_in.release(); d_out.release(); d_mid.release();
-    h_in.release(); h_out.release();
+    d_mid.release();
+    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zblocks.release(); d_zstatus.release(); h_zreads.release();
+    for (WaveSlot& w : slots) {
+        w.d_in.release(); w.d_out.release(); w.d_results.release();
+        w.h_in.release(); w.h_out.release(); w.h_results.release();
+        if (w.ev_in) cudaEventDestroy(w.ev_in);
+        if (w.ev_k) cudaEventDestroy(w.ev_k);
+        if (w.ev_out) cudaEventDestroy(w.ev_out);
+    }
     if (upload_done) cudaEventDestroy(upload_done);
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -386,8 +396,15 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
     if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
     vbz_b200_ctx* c = new vbz_b200_ctx();
     c->device = device;
-    if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
-        !cuda_ok(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming), "cudaEventCreate")) {
+    bool ok = cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              cuda_ok(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              cuda_ok(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              cuda_ok(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming), "cudaEventCreate");
+    for (vbz_b200_ctx::WaveSlot& w : c->slots)
+        ok = ok && cuda_ok(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming), "cudaEventCreate") &&
+             cuda_ok(cudaEventCreateWithFlags(&w.ev_k, cudaEventDisableTiming), "cudaEventCreate") &&
+             cuda_ok(cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming), "cudaEventCreate");
+    if (!ok) {
         delete c;
         return nullptr;
     }
@@ -471,6 +488,176 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
 }
 
 // ---- host-pointer batches -------------------------------------------------------------------------------------
+// A batch of host reads runs as WAVES of ~64 MiB through three slots (device in/out buffers, pinned staging,
+// events): while wave w is uploaded, wave w-1 is in the kernels and wave w-2 is downloaded and handed to the
+// caller, so the PCIe link (both directions) and the SMs work at the same time.  Two ways to move a read:
+//   direct  the caller's buffers are page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): the DMA
+//           engine reads and writes them in place, one copy per read;
+//   staged  pageable buffers: host threads (copy_pool.h) gather the wave into pinned staging, one DMA per wave.
+// Per-read results are known on the host one pipeline stage after the kernels ran; only then are a read's
+// bytes brought back (compress: exactly the bytes it produced).
+namespace vbz {
+
+struct HostJob {
+    ReadJob j;          // offsets are relative to the wave's buffers
+    uint32_t read;      // index into the caller's arrays
+    uint32_t in_slot;   // bytes reserved in the wave's input / output buffers (multiples of 16)
+    uint32_t out_slot;
+};
+struct HostBatch {
+    bool compress, sized;
+    Stage1Kind kind;
+    const void* const* src;
+    const vbz_size_t* src_size;
+    void* const* dst;
+    const vbz_size_t* dst_cap;
+    vbz_size_t* results;
+    std::vector<HostJob> jobs;
+};
+struct Wave { uint32_t k0, k1; uint64_t in_bytes, out_bytes; bool direct; };
+
+static bool host_pinned(const void* p)
+{
+#ifdef VBZ_CPUSIM
+    (void)p;
+    return false;
+#else
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+#endif
+}
+
+static size_t wave_budget(uint64_t total)
+{
+    if (const char* e = getenv("VBZ_B200_WAVE_MIB")) { const long v = atol(e); if (v > 0) return (size_t)v << 20; }
+    const uint64_t want = total / 24;  // enough waves that filling and draining the pipeline stays a small share
+    return (size_t)std::min<uint64_t>(std::max<uint64_t>(want, 8ull << 20), 96ull << 20);
+}
+
+static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
+{
+    const uint32_t m = (uint32_t)b.jobs.size();
+    if (m == 0) return 0;
+    // ---- plan the waves -------------------------------------------------------------------------------------------
+    uint64_t total = 0;
+    for (const HostJob& h : b.jobs) total += (uint64_t)h.in_slot + h.out_slot;
+    const size_t budget = wave_budget(total);
+    std::vector<Wave> waves;
+    uint64_t max_in = 0, max_out = 0;
+    uint32_t max_jobs = 0;
+    bool any_staged = false;
+    const char* force = getenv("VBZ_B200_HOST_PATH");  // "staged" / "direct": experiments and tests
+    for (uint32_t k = 0; k < m;) {
+        Wave w = {k, k, 0, 0, true};
+        while (w.k1 < m && (w.k1 == w.k0 || w.in_bytes + w.out_bytes + b.jobs[w.k1].in_slot + b.jobs[w.k1].out_slot <= budget)) {
+            HostJob& h = b.jobs[w.k1];
+            h.j.src_off = w.in_bytes;
+            h.j.dst_off = w.out_bytes;
+            w.in_bytes += h.in_slot;
+            w.out_bytes += h.out_slot;
+            ++w.k1;
+        }
+        // direct DMA needs page-locked buffers on both sides and reads large enough to be worth a copy call each
+        const uint32_t cnt = w.k1 - w.k0;
+        w.direct = (w.in_bytes + w.out_bytes) / cnt >= (64u << 10);
+        if (force && force[0] == 's') w.direct = false;
+        for (uint32_t q = w.k0; q < w.k1 && w.direct; ++q)
+            w.direct = (b.jobs[q].j.src_size == 0 || host_pinned(b.src[b.jobs[q].read])) && host_pinned(b.dst[b.jobs[q].read]);
+        any_staged |= !w.direct;
+        max_in = std::max(max_in, w.in_bytes);
+        max_out = std::max(max_out, w.out_bytes);
+        max_jobs = std::max(max_jobs, cnt);
+        waves.push_back(w);
+        k = w.k1;
+    }
+    const uint32_t W = (uint32_t)waves.size();
+    const int S = W > 1 ? vbz_b200_ctx::kWaveSlots : 1;
+    for (int s = 0; s < S; ++s) {
+        vbz_b200_ctx::WaveSlot& sl = ctx->slots[s];
+        if (!sl.d_in.ensure(max_in + 16) || !sl.d_out.ensure(max_out + 16) || !sl.d_results.ensure((size_t)max_jobs * 4) ||
+            !sl.h_results.ensure((size_t)max_jobs * 4))
+            return -1;
+        if (any_staged && (!sl.h_in.ensure(max_in + 16) || !sl.h_out.ensure(max_out + 16))) return -1;
+    }
+    cudaStream_t sk = ctx->stream, sh = ctx->s_h2d, sd = ctx->s_d2h;
+    std::vector<CopyTask> copies;
+    std::vector<ReadJob> wave_jobs;
+    int rc = 0;
+
+    // one iteration: upload + launch wave w, collect the results of wave w-1 and start its download, deliver wave w-2
+    for (uint32_t it = 0; it < W + 2 && rc == 0; ++it) {
+        if (it < W) {
+            const Wave& w = waves[it];
+            vbz_b200_ctx::WaveSlot& sl = ctx->slots[it % S];
+            uint8_t* d_in = sl.d_in.as<uint8_t>();
+            if (w.direct) {
+                for (uint32_t q = w.k0; q < w.k1; ++q) {
+                    const HostJob& h = b.jobs[q];
+                    if (h.j.src_size && !cuda_ok(cudaMemcpyAsync(d_in + h.j.src_off, b.src[h.read], h.j.src_size, cudaMemcpyHostToDevice, sh), "H2D input")) { rc = -1; break; }
+                }
+            } else {
+                copies.clear();
+                for (uint32_t q = w.k0; q < w.k1; ++q) {
+                    const HostJob& h = b.jobs[q];
+                    if (h.j.src_size) copies.push_back({sl.h_in.as<uint8_t>() + h.j.src_off, b.src[h.read], h.j.src_size});
+                }
+                CopyPool::instance().run(copies);
+                if (!cuda_ok(cudaMemcpyAsync(d_in, sl.h_in.p, w.in_bytes, cudaMemcpyHostToDevice, sh), "H2D input")) rc = -1;
+            }
+            if (rc != 0) break;
+            wave_jobs.resize(w.k1 - w.k0);
+            for (uint32_t q = w.k0; q < w.k1; ++q) wave_jobs[q - w.k0] = b.jobs[q].j;
+            // the kernels wait for the upload, and for the download that last used this slot's output buffer
+            if (!cuda_ok(cudaEventRecord(sl.ev_in, sh), "cudaEventRecord") || !cuda_ok(cudaStreamWaitEvent(sk, sl.ev_in, 0), "cudaStreamWaitEvent") ||
+                (it >= (uint32_t)S && !cuda_ok(cudaStreamWaitEvent(sk, sl.ev_out, 0), "cudaStreamWaitEvent"))) { rc = -1; break; }
+            const int e = b.compress ? compress_device_impl(ctx, d_in, sl.d_out.as<uint8_t>(), wave_jobs, sl.d_results.as<uint32_t>(), b.kind, b.sized, sk)
+                                     : decompress_device_impl(ctx, d_in, sl.d_out.as<uint8_t>(), wave_jobs, sl.d_results.as<uint32_t>(), b.kind, b.sized, sk);
+            if (e != 0) { rc = -1; break; }
+            if (!cuda_ok(cudaMemcpyAsync(sl.h_results.p, sl.d_results.p, (size_t)(w.k1 - w.k0) * 4, cudaMemcpyDeviceToHost, sk), "D2H results") ||
+                !cuda_ok(cudaEventRecord(sl.ev_k, sk), "cudaEventRecord")) { rc = -1; break; }
+        }
+        if (it >= 1 && it - 1 < W) {
+            const Wave& w = waves[it - 1];
+            vbz_b200_ctx::WaveSlot& sl = ctx->slots[(it - 1) % S];
+            if (!cuda_ok(cudaEventSynchronize(sl.ev_k), "batch kernels")) { rc = -1; break; }
+            const uint32_t* dres = sl.h_results.as<uint32_t>();
+            const uint8_t* d_out = sl.d_out.as<uint8_t>();
+            for (uint32_t q = w.k0; q < w.k1; ++q) {
+                const HostJob& h = b.jobs[q];
+                uint32_t r = dres[q - w.k0];
+                if (!is_error(r) && r > b.dst_cap[h.read]) r = b.sized ? kErrDestinationSize + 4 : kErrDestinationSize;  // (compress with a tight device slot)
+                b.results[h.read] = r;
+                if (is_error(r) || r == 0) continue;
+                uint8_t* to = w.direct ? (uint8_t*)b.dst[h.read] : sl.h_out.as<uint8_t>() + h.j.dst_off;
+                if (!cuda_ok(cudaMemcpyAsync(to, d_out + h.j.dst_off, r, cudaMemcpyDeviceToHost, sd), "D2H output")) { rc = -1; break; }
+            }
+            if (rc == 0 && !cuda_ok(cudaEventRecord(sl.ev_out, sd), "cudaEventRecord")) rc = -1;
+            if (rc != 0) break;
+        }
+        if (it >= 2) {
+            const Wave& w = waves[it - 2];
+            vbz_b200_ctx::WaveSlot& sl = ctx->slots[(it - 2) % S];
+            if (!cuda_ok(cudaEventSynchronize(sl.ev_out), "batch download")) { rc = -1; break; }
+            if (!w.direct) {
+                copies.clear();
+                for (uint32_t q = w.k0; q < w.k1; ++q) {
+                    const HostJob& h = b.jobs[q];
+                    const uint32_t r = b.results[h.read];
+                    if (!is_error(r) && r > 0) copies.push_back({b.dst[h.read], sl.h_out.as<uint8_t>() + h.j.dst_off, r});
+                }
+                CopyPool::instance().run(copies);
+            }
+        }
+    }
+    if (rc != 0) {  // leave nothing in flight that still points at the caller's buffers
+        cudaStreamSynchronize(sh); cudaStreamSynchronize(sk); cudaStreamSynchronize(sd);
+    }
+    return rc;
+}
+
+}  // namespace vbz
+
 extern "C" int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src, const vbz_size_t* src_size, void* const* dst,
                                        const vbz_size_t* dst_cap, vbz_size_t* results, uint32_t n, const CompressionOptions* o, int sized_i)
 {
@@ -479,12 +666,12 @@ extern "C" int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src
     if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
     const bool sized = sized_i != 0;
     const uint32_t hdr = sized ? 4u : 0u;
-    const Stage1Kind kind = classify_options(o);
+    HostBatch b;
+    b.compress = true; b.sized = sized; b.kind = classify_options(o);
+    b.src = src; b.src_size = src_size; b.dst = dst; b.dst_cap = dst_cap; b.results = results;
+    const Stage1Kind& kind = b.kind;
 
-    // pass 1: per-read checks in the reference's order; plain copies are done right here
-    std::vector<ReadJob> jobs;
-    std::vector<uint32_t> job_read;
-    uint64_t in_total = 0, out_total = 0;
+    // per-read checks in the reference's order; plain copies are done right here
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t code = 0;
         if (compress_precheck(kind, src_size[i], dst_cap[i], sized, &code)) { results[i] = code; continue; }
@@ -494,56 +681,22 @@ extern "C" int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src
             results[i] = src_size[i] + hdr;
             continue;
         }
-        ReadJob j;
-        j.src_off = in_total;
-        j.dst_off = out_total;
-        j.src_size = src_size[i];
-        in_total += align16(src_size[i]);
+        HostJob h;
+        h.read = i;
+        h.j.src_size = src_size[i];
+        h.in_slot = (uint32_t)std::min<uint64_t>(align16(src_size[i]), 0xFFFFFFF0u);
         uint64_t produced = kind.isz != 0 ? stage1_tight_bound(src_size[i] / (unsigned)kind.isz, kind) : src_size[i];
         if (kind.zstd_level != 0) produced = zstd_enc_worst_case(produced);
         const uint64_t slot = align16(hdr + produced);
+        if (slot > 0xFFFFFFF0ull) { results[i] = sized ? kErrOutOfMemory + 4 : kErrOutOfMemory; continue; }
         // with a zstd stage the caller's capacity decides between a frame and VBZ_ZSTD_ERROR (vbz.cpp:194-204)
-        j.dst_size = (uint32_t)std::min<uint64_t>(kind.zstd_level != 0 ? std::min<uint64_t>(slot, dst_cap[i]) : slot, 0xFFFFFFF0u);
-        out_total += slot;
-        jobs.push_back(j);
-        job_read.push_back(i);
+        h.j.dst_size = (uint32_t)(kind.zstd_level != 0 ? std::min<uint64_t>(slot, dst_cap[i]) : slot);
+        h.out_slot = (uint32_t)slot;
+        b.jobs.push_back(h);
     }
-    if (jobs.empty()) return 0;
+    if (b.jobs.empty()) return 0;
     if (!device_path_available(kind)) return -1;
-    const uint32_t m = (uint32_t)jobs.size();
-
-    // pass 2: stage inputs, run, fetch results
-    if (!ctx->h_in.ensure(in_total + 16) || !ctx->d_in.ensure(in_total + 16) || !ctx->d_out.ensure(out_total + 16) ||
-        !ctx->d_results.ensure((size_t)m * 4) || !ctx->h_results.ensure((size_t)m * 4))
-        return -1;
-    for (uint32_t k = 0; k < m; ++k)
-        if (jobs[k].src_size) memcpy(ctx->h_in.as<uint8_t>() + jobs[k].src_off, src[job_read[k]], jobs[k].src_size);
-    cudaStream_t s = ctx->stream;
-    if (!cuda_ok(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in_total, cudaMemcpyHostToDevice, s), "H2D input")) return -1;
-    if (compress_device_impl(ctx, ctx->d_in.as<uint8_t>(), ctx->d_out.as<uint8_t>(), jobs, ctx->d_results.as<uint32_t>(), kind, sized, s) != 0)
-        return -1;
-    if (!cuda_ok(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s), "D2H results") ||
-        !cuda_ok(cudaStreamSynchronize(s), "compress batch"))
-        return -1;
-    // pass 3: bring back exactly the bytes each read produced
-    const uint32_t* dres = ctx->h_results.as<uint32_t>();
-    if (!ctx->h_out.ensure(out_total + 16)) return -1;
-    for (uint32_t k = 0; k < m; ++k) {
-        results[job_read[k]] = dres[k];
-        if (!is_error(dres[k]) && dres[k] > 0 &&
-            !cuda_ok(cudaMemcpyAsync(ctx->h_out.as<uint8_t>() + jobs[k].dst_off, ctx->d_out.as<uint8_t>() + jobs[k].dst_off, dres[k],
-                                     cudaMemcpyDeviceToHost, s), "D2H output"))
-            return -1;
-    }
-    if (!cuda_ok(cudaStreamSynchronize(s), "compress batch (copy back)")) return -1;
-    for (uint32_t k = 0; k < m; ++k) {
-        const uint32_t i = job_read[k];
-        if (!is_error(dres[k]) && dres[k] > 0) {
-            if (dres[k] > dst_cap[i]) { results[i] = sized ? kErrDestinationSize + 4 : kErrDestinationSize; continue; }
-            memcpy(dst[i], ctx->h_out.as<uint8_t>() + jobs[k].dst_off, dres[k]);
-        }
-    }
-    return 0;
+    return run_host_batch(ctx, b);
 }
 
 extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* src, const vbz_size_t* src_size, void* const* dst,
@@ -554,11 +707,11 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
     if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
     const bool sized = sized_i != 0;
     const uint32_t hdr = sized ? 4u : 0u;
-    const Stage1Kind kind = classify_options(o);
+    HostBatch b;
+    b.compress = false; b.sized = sized; b.kind = classify_options(o);
+    b.src = src; b.src_size = src_size; b.dst = dst; b.dst_cap = dst_size; b.results = results;
+    const Stage1Kind& kind = b.kind;
 
-    std::vector<ReadJob> jobs;
-    std::vector<uint32_t> job_read;
-    uint64_t in_total = 0, out_total = 0;
     for (uint32_t i = 0; i < n; ++i) {
         if (kind.bad_isz) { results[i] = kErrIntegerSize; continue; }
         uint32_t exact = dst_size[i];
@@ -576,7 +729,7 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
             results[i] = src_size[i] - hdr;
             continue;
         }
-        ReadJob j;
+        HostJob h;
         if (kind.zstd_level != 0) {  // ref vbz/vbz.cpp:234-262: the frame must announce its content size
             const uint64_t fcs = zstd_frame_content_size((const uint8_t*)src[i] + hdr, src_size[i] - hdr);
             if (fcs == kZstdContentSizeUnknown || fcs == kZstdContentSizeError) { results[i] = kErrZstd; continue; }
@@ -584,42 +737,20 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
                 if (fcs > exact) { results[i] = kErrDestinationSize; continue; }
             } else {
                 if (fcs > (1ull << 31)) { results[i] = kErrOutOfMemory; continue; }  // the reference mallocs the content size here
-                j.mid_cap = fcs ? fcs : 1;
-                if (kind.bad_version) j.post_code = kErrVersion;
-                else if (exact % (unsigned)kind.isz != 0) j.post_code = kErrDestinationSize;
+                h.j.mid_cap = fcs ? fcs : 1;
+                if (kind.bad_version) h.j.post_code = kErrVersion;
+                else if (exact % (unsigned)kind.isz != 0) h.j.post_code = kErrDestinationSize;
             }
         }
-        j.src_off = in_total;
-        j.dst_off = out_total;
-        j.src_size = src_size[i];
-        j.dst_size = exact;
-        in_total += align16(src_size[i]);
-        out_total += align16(exact);
-        jobs.push_back(j);
-        job_read.push_back(i);
+        if (src_size[i] > 0xFFFFFFE0u || exact > 0xFFFFFFE0u) { results[i] = kErrOutOfMemory; continue; }
+        h.read = i;
+        h.j.src_size = src_size[i];
+        h.j.dst_size = exact;
+        h.in_slot = (uint32_t)align16(src_size[i]);
+        h.out_slot = (uint32_t)align16(exact);
+        b.jobs.push_back(h);
     }
-    if (jobs.empty()) return 0;
+    if (b.jobs.empty()) return 0;
     if (!device_path_available(kind, true)) return -1;
-    const uint32_t m = (uint32_t)jobs.size();
-
-    if (!ctx->h_in.ensure(in_total + 16) || !ctx->d_in.ensure(in_total + 16) || !ctx->d_out.ensure(out_total + 16) ||
-        !ctx->h_out.ensure(out_total + 16) || !ctx->d_results.ensure((size_t)m * 4) || !ctx->h_results.ensure((size_t)m * 4))
-        return -1;
-    for (uint32_t k = 0; k < m; ++k)
-        if (jobs[k].src_size) memcpy(ctx->h_in.as<uint8_t>() + jobs[k].src_off, src[job_read[k]], jobs[k].src_size);
-    cudaStream_t s = ctx->stream;
-    if (!cuda_ok(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in_total, cudaMemcpyHostToDevice, s), "H2D input")) return -1;
-    if (decompress_device_impl(ctx, ctx->d_in.as<uint8_t>(), ctx->d_out.as<uint8_t>(), jobs, ctx->d_results.as<uint32_t>(), kind, sized, s) != 0)
-        return -1;
-    if (!cuda_ok(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s), "D2H results") ||
-        !cuda_ok(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out_total, cudaMemcpyDeviceToHost, s), "D2H output") ||
-        !cuda_ok(cudaStreamSynchronize(s), "decompress batch"))
-        return -1;
-    const uint32_t* dres = ctx->h_results.as<uint32_t>();
-    for (uint32_t k = 0; k < m; ++k) {
-        const uint32_t i = job_read[k];
-        results[i] = dres[k];
-        if (!is_error(dres[k]) && dres[k] > 0) memcpy(dst[i], ctx->h_out.as<uint8_t>() + jobs[k].dst_off, dres[k]);
-    }
-    return 0;
+    return run_host_batch(ctx, b);
 }

@@ -45,9 +45,18 @@ struct vbz_b200_ctx {
     // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
     vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus;
     vbz::PinBuf h_zreads;
-    // bulk staging for the host-pointer API
-    vbz::DevBuf d_in, d_out, d_mid;
-    vbz::PinBuf h_in, h_out;
+    // intermediate stage-1 bytes of the two-stage paths
+    vbz::DevBuf d_mid;
+    // host-pointer API: a batch runs as WAVES through kWaveSlots slots so that the upload of wave w+1, the kernels of
+    // wave w and the download of wave w-1 overlap (csrc/host/batch.cpp: run_host_batch)
+    static constexpr int kWaveSlots = 3;
+    struct WaveSlot {
+        vbz::DevBuf d_in, d_out, d_results;
+        vbz::PinBuf h_in, h_out, h_results;
+        cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;  // upload done, kernels + results done, download done
+    };
+    WaveSlot slots[kWaveSlots];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
 
     ~vbz_b200_ctx();
 };
