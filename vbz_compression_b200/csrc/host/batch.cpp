@@ -137,7 +137,13 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     const uint32_t n = (uint32_t)reads.size();
     if (n == 0) return 0;
     const size_t bytes = (size_t)n * sizeof(ZstdRead);
-    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes())) return -1;
+    uint64_t unit_cap = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!reads[i].rejected) unit_cap += zstd_units_of(reads[i].dst_cap);
+    unit_cap = std::min<uint64_t>(std::max<uint64_t>(unit_cap, 8), 0x7FFFFFF0u);
+    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes()) ||
+        !ctx->d_zunits.ensure((size_t)unit_cap * sizeof(ZstdUnit)) || !ctx->d_zgeneral.ensure((size_t)n * 4))
+        return -1;
     if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
     if (!ctx->h_zreads.ensure(bytes)) return -1;
     memcpy(ctx->h_zreads.p, reads.data(), bytes);
@@ -152,10 +158,13 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.results = d_results;
     p.lit_scratch = ctx->d_zlit.as<uint8_t>();
     p.counter = ctx->d_zcounter.as<uint32_t>();
+    p.units = ctx->d_zunits.as<ZstdUnit>();
+    p.general = ctx->d_zgeneral.as<uint32_t>();
+    p.unit_cap = (uint32_t)unit_cap;
     p.n_reads = n;
     const int e = vbzk_zstd_decode(reinterpret_cast<const VbzkZstdDecParams*>(&p), stream);
     if (e) { cuda_ok((cudaError_t)e, "zstd_decode launch"); return -1; }
-    ctx->launches += 1;
+    ctx->launches += 3;  // walker, units kernel, general kernel
     return 0;
 }
 
@@ -365,7 +374,7 @@ vbz_b200_ctx::~vbz_b200_ctx()
     d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
     h_reads.release(); h_results.release();
     d_mid.release();
-    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zblocks.release(); d_zstatus.release(); h_zreads.release();
+    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); h_zreads.release();
     for (WaveSlot& w : slots) {
         w.d_in.release(); w.d_out.release(); w.d_results.release();
         w.h_in.release(); w.h_out.release(); w.h_results.release();

@@ -71,15 +71,31 @@ struct ZstdRead {
     uint32_t rejected;   // != 0: decided on the host; copy `preset` to results[]
     uint32_t preset;
 };
+// One piece of a "simple" frame (every block Raw, RLE, or Compressed with a literals section and no sequences): the
+// walker (zstd_walk_kernel) lists them, zstd_units_kernel executes them in parallel (csrc/zstd_dec_kernels.cuh).
+enum : uint32_t { kZUnitNop = 0, kZUnitCopy = 1, kZUnitFill = 2, kZUnitHuf = 3 };
+struct ZstdUnit {
+    uint64_t src_off;    // Copy: the bytes; Fill: the byte; Huf: the literals section (its header first), offsets into ZstdDecParams::src
+    uint64_t dst_off;    // offset into ZstdDecParams::dst
+    uint32_t n;          // Copy / Fill: bytes to produce; Huf: size of the literals section
+    uint32_t tab_back;   // Huf, treeless literals: distance back from src_off to the literals section that carries the tree
+    uint32_t read;       // whose result becomes kErrZstd if the unit fails
+    uint32_t kind;
+};
 struct ZstdDecParams {
     const uint8_t* src;
     uint8_t* dst;
     const ZstdRead* reads;
     uint32_t* results;   // per read: content bytes, or kErrZstd
-    uint8_t* lit_scratch;  // 128 KiB + 32 per warp of the grid
-    uint32_t* counter;   // work counter, zeroed before launch
+    uint8_t* lit_scratch;  // 128 KiB + 32 per warp of the general kernel's grid
+    uint32_t* counter;   // 4 words, zeroed before launch: [0] work counter of the general kernel, [1] units listed,
+                         // [2] frames left to the general kernel, [3] work counter of the units kernel
+    ZstdUnit* units;     // unit_cap entries
+    uint32_t* general;   // n_reads entries: the frames the walker left to the general kernel
+    uint32_t unit_cap;
     uint32_t n_reads;
 };
+VBZ_HD uint32_t zstd_units_of(uint32_t dst_cap) { return dst_cap / 8192u + 4u; }  // unit slots the host reserves per frame
 
 struct ZstdEncRead {
     uint64_t src_off;     // the content: bytes [src_off, src_off + size) of ZstdEncParams::src

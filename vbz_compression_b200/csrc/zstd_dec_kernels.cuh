@@ -20,6 +20,10 @@
 #pragma once
 #include "vbz_device.h"
 #include "svb_types.h"
+#ifdef VBZ_CPUSIM
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 namespace vbz {
 
@@ -167,9 +171,8 @@ __device__ bool z_fse_build(uint32_t* cell, uint16_t* next, const int16_t* norm,
 
 // ---- Huffman ------------------------------------------------------------------------------------------------
 // tree description -> weights[0..nw) (one lane).  Returns bytes consumed or 0 on error.
-__device__ uint32_t z_huf_read_weights(ZWarp* zw, const uint8_t* p, uint32_t n, int* nw_out)
+__device__ uint32_t z_huf_read_weights(uint8_t* w, uint32_t* wtab, int16_t* norm, uint16_t* next, const uint8_t* p, uint32_t n, int* nw_out)
 {
-    uint8_t* w = zw->weights;
     int nw = 0;
     uint32_t used;
     if (n < 1) return 0;
@@ -183,10 +186,10 @@ __device__ uint32_t z_huf_read_weights(ZWarp* zw, const uint8_t* p, uint32_t n, 
         used = 1 + (uint32_t)hb;
         if (used > n || hb == 0) return 0;
         int nsym, al;
-        const uint32_t hdr = z_fse_read_ncount(p + 1, (uint32_t)hb, 6, 255, zw->norm, &nsym, &al);
+        const uint32_t hdr = z_fse_read_ncount(p + 1, (uint32_t)hb, 6, 255, norm, &nsym, &al);
         if (!hdr) return 0;
-        uint32_t* cell = zw->wtab;
-        if (!z_fse_build(cell, zw->next, zw->norm, nsym, al)) return 0;
+        uint32_t* cell = wtab;
+        if (!z_fse_build(cell, next, norm, nsym, al)) return 0;
         ZBack b;
         if (!zb_init(b, p + 1 + hdr, (uint32_t)hb - hdr)) return 0;
         uint32_t s1 = zb_read(b, (uint32_t)al), s2 = zb_read(b, (uint32_t)al);
@@ -204,10 +207,9 @@ __device__ uint32_t z_huf_read_weights(ZWarp* zw, const uint8_t* p, uint32_t n, 
     *nw_out = nw;
     return used;
 }
-// weights -> decode table zw->huf (one lane).  Returns max_bits or 0 on error.
-__device__ int z_huf_build(ZWarp* zw, int nw)
+// weights -> decode table huf (one lane).  Returns max_bits or 0 on error.
+__device__ int z_huf_build(uint16_t* huf, uint8_t* w, int nw)
 {
-    uint8_t* w = zw->weights;
     uint32_t total = 0, rank[16];
     for (int i = 0; i < 16; ++i) rank[i] = 0;
     for (int i = 0; i < nw; ++i) {
@@ -231,36 +233,83 @@ __device__ int z_huf_build(ZWarp* zw, int nw)
         const int r = w[s];
         if (!r) continue;
         const uint32_t len = (1u << r) >> 1;
-        const uint16_t e = (uint16_t)((uint32_t)s | ((uint32_t)(max_bits + 1 - r) << 8));
-        for (uint32_t k = 0; k < len; ++k) zw->huf[start[r] + k] = e;
+        const uint32_t e = (uint32_t)s | ((uint32_t)(max_bits + 1 - r) << 8);
+        uint16_t* c = huf + start[r];  // a run of `len` cells starts at a multiple of len: wide stores are aligned
+        if (len >= 4) {
+            const uint2 e4 = make_uint2(e | (e << 16), e | (e << 16));
+            for (uint32_t k = 0; k < len; k += 4) *reinterpret_cast<uint2*>(c + k) = e4;
+        } else {
+            for (uint32_t k = 0; k < len; ++k) c[k] = (uint16_t)e;
+        }
         start[r] += len;
     }
     return max_bits;
 }
 // one Huffman stream (one lane): `count` symbols to out.  Returns true if the stream ends exactly.
+// The stream is read backwards through ALIGNED 32-bit words (the word holding the last byte first) into a 64-bit
+// window whose top bit is the next unread bit; one refill test per two symbols (2 x 11 bits <= 32).  Words below
+// `p & ~3` are never touched (a damaged stream reads zeros there and fails the final test), bytes of the lowest word
+// that precede p can only be looked at by the padding of a final table look-up, which does not depend on them.
+// Output leaves in 16-byte stores once `out` is aligned.
 __device__ bool z_huf_decode_stream(const uint16_t* huf, int max_bits, const uint8_t* p, uint32_t n, uint8_t* out, uint32_t count)
 {
-    ZBack b;
-    if (!zb_init(b, p, n)) return false;
-    const uint32_t mb = (uint32_t)max_bits;
+    if (n == 0 || p[n - 1] == 0) return false;
+    const uint32_t* lim = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>((uintptr_t)(p + n - 1) & ~(uintptr_t)3);
+    const uint32_t v0 = 8u * (uint32_t)((uintptr_t)(p + n - 1) & 3u) + (uint32_t)z_highbit(p[n - 1]);  // unread bits in the first word
+    // `avail` = bits of the stream proper
+    const long long avail = (long long)(n - 1) * 8 + z_highbit(p[n - 1]);
+    uint64_t buf = v0 ? ((uint64_t)*wp << (64 - v0)) : 0ull;
+    int nbits = (int)v0;
+    --wp;
+    const uint32_t* const wp0 = wp;
+    uint32_t nxt = wp >= lim ? *wp : 0u;
+    const uint32_t sh = 32u - (uint32_t)max_bits;
     uint32_t i = 0;
-    // fast part: a 32-bit window holds at least two symbols (max_bits <= 11) after a refill
-    while (i + 2 <= count && b.pos >= 32) {
-        const uint32_t win = zb_window(b);
-        const uint32_t e0 = huf[win >> (32 - mb)];
-        const uint32_t n0 = e0 >> 8;
-        const uint32_t e1 = huf[(win << n0) >> (32 - mb)];
-        out[i] = (uint8_t)e0;
-        out[i + 1] = (uint8_t)e1;
-        b.pos -= n0 + (e1 >> 8);
-        i += 2;
+#define Z_HUF_REFILL()                                              \
+    if (nbits < 32) {                                               \
+        buf |= (uint64_t)nxt << (32 - nbits);                       \
+        nbits += 32;                                                \
+        --wp;                                                       \
+        nxt = wp >= lim ? *wp : 0u;                                 \
+    }
+#define Z_HUF_SYM(dst_expr)                                         \
+    {                                                               \
+        const uint32_t e = huf[(uint32_t)(buf >> 32) >> sh];        \
+        buf <<= (e >> 8);                                           \
+        nbits -= (int)(e >> 8);                                     \
+        dst_expr;                                                   \
+    }
+    // head: up to the first 16-byte boundary of out
+    uint32_t head = (16u - (uint32_t)((uintptr_t)out & 15u)) & 15u;
+    if (head > count) head = count;
+    for (; i < head; ++i) {
+        Z_HUF_REFILL();
+        Z_HUF_SYM(out[i] = (uint8_t)e);
+    }
+    for (; i + 16 <= count; i += 16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t acc = 0;
+            Z_HUF_REFILL();
+            Z_HUF_SYM(acc = e & 0xFFu);
+            Z_HUF_SYM(acc |= (e & 0xFFu) << 8);
+            Z_HUF_REFILL();
+            Z_HUF_SYM(acc |= (e & 0xFFu) << 16);
+            Z_HUF_SYM(acc |= e << 24);
+            w[q] = acc;
+        }
+        *reinterpret_cast<uint4*>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     for (; i < count; ++i) {
-        const uint32_t e = huf[zb_peek(b, mb)];
-        out[i] = (uint8_t)e;
-        b.pos -= e >> 8;
+        Z_HUF_REFILL();
+        Z_HUF_SYM(out[i] = (uint8_t)e);
     }
-    return b.pos == 0;
+#undef Z_HUF_REFILL
+#undef Z_HUF_SYM
+    // bits handed to the window (32 per refill) minus bits still in it = bits used; the stream must end exactly
+    return (long long)v0 + 32ll * (long long)(wp0 - wp) - nbits == avail;
 }
 
 // ---- warp-wide copies -------------------------------------------------------------------------------------------
@@ -398,8 +447,8 @@ __device__ uint32_t z_decode_literals(ZWarp* zw, ZFrame& f, const uint8_t* p, ui
         uint32_t t = 0;
         if (lane == 0) {
             int nw = 0;
-            t = z_huf_read_weights(zw, q, left, &nw);
-            if (t) bits = z_huf_build(zw, nw);
+            t = z_huf_read_weights(zw->weights, zw->wtab, zw->norm, zw->next, q, left, &nw);
+            if (t) bits = z_huf_build(zw->huf, zw->weights, nw);
             if (!bits) t = 0;
         }
         t = __shfl_sync(0xffffffffu, t, 0);
@@ -686,23 +735,249 @@ __device__ uint32_t z_decompress(ZWarp* zw, const uint8_t* p, uint64_t n, uint8_
     return (uint32_t)total;
 }
 
+// The general kernel: whole frames, one warp each - the frames the walker did not list as units (sequences, checksums,
+// several frames in one buffer, anything malformed: this code decides their result).
 __global__ void __launch_bounds__(kZdecWarps * 32) zstd_decode_kernel(ZstdDecParams p)
 {
     VBZ_DYN_SMEM(smem);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     ZWarp* zw = reinterpret_cast<ZWarp*>(smem) + wid;
     uint8_t* lit_scratch = p.lit_scratch + (uint64_t)(blockIdx.x * kZdecWarps + wid) * kZLitStride;
+    const uint32_t n_general = p.counter[2];
     for (;;) {
-        uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(p.counter, 1u);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= p.n_reads) break;
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(p.counter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_general) break;
+        const uint32_t r = p.general[k];
         const ZstdRead rd = p.reads[r];
-        uint32_t res;
-        if (rd.rejected) res = rd.preset;
-        else res = z_decompress(zw, p.src + rd.src_off, rd.src_bytes, p.dst + rd.dst_off, rd.dst_cap, lit_scratch, lane);
+        const uint32_t res = z_decompress(zw, p.src + rd.src_off, rd.src_bytes, p.dst + rd.dst_off, rd.dst_cap, lit_scratch, lane);
         __syncwarp();
         if (lane == 0) p.results[r] = res;
+    }
+}
+
+// ---- block-parallel path ----------------------------------------------------------------------------------------
+// Signal frames are literals: VBZ's own writer emits nothing else, and whatever wrote the frame, a block without
+// sequences regenerates exactly its literals.  For such frames every block's position in the output follows from the
+// headers alone, so the blocks - and the four Huffman streams inside each - can all be decoded at the same time.
+//   zstd_walk_kernel   one THREAD per frame hops over the block headers (twice: count, then list) and turns the frame
+//                      into units; a frame it cannot fully vouch for goes to the general kernel's list instead
+//   zstd_units_kernel  persistent warps take 8 units at a time: 4 lanes per unit build its Huffman table in shared
+//                      memory and decode one stream each; Raw / RLE pieces are warp-wide copies and fills
+
+// header of a literals section.  Returns false if it does not fit in n bytes.
+__device__ __forceinline__ bool z_lit_header(const uint8_t* p, uint32_t n, int* type, uint32_t* hdr, uint32_t* regen, uint32_t* comp, int* streams)
+{
+    if (n < 1) return false;
+    const int t = p[0] & 3, sf = (p[0] >> 2) & 3;
+    *type = t;
+    *streams = 4;
+    *comp = 0;
+    if (t < 2) {
+        if (sf == 0 || sf == 2) { *hdr = 1; *regen = p[0] >> 3; }
+        else if (sf == 1) { if (n < 2) return false; *hdr = 2; *regen = z_le16(p) >> 4; }
+        else { if (n < 3) return false; *hdr = 3; *regen = z_le24(p) >> 4; }
+        return true;
+    }
+    if (n < 3) return false;
+    if (sf <= 1) { *hdr = 3; const uint32_t v = z_le24(p); *regen = (v >> 4) & 0x3FF; *comp = (v >> 14) & 0x3FF; if (sf == 0) *streams = 1; }
+    else if (sf == 2) { if (n < 4) return false; *hdr = 4; const uint32_t v = z_le32(p); *regen = (v >> 4) & 0x3FFF; *comp = (v >> 18) & 0x3FFF; }
+    else { if (n < 5) return false; *hdr = 5; const uint64_t v = (uint64_t)z_le32(p) | ((uint64_t)p[4] << 32); *regen = (uint32_t)((v >> 4) & 0x3FFFF); *comp = (uint32_t)((v >> 22) & 0x3FFFF); }
+    return true;
+}
+
+// One pass over a frame.  emit == nullptr: count.  Returns the number of units, or 0xFFFFFFFF if the frame is not for
+// this path.  *total = content bytes.
+__device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_t r, ZstdUnit* emit, uint32_t* total)
+{
+    const uint32_t kNo = 0xFFFFFFFFu;
+    const uint8_t* p = src + rd.src_off;
+    uint64_t n = rd.src_bytes;
+    uint64_t fcs;
+    bool has, ck;
+    const uint32_t h = z_frame_header(p, n, &fcs, &has, &ck);
+    if (!h || ck) return kNo;
+    p += h;
+    n -= h;
+    const uint64_t cap = rd.dst_cap;
+    uint64_t op = 0;
+    uint32_t units = 0;
+    const uint8_t* tab = nullptr;  // the last literals section that carried a tree
+    for (;;) {
+        if (n < 3) return kNo;
+        const uint32_t bh = z_le24(p);
+        const int last = bh & 1, type = (bh >> 1) & 3;
+        const uint32_t bs = bh >> 3;
+        p += 3;
+        n -= 3;
+        ZstdUnit u;
+        u.dst_off = rd.dst_off + op;
+        u.read = r;
+        u.tab_back = 0;
+        u.kind = kZUnitNop;
+        u.n = 0;
+        u.src_off = (uint64_t)(p - src);
+        uint32_t adv;
+        if (type == 0) {
+            if (bs > n || op + bs > cap) return kNo;
+            u.kind = kZUnitCopy; u.n = bs; adv = bs;
+        } else if (type == 1) {
+            if (n < 1 || op + bs > cap) return kNo;
+            u.kind = kZUnitFill; u.n = bs; adv = 1;
+        } else if (type == 2) {
+            if (bs > n || bs >= kZBlockMax) return kNo;
+            int lt, streams;
+            uint32_t hdr, regen, comp;
+            if (!z_lit_header(p, bs, &lt, &hdr, &regen, &comp, &streams)) return kNo;
+            const uint32_t sec = lt == 0 ? hdr + regen : lt == 1 ? hdr + 1 : hdr + comp;
+            if ((uint64_t)sec + 1 != bs || p[sec] != 0) return kNo;  // the block must end with "0 sequences"
+            if (regen > kZBlockMax || op + regen > cap) return kNo;
+            if (lt == 0) { u.kind = kZUnitCopy; u.src_off += hdr; u.n = regen; }
+            else if (lt == 1) { u.kind = kZUnitFill; u.src_off += hdr; u.n = regen; }
+            else {
+                if (lt == 2) tab = p;
+                else if (!tab) return kNo;
+                u.kind = kZUnitHuf; u.n = sec; u.tab_back = (uint32_t)(p - tab);
+            }
+            adv = bs;
+            op += regen;
+        } else return kNo;
+        if (type < 2) op += bs;
+        if (u.n != 0) {
+            if (emit) emit[units] = u;
+            ++units;
+        }
+        p += adv;
+        n -= adv;
+        if (last) break;
+    }
+    if (n != 0 || (has && op != fcs) || op > 0xFFFFFFF0ull) return kNo;
+    *total = (uint32_t)op;
+    return units;
+}
+
+__global__ void zstd_walk_kernel(ZstdDecParams p)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n_reads) return;
+    const ZstdRead rd = p.reads[r];
+    if (rd.rejected) { p.results[r] = rd.preset; return; }
+    uint32_t total = 0;
+    const uint32_t cnt = z_walk_frame(p.src, rd, r, nullptr, &total);
+    bool mine = cnt != 0xFFFFFFFFu;
+    if (mine && cnt != 0) {
+        const uint32_t base = atomicAdd(p.counter + 1, cnt);
+        if (base >= p.unit_cap || cnt > p.unit_cap - base) {  // out of slots: the units kernel stops at unit_cap
+            for (uint32_t k = base; k < p.unit_cap; ++k) p.units[k].kind = kZUnitNop;
+            mine = false;
+        } else z_walk_frame(p.src, rd, r, p.units + base, &total);
+    }
+    if (mine) p.results[r] = total;
+    else p.general[atomicAdd(p.counter + 2, 1u)] = r;
+#ifdef VBZ_CPUSIM
+    if (getenv("VBZ_B200_TRACE_WALK")) fprintf(stderr, "walk: read %u -> %s (%u units, %u bytes)\n", r, mine ? "units" : "general", mine ? cnt : 0u, total);
+#endif
+}
+
+constexpr int kZUnitWarps = 2;
+struct ZHufGroup {
+    uint16_t huf[2048];   // while the weights are read, the FSE scratch lives here: table 64 x u32, norm 256 x i16, next 256 x u16
+    uint8_t weights[256];
+};
+
+__global__ void __launch_bounds__(kZUnitWarps * 32) zstd_units_kernel(ZstdDecParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, j = lane & 3;
+    ZHufGroup* grp = reinterpret_cast<ZHufGroup*>(smem) + wid * 8 + g;
+    uint32_t n_units = p.counter[1];
+    if (n_units > p.unit_cap) n_units = p.unit_cap;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.counter + 3, 8u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_units) break;
+        ZstdUnit un = {0, 0, 0, 0, 0, kZUnitNop};
+        if (base + g < n_units) un = p.units[base + g];
+        const bool huf = un.kind == kZUnitHuf;
+        // ---- Huffman units: lane 0 of the group reads the tree, all four decode ------------------------------------------
+        bool ok = true;
+        const uint8_t* lp = p.src + un.src_off;
+        int lt = 0, streams = 4;
+        uint32_t hdr = 0, regen = 0, comp = 0, t = 0;
+        int bits = 0;
+        if (huf) {
+            ok = z_lit_header(lp, un.n, &lt, &hdr, &regen, &comp, &streams) && lt >= 2 && regen <= kZBlockMax && hdr + comp <= un.n &&
+                 !(streams == 4 && regen < 6);
+            if (ok && j == 0) {
+                const uint8_t* ts = lp + hdr;
+                uint32_t tn = comp;
+                if (lt == 3) {  // the tree of an earlier block of the frame
+                    const uint8_t* tp = lp - un.tab_back;
+                    int lt2, st2;
+                    uint32_t hdr2, regen2, comp2;
+                    z_lit_header(tp, 5, &lt2, &hdr2, &regen2, &comp2, &st2);  // (validated when that block was listed)
+                    ts = tp + hdr2;
+                    tn = comp2;
+                }
+                uint8_t* scratch = reinterpret_cast<uint8_t*>(grp->huf);
+                int nw = 0;
+                t = z_huf_read_weights(grp->weights, reinterpret_cast<uint32_t*>(scratch), reinterpret_cast<int16_t*>(scratch + 256),
+                                       reinterpret_cast<uint16_t*>(scratch + 768), ts, tn, &nw);
+                if (t) bits = z_huf_build(grp->huf, grp->weights, nw);
+            }
+        }
+        __syncwarp();
+        t = __shfl_sync(0xffffffffu, t, (int)(lane & ~3u));
+        bits = __shfl_sync(0xffffffffu, bits, (int)(lane & ~3u));
+        if (huf && ok) {
+            ok = bits != 0;
+            const uint8_t* q = lp + hdr;
+            uint32_t left = comp;
+            if (lt == 2) { q += t; left -= t; }  // t <= comp: read_weights never reads past what it was given
+            uint8_t* dst = p.dst + un.dst_off;
+            if (!ok) {
+            } else if (streams == 1) {
+                if (j == 0) ok = z_huf_decode_stream(grp->huf, bits, q, left, dst, regen);
+            } else if (left < 10) ok = false;
+            else {
+                const uint32_t s1 = z_le16(q), s2 = z_le16(q + 2), s3 = z_le16(q + 4);
+                const uint32_t seg = (regen + 3) / 4;
+                if (6 + s1 + s2 + s3 > left || 3 * seg > regen) ok = false;
+                else {
+                    const uint32_t s4 = left - 6 - s1 - s2 - s3;
+                    const uint32_t so = j == 0 ? 0u : j == 1 ? s1 : j == 2 ? s1 + s2 : s1 + s2 + s3;
+                    const uint32_t sn = j == 0 ? s1 : j == 1 ? s2 : j == 2 ? s3 : s4;
+                    ok = z_huf_decode_stream(grp->huf, bits, q + 6 + so, sn, dst + j * seg, j == 3 ? regen - 3 * seg : seg);
+                }
+            }
+        }
+        const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
+        if (j == 0 && ((bad >> (lane & ~3u)) & 0xFu)) p.results[un.read] = kErrZstd;
+        // ---- Raw / RLE pieces: the whole warp, one unit after the other ------------------------------------------------------------
+        const uint32_t plain = __ballot_sync(0xffffffffu, j == 0 && (un.kind == kZUnitCopy || un.kind == kZUnitFill));
+        for (uint32_t m = plain; m; m &= m - 1) {
+            const int owner = __ffs((int)m) - 1;
+            const uint32_t kind = __shfl_sync(0xffffffffu, un.kind, owner);
+            const uint32_t cn = __shfl_sync(0xffffffffu, un.n, owner);
+            const uint64_t so = __shfl_sync(0xffffffffu, un.src_off, owner), dof = __shfl_sync(0xffffffffu, un.dst_off, owner);
+            uint8_t* d = p.dst + dof;
+            const uint8_t* sp = p.src + so;
+            if (kind == kZUnitFill) {
+                const uint8_t v = sp[0];
+                z_warp_fill(d, v, cn, lane);
+            } else if ((((uintptr_t)d ^ (uintptr_t)sp) & 3u) == 0 && cn >= 64) {  // same word phase: bytes to the boundary, words, bytes
+                const uint32_t head = (4u - (uint32_t)((uintptr_t)d & 3u)) & 3u;
+                const uint32_t words = (cn - head) >> 2, done = head + 4 * words;
+                if (lane < head) d[lane] = sp[lane];
+                else if (lane >= 8 && lane - 8 < cn - done) d[done + lane - 8] = sp[done + lane - 8];
+                const uint32_t* s4 = reinterpret_cast<const uint32_t*>(sp + head);
+                uint32_t* d4 = reinterpret_cast<uint32_t*>(d + head);
+                for (uint32_t k = lane; k < words; k += 32) d4[k] = s4[k];
+            } else z_warp_copy(d, sp, cn, lane);
+        }
+        __syncwarp();
     }
 }
 

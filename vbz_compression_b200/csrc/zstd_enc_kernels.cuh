@@ -106,16 +106,15 @@ __device__ bool zenc_build_code(ZEncSmem* s, int nsym)
     int kraft = 0;
     for (int i = 0; i < n; ++i) kraft += 1 << (11 - s->len[s->order[i]]);
     int guard = 0;
-    while (kraft > 2048) {
-        int pick = -1;
-        for (int i = 0; i < n; ++i)
-            if (s->len[s->order[i]] < 11) { pick = i; break; }  // order[] is ascending by count
-        if (pick < 0 || ++guard > 4096) return false;
+    // order[] is ascending by count and a symbol only ever grows to 11, so "the rarest symbol that can still grow" is a
+    // pointer that moves one way: everything before it has reached 11 bits
+    for (int pick = 0; kraft > 2048;) {
+        while (pick < n && s->len[s->order[pick]] >= 11) ++pick;
+        if (pick >= n) return false;
         const int sym = s->order[pick];
         kraft -= 1 << (10 - s->len[sym]);
         s->len[sym]++;
     }
-    guard = 0;
     while (kraft < 2048) {
         const int slack = 2048 - kraft;
         int pick = -1;
