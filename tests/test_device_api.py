@@ -34,7 +34,8 @@ def _layout(lib, sizes, opts):
 
 @pytest.mark.parametrize("dtype,opts", [
     (np.int16, Options(True, 2, 0, 0)), (np.int16, Options(False, 2, 0, 0)), (np.int32, Options(True, 4, 0, 0)),
-    (np.uint32, Options(False, 4, 0, 0)), (np.int8, Options(True, 1, 0, 0)), (np.int8, Options(False, 1, 0, 0))])
+    (np.uint32, Options(False, 4, 0, 0)), (np.int8, Options(True, 1, 0, 0)), (np.int8, Options(False, 1, 0, 0)),
+    (np.int8, Options(True, 1, 0, 1)), (np.int8, Options(False, 1, 0, 1))])
 def test_device_batch_matches_oracle(dtype, opts):
     torch, batch, lib = _setup()
     port = ol.port()

@@ -20,10 +20,10 @@ def backend(request):
     return product.get(request.param)
 
 
-LEVEL0_OPTS = [Options(zz, isz, 0, ver) for zz in (True, False) for isz in (1, 2, 4) for ver in (0, 1) if not (isz == 1 and ver == 1)]
+LEVEL0_OPTS = [Options(zz, isz, 0, ver) for zz in (True, False) for isz in (1, 2, 4) for ver in (0, 1)]  # incl. the v1 "half" packing of int8
 
 
-@pytest.mark.parametrize("k", [k for k in golden_data.kats() if k["lvl"] == 0 and not (k["isz"] == 1 and k["ver"] == 1)], ids=lambda k: k["name"])
+@pytest.mark.parametrize("k", [k for k in golden_data.kats() if k["lvl"] == 0], ids=lambda k: k["name"])
 def test_kat_bytes(backend, k):
     capi = backend[0]
     arr = np.array(k["values"], dtype=k["dtype"])
@@ -43,9 +43,10 @@ def _cases(rng):
         yield data_gen.uniform_full_range(n, np.int32, rng)
         yield (rng.integers(0, 1 << 20, n)).astype(np.uint32)
         yield (rng.integers(-300, 300, n)).astype(np.int32)
-    for n in (1, 15, 16, 17, 8191, 8192, 8193, 20000):
+    for n in (1, 15, 16, 17, 511, 512, 513, 1025, 8191, 8192, 8193, 20000):
         yield data_gen.uniform_full_range(n, np.int8, rng)
         yield (rng.integers(-3, 4, n)).astype(np.int8)
+        yield (rng.integers(-1, 2, n) * (rng.random(n) < 0.3)).astype(np.int8)  # many zero values: code 0, no data nibbles
     yield data_gen.nanopore_like(70_000, rng)
 
 
@@ -152,7 +153,7 @@ def test_error_paths_match_oracle(backend):
     _, good = port.compress(arr, o, sized=True)
     for blob, ds in ((good, 200), (good, 199), (good, 202), (good[:3], 200), (good[:-1], 200), (good + b"\0", 200), (b"", 0), (b"\0\0\0\0", 0)):
         for sized in (True, False):
-            for oo in (o, Options(True, 4, 0, 0), Options(False, 2, 0, 0), Options(True, 1, 0, 0), Options(True, 2, 0, 3), Options(True, 0, 0, 0)):
+            for oo in (o, Options(True, 4, 0, 0), Options(False, 2, 0, 0), Options(True, 1, 0, 0), Options(True, 1, 0, 1), Options(False, 1, 0, 1), Options(True, 2, 0, 3), Options(True, 0, 0, 0)):
                 a = capi.decompress(blob, oo, ds, sized=sized)
                 b = port.decompress(blob, oo, ds, sized=sized)
                 assert a == b, (len(blob), ds, sized, oo.integer_size, oo.vbz_version, a[0], b[0])

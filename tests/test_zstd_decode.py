@@ -68,7 +68,7 @@ def test_full_vbz_decode_matches_oracle(backend):
     capi = backend[0]
     rng = np.random.default_rng(9)
     for dtype, o in ((np.int16, Options(True, 2, 1, 0)), (np.int16, Options(True, 2, 3, 1)), (np.int32, Options(True, 4, 1, 0)),
-                     (np.uint32, Options(False, 4, 3, 0)), (np.int8, Options(True, 1, 1, 0))):
+                     (np.uint32, Options(False, 4, 3, 0)), (np.int8, Options(True, 1, 1, 0)), (np.int8, Options(True, 1, 1, 1)), (np.uint8, Options(False, 1, 1, 1))):
         for n in (0, 1, 100, 5000, 30000):
             arr = data_gen.nanopore_like(n, rng).astype(dtype) if dtype != np.uint32 else rng.integers(0, 1 << 20, n).astype(np.uint32)
             for sized in (True, False):
@@ -107,7 +107,7 @@ def test_fuzz_corpus_level1_decode(backend):
     step = 1 if not capi.path.endswith("cpusim.so") else 5
     for blob in corpus[::step]:
         n = len(blob)
-        for o in (Options(True, 2, 1, 0), Options(False, 4, 1, 0), Options(True, 1, 1, 0), Options(False, 0, 1, 0)):
+        for o in (Options(True, 2, 1, 0), Options(False, 4, 1, 0), Options(True, 1, 1, 0), Options(True, 1, 1, 1), Options(False, 0, 1, 0)):
             for sized in (True, False):
                 for ds in sorted(set([0, 4, 64, n, 4 * n])):
                     a = capi.decompress(blob, o, ds, sized=sized)

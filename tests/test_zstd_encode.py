@@ -67,7 +67,7 @@ def test_kat_tiny_input_is_a_raw_block(backend):
 
 
 @pytest.mark.parametrize("dtype,o", [(np.int16, Options(True, 2, 1, 0)), (np.int16, Options(True, 2, 1, 1)), (np.int16, Options(False, 2, 3, 0)),
-                                     (np.int32, Options(True, 4, 1, 0)), (np.uint32, Options(False, 4, 3, 0)), (np.int8, Options(True, 1, 1, 0))])
+                                     (np.int32, Options(True, 4, 1, 0)), (np.uint32, Options(False, 4, 3, 0)), (np.int8, Options(True, 1, 1, 0)), (np.int8, Options(True, 1, 1, 1)), (np.uint8, Options(False, 1, 2, 1))])
 def test_full_vbz_roundtrip_and_reference_decodes(backend, dtype, o):
     capi = backend[0]
     ref = ol.ref()

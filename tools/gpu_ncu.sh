@@ -1,14 +1,16 @@
 #!/bin/bash
-# ncu passes (never a bench value): launch list of the bench command, and --set full captures of the codec kernels
-set -x
+# ncu --set full captures of the dominant kernels (one launch each, after warm-up launches), small batches.
+# usage: gpu_ncu.sh TAG [zstd|svb16|all]
+set -u
 mkdir -p gpurun_out
-R=${1:-20000}
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'svb|zstd|vbz' -c 400 --csv --log-file gpurun_out/launches_transform.csv \
-    python bench.py --reads $R --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_b1.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'svb|zstd|vbz' -c 400 --csv --log-file gpurun_out/launches_full.csv \
-    python bench.py --workload full --reads $R --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_b2.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'svb16_(en|de)code_kernel' -s 2 -c 2 -o gpurun_out/prof_svb16 -f \
-    python bench.py --reads $R --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_b3.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'zstd_(en|de)code_kernel' -s 2 -c 2 -o gpurun_out/prof_zstd -f \
-    python bench.py --workload full --reads $R --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_b4.log 2>&1
+T=${1:-r02}
+W=${2:-all}
+if [ "$W" = all ] || [ "$W" = zstd ]; then
+ncu --set full --clock-control none --import-source on -k regex:'zstd_units_kernel|zstd_encode_kernel' --launch-skip 2 --launch-count 2 -f -o gpurun_out/${T}_zstd \
+    python bench.py --workload full --reads 8000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${T}_ncu_zstd.log 2>&1
+fi
+if [ "$W" = all ] || [ "$W" = svb16 ]; then
+ncu --set full --clock-control none --import-source on -k regex:'svb16_encode_kernel|svb16_decode_kernel|svb16_tile_sums_kernel' --launch-skip 3 --launch-count 3 -f -o gpurun_out/${T}_svb16 \
+    python bench.py --reads 20000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${T}_ncu_svb16.log 2>&1
+fi
 ls -la gpurun_out

@@ -1,12 +1,14 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, bench (both workloads), ncu launch list + full captures. Outputs -> gpurun_out/
-set -x
+# One GPU-box visit: parity tests, ncu launch lists of the bench command, then the two bench lines (not under ncu).
+set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt
-nproc >> gpurun_out/gpu.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_transform.json 2> gpurun_out/bench_transform.err; tail -c 3000 gpurun_out/bench_transform.json
-timeout 600 python bench.py --workload full --steps 3 --warmup 3 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 3000 gpurun_out/bench_full.json
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_transform.json 2>&1
-timeout 600 python bench.py --impl reference --workload full --steps 2 --warmup 1 > gpurun_out/bench_ref_full.json 2>&1
+T=${1:-r02}
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/${T}_gpu_tests.log
+for W in transform full; do
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'svb|zstd|vbz' -c 400 --csv --log-file gpurun_out/${T}_launches_${W}.csv \
+      python bench.py --workload $W --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${T}_ncu_bench_${W}.log 2>&1
+done
+python bench.py --steps 5 --warmup 3 > gpurun_out/${T}_bench_transform.json 2> gpurun_out/${T}_bench_transform.err
+python bench.py --workload full --steps 3 --warmup 3 > gpurun_out/${T}_bench_full.json 2> gpurun_out/${T}_bench_full.err
+tail -3 gpurun_out/${T}_gpu_tests.log
+cat gpurun_out/${T}_bench_transform.json gpurun_out/${T}_bench_full.json

@@ -76,6 +76,29 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
 {
     const uint32_t n = (uint32_t)reads.size();
     if (n == 0) return 0;
+    if (kind.half) {  // v1 nibble packing of int8: one warp per read, no tiles, no look-back (csrc/svb_half_kernels.cuh)
+        if (!ctx->d_reads.ensure((size_t)n * sizeof(SvbRead))) return -1;
+        if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
+        if (!ctx->h_reads.ensure((size_t)n * sizeof(SvbRead))) return -1;
+        memcpy(ctx->h_reads.p, reads.data(), (size_t)n * sizeof(SvbRead));
+        if (!cuda_ok(cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.p, (size_t)n * sizeof(SvbRead), cudaMemcpyHostToDevice, stream), "upload descriptors") ||
+            !cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord"))
+            return -1;
+        SvbParams p;
+        memset(&p, 0, sizeof(p));
+        p.src = d_src;
+        p.dst = d_dst;
+        p.reads = ctx->d_reads.as<SvbRead>();
+        p.results = d_results;
+        p.src_sizes = d_src_sizes;
+        p.hdr_bytes = hdr_bytes;
+        p.n_reads = n;
+        const VbzkSvbParams* pp = reinterpret_cast<const VbzkSvbParams*>(&p);
+        const int e = decode ? vbzk_svb_half_decode(kind.zz, pp, stream) : vbzk_svb_half_encode(kind.zz, pp, stream);
+        if (e) { cuda_ok((cudaError_t)e, decode ? "svb_half_decode launch" : "svb_half_encode launch"); return -1; }
+        ctx->launches += 1;
+        return 0;
+    }
     uint64_t tiles = 0;
     const uint32_t tile_values = vbzk_svb_tile_values(kind.isz, kind.mode);
     for (uint32_t i = 0; i < n; ++i) {
@@ -213,12 +236,8 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
 
 static bool device_path_available(const Stage1Kind& kind, bool decode = false)
 {
-    (void)decode;
-    if (kind.half) {
-        set_last_error("this option combination is not implemented on the device yet");
-        return false;
-    }
-    return true;
+    (void)decode; (void)kind;
+    return true;  // every option combination of the reference has a device path
 }
 
 // ---- compress / decompress, device-resident ------------------------------------------------------------------

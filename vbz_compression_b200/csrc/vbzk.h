@@ -22,6 +22,10 @@ int vbzk_svb_encode(int integer_size, int zigzag, int mode, const struct VbzkSvb
 /* decode pre-pass: fills SvbParams::wtile_off from the control bytes (must precede vbzk_svb_decode) */
 int vbzk_svb_key_offsets(int integer_size, int mode, const struct VbzkSvbParams* params, void* stream);
 int vbzk_svb_decode(int integer_size, int zigzag, int mode, const struct VbzkSvbParams* params, uint32_t n_tiles, void* stream);
+/* stage 1, v1 "half" packing (integer_size 1, vbz_version 1; csrc/svb_half_kernels.cuh): one warp per read, no tile tables -
+ * only src, dst, reads, results, src_sizes, hdr_bytes and n_reads of the params are used */
+int vbzk_svb_half_encode(int zigzag, const struct VbzkSvbParams* params, void* stream);
+int vbzk_svb_half_decode(int zigzag, const struct VbzkSvbParams* params, void* stream);
 
 /* stage 2, decode: one zstd frame per read (csrc/zstd_dec_kernels.cuh).  The launch uses vbzk_zstd_decode_grid() CTAs
  * whatever the batch size; lit_scratch must hold vbzk_zstd_decode_scratch_bytes() bytes and *counter must be 0. */

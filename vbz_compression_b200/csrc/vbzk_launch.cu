@@ -2,6 +2,7 @@
 #include "vbzk.h"
 #include "svb_kernels.cuh"
 #include "svb16_kernels.cuh"
+#include "svb_half_kernels.cuh"
 #include "zstd_dec_kernels.cuh"
 #include "zstd_enc_kernels.cuh"
 
@@ -140,6 +141,26 @@ extern "C" int vbzk_svb_decode(int isz, int zz, int mode, const VbzkSvbParams* p
 {
     if (isz == 2 && zz && mode == kModeI16X86 && n_tiles) return launch_s16_decode(*reinterpret_cast<const SvbParams*>(params), n_tiles, stream);
     VBZK_DISPATCH(launch_decode)
+}
+
+// ---- v1 "half" packing (int8): one warp per read -----------------------------------------------------------------
+extern "C" int vbzk_svb_half_encode(int zz, const VbzkSvbParams* params, void* stream)
+{
+    const SvbParams& p = *reinterpret_cast<const SvbParams*>(params);
+    if (p.n_reads == 0) return 0;
+    const uint32_t grid = (p.n_reads + kHalfWarps - 1) / kHalfWarps, smem = kHalfWarps * kHalfStage;
+    if (zz) VBZ_LAUNCH(svb_half_encode_kernel<true>, grid, kHalfWarps * 32, smem, (vbz_stream_t)stream, p);
+    else VBZ_LAUNCH(svb_half_encode_kernel<false>, grid, kHalfWarps * 32, smem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+extern "C" int vbzk_svb_half_decode(int zz, const VbzkSvbParams* params, void* stream)
+{
+    const SvbParams& p = *reinterpret_cast<const SvbParams*>(params);
+    if (p.n_reads == 0) return 0;
+    const uint32_t grid = (p.n_reads + kHalfWarps - 1) / kHalfWarps, smem = kHalfWarps * kHalfStage;
+    if (zz) VBZ_LAUNCH(svb_half_decode_kernel<true>, grid, kHalfWarps * 32, smem, (vbz_stream_t)stream, p);
+    else VBZ_LAUNCH(svb_half_decode_kernel<false>, grid, kHalfWarps * 32, smem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
 }
 
 // ---- stage 2 (zstd) ---------------------------------------------------------------------------------------------
