@@ -165,7 +165,8 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
         if (!reads[i].rejected) unit_cap += zstd_units_of(reads[i].dst_cap);
     unit_cap = std::min<uint64_t>(std::max<uint64_t>(unit_cap, 8), 0x7FFFFFF0u);
     if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes()) ||
-        !ctx->d_zunits.ensure((size_t)unit_cap * sizeof(ZstdUnit)) || !ctx->d_zgeneral.ensure((size_t)n * 4))
+        !ctx->d_zunits.ensure((size_t)unit_cap * sizeof(ZstdUnit)) || !ctx->d_zgroups.ensure((size_t)unit_cap * sizeof(ZstdGroup)) ||
+        !ctx->d_zgeneral.ensure((size_t)n * 4))
         return -1;
     if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
     if (!ctx->h_zreads.ensure(bytes)) return -1;
@@ -182,6 +183,7 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.lit_scratch = ctx->d_zlit.as<uint8_t>();
     p.counter = ctx->d_zcounter.as<uint32_t>();
     p.units = ctx->d_zunits.as<ZstdUnit>();
+    p.groups = ctx->d_zgroups.as<ZstdGroup>();
     p.general = ctx->d_zgeneral.as<uint32_t>();
     p.unit_cap = (uint32_t)unit_cap;
     p.n_reads = n;
@@ -393,7 +395,7 @@ vbz_b200_ctx::~vbz_b200_ctx()
     d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
     h_reads.release(); h_results.release();
     d_mid.release();
-    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); h_zreads.release();
+    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); h_zreads.release();
     for (WaveSlot& w : slots) {
         w.d_in.release(); w.d_out.release(); w.d_results.release();
         w.h_in.release(); w.h_out.release(); w.h_results.release();

@@ -43,7 +43,7 @@ struct vbz_b200_ctx {
     vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
     vbz::PinBuf h_reads, h_results;
     // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
-    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zunits, d_zgeneral;
+    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zunits, d_zgroups, d_zgeneral;
     vbz::PinBuf h_zreads;
     // intermediate stage-1 bytes of the two-stage paths
     vbz::DevBuf d_mid;

@@ -58,11 +58,12 @@ inline uint64_t zstd_compress_bound(uint64_t n)
     return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0);
 }
 inline bool is_error(uint32_t v) { return v >= kErrOutOfMemory; }
-// Largest frame the device encoder writes for `n` content bytes: frame header, then per 32 KiB block a 3-byte
-// header and at most the block itself (csrc/zstd_enc_kernels.cuh).  Never above ZSTD_compressBound(n).
+// Largest frame the device encoder writes for `n` content bytes: frame header, then per 8 KiB block (two regions,
+// each with a partial last block) a 3-byte header and at most the block itself (csrc/zstd_enc_kernels.cuh).
+// Never above ZSTD_compressBound(n).
 inline uint64_t zstd_enc_worst_case(uint64_t n)
 {
-    const uint64_t blocks = n ? (n + kZEncBlock - 1) / kZEncBlock : 1;
+    const uint64_t blocks = n / kZEncSub + 2;
     return 9 + 3 * blocks + n;
 }
 

@@ -82,20 +82,22 @@ struct ZstdUnit {
     uint32_t read;       // whose result becomes kErrZstd if the unit fails
     uint32_t kind;
 };
+struct ZstdGroup { uint32_t first, count; };  // units [first, first + count): decoded together by one CTA of zstd_units_kernel
 struct ZstdDecParams {
     const uint8_t* src;
     uint8_t* dst;
     const ZstdRead* reads;
     uint32_t* results;   // per read: content bytes, or kErrZstd
     uint8_t* lit_scratch;  // 128 KiB + 32 per warp of the general kernel's grid
-    uint32_t* counter;   // 4 words, zeroed before launch: [0] work counter of the general kernel, [1] units listed,
-                         // [2] frames left to the general kernel, [3] work counter of the units kernel
+    uint32_t* counter;   // 8 words, zeroed before launch: [0] work counter of the general kernel, [1] units listed,
+                         // [2] frames left to the general kernel, [3] work counter of the units kernel, [4] groups listed
     ZstdUnit* units;     // unit_cap entries
+    ZstdGroup* groups;   // unit_cap entries
     uint32_t* general;   // n_reads entries: the frames the walker left to the general kernel
     uint32_t unit_cap;
     uint32_t n_reads;
 };
-VBZ_HD uint32_t zstd_units_of(uint32_t dst_cap) { return dst_cap / 8192u + 4u; }  // unit slots the host reserves per frame
+VBZ_HD uint32_t zstd_units_of(uint32_t dst_cap) { return dst_cap / 8192u + 6u; }  // unit slots the host reserves per frame
 
 struct ZstdEncRead {
     uint64_t src_off;     // the content: bytes [src_off, src_off + size) of ZstdEncParams::src
@@ -121,7 +123,8 @@ struct ZstdEncParams {
     uint32_t err_add;            // what the sized entry point adds to error codes (ref vbz/vbz.cpp:329)
     uint32_t n_reads, n_blocks;
 };
-constexpr uint32_t kZEncBlock = 32u * 1024u;   // content bytes per block written by the encoder
+constexpr uint32_t kZEncBlock = 128u * 1024u;  // content bytes per GROUP of the encoder: blocks that share one Huffman table
+constexpr uint32_t kZEncSub = 8u * 1024u;     // content bytes per block written by the encoder
 constexpr uint32_t kZBlockMax = 128u * 1024u;
 constexpr int kZdecWarps = 4;
 constexpr uint32_t kZLitStride = kZBlockMax + 32;  // literal scratch per decoding warp

@@ -177,13 +177,12 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     // 1. frames -> units (or the general kernel's list)
     VBZ_LAUNCH(zstd_walk_kernel, (p.n_reads + 127) / 128, 128, 0, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
-    // 2. the units, 8 per warp at a time; the grid is sized for the most there can be
-    const uint32_t usmem = (uint32_t)(sizeof(ZHufGroup) * 8 * kZUnitWarps);
+    // 2. the groups of units, a CTA of 64 threads each from a work counter; the grid is sized for the most there can be
+    const uint32_t usmem = (uint32_t)sizeof(ZGroupSmem);
     if (int e = VBZK_SET_SMEM(zstd_units_kernel, usmem)) return e;
-    static const uint32_t ugrid_max = persistent_grid(zstd_units_kernel, kZUnitWarps * 32, usmem, 0xFFFFFFFFu);
-    uint32_t ugrid = (p.unit_cap + 8 * kZUnitWarps - 1) / (8 * kZUnitWarps);
-    if (ugrid > ugrid_max) ugrid = ugrid_max;
-    if (ugrid) VBZ_LAUNCH(zstd_units_kernel, ugrid, kZUnitWarps * 32, usmem, (vbz_stream_t)stream, p);
+    static const uint32_t ugrid_max = persistent_grid(zstd_units_kernel, kZUnitThreads, usmem, 0xFFFFFFFFu);
+    uint32_t ugrid = p.unit_cap < ugrid_max ? p.unit_cap : ugrid_max;
+    if (ugrid) VBZ_LAUNCH(zstd_units_kernel, ugrid, kZUnitThreads, usmem, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
     // 3. whatever the walker left over, a warp per frame
     const uint32_t smem = (uint32_t)(sizeof(ZWarp) * kZdecWarps);

@@ -789,7 +789,8 @@ __device__ __forceinline__ bool z_lit_header(const uint8_t* p, uint32_t n, int* 
 
 // One pass over a frame.  emit == nullptr: count.  Returns the number of units, or 0xFFFFFFFF if the frame is not for
 // this path.  *total = content bytes.
-__device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_t r, ZstdUnit* emit, uint32_t* total)
+__device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_t r, ZstdUnit* emit, uint32_t* total, ZstdGroup* gemit,
+                                 uint32_t unit_base, uint32_t* n_groups)
 {
     const uint32_t kNo = 0xFFFFFFFFu;
     const uint8_t* p = src + rd.src_off;
@@ -802,8 +803,11 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
     n -= h;
     const uint64_t cap = rd.dst_cap;
     uint64_t op = 0;
-    uint32_t units = 0;
+    uint32_t units = 0, groups = 0;
     const uint8_t* tab = nullptr;  // the last literals section that carried a tree
+    // a GROUP = up to 16 consecutive Huffman units decoded with the same table (the one that carries the tree and the
+    // treeless ones after it), or a single Raw / RLE piece
+    uint32_t g_first = 0, g_count = 0;
     for (;;) {
         if (n < 3) return kNo;
         const uint32_t bh = z_le24(p);
@@ -845,15 +849,29 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
         } else return kNo;
         if (type < 2) op += bs;
         if (u.n != 0) {
+            const bool extend = u.kind == kZUnitHuf && u.tab_back != 0 && g_count != 0 && g_count < 16;  // (an open group is always a Huffman one)
+            if (!extend) {
+                if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; }
+                g_first = units;
+                g_count = 0;
+            }
             if (emit) emit[units] = u;
             ++units;
+            ++g_count;
+            if (u.kind != kZUnitHuf) {  // Raw / RLE pieces stand alone
+                if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count};
+                ++groups;
+                g_count = 0;
+            }
         }
         p += adv;
         n -= adv;
         if (last) break;
     }
     if (n != 0 || (has && op != fcs) || op > 0xFFFFFFF0ull) return kNo;
+    if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; }
     *total = (uint32_t)op;
+    *n_groups = groups;
     return units;
 }
 
@@ -863,121 +881,200 @@ __global__ void zstd_walk_kernel(ZstdDecParams p)
     if (r >= p.n_reads) return;
     const ZstdRead rd = p.reads[r];
     if (rd.rejected) { p.results[r] = rd.preset; return; }
-    uint32_t total = 0;
-    const uint32_t cnt = z_walk_frame(p.src, rd, r, nullptr, &total);
+    uint32_t total = 0, gcnt = 0;
+    const uint32_t cnt = z_walk_frame(p.src, rd, r, nullptr, &total, nullptr, 0, &gcnt);
     bool mine = cnt != 0xFFFFFFFFu;
     if (mine && cnt != 0) {
         const uint32_t base = atomicAdd(p.counter + 1, cnt);
-        if (base >= p.unit_cap || cnt > p.unit_cap - base) {  // out of slots: the units kernel stops at unit_cap
-            for (uint32_t k = base; k < p.unit_cap; ++k) p.units[k].kind = kZUnitNop;
+        const uint32_t gbase = atomicAdd(p.counter + 4, gcnt);
+        if (base >= p.unit_cap || cnt > p.unit_cap - base || gbase >= p.unit_cap || gcnt > p.unit_cap - gbase) {
+            // out of slots: the units kernel stops at unit_cap; what was allotted here stays empty
+            for (uint32_t k = gbase; k < p.unit_cap && k - gbase < gcnt; ++k) p.groups[k] = ZstdGroup{0, 0};
             mine = false;
-        } else z_walk_frame(p.src, rd, r, p.units + base, &total);
+        } else z_walk_frame(p.src, rd, r, p.units + base, &total, p.groups + gbase, base, &gcnt);
     }
     if (mine) p.results[r] = total;
     else p.general[atomicAdd(p.counter + 2, 1u)] = r;
 #ifdef VBZ_CPUSIM
-    if (getenv("VBZ_B200_TRACE_WALK")) fprintf(stderr, "walk: read %u -> %s (%u units, %u bytes)\n", r, mine ? "units" : "general", mine ? cnt : 0u, total);
+    if (getenv("VBZ_B200_TRACE_WALK")) fprintf(stderr, "walk: read %u -> %s (%u units, %u groups, %u bytes)\n", r, mine ? "units" : "general", mine ? cnt : 0u, mine ? gcnt : 0u, total);
 #endif
 }
 
-constexpr int kZUnitWarps = 2;
-struct ZHufGroup {
-    uint16_t huf[2048];   // while the weights are read, the FSE scratch lives here: table 64 x u32, norm 256 x i16, next 256 x u16
+// ---- the units kernel: one CTA of 64 threads per group -------------------------------------------------------------------
+// The table is built once per group, by all threads; then every unit of the group gets 4 lanes, one per Huffman stream:
+// with the writer of csrc/zstd_enc_kernels.cuh (16 blocks of 8 KiB per table) all 64 lanes decode 2 KiB each.  Frames of
+// other writers (libzstd: one tree per 128 KiB block, or a few treeless blocks after it) use 4 lanes per block.
+constexpr int kZUnitThreads = 64;
+struct ZGroupSmem {
+    uint16_t huf[2048];    // sym | nbBits << 8.  While the weights are read: the tree description (160 bytes at +2048) and the FSE
+                           // scratch (table 64 x u32, norm 256 x i16, next 256 x u16 at +0)
     uint8_t weights[256];
+    uint16_t pos[256];     // first cell of each symbol
+    uint32_t rank[16], start[16];
+    uint32_t v[8];         // [0] group index, [1] weights, [2] tree bytes, [3] max_bits (0 = bad table), [4] sum of 2^(w-1), [5] error
 };
 
-__global__ void __launch_bounds__(kZUnitWarps * 32) zstd_units_kernel(ZstdDecParams p)
+// weights[0..nw) -> decode table, all threads of the CTA.  Returns max_bits or 0 on error (same checks as z_huf_build).
+__device__ __forceinline__ int z_huf_build_cta(ZGroupSmem* sm, int nw, uint32_t tid)
+{
+    if (tid < 16) sm->rank[tid] = 0;
+    if (tid == 0) { sm->v[4] = 0; sm->v[5] = 0; }
+    __syncthreads();
+    for (int i = (int)tid; i < nw; i += kZUnitThreads) {
+        const uint32_t w = sm->weights[i];
+        if (w > 12) { sm->v[5] = 1; continue; }
+        atomicAdd(&sm->rank[w], 1u);
+        atomicAdd(&sm->v[4], (1u << w) >> 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int max_bits = 0;
+        const uint32_t total = sm->v[4];
+        if (!sm->v[5] && total != 0 && nw > 0 && nw < 256) {
+            max_bits = z_highbit(total) + 1;
+            const uint32_t rest = (1u << max_bits) - total;
+            if (max_bits > 11 || (rest & (rest - 1)) != 0) max_bits = 0;  // HUF_TABLELOG_MAX of the format
+            else {
+                const uint32_t wl = (uint32_t)z_highbit(rest) + 1;
+                sm->weights[nw] = (uint8_t)wl;
+                sm->rank[wl]++;
+                if (sm->rank[1] < 2 || (sm->rank[1] & 1)) max_bits = 0;
+                uint32_t acc = 0;
+                for (int r = 1; r <= 12; ++r) { sm->start[r] = acc; acc += sm->rank[r] << (r - 1); }
+            }
+        }
+        sm->v[3] = (uint32_t)max_bits;
+    }
+    __syncthreads();
+    const int max_bits = (int)sm->v[3];
+    if (!max_bits) return 0;
+    nw += 1;
+    // cells: weight 1 (longest codes) first, symbols ascending within a weight.  Thread r walks the symbols of weight r.
+    if (tid >= 1 && tid <= 12 && sm->rank[tid]) {
+        uint32_t cur = sm->start[tid];
+        const uint32_t len = (1u << tid) >> 1;
+        for (int sy = 0; sy < nw; ++sy)
+            if (sm->weights[sy] == tid) { sm->pos[sy] = (uint16_t)cur; cur += len; }
+    }
+    __syncthreads();
+    for (int sy = (int)tid; sy < nw; sy += kZUnitThreads) {
+        const uint32_t r = sm->weights[sy];
+        if (!r) continue;
+        const uint32_t len = (1u << r) >> 1;
+        const uint32_t e = (uint32_t)sy | ((uint32_t)(max_bits + 1 - (int)r) << 8);
+        uint16_t* c = sm->huf + sm->pos[sy];  // a run of `len` cells starts at a multiple of len: wide stores are aligned
+        const uint32_t e2 = e | (e << 16);
+        if (len >= 8) {
+            const uint4 e8 = make_uint4(e2, e2, e2, e2);
+            for (uint32_t k = 0; k < len; k += 8) *reinterpret_cast<uint4*>(c + k) = e8;
+        } else if (len == 4) *reinterpret_cast<uint2*>(c) = make_uint2(e2, e2);
+        else if (len == 2) *reinterpret_cast<uint32_t*>(c) = e2;
+        else c[0] = (uint16_t)e;
+    }
+    __syncthreads();
+    return max_bits;
+}
+
+__global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams p)
 {
     VBZ_DYN_SMEM(smem);
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, j = lane & 3;
-    ZHufGroup* grp = reinterpret_cast<ZHufGroup*>(smem) + wid * 8 + g;
-    uint32_t n_units = p.counter[1];
-    if (n_units > p.unit_cap) n_units = p.unit_cap;
+    ZGroupSmem* sm = reinterpret_cast<ZGroupSmem*>(smem);
+    const uint32_t tid = threadIdx.x, j = tid & 3;
+    uint32_t n_groups = p.counter[4];
+    if (n_groups > p.unit_cap) n_groups = p.unit_cap;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.counter + 3, 8u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_units) break;
-        ZstdUnit un = {0, 0, 0, 0, 0, kZUnitNop};
-        if (base + g < n_units) un = p.units[base + g];
-        const bool huf = un.kind == kZUnitHuf;
-        // ---- Huffman units: lane 0 of the group reads the tree, all four decode ------------------------------------------
-        bool ok = true;
-        const uint8_t* lp = p.src + un.src_off;
-        int lt = 0, streams = 4;
-        uint32_t hdr = 0, regen = 0, comp = 0, t = 0;
-        int bits = 0;
-        if (huf) {
-            ok = z_lit_header(lp, un.n, &lt, &hdr, &regen, &comp, &streams) && lt >= 2 && regen <= kZBlockMax && hdr + comp <= un.n &&
-                 !(streams == 4 && regen < 6);
-            if (ok && j == 0) {
-                const uint8_t* ts = lp + hdr;
-                uint32_t tn = comp;
-                if (lt == 3) {  // the tree of an earlier block of the frame
-                    const uint8_t* tp = lp - un.tab_back;
-                    int lt2, st2;
-                    uint32_t hdr2, regen2, comp2;
-                    z_lit_header(tp, 5, &lt2, &hdr2, &regen2, &comp2, &st2);  // (validated when that block was listed)
-                    ts = tp + hdr2;
-                    tn = comp2;
-                }
-                uint8_t* scratch = reinterpret_cast<uint8_t*>(grp->huf);
-                int nw = 0;
-                t = z_huf_read_weights(grp->weights, reinterpret_cast<uint32_t*>(scratch), reinterpret_cast<int16_t*>(scratch + 256),
-                                       reinterpret_cast<uint16_t*>(scratch + 768), ts, tn, &nw);
-                if (t) bits = z_huf_build(grp->huf, grp->weights, nw);
-            }
-        }
-        __syncwarp();
-        t = __shfl_sync(0xffffffffu, t, (int)(lane & ~3u));
-        bits = __shfl_sync(0xffffffffu, bits, (int)(lane & ~3u));
-        if (huf && ok) {
-            ok = bits != 0;
-            const uint8_t* q = lp + hdr;
-            uint32_t left = comp;
-            if (lt == 2) { q += t; left -= t; }  // t <= comp: read_weights never reads past what it was given
-            uint8_t* dst = p.dst + un.dst_off;
-            if (!ok) {
-            } else if (streams == 1) {
-                if (j == 0) ok = z_huf_decode_stream(grp->huf, bits, q, left, dst, regen);
-            } else if (left < 10) ok = false;
-            else {
-                const uint32_t s1 = z_le16(q), s2 = z_le16(q + 2), s3 = z_le16(q + 4);
-                const uint32_t seg = (regen + 3) / 4;
-                if (6 + s1 + s2 + s3 > left || 3 * seg > regen) ok = false;
-                else {
-                    const uint32_t s4 = left - 6 - s1 - s2 - s3;
-                    const uint32_t so = j == 0 ? 0u : j == 1 ? s1 : j == 2 ? s1 + s2 : s1 + s2 + s3;
-                    const uint32_t sn = j == 0 ? s1 : j == 1 ? s2 : j == 2 ? s3 : s4;
-                    ok = z_huf_decode_stream(grp->huf, bits, q + 6 + so, sn, dst + j * seg, j == 3 ? regen - 3 * seg : seg);
-                }
-            }
-        }
-        const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
-        if (j == 0 && ((bad >> (lane & ~3u)) & 0xFu)) p.results[un.read] = kErrZstd;
-        // ---- Raw / RLE pieces: the whole warp, one unit after the other ------------------------------------------------------------
-        const uint32_t plain = __ballot_sync(0xffffffffu, j == 0 && (un.kind == kZUnitCopy || un.kind == kZUnitFill));
-        for (uint32_t m = plain; m; m &= m - 1) {
-            const int owner = __ffs((int)m) - 1;
-            const uint32_t kind = __shfl_sync(0xffffffffu, un.kind, owner);
-            const uint32_t cn = __shfl_sync(0xffffffffu, un.n, owner);
-            const uint64_t so = __shfl_sync(0xffffffffu, un.src_off, owner), dof = __shfl_sync(0xffffffffu, un.dst_off, owner);
-            uint8_t* d = p.dst + dof;
-            const uint8_t* sp = p.src + so;
-            if (kind == kZUnitFill) {
+        __syncthreads();  // the previous group's table and scalars are no longer in use
+        if (tid == 0) sm->v[0] = atomicAdd(p.counter + 3, 1u);
+        __syncthreads();
+        const uint32_t g = sm->v[0];
+        if (g >= n_groups) break;
+        const ZstdGroup grp = p.groups[g];
+        if (grp.count == 0) continue;
+        const ZstdUnit u0 = p.units[grp.first];
+        if (u0.kind == kZUnitCopy || u0.kind == kZUnitFill) {  // Raw / RLE piece: the whole CTA
+            uint8_t* d = p.dst + u0.dst_off;
+            const uint8_t* sp = p.src + u0.src_off;
+            const uint32_t cn = u0.n;
+            if (u0.kind == kZUnitFill) {
                 const uint8_t v = sp[0];
-                z_warp_fill(d, v, cn, lane);
+                for (uint32_t k = tid; k < cn; k += kZUnitThreads) d[k] = v;
             } else if ((((uintptr_t)d ^ (uintptr_t)sp) & 3u) == 0 && cn >= 64) {  // same word phase: bytes to the boundary, words, bytes
                 const uint32_t head = (4u - (uint32_t)((uintptr_t)d & 3u)) & 3u;
                 const uint32_t words = (cn - head) >> 2, done = head + 4 * words;
-                if (lane < head) d[lane] = sp[lane];
-                else if (lane >= 8 && lane - 8 < cn - done) d[done + lane - 8] = sp[done + lane - 8];
+                if (tid < head) d[tid] = sp[tid];
+                else if (tid >= 8 && tid - 8 < cn - done) d[done + tid - 8] = sp[done + tid - 8];
                 const uint32_t* s4 = reinterpret_cast<const uint32_t*>(sp + head);
                 uint32_t* d4 = reinterpret_cast<uint32_t*>(d + head);
-                for (uint32_t k = lane; k < words; k += 32) d4[k] = s4[k];
-            } else z_warp_copy(d, sp, cn, lane);
+                for (uint32_t k = tid; k < words; k += kZUnitThreads) d4[k] = s4[k];
+            } else {
+                for (uint32_t k = tid; k < cn; k += kZUnitThreads) d[k] = sp[k];
+            }
+            continue;
         }
-        __syncwarp();
+        if (u0.kind != kZUnitHuf) continue;
+        // ---- the group's table: the tree sits in the literals section tab_back bytes before the first unit's ----------------------
+        int bits = 0;
+        {
+            const uint8_t* tp = p.src + u0.src_off - u0.tab_back;
+            int lt2 = 0, st2 = 0;
+            uint32_t hdr2 = 0, regen2 = 0, comp2 = 0;
+            const bool hok = z_lit_header(tp, u0.tab_back ? 5u : u0.n, &lt2, &hdr2, &regen2, &comp2, &st2) && lt2 == 2 && (u0.tab_back != 0 || hdr2 + comp2 <= u0.n);
+            // the description is at most 1 + 127 bytes (FSE) or 1 + 64 (direct): stage it in shared memory for the serial reader
+            uint8_t* tree = reinterpret_cast<uint8_t*>(sm->huf) + 2048;
+            const uint32_t tn = hok ? (comp2 < 160u ? comp2 : 160u) : 0u;
+            for (uint32_t k = tid; k < tn; k += kZUnitThreads) tree[k] = tp[hdr2 + k];
+            __syncthreads();
+            if (tid == 0) {
+                int nw = 0;
+                uint32_t t = 0;
+                if (hok) {
+                    uint8_t* scratch = reinterpret_cast<uint8_t*>(sm->huf);
+                    t = z_huf_read_weights(sm->weights, reinterpret_cast<uint32_t*>(scratch), reinterpret_cast<int16_t*>(scratch + 256),
+                                           reinterpret_cast<uint16_t*>(scratch + 768), tree, tn, &nw);
+                }
+                sm->v[1] = (uint32_t)nw;
+                sm->v[2] = t;
+            }
+            __syncthreads();
+            if (sm->v[2]) bits = z_huf_build_cta(sm, (int)sm->v[1], tid);
+        }
+        const uint32_t t = sm->v[2];
+        // ---- the units, 16 at a time: 4 lanes each -----------------------------------------------------------------------------
+        for (uint32_t k0 = 0; k0 < grp.count; k0 += 16) {
+            const uint32_t ui = k0 + (tid >> 2);
+            if (ui >= grp.count) continue;
+            const ZstdUnit un = p.units[grp.first + ui];
+            const uint8_t* lp = p.src + un.src_off;
+            int lt = 0, streams = 4;
+            uint32_t hdr = 0, regen = 0, comp = 0;
+            bool ok = bits != 0 && un.kind == kZUnitHuf && z_lit_header(lp, un.n, &lt, &hdr, &regen, &comp, &streams) && lt >= 2 && regen <= kZBlockMax &&
+                      hdr + comp <= un.n && !(streams == 4 && regen < 6);
+            if (ok) {
+                const uint8_t* q = lp + hdr;
+                uint32_t left = comp;
+                if (lt == 2) {  // this unit carries the tree (t <= comp: read_weights never reads past what it was given)
+                    if (t > left) ok = false;
+                    else { q += t; left -= t; }
+                }
+                uint8_t* dst = p.dst + un.dst_off;
+                if (!ok) {
+                } else if (streams == 1) {
+                    if (j == 0) ok = z_huf_decode_stream(sm->huf, bits, q, left, dst, regen);
+                } else if (left < 10) ok = false;
+                else {
+                    const uint32_t s1 = z_le16(q), s2 = z_le16(q + 2), s3 = z_le16(q + 4);
+                    const uint32_t seg = (regen + 3) / 4;
+                    if (6 + s1 + s2 + s3 > left || 3 * seg > regen) ok = false;
+                    else {
+                        const uint32_t s4 = left - 6 - s1 - s2 - s3;
+                        const uint32_t so = j == 0 ? 0u : j == 1 ? s1 : j == 2 ? s1 + s2 : s1 + s2 + s3;
+                        const uint32_t sn = j == 0 ? s1 : j == 1 ? s2 : j == 2 ? s3 : s4;
+                        ok = z_huf_decode_stream(sm->huf, bits, q + 6 + so, sn, dst + j * seg, j == 3 ? regen - 3 * seg : seg);
+                    }
+                }
+            }
+            if (!ok) p.results[un.read] = kErrZstd;
+        }
     }
 }
 

@@ -7,31 +7,39 @@
 // reference's vbz_decompress to the same bytes - the parity tests check exactly that.
 //
 // What is emitted.  On nanopore signal zstd level 1 finds almost no matches: 98 % of its output is Huffman-coded
-// literals.  This writer therefore entropy-codes and does not search: the content is cut
-// into blocks of 32 KiB; every block is, whichever is smallest, an RLE block, a Compressed block holding one
-// Huffman-coded literals section (own length-limited code, <= 11 bits, weights FSE-compressed or direct, 1 or 4
-// streams) and no sequences, or a Raw block.  The compression level only has to be non-zero.
+// literals.  This writer therefore entropy-codes and does not search.  The content is cut
+// into GROUPS of 128 KiB that share one Huffman code (own length-limited code, <= 11 bits, weights FSE-compressed
+// or direct), and every group into SUB-BLOCKS of 8 KiB, each its own zstd block: a Compressed block holding one
+// Huffman literals section (4 streams; 1 below 1 KiB) and no sequences - the first one of the group carries the
+// tree, the others are "treeless" (they reuse it, RFC 8878 3.1.1.3.1.1) - or a Raw block when that is smaller.  A
+// group of one repeated byte is a single RLE block, an incompressible one a single Raw block.  Small blocks with a
+// shared table are what lets the DECODER run 64 Huffman streams per table at once (csrc/zstd_dec_kernels.cuh);
+// the table is also built once per 128 KiB here.  The compression level only has to be non-zero.
 //
-// Parallelism: one CTA (4 warps) per block, blocks numbered frame-major.
-//   histogram   per-warp shared-memory histograms, merged
+// Parallelism: one CTA (8 warps) per group, groups numbered frame-major.
+//   histogram   128-bit loads, per-warp shared-memory histograms (zero bytes counted in a register), merged
 //   code        rank sort of the 256 counts by all threads; the two-queue Huffman construction, the length
 //               limiting and the (small) FSE coding of the weights are serial work of one thread
-//   streams     a warp per stream; each lane owns a contiguous run of symbols, sums its code lengths, a shuffle
-//               scan gives its bit offset, and it writes its bits into the shared-memory staging area (plain
-//               stores for the words it owns, atomicOr for the two it shares with its neighbours)
-//   out         the size of the block is posted, a decoupled look-back over the frame's earlier blocks
-//               (csrc/svb_kernels.cuh) gives its position, the CTA copies the staging area out
+//   sizes       a warp per stream, 8 streams after each other: a lane owns a contiguous run of <= 64 symbols, which
+//               it loads with aligned 128-bit loads and shifts into place in registers; code lengths are summed, a
+//               shuffle scan gives the lane's bit offset (kept for the next pass) and the stream's size
+//   position    one thread sizes the sub-blocks; the group's size is posted, a decoupled look-back over the
+//               frame's earlier groups (csrc/svb_kernels.cuh) gives its position
+//   pack        two sub-blocks at a time (4 warps = 4 streams each): codes of two symbols are merged and OR-ed
+//               into a zeroed shared-memory staging area, which then leaves with aligned 128-bit stores
 #pragma once
 #include "zstd_dec_kernels.cuh"
 #include "svb_kernels.cuh"
 
 namespace vbz {
 
-constexpr int kZencThreads = 128;
+constexpr int kZencThreads = 256;
 constexpr int kZencWarps = kZencThreads / 32;
+constexpr uint32_t kZSubs = kZEncBlock / kZEncSub;   // sub-blocks per group (16)
+constexpr uint32_t kZStreams = kZSubs * 4;           // Huffman streams per group (64)
 
 struct ZEncSmem {
-    uint32_t hist[kZencWarps][256];
+    uint32_t hist[kZencWarps][256];  // after the histogram: the lanes' bit offsets, uint16_t[kZStreams][32]
     uint32_t cnt[256];
     uint32_t code[256];       // code | len << 16
     uint8_t order[256];       // symbols by ascending count
@@ -46,9 +54,13 @@ struct ZEncSmem {
     uint8_t tree[160];        // the Huffman tree description
     uint32_t v[16];           // scalars shared by the CTA (see the kZv* indices)
     uint64_t excl;
-    alignas(16) uint8_t stage[kZEncBlock + 64];  // sized header, frame header, block header, block payload
+    uint32_t sbits[kZStreams];     // bits of every stream of the group
+    uint32_t sub_off[kZSubs + 1];  // where each sub-block starts in the group's output
+    uint8_t sub_kind[kZSubs];      // kZKindRaw / kZKindHuf
+    uint8_t sub_tree[kZSubs];      // != 0: this sub-block carries the tree
+    alignas(16) uint8_t stage[2][kZEncSub + 96];  // (sized header, frame header,) block header, block payload; slack for the copy
 };
-enum { kZvNsym = 0, kZvMaxBits, kZvTreeBytes, kZvKind, kZvStreams, kZvBits0, kZvBits1, kZvBits2, kZvBits3, kZvTotal };
+enum { kZvNsym = 0, kZvMaxBits, kZvTreeBytes, kZvKind, kZvTotal, kZvPre };
 enum { kZKindRaw = 0, kZKindRle = 1, kZKindHuf = 2 };
 
 // little-endian bit writer that grows upward from bit 0 of a byte buffer (one thread)
@@ -266,41 +278,103 @@ __device__ uint32_t zenc_describe_tree(ZEncSmem* s)
     return direct;
 }
 
-// ---- one Huffman stream (one warp): symbols src[0..count) -> bits at stage (zeroed), returns the bit count -----------
-// Lane l owns the symbols [count - (l+1)*C, count - l*C) (the stream is written from the last symbol up).
-__device__ __forceinline__ uint32_t zenc_stream_bits(const uint32_t* code, const uint8_t* src, uint32_t count, uint32_t lane, uint32_t* chunk_out)
+// ---- a lane's run of symbols ------------------------------------------------------------------------------------
+// bytes [p, p + n), n <= 64, any alignment -> r[0..15], little-endian (bytes past n are unspecified).  Aligned
+// 128-bit loads; the 16-byte granules that hold the first and the last byte are read whole.
+__device__ __forceinline__ void zenc_load_run(const uint8_t* p, uint32_t n, uint32_t (&r)[16])
+{
+    const uint4* q = reinterpret_cast<const uint4*>((uintptr_t)p & ~(uintptr_t)15);
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 15u);
+    const uint32_t chunks = n ? (sh + n + 15) >> 4 : 0;  // 0..5
+    uint32_t w[20];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        uint4 t = make_uint4(0, 0, 0, 0);
+        if ((uint32_t)k < chunks) t = q[k];
+        w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
+    }
+    const uint32_t wo = sh >> 2, bs = 8u * (sh & 3u);
+    if (wo == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i], w[i + 1], bs);
+    } else if (wo == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i + 1], w[i + 2], bs);
+    } else if (wo == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i + 2], w[i + 3], bs);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i + 3], w[i + 4], bs);
+    }
+}
+// Lane l of the stream's warp owns the symbols [count - (l+1) C, count - l C), C = ceil(count / 32) <= 64: the
+// stream is written from its last symbol up, so lane 0 writes the lowest bits.
+__device__ __forceinline__ void zenc_lane_run(uint32_t count, uint32_t lane, uint32_t* lo, uint32_t* n)
 {
     const uint32_t C = (count + 31) / 32;
+    const uint32_t hi = count > lane * C ? count - lane * C : 0;
+    *lo = hi > C ? hi - C : 0;
+    *n = hi - *lo;
+}
+__device__ __forceinline__ uint32_t zenc_run_bits(const uint8_t* len, const uint32_t (&r)[16], uint32_t n)
+{
     uint32_t bits = 0;
-    const uint32_t hi = count > lane * C ? count - lane * C : 0, lo = hi > C ? hi - C : 0;
-    for (uint32_t i = lo; i < hi; ++i) bits += code[src[i]] >> 16;
-    *chunk_out = C;
+#pragma unroll
+    for (int i = 0; i < 64; ++i)
+        if ((uint32_t)i < n) bits += len[(r[i >> 2] >> (8 * (i & 3))) & 0xFFu];
     return bits;
 }
-__device__ __forceinline__ void zenc_stream_write(const uint32_t* code, const uint8_t* src, uint32_t count, uint32_t lane, uint32_t C, uint32_t bit0,
-                                                  uint8_t* stage)
+// the run's codes, last symbol first, OR-ed into the zeroed staging words from bit `bit0` on
+__device__ __forceinline__ void zenc_run_write(const uint32_t* code, const uint32_t (&r)[16], uint32_t n, uint32_t bit0, uint32_t* words)
 {
-    // stage is 4-byte aligned; this lane's bits start at bit0
-    uint32_t* words = reinterpret_cast<uint32_t*>(stage);
-    const uint32_t hi = count > lane * C ? count - lane * C : 0, lo = hi > C ? hi - C : 0;
-    if (hi == lo) return;
-    uint32_t wi = bit0 >> 5;
-    uint32_t nb = bit0 & 31u;
+    uint32_t wi = bit0 >> 5, nb = bit0 & 31u;
     uint64_t acc = 0;
-    bool first = true;
-    for (uint32_t i = hi; i-- > lo;) {
-        const uint32_t c = code[src[i]];
-        acc |= (uint64_t)(c & 0xFFFFu) << nb;
-        nb += c >> 16;
-        if (nb >= 32) {
-            if (first) { atomicOr(words + wi, (uint32_t)acc); first = false; }
-            else words[wi] = (uint32_t)acc;
-            ++wi;
-            acc >>= 32;
-            nb -= 32;
+#pragma unroll
+    for (int k = 31; k >= 0; --k) {
+        if ((uint32_t)(2 * k) < n) {  // symbols 2k+1 (if it exists) and 2k, in that order
+            const uint32_t c0 = code[(r[k >> 1] >> (16 * (k & 1))) & 0xFFu];
+            uint32_t v = c0 & 0xFFFFu, l = c0 >> 16;
+            if ((uint32_t)(2 * k + 1) < n) {
+                const uint32_t c1 = code[(r[k >> 1] >> (16 * (k & 1) + 8)) & 0xFFu];
+                v = (c1 & 0xFFFFu) | (v << (c1 >> 16));
+                l += c1 >> 16;
+            }
+            acc |= (uint64_t)v << nb;
+            nb += l;
+            if (nb >= 32) {
+                atomicOr(words + wi, (uint32_t)acc);
+                ++wi;
+                acc >>= 32;
+                nb -= 32;
+            }
         }
     }
     if (nb) atomicOr(words + wi, (uint32_t)acc);
+}
+
+// `nthreads` threads (t = 0 .. nthreads-1) copy n bytes from a 16-byte aligned staging area to an arbitrarily aligned
+// global address: aligned 128-bit stores, each fed by two aligned 128-bit shared loads re-aligned with funnel shifts
+// (the staging area must be readable 32 bytes past the end).
+__device__ __forceinline__ void zenc_copy_out(uint8_t* g, const uint8_t* stage, uint32_t n, uint32_t t, uint32_t nthreads)
+{
+    uint32_t head = (16u - (uint32_t)((uintptr_t)g & 15u)) & 15u;
+    if (head > n) head = n;
+    const uint32_t nchunks = (n - head) >> 4, done = head + (nchunks << 4);
+    if (t < head) g[t] = stage[t];
+    else if (t >= 32 && t - 32 < n - done) g[done + t - 32] = stage[done + t - 32];
+    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+    uint4* g4 = reinterpret_cast<uint4*>(g + head);
+    const uint32_t wsel = head >> 2, sh = 8u * (head & 3u);
+    for (uint32_t c = t; c < nchunks; c += nthreads) {
+        const uint4 A = s4[c], B = s4[c + 1];
+        uint32_t w0, w1, w2, w3, w4;
+        if (wsel == 0) { w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; }
+        else if (wsel == 1) { w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; }
+        else if (wsel == 2) { w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; }
+        else { w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; }
+        g4[c] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
 }
 
 __global__ void zstd_enc_fill_blocks_kernel(const ZstdEncRead* reads, uint32_t n_reads, uint32_t* block_read)
@@ -311,6 +385,18 @@ __global__ void zstd_enc_fill_blocks_kernel(const ZstdEncRead* reads, uint32_t n
     for (uint32_t i = lane; i < rd.n_blocks; i += 32) block_read[rd.first_block + i] = warp;
 }
 
+// geometry of sub-block q of a group of B bytes
+struct ZSub { uint32_t start, bytes, streams, seg; };
+__device__ __forceinline__ ZSub zenc_sub(uint32_t B, uint32_t q)
+{
+    ZSub s;
+    s.start = q * kZEncSub;
+    s.bytes = B - s.start < kZEncSub ? B - s.start : kZEncSub;
+    s.streams = s.bytes < 1024 ? 1u : 4u;
+    s.seg = s.streams == 1 ? s.bytes : (s.bytes + 3) / 4;
+    return s;
+}
+
 __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams p)
 {
     VBZ_DYN_SMEM(smem);
@@ -319,57 +405,80 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     const uint32_t b = blockIdx.x;
     const uint32_t r = p.block_read[b];
     const ZstdEncRead rd = p.reads[r];
-    const uint32_t bi = b - rd.first_block;
+    const uint32_t gi = b - rd.first_block;
     if (rd.rejected) {
-        if (bi == 0 && tid == 0) p.results[r] = rd.preset;
+        if (gi == 0 && tid == 0) p.results[r] = rd.preset;
         return;
     }
     const uint32_t content = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
     if (p.src_sizes && content >= kErrOutOfMemory) {  // stage 1 reported an error for this read
-        if (bi == 0 && tid == 0) p.results[r] = content;
+        if (gi == 0 && tid == 0) p.results[r] = content;
         return;
     }
-    // blocks of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'), then the rest
+    // groups of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'), then the rest
     const uint32_t split = rd.split < content ? rd.split : 0u;
     const uint32_t n_a = (split + kZEncBlock - 1) / kZEncBlock, n_b = (content - split + kZEncBlock - 1) / kZEncBlock;
-    const uint32_t nblk = n_a + n_b ? n_a + n_b : 1u;
-    if (bi >= nblk) return;  // the table was sized for the largest content stage 1 could have produced
-    const uint32_t start = bi < n_a ? bi * kZEncBlock : split + (bi - n_a) * kZEncBlock;
-    const uint32_t region_end = bi < n_a ? split : content;
+    const uint32_t ngrp = n_a + n_b ? n_a + n_b : 1u;
+    if (gi >= ngrp) return;  // the table was sized for the largest content stage 1 could have produced
+    const uint32_t start = gi < n_a ? gi * kZEncBlock : split + (gi - n_a) * kZEncBlock;
+    const uint32_t region_end = gi < n_a ? split : content;
     const uint32_t B = region_end - start < kZEncBlock ? region_end - start : kZEncBlock;
-    const bool last = bi + 1 == nblk;
+    const bool last = gi + 1 == ngrp;
     const uint8_t* src = p.src + rd.src_off + start;
+    const uint32_t nsub = B ? (B + kZEncSub - 1) / kZEncSub : 1u;
 
-    // ---- zero the staging area and the histograms; headers that do not depend on the payload ---------------------------
-    for (uint32_t i = tid; i < (kZEncBlock + 64) / 16; i += kZencThreads) reinterpret_cast<uint4*>(s->stage)[i] = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < kZencWarps * 256; i += kZencThreads) (&s->hist[0][0])[i] = 0;
-    __syncthreads();
-    uint32_t pre = 0;  // bytes before the block header
-    if (bi == 0) {
-        if (p.hdr_bytes) pre = 4;
+    // bytes before the first block header: the sized header and the frame header, in front of the frame's first group
+    uint32_t pre = 0;
+    uint8_t prebuf[16];
+    if (gi == 0) {
+        if (p.hdr_bytes) { prebuf[0] = (uint8_t)rd.hdr_value; prebuf[1] = (uint8_t)(rd.hdr_value >> 8); prebuf[2] = (uint8_t)(rd.hdr_value >> 16); prebuf[3] = (uint8_t)(rd.hdr_value >> 24); pre = 4; }
         const uint32_t fcs_bytes = content < 256 ? 1u : (content < 65536 + 256 ? 2u : 4u);
-        if (tid == 0) {
-            uint8_t* h = s->stage;
-            if (p.hdr_bytes) { h[0] = (uint8_t)rd.hdr_value; h[1] = (uint8_t)(rd.hdr_value >> 8); h[2] = (uint8_t)(rd.hdr_value >> 16); h[3] = (uint8_t)(rd.hdr_value >> 24); }
-            h += pre;
-            h[0] = 0x28; h[1] = 0xB5; h[2] = 0x2F; h[3] = 0xFD;
-            h[4] = (uint8_t)(0x20 | (fcs_bytes == 1 ? 0x00 : fcs_bytes == 2 ? 0x40 : 0x80));  // single segment, content size present
-            const uint32_t f = fcs_bytes == 2 ? content - 256 : content;
-            for (uint32_t k = 0; k < fcs_bytes; ++k) h[5 + k] = (uint8_t)(f >> (8 * k));
-        }
+        prebuf[pre] = 0x28; prebuf[pre + 1] = 0xB5; prebuf[pre + 2] = 0x2F; prebuf[pre + 3] = 0xFD;
+        prebuf[pre + 4] = (uint8_t)(0x20 | (fcs_bytes == 1 ? 0x00 : fcs_bytes == 2 ? 0x40 : 0x80));  // single segment, content size present
+        const uint32_t f = fcs_bytes == 2 ? content - 256 : content;
+        for (uint32_t k = 0; k < fcs_bytes; ++k) prebuf[pre + 5 + k] = (uint8_t)(f >> (8 * k));
         pre += 5 + fcs_bytes;
     }
-    uint8_t* blk = s->stage + pre;  // block header, then the payload
+    __syncthreads();
 
-    // ---- histogram ----------------------------------------------------------------------------------------------------
-    for (uint32_t i = tid; i < B; i += kZencThreads) atomicAdd(&s->hist[wid][src[i]], 1u);
+    // ---- histogram: 128-bit loads over the aligned body, bytes at the two ends ----------------------------------------
+    {
+        uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
+        if (head > B) head = B;
+        const uint32_t nch = (B - head) >> 4, done = head + (nch << 4);
+        uint32_t* h = s->hist[wid];
+        uint32_t zeros = 0;
+        if (tid < head) atomicAdd(h + src[tid], 1u);
+        else if (tid >= 32 && tid - 32 < B - done) atomicAdd(h + src[done + tid - 32], 1u);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+        for (uint32_t c = tid; c < nch; c += kZencThreads) {
+            const uint4 q = s4[c];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t v = (w[k] >> (8 * j)) & 0xFFu;
+                    if (v) atomicAdd(h + v, 1u);
+                    else ++zeros;
+                }
+            }
+        }
+        if (zeros) atomicAdd(h, zeros);
+    }
     __syncthreads();
-    for (uint32_t i = tid; i < 256; i += kZencThreads) s->cnt[i] = s->hist[0][i] + s->hist[1][i] + s->hist[2][i] + s->hist[3][i];
+    {
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < kZencWarps; ++w) c += s->hist[w][tid];
+        s->cnt[tid] = c;
+    }
     __syncthreads();
-    // rank sort of the symbols that occur, ascending by (count, symbol)
+    // rank sort of the symbols that occur, ascending by (count, symbol): thread = symbol
     uint32_t nsym = 0;
-    for (uint32_t sym = tid; sym < 256; sym += kZencThreads) {
-        const uint32_t c = s->cnt[sym];
+    {
+        const uint32_t sym = tid, c = s->cnt[sym];
         if (c) {
             uint32_t rank = 0;
             for (uint32_t j = 0; j < 256; ++j) {
@@ -377,16 +486,18 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
                 rank += (cj != 0 && (cj < c || (cj == c && j < sym))) ? 1u : 0u;
             }
             s->order[rank] = (uint8_t)sym;
-            nsym++;
+            nsym = 1;
         }
     }
     nsym = __reduce_add_sync(0xffffffffu, nsym);
-    if (lane == 0) s->v[12 + wid] = nsym;
+    if (lane == 0) s->v[8 + wid] = nsym;
     __syncthreads();
-    nsym = s->v[12] + s->v[13] + s->v[14] + s->v[15];
+    nsym = 0;
+#pragma unroll
+    for (int w = 0; w < kZencWarps; ++w) nsym += s->v[8 + w];
     __syncthreads();
 
-    // ---- the code and the kind of block (one thread) -----------------------------------------------------------------------
+    // ---- the code and the kind of group (one thread) ---------------------------------------------------------------------
     if (tid == 0) {
         uint32_t kind = kZKindRaw, tree_bytes = 0;
         if (B > 0 && nsym == 1) kind = kZKindRle;
@@ -401,76 +512,69 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     __syncthreads();
     uint32_t kind = s->v[kZvKind];
     const uint32_t tree_bytes = s->v[kZvTreeBytes];
+    uint16_t* lane_off = reinterpret_cast<uint16_t*>(&s->hist[0][0]);  // [stream][lane]
 
-    // ---- stream sizes: a warp per stream ---------------------------------------------------------------------------------------
-    const uint32_t streams = B < 1024 ? 1u : 4u;
-    const uint32_t seg = (B + 3) / 4;
-    uint32_t s_off = 0, s_cnt = 0, chunk = 0, my_bits = 0, lane_bit0 = 0;
+    // ---- sizes: every stream of the group, a warp per stream ----------------------------------------------------------------
     if (kind == kZKindHuf) {
-        if (streams == 1) { s_off = 0; s_cnt = wid == 0 ? B : 0; }
-        else { s_off = wid * seg; s_cnt = wid == 3 ? B - 3 * seg : seg; }
-        my_bits = zenc_stream_bits(s->code, src + s_off, s_cnt, lane, &chunk);
-        const uint32_t incl = warp_scan_u32(my_bits);
-        lane_bit0 = incl - my_bits;
-        if (lane == 31) s->v[kZvBits0 + wid] = incl;
+        for (uint32_t sidx = wid; sidx < nsub * 4; sidx += kZencWarps) {
+            const ZSub sb = zenc_sub(B, sidx >> 2);
+            const uint32_t j = sidx & 3u;
+            uint32_t bits = 0;
+            if (j < sb.streams && sb.bytes >= 32) {
+                const uint32_t cnt = (sb.streams == 4 && j == 3) ? sb.bytes - 3 * sb.seg : sb.seg;
+                uint32_t lo, n, run[16];
+                zenc_lane_run(cnt, lane, &lo, &n);
+                zenc_load_run(src + sb.start + j * sb.seg + lo, n, run);
+                bits = zenc_run_bits(s->len, run, n);
+            }
+            const uint32_t incl = warp_scan_u32(bits);
+            lane_off[sidx * 32 + lane] = (uint16_t)(incl - bits);
+            if (lane == 31) s->sbits[sidx] = incl;
+        }
     }
     __syncthreads();
-    uint32_t sbytes[4] = {0, 0, 0, 0}, comp = 0, lit_hdr = 0;
-    if (kind == kZKindHuf) {
-        for (uint32_t k = 0; k < streams; ++k) sbytes[k] = (s->v[kZvBits0 + k] >> 3) + 1;  // + the marker bit
-        comp = tree_bytes + (streams == 4 ? 6 : 0) + sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3];
-        lit_hdr = (streams == 1 || (B < 1024 && comp < 1024)) ? 3u : ((B < 16384 && comp < 16384) ? 4u : 5u);
-        if (streams == 1 && comp >= 1024) kind = kZKindRaw;
-        if (lit_hdr + comp + 1 >= B) kind = kZKindRaw;  // not smaller than the bytes themselves
-    }
-
-    // ---- payload ----------------------------------------------------------------------------------------------------------------------
-    const uint32_t payload = kind == kZKindHuf ? lit_hdr + comp + 1 : (kind == kZKindRle ? 1u : B);  // Huffman: literals section + "0 sequences"
+    // ---- sub-block kinds and sizes (one thread) -----------------------------------------------------------------------------
     if (tid == 0) {
-        const uint32_t bsize = kind == kZKindRle ? B : payload;
-        const uint32_t bh = (last ? 1u : 0u) | ((kind == kZKindHuf ? 2u : kind == kZKindRle ? 1u : 0u) << 1) | (bsize << 3);
-        blk[0] = (uint8_t)bh; blk[1] = (uint8_t)(bh >> 8); blk[2] = (uint8_t)(bh >> 16);
-    }
-    if (kind == kZKindHuf) {
-        uint8_t* lit = blk + 3;
-        if (tid == 0) {
-            const uint32_t sf = lit_hdr == 3 ? (streams == 1 ? 0u : 1u) : (lit_hdr == 4 ? 2u : 3u);
-            uint64_t v = 2u | (sf << 2);
-            if (lit_hdr == 3) v |= ((uint64_t)B << 4) | ((uint64_t)comp << 14);
-            else if (lit_hdr == 4) v |= ((uint64_t)B << 4) | ((uint64_t)comp << 18);
-            else v |= ((uint64_t)B << 4) | ((uint64_t)comp << 22);
-            for (uint32_t k = 0; k < lit_hdr; ++k) lit[k] = (uint8_t)(v >> (8 * k));
-        }
-        for (uint32_t k = tid; k < tree_bytes; k += kZencThreads) lit[lit_hdr + k] = s->tree[k];
-        uint8_t* body = lit + lit_hdr + tree_bytes;
-        if (streams == 4) {
-            if (tid < 3) { body[2 * tid] = (uint8_t)sbytes[tid]; body[2 * tid + 1] = (uint8_t)(sbytes[tid] >> 8); }
-            body += 6;
-        }
-        __syncthreads();  // byte-wise header writes land before the word-wise stream writes next to them
-        // each stream starts at a byte position; the bit writer works on aligned words, so shift by the byte phase
-        if (wid < streams) {
-            uint32_t so = 0;
-            for (uint32_t k = 0; k < wid; ++k) so += sbytes[k];
-            uint8_t* sp = body + so;
-            const uint32_t phase = (uint32_t)((uintptr_t)sp & 3u);
-            zenc_stream_write(s->code, src + s_off, s_cnt, lane, chunk, lane_bit0 + 8 * phase, sp - phase);
-            if (lane == 0) {  // the marker bit above the last bit
-                const uint32_t mb = s->v[kZvBits0 + wid] + 8 * phase;
-                atomicOr(reinterpret_cast<uint32_t*>(sp - phase) + (mb >> 5), 1u << (mb & 31u));
+        uint32_t off = pre;
+        if (kind == kZKindHuf) {
+            bool tree_out = false, any = false;
+            for (uint32_t q = 0; q < nsub; ++q) {
+                const ZSub sb = zenc_sub(B, q);
+                uint32_t payload = sb.bytes;
+                s->sub_kind[q] = kZKindRaw;
+                s->sub_tree[q] = 0;
+                if (sb.bytes >= 32) {
+                    uint32_t comp = (tree_out ? 0u : tree_bytes) + (sb.streams == 4 ? 6u : 0u);
+                    for (uint32_t j = 0; j < sb.streams; ++j) comp += (s->sbits[q * 4 + j] >> 3) + 1;  // + the marker bit
+                    const uint32_t lit_hdr = sb.streams == 1 ? 3u : 4u;  // 4 streams: 1024 <= regenerated size <= 8192 and comp below it
+                    const uint32_t huf = lit_hdr + comp + 1;             // + "0 sequences"
+                    if (huf < sb.bytes && comp < (sb.streams == 1 ? 1024u : 16384u)) {
+                        payload = huf;
+                        s->sub_kind[q] = kZKindHuf;
+                        s->sub_tree[q] = tree_out ? 0 : 1;
+                        tree_out = true;
+                        any = true;
+                    }
+                }
+                s->sub_off[q] = off;
+                off += 3 + payload;
             }
+            s->sub_off[nsub] = off;
+            if (!any) { kind = kZKindRaw; off = pre; }  // nothing gained anywhere: one Raw block for the group
         }
-    } else if (kind == kZKindRle) {
-        if (tid == 0) blk[3] = src[0];
-    } else {
-        for (uint32_t i = tid; i < B; i += kZencThreads) blk[3 + i] = src[i];
+        if (kind == kZKindRle) off = pre + 3 + 1;
+        else if (kind == kZKindRaw) off = pre + 3 + B;
+        s->v[kZvKind] = kind;
+        s->v[kZvTotal] = off;
     }
-    const uint32_t total = pre + 3 + payload;
+    __syncthreads();
+    kind = s->v[kZvKind];
+    const uint32_t total = s->v[kZvTotal];
 
-    // ---- position inside the frame (look-back over the frame's earlier blocks), copy out ----------------------------------------------------
+    // ---- position inside the frame: look-back over the frame's earlier groups -------------------------------------------------
     if (wid == 0) {
         uint64_t excl = 0;
-        if (bi == 0) {
+        if (gi == 0) {
             if (lane == 0) vbz_st_volatile_u64(p.status + b, kStInclusive | total);
         } else {
             if (lane == 0) vbz_st_volatile_u64(p.status + b, kStAggregate | total);
@@ -482,11 +586,95 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     __syncthreads();
     const uint64_t excl = s->excl;
     const uint64_t end = excl + total;
-    if (end <= rd.dst_cap) {
-        uint8_t* dst = p.dst + rd.dst_off + excl;
-        for (uint32_t i = tid; i < total; i += kZencThreads) dst[i] = s->stage[i];
+    const bool fits = end <= rd.dst_cap;
+    if (last && tid == 0) p.results[r] = fits ? (uint32_t)end : kErrZstd + p.err_add;  // ZSTD_compress: dstSize_tooSmall (vbz.cpp:201-204)
+    uint8_t* dst = p.dst + rd.dst_off + excl;
+
+    if (kind != kZKindHuf) {
+        if (!fits) return;
+        const uint32_t bh = (last ? 1u : 0u) | ((kind == kZKindRle ? 1u : 0u) << 1) | (B << 3);
+        if (tid == 0) {
+            for (uint32_t k = 0; k < pre; ++k) dst[k] = prebuf[k];
+            dst[pre] = (uint8_t)bh; dst[pre + 1] = (uint8_t)(bh >> 8); dst[pre + 2] = (uint8_t)(bh >> 16);
+            if (kind == kZKindRle) dst[pre + 3] = src[0];
+        }
+        if (kind == kZKindRaw)
+            for (uint32_t i = tid; i < B; i += kZencThreads) dst[pre + 3 + i] = src[i];
+        return;
     }
-    if (last && tid == 0) p.results[r] = end <= rd.dst_cap ? (uint32_t)end : kErrZstd + p.err_add;  // ZSTD_compress: dstSize_tooSmall (vbz.cpp:201-204)
+
+    // ---- pack: two sub-blocks at a time, four warps (= four streams) each ---------------------------------------------------------
+    const uint32_t half = wid >> 2, j = wid & 3u, ht = tid & 127u;
+    uint8_t* stage = s->stage[half];
+    for (uint32_t q0 = 0; q0 < nsub; q0 += 2) {
+        const uint32_t q = q0 + half;
+        const bool live = q < nsub;
+        const ZSub sb = zenc_sub(B, live ? q : 0);
+        const uint32_t skind = live ? s->sub_kind[q] : kZKindRaw;
+        const uint32_t front = (live && q == 0) ? pre : 0u;  // the frame's headers travel with its first sub-block
+        for (uint32_t i = ht; i < (kZEncSub + 96) / 16; i += 128) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        uint8_t* blk = stage + front;
+        uint32_t sbytes[4] = {0, 0, 0, 0};
+        uint32_t lit_hdr = 0, tb = 0;
+        if (live) {
+            const uint32_t out_bytes = s->sub_off[q + 1] - s->sub_off[q] - (q == 0 ? 0u : 0u);
+            const uint32_t payload = out_bytes - 3;
+            if (ht == 0) {
+                for (uint32_t k = 0; k < front; ++k) stage[k] = prebuf[k];
+                const bool blast = last && q + 1 == nsub;
+                const uint32_t bh = (blast ? 1u : 0u) | ((skind == kZKindHuf ? 2u : 0u) << 1) | (payload << 3);
+                blk[0] = (uint8_t)bh; blk[1] = (uint8_t)(bh >> 8); blk[2] = (uint8_t)(bh >> 16);
+            }
+            if (skind == kZKindHuf) {
+                tb = s->sub_tree[q] ? tree_bytes : 0u;
+                lit_hdr = sb.streams == 1 ? 3u : 4u;
+                uint32_t comp = tb + (sb.streams == 4 ? 6u : 0u);
+                for (uint32_t k = 0; k < sb.streams; ++k) { sbytes[k] = (s->sbits[q * 4 + k] >> 3) + 1; comp += sbytes[k]; }
+                uint8_t* lit = blk + 3;
+                if (ht == 0) {
+                    const uint32_t type = s->sub_tree[q] ? 2u : 3u;  // Compressed / Treeless
+                    uint32_t v = type | ((sb.streams == 1 ? 0u : 2u) << 2) | (sb.bytes << 4);
+                    v |= sb.streams == 1 ? (comp << 14) : (comp << 18);
+                    for (uint32_t k = 0; k < lit_hdr; ++k) lit[k] = (uint8_t)(v >> (8 * k));
+                }
+                for (uint32_t k = ht; k < tb; k += 128) lit[lit_hdr + k] = s->tree[k];
+                if (sb.streams == 4 && ht >= 32 && ht < 35) {
+                    const uint32_t k = ht - 32;
+                    lit[lit_hdr + tb + 2 * k] = (uint8_t)sbytes[k];
+                    lit[lit_hdr + tb + 2 * k + 1] = (uint8_t)(sbytes[k] >> 8);
+                }
+            } else {
+                const uint8_t* from = src + sb.start;
+                for (uint32_t i = ht; i < sb.bytes; i += 128) blk[3 + i] = from[i];
+            }
+        }
+        __syncthreads();  // byte-wise header writes land before the word-wise stream writes next to them
+        if (live && skind == kZKindHuf && j < sb.streams) {
+            uint8_t* body = blk + 3 + lit_hdr + tb + (sb.streams == 4 ? 6u : 0u);
+            uint32_t so = 0;
+            for (uint32_t k = 0; k < j; ++k) so += sbytes[k];
+            uint8_t* sp = body + so;
+            // each stream starts at a byte position; the bit writer works on aligned words, so shift by the byte phase
+            const uint32_t phase = (uint32_t)((uintptr_t)sp & 3u);
+            uint32_t* words = reinterpret_cast<uint32_t*>(sp - phase);
+            const uint32_t cnt = (sb.streams == 4 && j == 3) ? sb.bytes - 3 * sb.seg : sb.seg;
+            uint32_t lo, n, run[16];
+            zenc_lane_run(cnt, lane, &lo, &n);
+            zenc_load_run(src + sb.start + j * sb.seg + lo, n, run);
+            if (n) zenc_run_write(s->code, run, n, (uint32_t)lane_off[(q * 4 + j) * 32 + lane] + 8 * phase, words);
+            if (lane == 0) {  // the marker bit above the last bit
+                const uint32_t mb = s->sbits[q * 4 + j] + 8 * phase;
+                atomicOr(words + (mb >> 5), 1u << (mb & 31u));
+            }
+        }
+        __syncthreads();
+        if (live) {
+            const uint32_t o0 = q == 0 ? 0u : s->sub_off[q], o1 = s->sub_off[q + 1];  // sub-block 0 starts at 0 with the frame's headers
+            if (excl + o1 <= rd.dst_cap) zenc_copy_out(dst + o0, stage, o1 - o0, ht, 128);
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace vbz
