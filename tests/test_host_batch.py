@@ -66,10 +66,63 @@ def test_waves_match_oracle(backend, level, wave_mib, monkeypatch):
             assert blob == bp
 
 
+@pytest.mark.parametrize("upload", ["kernel", "dma"])
+@pytest.mark.parametrize("level", [0, 1])
+def test_transfer_kernels_any_alignment(level, upload, monkeypatch):
+    """Page-locked caller buffers are read and written in place by the transfer kernels (csrc/xfer_kernels.cuh), whatever
+    their byte alignment.  Runs on the emulator, which shares one address space with its "device"."""
+    _, batch, lib = product.get("cpusim")
+    monkeypatch.setenv("VBZ_CPUSIM_PINNED", "1")
+    monkeypatch.setenv("VBZ_B200_UPLOAD", upload)
+    monkeypatch.setenv("VBZ_B200_WAVE_MIB", "1")
+    rng = np.random.default_rng(77 + level)
+    lens = [int(x) for x in rng.integers(1, 60_000, 24)] + [0, 7, 8, 9, 40_000]
+    o = Options(True, 2, level, 1)
+    opts = CompressionOptions(True, 2, level, 1)
+    n = len(lens)
+    reads = [data_gen.nanopore_like(x, rng) for x in lens]
+    # sources back to back from an odd address (two runs: a gap after read 10); destinations at odd, spaced addresses
+    gaps = [5 if i == 11 else 0 for i in range(n)]
+    offs = np.cumsum([1] + [2 * lens[i] + gaps[i + 1] if i + 1 < n else 0 for i in range(n)])[:n]
+    src = np.zeros(int(offs[-1]) + 2 * lens[-1] + 64, np.uint8)
+    for a, off in zip(reads, offs):
+        src[int(off):int(off) + a.nbytes] = a.view(np.uint8)
+    caps = [int(lib.vbz_max_compressed_size(2 * x, ctypes.byref(opts))) for x in lens]
+    coffs = np.cumsum([3] + [c + 3 for c in caps])[:n]
+    comp = np.full(int(coffs[-1]) + caps[-1] + 64, 0xEE, np.uint8)
+    back = np.full(src.size, 0xDD, np.uint8)
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    srcp = (vp * n)(*[src.ctypes.data + int(x) for x in offs])
+    cp = (vp * n)(*[comp.ctypes.data + int(x) for x in coffs])
+    bp = (vp * n)(*[back.ctypes.data + int(x) for x in offs])
+    ssz = (u32 * n)(*[2 * x for x in lens])
+    ccap = (u32 * n)(*caps)
+    res_c, res_d = (u32 * n)(), (u32 * n)()
+    l0 = batch.kernel_launches
+    assert lib.vbz_b200_compress_batch(batch.ctx, srcp, ssz, cp, ccap, res_c, n, ctypes.byref(opts), 1) == 0, lib.vbz_b200_last_error()
+    assert lib.vbz_b200_decompress_batch(batch.ctx, cp, res_c, bp, ssz, res_d, n, ctypes.byref(opts), 1) == 0, lib.vbz_b200_last_error()
+    assert batch.kernel_launches > l0
+    for i, a in enumerate(reads):
+        assert res_d[i] == a.nbytes
+        blob = comp[int(coffs[i]):int(coffs[i]) + res_c[i]].tobytes()
+        if level == 0:
+            rp, bpo = port.compress(a, o, sized=True)
+            assert res_c[i] == rp and blob == bpo
+        else:
+            r2, dec = port.decompress(blob, o, a.nbytes, sized=True)
+            assert r2 == a.nbytes and dec == a.tobytes()
+        assert back[int(offs[i]):int(offs[i]) + a.nbytes].tobytes() == a.tobytes()
+        # nothing outside a read's own bytes is written
+        end = int(coffs[i]) + res_c[i]
+        assert (comp[end:end + 3] == 0xEE).all() and (comp[int(coffs[i]) - 3:int(coffs[i])] == 0xEE).all()
+    assert back[0] == 0xDD and (back[int(offs[-1]) + 2 * lens[-1]:] == 0xDD).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("level", [0, 1])
 def test_direct_dma_from_pinned_buffers(level):
-    """Page-locked caller buffers are read and written in place by the DMA engine (no staging copy)."""
+    """Page-locked caller buffers are read and written in place by the device (transfer kernels, or run-by-run DMA
+    for host-contiguous inputs), no staging copy."""
     import torch
     _, batch, lib = product.get("gpu")
     rng = np.random.default_rng(5)
@@ -92,15 +145,16 @@ def test_direct_dma_from_pinned_buffers(level):
     ssz = (u32 * n)(*[int(x) * 2 for x in lens])
     ccap = (u32 * n)(*caps)
     res_c, res_d = (u32 * n)(), (u32 * n)()
-    for path in ("direct", "staged"):
-        os.environ["VBZ_B200_HOST_PATH"] = path
+    for path in ("kernel", "dma", "staged"):
+        os.environ["VBZ_B200_HOST_PATH"] = "staged" if path == "staged" else "auto"
+        os.environ["VBZ_B200_UPLOAD"] = "dma" if path == "dma" else "kernel"
         os.environ["VBZ_B200_WAVE_MIB"] = "8"
         try:
             host_c.zero_(); host_back.zero_()
             assert lib.vbz_b200_compress_batch(batch.ctx, srcp, ssz, cp, ccap, res_c, n, ctypes.byref(opts), 1) == 0, lib.vbz_b200_last_error()
             assert lib.vbz_b200_decompress_batch(batch.ctx, cp, res_c, bp, ssz, res_d, n, ctypes.byref(opts), 1) == 0, lib.vbz_b200_last_error()
         finally:
-            del os.environ["VBZ_B200_HOST_PATH"], os.environ["VBZ_B200_WAVE_MIB"]
+            del os.environ["VBZ_B200_HOST_PATH"], os.environ["VBZ_B200_WAVE_MIB"], os.environ["VBZ_B200_UPLOAD"]
         assert list(res_d) == [int(x) * 2 for x in lens]
         assert torch.equal(host_in, host_back), path
         if level == 0:

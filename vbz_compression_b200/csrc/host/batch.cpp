@@ -7,6 +7,8 @@
 // including the order in which option / size errors are detected.  All sample arithmetic happens in
 // the kernels; the host only validates sizes, lays buffers out and moves bytes.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -55,6 +57,45 @@ bool PinBuf::ensure(size_t n)
 }
 void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
+bool StageRing::init()
+{
+    for (cudaEvent_t& e : ev)
+        if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return false;
+    return true;
+}
+void* StageRing::take(size_t n)
+{
+    cur = (cur + 1) % kEntries;
+    if (!cuda_ok(cudaEventSynchronize(ev[cur]), "cudaEventSynchronize")) return nullptr;
+    if (!buf[cur].ensure(n ? n : 1)) return nullptr;
+    return buf[cur].p;
+}
+bool StageRing::mark(cudaStream_t s) { return cuda_ok(cudaEventRecord(ev[cur], s), "cudaEventRecord"); }
+void StageRing::release()
+{
+    for (PinBuf& b : buf) b.release();
+    for (cudaEvent_t& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+}
+
+static bool zero_device(vbz_b200_ctx* ctx, void* d, size_t bytes, cudaStream_t stream)
+{
+    const int e = vbzk_zero_words(d, bytes, stream);
+    if (e) { cuda_ok((cudaError_t)e, "reset device state"); return false; }
+    ctx->launches += 1;
+    return true;
+}
+// copies n bytes of descriptors to the device through the pinned ring, without waiting for the stream
+static bool upload_descriptors(vbz_b200_ctx* ctx, void* d_to, const void* from, size_t n, cudaStream_t stream)
+{
+    void* h = ctx->stage.take(n + 4);
+    if (!h) return false;
+    memcpy(h, from, n);
+    const int e = vbzk_copy_words(d_to, h, (n + 3) & ~(size_t)3, stream);  // by kernel: never queues behind a wave's DMA
+    if (e) { cuda_ok((cudaError_t)e, "upload descriptors"); return false; }
+    ctx->launches += 1;
+    return ctx->stage.mark(stream);
+}
+
 static inline uint64_t align16(uint64_t v) { return (v + 15) & ~(uint64_t)15; }
 
 // One read of a device-resident batch as the host sees it.
@@ -78,12 +119,7 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     if (n == 0) return 0;
     if (kind.half) {  // v1 nibble packing of int8: one warp per read, no tiles, no look-back (csrc/svb_half_kernels.cuh)
         if (!ctx->d_reads.ensure((size_t)n * sizeof(SvbRead))) return -1;
-        if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
-        if (!ctx->h_reads.ensure((size_t)n * sizeof(SvbRead))) return -1;
-        memcpy(ctx->h_reads.p, reads.data(), (size_t)n * sizeof(SvbRead));
-        if (!cuda_ok(cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.p, (size_t)n * sizeof(SvbRead), cudaMemcpyHostToDevice, stream), "upload descriptors") ||
-            !cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord"))
-            return -1;
+        if (!upload_descriptors(ctx, ctx->d_reads.p, reads.data(), (size_t)n * sizeof(SvbRead), stream)) return -1;
         SvbParams p;
         memset(&p, 0, sizeof(p));
         p.src = d_src;
@@ -112,14 +148,8 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
         !ctx->d_status.ensure((status_words + 1) * 8) || (decode && !ctx->d_wtoff.ensure((size_t)n_tiles * kSvbWarps * 4)) ||
         (kind.mode == kModeI16X86 && !ctx->d_issue.ensure((size_t)n_tiles * 32)))
         return -1;
-    // the pinned staging may still be feeding the previous batch's upload
-    if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
-    if (!ctx->h_reads.ensure((size_t)n * sizeof(SvbRead))) return -1;
-    memcpy(ctx->h_reads.p, reads.data(), (size_t)n * sizeof(SvbRead));
-    if (!cuda_ok(cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.p, (size_t)n * sizeof(SvbRead), cudaMemcpyHostToDevice, stream), "upload descriptors"))
-        return -1;
-    if (!cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord")) return -1;
-    if (!cuda_ok(cudaMemsetAsync(ctx->d_status.p, 0, (status_words + 1) * 8, stream), "reset look-back state")) return -1;
+    if (!upload_descriptors(ctx, ctx->d_reads.p, reads.data(), (size_t)n * sizeof(SvbRead), stream)) return -1;
+    if (!zero_device(ctx, ctx->d_status.p, (status_words + 1) * 8, stream)) return -1;
 
     int e = vbzk_svb_fill_tiles(ctx->d_reads.as<VbzkSvbRead>(), n, tile_values, ctx->d_tiles.as<uint32_t>(), stream);
     if (e) { cuda_ok((cudaError_t)e, "svb_fill_tiles launch"); return -1; }
@@ -140,6 +170,7 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
     p.n_reads = n;
     p.n_tiles = n_tiles;
     { const char* dbg = getenv("VBZ_B200_DEBUG"); p.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
+    p.ctas_per_sm = ctx->codec_ctas_per_sm;
     const VbzkSvbParams* pp = reinterpret_cast<const VbzkSvbParams*>(&p);
     if (decode) {
         e = vbzk_svb_key_offsets(kind.isz, kind.mode, pp, stream);
@@ -168,12 +199,8 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
         !ctx->d_zunits.ensure((size_t)unit_cap * sizeof(ZstdUnit)) || !ctx->d_zgroups.ensure((size_t)unit_cap * sizeof(ZstdGroup)) ||
         !ctx->d_zgeneral.ensure((size_t)n * 4))
         return -1;
-    if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
-    if (!ctx->h_zreads.ensure(bytes)) return -1;
-    memcpy(ctx->h_zreads.p, reads.data(), bytes);
-    if (!cuda_ok(cudaMemcpyAsync(ctx->d_zreads.p, ctx->h_zreads.p, bytes, cudaMemcpyHostToDevice, stream), "upload frame descriptors") ||
-        !cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord") ||
-        !cuda_ok(cudaMemsetAsync(ctx->d_zcounter.p, 0, 256, stream), "reset work counter"))
+    if (!upload_descriptors(ctx, ctx->d_zreads.p, reads.data(), bytes, stream) ||
+        !zero_device(ctx, ctx->d_zcounter.p, 256, stream))
         return -1;
     ZstdDecParams p;
     p.src = d_src;
@@ -209,12 +236,8 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     const uint32_t n_blocks = (uint32_t)blocks;
     const size_t bytes = (size_t)n * sizeof(ZstdEncRead);
     if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zblocks.ensure((size_t)n_blocks * 4) || !ctx->d_zstatus.ensure((size_t)n_blocks * 8)) return -1;
-    if (!cuda_ok(cudaEventSynchronize(ctx->upload_done), "cudaEventSynchronize")) return -1;
-    if (!ctx->h_zreads.ensure(bytes)) return -1;
-    memcpy(ctx->h_zreads.p, reads.data(), bytes);
-    if (!cuda_ok(cudaMemcpyAsync(ctx->d_zreads.p, ctx->h_zreads.p, bytes, cudaMemcpyHostToDevice, stream), "upload frame descriptors") ||
-        !cuda_ok(cudaEventRecord(ctx->upload_done, stream), "cudaEventRecord") ||
-        !cuda_ok(cudaMemsetAsync(ctx->d_zstatus.p, 0, (size_t)n_blocks * 8, stream), "reset look-back state"))
+    if (!upload_descriptors(ctx, ctx->d_zreads.p, reads.data(), bytes, stream) ||
+        !zero_device(ctx, ctx->d_zstatus.p, (size_t)n_blocks * 8, stream))
         return -1;
     int e = vbzk_zstd_enc_fill_blocks(ctx->d_zreads.as<VbzkZstdEncRead>(), n, ctx->d_zblocks.as<uint32_t>(), stream);
     if (e) { cuda_ok((cudaError_t)e, "zstd_enc_fill_blocks launch"); return -1; }
@@ -393,19 +416,20 @@ using namespace vbz;
 vbz_b200_ctx::~vbz_b200_ctx()
 {
     d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
-    h_reads.release(); h_results.release();
+    h_results.release(); stage.release();
     d_mid.release();
-    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); h_zreads.release();
+    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release();
     for (WaveSlot& w : slots) {
-        w.d_in.release(); w.d_out.release(); w.d_results.release();
+        w.d_in.release(); w.d_out.release(); w.d_results.release(); w.d_pack.release(); w.d_xin.release(); w.d_xout.release();
         w.h_in.release(); w.h_out.release(); w.h_results.release();
         if (w.ev_in) cudaEventDestroy(w.ev_in);
         if (w.ev_k) cudaEventDestroy(w.ev_k);
         if (w.ev_out) cudaEventDestroy(w.ev_out);
+        if (w.ev_outs) cudaEventDestroy(w.ev_outs);
     }
-    if (upload_done) cudaEventDestroy(upload_done);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
+    if (s_d2hs) cudaStreamDestroy(s_d2hs);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -429,11 +453,13 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
     bool ok = cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate") &&
-              cuda_ok(cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming), "cudaEventCreate");
+              cuda_ok(cudaStreamCreateWithFlags(&c->s_d2hs, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              c->stage.init();
     for (vbz_b200_ctx::WaveSlot& w : c->slots)
         ok = ok && cuda_ok(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming), "cudaEventCreate") &&
              cuda_ok(cudaEventCreateWithFlags(&w.ev_k, cudaEventDisableTiming), "cudaEventCreate") &&
-             cuda_ok(cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming), "cudaEventCreate");
+             cuda_ok(cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming), "cudaEventCreate") &&
+             cuda_ok(cudaEventCreateWithFlags(&w.ev_outs, cudaEventDisableTiming), "cudaEventCreate");
     if (!ok) {
         delete c;
         return nullptr;
@@ -518,14 +544,24 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
 }
 
 // ---- host-pointer batches -------------------------------------------------------------------------------------
-// A batch of host reads runs as WAVES of ~64 MiB through three slots (device in/out buffers, pinned staging,
-// events): while wave w is uploaded, wave w-1 is in the kernels and wave w-2 is downloaded and handed to the
-// caller, so the PCIe link (both directions) and the SMs work at the same time.  Two ways to move a read:
-//   direct  the caller's buffers are page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): the DMA
-//           engine reads and writes them in place, one copy per read;
-//   staged  pageable buffers: host threads (copy_pool.h) gather the wave into pinned staging, one DMA per wave.
-// Per-read results are known on the host one pipeline stage after the kernels ran; only then are a read's
-// bytes brought back (compress: exactly the bytes it produced).
+// A batch of host reads runs as WAVES (16 .. 256 MiB of input + output) through kWaveSlots slots (device in/out buffers, pinned staging,
+// events).  The host enqueues the upload, the kernels and the download of wave w, then turns to wave w-D
+// (D = kWaveSlots - 2), whose kernels have long finished, reads its per-read results, and finally hands wave w-D-1 to
+// the caller.  The upload queue therefore always holds D waves and the PCIe link (both directions) and the SMs work at
+// the same time; nothing on the host waits for a stream it has just fed.
+//
+// Moving bytes.  Measured on the B200 box (tools/probe/pcie_probe.cu, xfer_probe.cu): one large DMA runs at 55 GB/s,
+// but every cudaMemcpyAsync costs the copy engine ~4 us on top of its transfer time (8-14 us while the link is busy
+// in the other direction), so one copy per read (430 KB on average) delivers 36 GB/s, and 27 GB/s with both
+// directions busy.  Hence no per-read DMA anywhere.  Per read and per direction:
+//   direct  the caller's buffer is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): ONE transfer
+//           kernel per wave and direction (csrc/xfer_kernels.cuh) reads / writes the caller's buffers in place over
+//           the link, any alignment, exact sizes (a compressed read's size is taken from the device-side result, so
+//           the download does not wait for the host).  Uploads whose reads sit back to back in host memory are
+//           fetched run by run with large DMAs instead (the copy engine coexists best with a downloading kernel:
+//           48 GB/s each way) and spread to their 16-byte aligned slots by the same kernel, device to device;
+//   staged  pageable buffers: host threads (copy_pool.h) gather the wave's staged reads into pinned staging, which
+//           crosses the link as ONE DMA per wave.  Staged reads sit first in the wave's device buffers.
 namespace vbz {
 
 struct HostJob {
@@ -533,6 +569,8 @@ struct HostJob {
     uint32_t read;      // index into the caller's arrays
     uint32_t in_slot;   // bytes reserved in the wave's input / output buffers (multiples of 16)
     uint32_t out_slot;
+    bool in_direct = false, out_direct = false;
+    uint64_t src_dev = 0, dst_dev = 0;  // device-visible addresses of page-locked caller buffers
 };
 struct HostBatch {
     bool compress, sized;
@@ -544,144 +582,337 @@ struct HostBatch {
     vbz_size_t* results;
     std::vector<HostJob> jobs;
 };
-struct Wave { uint32_t k0, k1; uint64_t in_bytes, out_bytes; bool direct; };
+struct Wave {
+    uint32_t k0, k1;
+    uint64_t in_bytes, out_bytes;    // whole device buffers of the wave
+    uint64_t in_staged, out_staged;  // their leading parts that travel through pinned staging
+    uint64_t in_direct_bytes;        // bytes of the reads uploaded in place
+    uint32_t in_runs;                // host-contiguous runs among them
+    uint32_t n_in_direct, n_out_direct;
+};
 
-static bool host_pinned(const void* p)
+// page-locked and visible to the device?  -> its device-side address
+static bool host_pinned(const void* p, uint64_t* dev)
 {
 #ifdef VBZ_CPUSIM
-    (void)p;
-    return false;
+    *dev = (uint64_t)(uintptr_t)p;
+    return getenv("VBZ_CPUSIM_PINNED") != nullptr;  // the emulator's "device" shares the address space
 #else
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+    *dev = (uint64_t)(uintptr_t)a.devicePointer;
+    return true;
 #endif
 }
 
-static size_t wave_budget(uint64_t total)
+// Wave sizes.  Large waves amortise the per-wave costs (a dozen launches, the fixed part of the zstd kernels), but the
+// first wave's upload and the last wave's download overlap with nothing, so waves grow geometrically from 16 MiB to
+// the cap and shrink again towards the end of the batch.  VBZ_B200_WAVE_MIB fixes the size (tests).
+struct WaveSizer {
+    size_t fixed = 0, cap, prev = 0;
+    explicit WaveSizer(uint64_t total)
+    {
+        if (const char* e = getenv("VBZ_B200_WAVE_MIB")) { const long v = atol(e); if (v > 0) fixed = (size_t)v << 20; }
+        cap = (size_t)std::min<uint64_t>(std::max<uint64_t>(total / 12, 16ull << 20), 256ull << 20);
+    }
+    size_t next(uint64_t remaining)
+    {
+        if (fixed) return fixed;
+        uint64_t b = prev ? 2 * (uint64_t)prev : (16ull << 20);
+        b = std::min<uint64_t>(std::min<uint64_t>(b, cap), remaining / 2);
+        prev = (size_t)std::max<uint64_t>(b, 16ull << 20);
+        return prev;
+    }
+};
+static uint32_t env_u32(const char* name, uint32_t dflt)
 {
-    if (const char* e = getenv("VBZ_B200_WAVE_MIB")) { const long v = atol(e); if (v > 0) return (size_t)v << 20; }
-    const uint64_t want = total / 24;  // enough waves that filling and draining the pipeline stays a small share
-    return (size_t)std::min<uint64_t>(std::max<uint64_t>(want, 8ull << 20), 96ull << 20);
+    if (const char* e = getenv(name)) { const long v = atol(e); if (v > 0) return (uint32_t)v; }
+    return dflt;
+}
+
+struct HostTrace {  // VBZ_B200_TRACE=1: where the host thread of a batch spends its time (stderr)
+    bool on = getenv("VBZ_B200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double acc[8] = {};
+    void lap(int k)
+    {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        acc[k] += std::chrono::duration<double, std::milli>(t - t0).count();
+        t0 = t;
+    }
+    // device-side timeline of the waves: events around upload / kernels / download
+    std::vector<cudaEvent_t> ev;
+    void mark(cudaStream_t s)
+    {
+#ifndef VBZ_CPUSIM
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+#else
+        (void)s;
+#endif
+    }
+    void timeline()
+    {
+#ifndef VBZ_CPUSIM
+        if (!on || ev.size() < 6) return;
+        const size_t waves = ev.size() / 6;
+        double sum[3] = {}, span = 0;
+        float ms = 0;
+        for (size_t w = 0; w < waves; ++w)
+            for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&ms, ev[w * 6 + 2 * k], ev[w * 6 + 2 * k + 1]); sum[k] += ms; }
+        cudaEventElapsedTime(&ms, ev[0], ev[waves * 6 - 1]);
+        span = ms;
+        fprintf(stderr, "[vbz_b200] device timeline: %zu waves in %.2f ms; per wave upload %.3f  kernels %.3f  download %.3f ms\n", waves, span,
+                sum[0] / waves, sum[1] / waves, sum[2] / waves);
+        for (size_t w = 0; w < waves && w < 8; ++w) {
+            float t[6];
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], ev[0], ev[w * 6 + k]);
+            fprintf(stderr, "[vbz_b200]   wave %zu: upload %.3f-%.3f  kernels %.3f-%.3f  download %.3f-%.3f\n", w, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+#endif
+    }
+    void report(uint32_t reads, uint32_t waves, uint32_t dma_in, uint32_t dma_out, uint32_t xfers)
+    {
+        if (on)
+            fprintf(stderr, "[vbz_b200] %u reads, %u waves, %u+%u DMAs, %u transfer kernels: plan %.2f  gather %.2f  upload-issue %.2f  launch %.2f  wait-kernels %.2f  staged-d2h-issue %.2f  wait-download %.2f  scatter %.2f ms\n",
+                    reads, waves, dma_in, dma_out, xfers, acc[0], acc[6], acc[1], acc[2], acc[3], acc[4], acc[5], acc[7]);
+    }
+};
+
+// uploads the records and launches one transfer kernel
+static bool enqueue_xfer(vbz_b200_ctx* ctx, DevBuf& d_records, std::vector<XferRead>& recs, const uint32_t* d_sizes, uint32_t ctas, cudaStream_t stream)
+{
+    if (recs.empty()) return true;
+    uint32_t chunks = 0;
+    for (XferRead& r : recs) { r.first_chunk = chunks; chunks += xfer_chunks_of(r.n); }
+    const size_t bytes = recs.size() * sizeof(XferRead);
+    if (!d_records.ensure(bytes) || !upload_descriptors(ctx, d_records.p, recs.data(), bytes, stream)) return false;
+    XferParams p;
+    p.reads = d_records.as<XferRead>();
+    p.sizes = d_sizes;
+    p.n_reads = (uint32_t)recs.size();
+    p.n_chunks = chunks;
+    const int e = vbzk_xfer(reinterpret_cast<const VbzkXferParams*>(&p), ctas, stream);
+    if (e) { cuda_ok((cudaError_t)e, "xfer launch"); return false; }
+    ctx->launches += 1;
+    return true;
 }
 
 static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
 {
     const uint32_t m = (uint32_t)b.jobs.size();
     if (m == 0) return 0;
+    HostTrace tr;
     // ---- plan the waves -------------------------------------------------------------------------------------------
     uint64_t total = 0;
     for (const HostJob& h : b.jobs) total += (uint64_t)h.in_slot + h.out_slot;
-    const size_t budget = wave_budget(total);
+    WaveSizer sizer(total);
+    uint64_t planned = 0;
+    const char* force = getenv("VBZ_B200_HOST_PATH");  // "staged": never touch caller buffers from the device (experiments and tests)
+    const bool never_direct = force && force[0] == 's';
+    const char* up_mode = getenv("VBZ_B200_UPLOAD");   // "kernel" / "dma": how page-locked inputs are fetched (default: by run length)
+    const uint32_t up_ctas = env_u32("VBZ_B200_XFER_UP_CTAS", 32), spread_ctas = env_u32("VBZ_B200_XFER_SPREAD_CTAS", 148),
+                   down_ctas = env_u32("VBZ_B200_XFER_DOWN_CTAS", 16);
     std::vector<Wave> waves;
-    uint64_t max_in = 0, max_out = 0;
+    uint64_t max_in = 0, max_out = 0, max_in_staged = 0, max_out_staged = 0, max_in_direct = 0;
     uint32_t max_jobs = 0;
-    bool any_staged = false;
-    const char* force = getenv("VBZ_B200_HOST_PATH");  // "staged" / "direct": experiments and tests
     for (uint32_t k = 0; k < m;) {
-        Wave w = {k, k, 0, 0, true};
-        while (w.k1 < m && (w.k1 == w.k0 || w.in_bytes + w.out_bytes + b.jobs[w.k1].in_slot + b.jobs[w.k1].out_slot <= budget)) {
-            HostJob& h = b.jobs[w.k1];
-            h.j.src_off = w.in_bytes;
-            h.j.dst_off = w.out_bytes;
-            w.in_bytes += h.in_slot;
-            w.out_bytes += h.out_slot;
+        Wave w = {k, k, 0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t budget = sizer.next(total - planned);
+        uint64_t sum = 0;
+        while (w.k1 < m && (w.k1 == w.k0 || sum + b.jobs[w.k1].in_slot + b.jobs[w.k1].out_slot <= budget)) {
+            sum += (uint64_t)b.jobs[w.k1].in_slot + b.jobs[w.k1].out_slot;
             ++w.k1;
         }
-        // direct DMA needs page-locked buffers on both sides and reads large enough to be worth a copy call each
-        const uint32_t cnt = w.k1 - w.k0;
-        w.direct = (w.in_bytes + w.out_bytes) / cnt >= (64u << 10);
-        if (force && force[0] == 's') w.direct = false;
-        for (uint32_t q = w.k0; q < w.k1 && w.direct; ++q)
-            w.direct = (b.jobs[q].j.src_size == 0 || host_pinned(b.src[b.jobs[q].read])) && host_pinned(b.dst[b.jobs[q].read]);
-        any_staged |= !w.direct;
+        planned += sum;
+        uint64_t prev_end = 0;
+        for (uint32_t q = w.k0; q < w.k1; ++q) {
+            HostJob& h = b.jobs[q];
+            h.in_direct = !never_direct && h.j.src_size != 0 && host_pinned(b.src[h.read], &h.src_dev);
+            h.out_direct = !never_direct && host_pinned(b.dst[h.read], &h.dst_dev);
+            if (h.in_direct) {
+                if (w.n_in_direct == 0 || (uint64_t)(uintptr_t)b.src[h.read] != prev_end) ++w.in_runs;
+                prev_end = (uint64_t)(uintptr_t)b.src[h.read] + h.j.src_size;
+                w.in_direct_bytes += h.j.src_size;
+                ++w.n_in_direct;
+            }
+            w.n_out_direct += h.out_direct;
+        }
+        for (int pass = 0; pass < 2; ++pass) {  // staged reads first, then the direct ones
+            for (uint32_t q = w.k0; q < w.k1; ++q) {
+                HostJob& h = b.jobs[q];
+                if ((int)h.in_direct == pass) { h.j.src_off = w.in_bytes; w.in_bytes += h.in_slot; }
+                if ((int)h.out_direct == pass) { h.j.dst_off = w.out_bytes; w.out_bytes += h.out_slot; }
+            }
+            if (pass == 0) { w.in_staged = w.in_bytes; w.out_staged = w.out_bytes; }
+        }
         max_in = std::max(max_in, w.in_bytes);
         max_out = std::max(max_out, w.out_bytes);
-        max_jobs = std::max(max_jobs, cnt);
+        max_in_staged = std::max(max_in_staged, w.in_staged);
+        max_out_staged = std::max(max_out_staged, w.out_staged);
+        max_in_direct = std::max(max_in_direct, w.in_direct_bytes);
+        max_jobs = std::max(max_jobs, w.k1 - w.k0);
         waves.push_back(w);
         k = w.k1;
     }
     const uint32_t W = (uint32_t)waves.size();
     const int S = W > 1 ? vbz_b200_ctx::kWaveSlots : 1;
+    const uint32_t D = W > 1 ? (uint32_t)S - 2 : 1;  // waves between enqueueing the kernels and looking at their results
     for (int s = 0; s < S; ++s) {
         vbz_b200_ctx::WaveSlot& sl = ctx->slots[s];
         if (!sl.d_in.ensure(max_in + 16) || !sl.d_out.ensure(max_out + 16) || !sl.d_results.ensure((size_t)max_jobs * 4) ||
             !sl.h_results.ensure((size_t)max_jobs * 4))
             return -1;
-        if (any_staged && (!sl.h_in.ensure(max_in + 16) || !sl.h_out.ensure(max_out + 16))) return -1;
+        if ((max_in_staged && !sl.h_in.ensure(max_in_staged + 16)) || (max_out_staged && !sl.h_out.ensure(max_out_staged + 16))) return -1;
     }
-    cudaStream_t sk = ctx->stream, sh = ctx->s_h2d, sd = ctx->s_d2h;
+    cudaStream_t sk = ctx->stream, sh = ctx->s_h2d, sd = ctx->s_d2h, sds = ctx->s_d2hs;
+    struct CtaCap {  // the codec shares the SMs with the transfer kernels for the duration of the batch
+        vbz_b200_ctx* c;
+        CtaCap(vbz_b200_ctx* ctx, uint32_t v) : c(ctx) { c->codec_ctas_per_sm = v; }
+        ~CtaCap() { c->codec_ctas_per_sm = 0; }
+    } cap(ctx, W > 1 ? env_u32("VBZ_B200_CODEC_CTAS_PER_SM", 3) : 0);
+    tr.lap(0);
     std::vector<CopyTask> copies;
     std::vector<ReadJob> wave_jobs;
+    std::vector<XferRead> recs;
+    uint32_t dma_in = 0, dma_out = 0, xfers = 0;
     int rc = 0;
 
-    // one iteration: upload + launch wave w, collect the results of wave w-1 and start its download, deliver wave w-2
-    for (uint32_t it = 0; it < W + 2 && rc == 0; ++it) {
+    // one iteration: upload + launch + download wave w, collect the results of wave w-D, deliver wave w-D-1
+    for (uint32_t it = 0; it < W + D + 1 && rc == 0; ++it) {
         if (it < W) {
             const Wave& w = waves[it];
             vbz_b200_ctx::WaveSlot& sl = ctx->slots[it % S];
             uint8_t* d_in = sl.d_in.as<uint8_t>();
-            if (w.direct) {
-                for (uint32_t q = w.k0; q < w.k1; ++q) {
-                    const HostJob& h = b.jobs[q];
-                    if (h.j.src_size && !cuda_ok(cudaMemcpyAsync(d_in + h.j.src_off, b.src[h.read], h.j.src_size, cudaMemcpyHostToDevice, sh), "H2D input")) { rc = -1; break; }
-                }
-            } else {
+            uint8_t* d_out = sl.d_out.as<uint8_t>();
+            tr.mark(sh);
+            if (w.in_staged) {
                 copies.clear();
                 for (uint32_t q = w.k0; q < w.k1; ++q) {
                     const HostJob& h = b.jobs[q];
-                    if (h.j.src_size) copies.push_back({sl.h_in.as<uint8_t>() + h.j.src_off, b.src[h.read], h.j.src_size});
+                    if (!h.in_direct && h.j.src_size) copies.push_back({sl.h_in.as<uint8_t>() + h.j.src_off, b.src[h.read], h.j.src_size});
                 }
                 CopyPool::instance().run(copies);
-                if (!cuda_ok(cudaMemcpyAsync(d_in, sl.h_in.p, w.in_bytes, cudaMemcpyHostToDevice, sh), "H2D input")) rc = -1;
+                tr.lap(6);
+                if (!cuda_ok(cudaMemcpyAsync(d_in, sl.h_in.p, w.in_staged, cudaMemcpyHostToDevice, sh), "H2D input")) { rc = -1; break; }
+                ++dma_in;
+            }
+            if (w.n_in_direct) {
+                // long host-contiguous runs: a DMA per run into d_pack, then device-to-device into the slots; else straight from the host
+                bool by_dma = w.in_direct_bytes / w.in_runs >= (2u << 20);
+                if (up_mode) by_dma = up_mode[0] == 'd';
+                if (by_dma && !sl.d_pack.ensure(max_in_direct + 16)) { rc = -1; break; }
+                uint8_t* d_pack = sl.d_pack.as<uint8_t>();
+                recs.clear();
+                uint64_t run_src = 0, run_len = 0, run_pack = 0, packed = 0;
+                for (uint32_t q = w.k0; q < w.k1 && rc == 0; ++q) {
+                    const HostJob& h = b.jobs[q];
+                    if (!h.in_direct) continue;
+                    uint64_t from = h.src_dev;
+                    if (by_dma) {
+                        const uint64_t host_at = (uint64_t)(uintptr_t)b.src[h.read];
+                        if (run_len && host_at != run_src + run_len) {
+                            if (!cuda_ok(cudaMemcpyAsync(d_pack + run_pack, (const void*)(uintptr_t)run_src, run_len, cudaMemcpyHostToDevice, sh), "H2D input")) rc = -1;
+                            ++dma_in;
+                            run_len = 0;
+                        }
+                        if (run_len == 0) { run_src = host_at; run_pack = packed; }
+                        from = (uint64_t)(uintptr_t)(d_pack + packed);
+                        run_len += h.j.src_size;
+                        packed += h.j.src_size;
+                    }
+                    recs.push_back({from, (uint64_t)(uintptr_t)(d_in + h.j.src_off), h.j.src_size, 0, 0, 0});
+                }
+                if (rc == 0 && by_dma && run_len) {
+                    if (!cuda_ok(cudaMemcpyAsync(d_pack + run_pack, (const void*)(uintptr_t)run_src, run_len, cudaMemcpyHostToDevice, sh), "H2D input")) rc = -1;
+                    ++dma_in;
+                }
+                if (rc == 0 && !enqueue_xfer(ctx, sl.d_xin, recs, nullptr, by_dma ? spread_ctas : up_ctas, sh)) rc = -1;
+                ++xfers;
             }
             if (rc != 0) break;
+            tr.mark(sh);
+            tr.lap(1);
             wave_jobs.resize(w.k1 - w.k0);
             for (uint32_t q = w.k0; q < w.k1; ++q) wave_jobs[q - w.k0] = b.jobs[q].j;
-            // the kernels wait for the upload, and for the download that last used this slot's output buffer
+            // the kernels wait for the upload, and for the downloads that last used this slot's output buffer
             if (!cuda_ok(cudaEventRecord(sl.ev_in, sh), "cudaEventRecord") || !cuda_ok(cudaStreamWaitEvent(sk, sl.ev_in, 0), "cudaStreamWaitEvent") ||
-                (it >= (uint32_t)S && !cuda_ok(cudaStreamWaitEvent(sk, sl.ev_out, 0), "cudaStreamWaitEvent"))) { rc = -1; break; }
-            const int e = b.compress ? compress_device_impl(ctx, d_in, sl.d_out.as<uint8_t>(), wave_jobs, sl.d_results.as<uint32_t>(), b.kind, b.sized, sk)
-                                     : decompress_device_impl(ctx, d_in, sl.d_out.as<uint8_t>(), wave_jobs, sl.d_results.as<uint32_t>(), b.kind, b.sized, sk);
+                (it >= (uint32_t)S && (!cuda_ok(cudaStreamWaitEvent(sk, sl.ev_out, 0), "cudaStreamWaitEvent") ||
+                                       !cuda_ok(cudaStreamWaitEvent(sk, sl.ev_outs, 0), "cudaStreamWaitEvent")))) { rc = -1; break; }
+            tr.mark(sk);
+            const int e = b.compress ? compress_device_impl(ctx, d_in, d_out, wave_jobs, sl.d_results.as<uint32_t>(), b.kind, b.sized, sk)
+                                     : decompress_device_impl(ctx, d_in, d_out, wave_jobs, sl.d_results.as<uint32_t>(), b.kind, b.sized, sk);
             if (e != 0) { rc = -1; break; }
-            if (!cuda_ok(cudaMemcpyAsync(sl.h_results.p, sl.d_results.p, (size_t)(w.k1 - w.k0) * 4, cudaMemcpyDeviceToHost, sk), "D2H results") ||
-                !cuda_ok(cudaEventRecord(sl.ev_k, sk), "cudaEventRecord")) { rc = -1; break; }
+            if (const int ce = vbzk_copy_words(sl.h_results.p, sl.d_results.p, (size_t)(w.k1 - w.k0) * 4, sk)) { cuda_ok((cudaError_t)ce, "results to host"); rc = -1; break; }
+            ctx->launches += 1;
+            if (!cuda_ok(cudaEventRecord(sl.ev_k, sk), "cudaEventRecord")) { rc = -1; break; }
+            tr.mark(sk);
+            // download in place: the transfer kernel takes each read's size from the device-side result
+            if (!cuda_ok(cudaStreamWaitEvent(sd, sl.ev_k, 0), "cudaStreamWaitEvent")) { rc = -1; break; }
+            tr.mark(sd);
+            if (w.n_out_direct) {
+                recs.clear();
+                for (uint32_t q = w.k0; q < w.k1; ++q) {
+                    const HostJob& h = b.jobs[q];
+                    if (!h.out_direct) continue;
+                    const uint32_t most = b.compress ? std::min<uint32_t>(h.out_slot, b.dst_cap[h.read]) : h.j.dst_size;
+                    recs.push_back({(uint64_t)(uintptr_t)(d_out + h.j.dst_off), h.dst_dev, most, q - w.k0, 0, 0});
+                }
+                if (!enqueue_xfer(ctx, sl.d_xout, recs, sl.d_results.as<uint32_t>(), down_ctas, sd)) { rc = -1; break; }
+                ++xfers;
+            }
+            if (!cuda_ok(cudaEventRecord(sl.ev_out, sd), "cudaEventRecord")) { rc = -1; break; }
+            tr.mark(sd);
+            tr.lap(2);
         }
-        if (it >= 1 && it - 1 < W) {
-            const Wave& w = waves[it - 1];
-            vbz_b200_ctx::WaveSlot& sl = ctx->slots[(it - 1) % S];
+        if (it >= D && it - D < W) {
+            const Wave& w = waves[it - D];
+            vbz_b200_ctx::WaveSlot& sl = ctx->slots[(it - D) % S];
             if (!cuda_ok(cudaEventSynchronize(sl.ev_k), "batch kernels")) { rc = -1; break; }
+            tr.lap(3);
             const uint32_t* dres = sl.h_results.as<uint32_t>();
-            const uint8_t* d_out = sl.d_out.as<uint8_t>();
+            uint64_t staged_end = 0;  // the staged part of the output buffer, up to the last byte a read produced
             for (uint32_t q = w.k0; q < w.k1; ++q) {
                 const HostJob& h = b.jobs[q];
                 uint32_t r = dres[q - w.k0];
                 if (!is_error(r) && r > b.dst_cap[h.read]) r = b.sized ? kErrDestinationSize + 4 : kErrDestinationSize;  // (compress with a tight device slot)
                 b.results[h.read] = r;
-                if (is_error(r) || r == 0) continue;
-                uint8_t* to = w.direct ? (uint8_t*)b.dst[h.read] : sl.h_out.as<uint8_t>() + h.j.dst_off;
-                if (!cuda_ok(cudaMemcpyAsync(to, d_out + h.j.dst_off, r, cudaMemcpyDeviceToHost, sd), "D2H output")) { rc = -1; break; }
+                if (!is_error(r) && r != 0 && !h.out_direct) staged_end = std::max<uint64_t>(staged_end, h.j.dst_off + r);
             }
-            if (rc == 0 && !cuda_ok(cudaEventRecord(sl.ev_out, sd), "cudaEventRecord")) rc = -1;
-            if (rc != 0) break;
+            if (staged_end) {
+                if (!cuda_ok(cudaMemcpyAsync(sl.h_out.p, sl.d_out.p, staged_end, cudaMemcpyDeviceToHost, sds), "D2H output")) { rc = -1; break; }
+                ++dma_out;
+            }
+            if (!cuda_ok(cudaEventRecord(sl.ev_outs, sds), "cudaEventRecord")) { rc = -1; break; }
+            tr.lap(4);
         }
-        if (it >= 2) {
-            const Wave& w = waves[it - 2];
-            vbz_b200_ctx::WaveSlot& sl = ctx->slots[(it - 2) % S];
-            if (!cuda_ok(cudaEventSynchronize(sl.ev_out), "batch download")) { rc = -1; break; }
-            if (!w.direct) {
+        if (it >= D + 1) {
+            const Wave& w = waves[it - D - 1];
+            vbz_b200_ctx::WaveSlot& sl = ctx->slots[(it - D - 1) % S];
+            if (!cuda_ok(cudaEventSynchronize(sl.ev_out), "batch download") || !cuda_ok(cudaEventSynchronize(sl.ev_outs), "batch download")) { rc = -1; break; }
+            tr.lap(5);
+            if (w.out_staged) {
                 copies.clear();
                 for (uint32_t q = w.k0; q < w.k1; ++q) {
                     const HostJob& h = b.jobs[q];
                     const uint32_t r = b.results[h.read];
-                    if (!is_error(r) && r > 0) copies.push_back({b.dst[h.read], sl.h_out.as<uint8_t>() + h.j.dst_off, r});
+                    if (!h.out_direct && !is_error(r) && r > 0) copies.push_back({b.dst[h.read], sl.h_out.as<uint8_t>() + h.j.dst_off, r});
                 }
                 CopyPool::instance().run(copies);
+                tr.lap(7);
             }
         }
     }
+    tr.report(m, W, dma_in, dma_out, xfers);
+    if (rc == 0) tr.timeline();
     if (rc != 0) {  // leave nothing in flight that still points at the caller's buffers
-        cudaStreamSynchronize(sh); cudaStreamSynchronize(sk); cudaStreamSynchronize(sd);
+        cudaStreamSynchronize(sh); cudaStreamSynchronize(sk); cudaStreamSynchronize(sd); cudaStreamSynchronize(sds);
     }
     return rc;
 }

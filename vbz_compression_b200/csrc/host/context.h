@@ -31,32 +31,49 @@ struct PinBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// Pinned staging for descriptor uploads.  An upload reads its block asynchronously, so a block may only be rewritten
+// once the copy that used it has completed: kEntries blocks are handed out round robin, each guarded by the event of
+// its last upload - with several waves in flight the event of 16 uploads ago has long fired and take() never blocks.
+struct StageRing {
+    static constexpr int kEntries = 16;
+    PinBuf buf[kEntries];
+    cudaEvent_t ev[kEntries] = {};
+    int cur = 0;
+    bool init();
+    void* take(size_t n);          // nullptr on failure (last error set)
+    bool mark(cudaStream_t s);     // call after enqueueing the copy that reads the block returned by take()
+    void release();
+};
+
 }  // namespace vbz
 
 struct vbz_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t upload_done = nullptr;  // guards reuse of the pinned descriptor staging
+    vbz::StageRing stage;  // pinned descriptor staging
     uint64_t launches = 0;
+    uint32_t codec_ctas_per_sm = 0;  // != 0 while a host batch runs: room for the transfer kernels (SvbParams::ctas_per_sm)
 
     // descriptors and look-back state (stage 1)
     vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
-    vbz::PinBuf h_reads, h_results;
+    vbz::PinBuf h_results;
     // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
     vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zunits, d_zgroups, d_zgeneral;
-    vbz::PinBuf h_zreads;
     // intermediate stage-1 bytes of the two-stage paths
     vbz::DevBuf d_mid;
     // host-pointer API: a batch runs as WAVES through kWaveSlots slots so that the upload of wave w+1, the kernels of
     // wave w and the download of wave w-1 overlap (csrc/host/batch.cpp: run_host_batch)
-    static constexpr int kWaveSlots = 3;
+    static constexpr int kWaveSlots = 5;
     struct WaveSlot {
         vbz::DevBuf d_in, d_out, d_results;
+        vbz::DevBuf d_pack;         // host-contiguous runs of reads land here by DMA before they are spread to their slots
+        vbz::DevBuf d_xin, d_xout;  // transfer records of the wave (csrc/xfer_kernels.cuh)
         vbz::PinBuf h_in, h_out, h_results;
-        cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;  // upload done, kernels + results done, download done
+        // upload done; kernels + results done; download by kernel done; download of the staged part done
+        cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr, ev_outs = nullptr;
     };
     WaveSlot slots[kWaveSlots];
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_d2hs = nullptr;
 
     ~vbz_b200_ctx();
 };

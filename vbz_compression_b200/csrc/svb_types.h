@@ -60,6 +60,8 @@ struct SvbParams {
     uint32_t n_reads;
     uint32_t n_tiles;
     uint32_t debug;             // experiments only (VBZ_B200_DEBUG); 0 in production
+    uint32_t ctas_per_sm;       // int16 path: cap on the persistent CTAs per SM (0 = as many as fit).  The host-wave pipeline leaves
+                                // a quarter of every SM to the transfer kernels that run next to the codec (csrc/xfer_kernels.cuh)
 };
 
 // ---- stage 2 (zstd) ----------------------------------------------------------------------------------------
@@ -143,5 +145,31 @@ VBZ_HD uint32_t svb_tiles_of(uint32_t n_values, uint32_t tile_values)
     uint32_t t = (uint32_t)(((uint64_t)n_values + tile_values - 1) / tile_values);
     return t ? t : 1;  // an empty read still owns one (empty) tile: it writes the header and the result
 }
+
+// ---- host <-> device transfers of a wave by kernel (csrc/xfer_kernels.cuh) ------------------------------------------
+// One read of a transfer.  `n` is the byte count, unless the launch carries a device array of sizes (downloads
+// after compression: the size is the kernel-produced result): then bytes = sizes[idx] when that is a valid size
+// no larger than n, else nothing is copied (the host reports the error).
+struct XferRead {
+    uint64_t src;
+    uint64_t dst;
+    uint32_t n;
+    uint32_t idx;
+    uint32_t first_chunk;
+    uint32_t pad;
+};
+struct XferParams {
+    const XferRead* reads;
+    const uint32_t* sizes;  // nullptr: XferRead::n is exact
+    uint32_t n_reads;
+    uint32_t n_chunks;
+};
+
+constexpr uint32_t kXferThreads = 128;   // a CTA fits next to the codec's persistent CTAs (<= 16K registers)
+constexpr uint32_t kXferChunkVecs = 1024;  // 128-bit words of the destination per chunk (16 KiB)
+constexpr uint32_t kXferRows = 8;          // rows of 32 x 16 bytes a warp keeps in flight
+
+// chunks a read of at most n bytes can need, whatever its destination alignment
+VBZ_HD uint32_t xfer_chunks_of(uint32_t n) { return n / (16u * kXferChunkVecs) + 1; }
 
 }  // namespace vbz

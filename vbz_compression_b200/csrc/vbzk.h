@@ -41,6 +41,16 @@ uint32_t vbzk_zstd_enc_block_bytes(void);
 int vbzk_zstd_enc_fill_blocks(const struct VbzkZstdEncRead* d_reads, uint32_t n_reads, uint32_t* d_block_read, void* stream);
 int vbzk_zstd_encode(const struct VbzkZstdEncParams* params, void* stream);
 
+/* host <-> device transfer of a wave of reads by ONE kernel (csrc/xfer_kernels.cuh): either side may be page-locked host
+ * memory (its device-visible address) with any byte alignment */
+struct VbzkXferParams; /* == vbz::XferParams */
+uint32_t vbzk_xfer_chunks_of(uint32_t max_bytes);
+int vbzk_xfer(const struct VbzkXferParams* params, uint32_t ctas, void* stream);
+/* control-plane moves by kernel instead of the copy engine (see csrc/xfer_kernels.cuh): 16-byte aligned pointers, bytes a multiple
+ * of 4; src / dst may be page-locked host memory */
+int vbzk_copy_words(void* dst, const void* src, uint64_t bytes, void* stream);
+int vbzk_zero_words(void* dst, uint64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@
 #include "svb_half_kernels.cuh"
 #include "zstd_dec_kernels.cuh"
 #include "zstd_enc_kernels.cuh"
+#include "xfer_kernels.cuh"
 
 using namespace vbz;
 
@@ -66,16 +67,17 @@ static int launch_key_offsets(const SvbParams& p, void* stream)
 }
 // ---- int16 x86-semantics path (csrc/svb16_kernels.cuh): persistent CTAs, as many as are co-resident -----------
 template <class K>
-static uint32_t persistent_grid(K kernel, int threads, uint32_t smem, uint32_t n_tiles)
+static uint32_t persistent_grid(K kernel, int threads, uint32_t smem, uint32_t n_tiles, uint32_t ctas_per_sm)
 {
 #ifdef VBZ_CPUSIM
-    (void)kernel; (void)threads; (void)smem;
+    (void)kernel; (void)threads; (void)smem; (void)ctas_per_sm;
     return n_tiles < 3 ? n_tiles : 3;
 #else
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || sms <= 0 || per_sm <= 0)
         return n_tiles < 148 ? n_tiles : 148;
+    if (ctas_per_sm && (uint32_t)per_sm > ctas_per_sm) per_sm = (int)ctas_per_sm;
     const uint32_t g = (uint32_t)sms * (uint32_t)per_sm;
     return n_tiles < g ? n_tiles : g;
 #endif
@@ -85,7 +87,7 @@ template <class K>
 static int launch_persistent(K kernel, uint32_t smem, const SvbParams& p, uint32_t n_tiles, void* stream)
 {
     if (int e = VBZK_SET_SMEM(kernel, smem)) return e;
-    const uint32_t grid = persistent_grid(kernel, kS16Threads, smem, n_tiles);
+    const uint32_t grid = persistent_grid(kernel, kS16Threads, smem, n_tiles, p.ctas_per_sm);
 #ifdef VBZ_CPUSIM
     VBZ_LAUNCH(kernel, grid, kS16Threads, smem, (vbz_stream_t)stream, p);
     return 0;
@@ -166,7 +168,7 @@ extern "C" int vbzk_svb_half_decode(int zz, const VbzkSvbParams* params, void* s
 // ---- stage 2 (zstd) ---------------------------------------------------------------------------------------------
 extern "C" uint32_t vbzk_zstd_decode_grid(void)
 {
-    static const uint32_t g = persistent_grid(zstd_decode_kernel, kZdecWarps * 32, (uint32_t)(sizeof(ZWarp) * kZdecWarps), 0xFFFFFFFFu);
+    static const uint32_t g = persistent_grid(zstd_decode_kernel, kZdecWarps * 32, (uint32_t)(sizeof(ZWarp) * kZdecWarps), 0xFFFFFFFFu, 0);
     return g;
 }
 extern "C" uint64_t vbzk_zstd_decode_scratch_bytes(void) { return (uint64_t)vbzk_zstd_decode_grid() * kZdecWarps * kZLitStride; }
@@ -180,7 +182,7 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     // 2. the groups of units, a CTA of 64 threads each from a work counter; the grid is sized for the most there can be
     const uint32_t usmem = (uint32_t)sizeof(ZGroupSmem);
     if (int e = VBZK_SET_SMEM(zstd_units_kernel, usmem)) return e;
-    static const uint32_t ugrid_max = persistent_grid(zstd_units_kernel, kZUnitThreads, usmem, 0xFFFFFFFFu);
+    static const uint32_t ugrid_max = persistent_grid(zstd_units_kernel, kZUnitThreads, usmem, 0xFFFFFFFFu, 0);
     uint32_t ugrid = p.unit_cap < ugrid_max ? p.unit_cap : ugrid_max;
     if (ugrid) VBZ_LAUNCH(zstd_units_kernel, ugrid, kZUnitThreads, usmem, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
@@ -208,5 +210,33 @@ extern "C" int vbzk_zstd_encode(const VbzkZstdEncParams* params, void* stream)
     const uint32_t smem = (uint32_t)sizeof(ZEncSmem);
     if (int e = VBZK_SET_SMEM(zstd_encode_kernel, smem)) return e;
     VBZ_LAUNCH(zstd_encode_kernel, p.n_blocks, kZencThreads, smem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+
+// ---- host <-> device transfers of a wave by kernel (csrc/xfer_kernels.cuh) ----------------------------------------------
+extern "C" uint32_t vbzk_xfer_chunks_of(uint32_t n) { return xfer_chunks_of(n); }
+extern "C" int vbzk_xfer(const VbzkXferParams* params, uint32_t ctas, void* stream)
+{
+    const XferParams& p = *reinterpret_cast<const XferParams*>(params);
+    if (p.n_reads == 0 || p.n_chunks == 0) return 0;
+    const uint32_t need = (p.n_chunks + kXferThreads / 32 - 1) / (kXferThreads / 32);
+    VBZ_LAUNCH(xfer_kernel, need < ctas ? need : ctas, kXferThreads, 0, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+static uint32_t words_grid(uint64_t n_words)
+{
+    const uint64_t g = (n_words / 4 + 255) / 256;
+    return (uint32_t)(g < 1 ? 1 : (g > 1184 ? 1184 : g));
+}
+extern "C" int vbzk_copy_words(void* dst, const void* src, uint64_t bytes, void* stream)
+{
+    if (bytes == 0) return 0;
+    VBZ_LAUNCH(words_copy_kernel, words_grid(bytes / 4), 256, 0, (vbz_stream_t)stream, (uint32_t*)dst, (const uint32_t*)src, bytes / 4);
+    return VBZK_LAST_ERROR();
+}
+extern "C" int vbzk_zero_words(void* dst, uint64_t bytes, void* stream)
+{
+    if (bytes == 0) return 0;
+    VBZ_LAUNCH(words_zero_kernel, words_grid(bytes / 4), 256, 0, (vbz_stream_t)stream, (uint32_t*)dst, bytes / 4);
     return VBZK_LAST_ERROR();
 }
