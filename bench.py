@@ -4,17 +4,21 @@
     python bench.py --gpus N --steps K --warmup W                 (N > 1: launched under torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): transform-only VBZ {zigzag, int16, zstd 0, v0} on
-100,000 synthetic nanopore-like int16 reads of 10k-1M samples (lengths floor(exp(U[ln 1e4, ln 1e6])),
-numpy default_rng(20261017 + rank); ~43 GB raw per GPU), generated on the device.  One STEP = encode the
-whole batch, then decode it, inputs resident in HBM (`value`).  `--workload full` adds the zstd stage
-(configs[2]) once it exists on the device.
+Workload (default, BASELINE.json configs[2]): full VBZ {zigzag, int16, zstd 1, v1} - the options
+the reference's users run (pyvbz and the H5Z filter default to level 1) and the path BASELINE's north_star
+describes (stage 1 + zstd, compression ratio next to the reference's) - on synthetic nanopore-like int16
+reads of 10k-1M samples (lengths floor(exp(U[ln 1e4, ln 1e6])), numpy default_rng(20261017 + rank)), generated
+on the device: 40,000 reads (~17 GB raw) per GPU, the most that leaves room for the four batch-sized buffers
+of the two-stage path.  One STEP = encode the whole batch, then decode it, inputs resident in HBM (`value`).
+The same run also times the transform stage alone (configs[1], zstd level 0) on the same batch and reports it
+as `transform_stage`, with its own HBM roofline; `--workload transform` makes that the whole benchmark
+(100,000 reads, ~43 GB raw per GPU).
 
 Metric: raw-sample GB/s = raw bytes that went through the codec (encode pass + decode pass) / time.
 Weak scaling: every rank processes its own batch of the same shape; no data-path collective.
 
 Printed JSON line: see the contract in the task description; extra keys `encode_gbs`, `decode_gbs`,
-`ratio`, `roofline`, `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
+`ratio`, `roofline` (dominant kernel group + every stage), `transform_stage`, `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
 """
 import argparse
 import ctypes
@@ -42,9 +46,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="transform", choices=["transform", "full"])
-    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: 100,000 for the transform workload; 40,000 for "
-                    "--workload full, whose two-stage pipeline keeps a fourth batch-sized buffer in HBM)")
+    ap.add_argument("--workload", default="full", choices=["transform", "full"])
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: 40,000 for the full workload, whose two-stage pipeline keeps "
+                    "a fourth batch-sized buffer in HBM; 100,000 for --workload transform)")
     ap.add_argument("--cpu-sample-gib", type=float, default=1.0, help="raw GiB of the workload timed on the host cores")
     ap.add_argument("--e2e-sample-gib", type=float, default=2.0, help="raw GiB of the workload timed end to end with host buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -316,7 +320,13 @@ def main_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        # nvidia-smi's own start-up takes driver locks that stall kernel launches for most of a second: begin timing only
+        # once it is sampling
+        t_wait = time.time()
+        while len(sampler.lines) < 2 and time.time() - t_wait < 8.0:
+            time.sleep(0.05)
+    if world > 1:
+        dist.barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     l0 = batch.kernel_launches
     torch.cuda.synchronize()
@@ -330,6 +340,8 @@ def main_ours(args):
     enc_ms = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]
     dec_ms = [ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[-1])
+    if os.environ.get("VBZ_BENCH_VERBOSE"):
+        sys.stderr.write("rank %d encode ms %s decode ms %s\n" % (rank, [round(x, 2) for x in enc_ms], [round(x, 2) for x in dec_ms]))
     t = torch.tensor([total_ms, float(np.mean(enc_ms)), float(np.mean(dec_ms))], dtype=torch.float64, device=dev)
     b = torch.tensor([raw_bytes, comp_bytes], dtype=torch.float64, device=dev)
     if world > 1:
@@ -345,7 +357,7 @@ def main_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (per-launch algorithmic bytes / average launch time) --------------
+    # ---- per-stage times (CUDA events inside the library, on the launching stream) and the transform stage alone --------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -353,16 +365,97 @@ def main_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
-    alg_bytes = raw_bytes + (comp_bytes - 4 * n)  # samples once + control/data bytes once (per GPU, per launch)
-    enc_gbs_alg = alg_bytes / (float(np.mean(enc_ms)) * 1e-3) / 1e9
-    dec_gbs_alg = alg_bytes / (float(np.mean(dec_ms)) * 1e-3) / 1e9
-    dom = "svb_decode_kernel" if np.mean(dec_ms) >= np.mean(enc_ms) else "svb_encode_kernel"
-    ach = min(enc_gbs_alg, dec_gbs_alg)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "encode": {"achieved": enc_gbs_alg, "frac": enc_gbs_alg / peak, "ms": float(np.mean(enc_ms))},
-                "decode": {"achieved": dec_gbs_alg, "frac": dec_gbs_alg / peak, "ms": float(np.mean(dec_ms))},
-                "note": "launch time = CUDA events around the whole encode (decode) call on the launching stream: descriptor upload + tile table + look-back reset + the kernel"}
+    f1, f2 = ctypes.c_float(), ctypes.c_float()
+    lib.vbz_b200_set_stage_timing(batch.ctx, 1)
+    st = {"enc1": [], "enc2": [], "dec2": [], "dec1": []}
+    for _ in range(3):
+        encode()
+        assert lib.vbz_b200_stage_times(batch.ctx, ctypes.byref(f1), ctypes.byref(f2)) == 0
+        st["enc1"].append(f1.value); st["enc2"].append(f2.value)
+        decode()
+        assert lib.vbz_b200_stage_times(batch.ctx, ctypes.byref(f1), ctypes.byref(f2)) == 0
+        st["dec1"].append(f1.value); st["dec2"].append(f2.value)
+    lib.vbz_b200_set_stage_timing(batch.ctx, 0)
+    st = {k: float(np.mean(v)) for k, v in st.items()}
+
+    transform_stage = None
+    s1_bytes = comp_bytes - 4 * n  # stage-1 bytes of the batch (control + data bytes)
+    if args.workload == "full":
+        # BASELINE configs[1] on the same resident batch: {zigzag, int16, zstd 0, v0}
+        t_opts = options_for("transform")
+        t_caps = np.array([lib.vbz_b200_compress_bound(int(s), ctypes.byref(t_opts), 1) for s in src_size], np.uint32)
+        t_size = [None]
+
+        def t_encode():
+            batch.compress_device(d_src.data_ptr(), src_off, src_size, d_cmp.data_ptr(), dst_off, t_caps, d_res_c.data_ptr(), t_opts, True, stream)
+
+        def t_decode():
+            batch.decompress_device(d_cmp.data_ptr(), dst_off, t_size[0], d_back.data_ptr(), src_off, src_size, d_res_d.data_ptr(), t_opts, True, stream)
+
+        t_encode()
+        torch.cuda.synchronize()
+        t_size[0] = d_res_c.cpu().numpy().view(np.uint32).copy()
+        assert (t_size[0] < 0xFFFFFFF9).all()
+        s1_bytes = int(t_size[0].astype(np.int64).sum()) - 4 * n
+        d_back.zero_()
+        t_decode()
+        torch.cuda.synchronize()
+        assert (d_res_d.cpu().numpy().view(np.uint32) == src_size).all()
+        for i in (0, n // 3, n - 1):  # (the 16-byte padding between reads is never written: compare reads, not the buffer)
+            o, z = int(src_off[i]), int(src_size[i])
+            assert torch.equal(d_back[o:o + z], d_src[o:o + z]), "transform stage round trip mismatch"
+        for _ in range(2):
+            t_encode(); t_decode()
+        tk = max(3, min(args.steps, 5))
+        tev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * tk + 1)]
+        torch.cuda.synchronize()
+        tev[0].record()
+        for k in range(tk):
+            t_encode(); tev[2 * k + 1].record()
+            t_decode(); tev[2 * k + 2].record()
+        torch.cuda.synchronize()
+        te = float(np.mean([tev[2 * k].elapsed_time(tev[2 * k + 1]) for k in range(tk)]))
+        td = float(np.mean([tev[2 * k + 1].elapsed_time(tev[2 * k + 2]) for k in range(tk)]))
+        t_alg = raw_bytes + s1_bytes
+        transform_stage = {
+            "workload": "transform-only VBZ (delta+zigzag+StreamVByte, zstd level 0), int16 - BASELINE configs[1] on the same resident batch (this rank)",
+            "steps": tk, "value": combined_gbs(raw_bytes, te * 1e-3, td * 1e-3), "unit": "GB/s",
+            "encode_gbs": raw_bytes / te / 1e6, "decode_gbs": raw_bytes / td / 1e6, "ratio": (s1_bytes + 4 * n) / raw_bytes,
+            "roofline": {"bound": "hbm", "kernel": "svb16_decode_kernel" if td >= te else "svb16_encode_kernel", "peak": peak, "unit": "GB/s",
+                         "algorithmic_bytes_per_launch": t_alg, "achieved": t_alg / max(te, td) / 1e6, "frac": t_alg / max(te, td) / 1e6 / peak,
+                         "encode": {"achieved": t_alg / te / 1e6, "frac": t_alg / te / 1e6 / peak, "ms": te},
+                         "decode": {"achieved": t_alg / td / 1e6, "frac": t_alg / td / 1e6 / peak, "ms": td}}}
+        # back to the workload's own compressed batch for whatever follows
+        encode()
+        torch.cuda.synchronize()
+
+    # ---- roofline: algorithmic bytes of each kernel group / its live time; the headline entry is the slowest group ----------
+    # stage 1 moves the samples once and the control + data bytes once; the zstd stage moves the stage-1 bytes once and
+    # the frames once.  Times: CUDA events on the launching stream around the group's launches
+    # (descriptor upload + tables + look-back reset + the kernels).
+    alg1 = raw_bytes + s1_bytes
+    alg2 = s1_bytes + comp_bytes
+    groups = {}
+    if args.workload == "full":
+        groups = {"svb16_encode_kernel": (alg1, st["enc1"]), "zstd_encode_kernel": (alg2, st["enc2"]),
+                  "zstd_units_kernel (decode)": (alg2, st["dec2"]), "svb16_decode_kernel": (alg1, st["dec1"])}
+    else:
+        groups = {"svb16_encode_kernel": (alg1, float(np.mean(enc_ms))), "svb16_decode_kernel": (alg1, float(np.mean(dec_ms)))}
+    dom = max(groups, key=lambda k: groups[k][1])
+    stages = {k: {"algorithmic_bytes_per_launch": b_, "ms": ms_, "achieved": b_ / ms_ / 1e6, "frac": b_ / ms_ / 1e6 / peak} for k, (b_, ms_) in groups.items()}
+    traffic = None
+    try:  # DRAM bytes per algorithmic byte of the dominant kernel from the committed `ncu --set full` capture, scaled to this launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        key = dom.split(" ")[0]
+        if key in tj:
+            traffic = tj[key]["dram_bytes_per_algorithmic_byte"] * groups[dom][0]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": groups[dom][0], "stages": stages,
+                "note": "dominant = the kernel group with the largest share of the step; time = CUDA events on the launching stream around the "
+                        "group's launches (descriptor upload + tables + look-back reset + the kernels); the entropy stage is issue-bound integer "
+                        "work, its HBM fraction is reported for completeness; the HBM-bound kernels are the two svb16 ones (see transform_stage)"}
 
     # ---- CPU baseline (bounded sample of the same workload on the host cores) ---------------------------------
     cpu = None
@@ -389,7 +482,7 @@ def main_ours(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": workload_config(args, opts),
         "encode_gbs": all_raw / (enc_m * 1e-3) / 1e9, "decode_gbs": all_raw / (dec_m * 1e-3) / 1e9, "ratio": all_comp / all_raw,
-        "raw_bytes_per_gpu": raw_bytes, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        "raw_bytes_per_gpu": raw_bytes, "roofline": roofline, "transform_stage": transform_stage, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
     }
     print(json.dumps(line))
     if world > 1:

@@ -77,6 +77,12 @@ VBZ_EXPORT int vbz_b200_synchronize(vbz_b200_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 VBZ_EXPORT uint64_t vbz_b200_kernel_launches(vbz_b200_ctx* ctx);
 
+/* Optional: time the two stages of each *_device call with CUDA events on the call's stream (bench.py's roofline lines).
+ * vbz_b200_stage_times waits for the last call and returns the milliseconds its stage-1 kernels (delta + zigzag + StreamVByte,
+ * ref vbz/v0, vbz/v1) and its zstd-stage kernels (ref vbz/vbz.cpp:194-204, 236-272) took, launch overheads included. */
+VBZ_EXPORT int vbz_b200_set_stage_timing(vbz_b200_ctx* ctx, int on);
+VBZ_EXPORT int vbz_b200_stage_times(vbz_b200_ctx* ctx, float* stage1_ms, float* zstd_ms);
+
 #if defined(__cplusplus)
 }
 #endif

@@ -42,6 +42,9 @@ def bind(lib):
     lib.vbz_b200_stream.restype, lib.vbz_b200_stream.argtypes = vp, [vp]
     lib.vbz_b200_synchronize.restype, lib.vbz_b200_synchronize.argtypes = ctypes.c_int, [vp]
     lib.vbz_b200_kernel_launches.restype, lib.vbz_b200_kernel_launches.argtypes = ctypes.c_uint64, [vp]
+    lib.vbz_b200_set_stage_timing.restype, lib.vbz_b200_set_stage_timing.argtypes = ctypes.c_int, [vp, ctypes.c_int]
+    lib.vbz_b200_stage_times.restype = ctypes.c_int
+    lib.vbz_b200_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     for n in ("vbz_b200_compress_batch", "vbz_b200_decompress_batch"):
         f = getattr(lib, n)
         f.restype, f.argtypes = ctypes.c_int, [vp, ctypes.POINTER(vp), u32p, ctypes.POINTER(vp), u32p, u32p, u32, P, ctypes.c_int]
@@ -62,7 +65,7 @@ EXPORTED_SYMBOLS = [
     "vbz_decompress_sized", "vbz_decompressed_size",
     "vbz_b200_device_count", "vbz_b200_create", "vbz_b200_destroy", "vbz_b200_last_error", "vbz_b200_compress_batch",
     "vbz_b200_decompress_batch", "vbz_b200_compress_device", "vbz_b200_decompress_device", "vbz_b200_synchronize",
-    "vbz_b200_kernel_launches", "vbz_b200_compress_bound", "vbz_b200_stream",
+    "vbz_b200_kernel_launches", "vbz_b200_compress_bound", "vbz_b200_stream", "vbz_b200_set_stage_timing", "vbz_b200_stage_times",
     "H5PLget_plugin_type", "H5PLget_plugin_info", "vbz_plugin_info", "vbz_b200_h5z_filter",
 ]
 

@@ -235,7 +235,9 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     if (blocks > 0x7FFFFFFFull) { set_last_error("batch too large: more than 2^31 zstd blocks"); return -1; }
     const uint32_t n_blocks = (uint32_t)blocks;
     const size_t bytes = (size_t)n * sizeof(ZstdEncRead);
-    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zblocks.ensure((size_t)n_blocks * 4) || !ctx->d_zstatus.ensure((size_t)n_blocks * 8)) return -1;
+    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zblocks.ensure((size_t)n_blocks * 4) || !ctx->d_zstatus.ensure((size_t)n_blocks * 8) ||
+        !ctx->d_zcodes.ensure((size_t)n_blocks * kZGroupCodeBytes))
+        return -1;
     if (!upload_descriptors(ctx, ctx->d_zreads.p, reads.data(), bytes, stream) ||
         !zero_device(ctx, ctx->d_zstatus.p, (size_t)n_blocks * 8, stream))
         return -1;
@@ -247,6 +249,7 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.reads = ctx->d_zreads.as<ZstdEncRead>();
     p.block_read = ctx->d_zblocks.as<uint32_t>();
     p.src_sizes = d_src_sizes;
+    p.codes = ctx->d_zcodes.as<uint8_t>();
     p.status = ctx->d_zstatus.as<uint64_t>();
     p.results = d_results;
     p.hdr_bytes = sized ? 4u : 0u;
@@ -255,7 +258,7 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.n_blocks = n_blocks;
     e = vbzk_zstd_encode(reinterpret_cast<const VbzkZstdEncParams*>(&p), stream);
     if (e) { cuda_ok((cudaError_t)e, "zstd_encode launch"); return -1; }
-    ctx->launches += 2;
+    ctx->launches += 3;  // block table, codes, frames
     return 0;
 }
 
@@ -302,6 +305,7 @@ static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t
         if (!zstd) return enqueue_stage1(ctx, false, kind, d_src, d_dst, reads, sized ? 4u : 0u, d_results, nullptr, stream);
         if (!ctx->d_mid.ensure(mid_total + 16) || !ctx->d_sizes.ensure((size_t)n * 4)) return -1;
         if (enqueue_stage1(ctx, false, kind, d_src, ctx->d_mid.as<uint8_t>(), reads, 0, ctx->d_sizes.as<uint32_t>(), nullptr, stream) != 0) return -1;
+        if (ctx->stage_timing) { cudaEventRecord(ctx->t_mid, stream); ctx->t_mid_set = true; }
     }
     // stage 2: one zstd frame per read (ref vbz/vbz.cpp:194-204)
     std::vector<ZstdEncRead> zr(n);
@@ -379,6 +383,7 @@ static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8
             zdst = ctx->d_mid.as<uint8_t>();
         }
         if (enqueue_zstd_decode(ctx, d_src, zdst, zr, zres, stream) != 0) return -1;
+        if (ctx->stage_timing && kind.isz != 0) { cudaEventRecord(ctx->t_mid, stream); ctx->t_mid_set = true; }
         if (kind.isz == 0) return 0;
         s1_src = ctx->d_mid.as<uint8_t>();
         s1_sizes = ctx->d_sizes.as<uint32_t>();
@@ -418,7 +423,7 @@ vbz_b200_ctx::~vbz_b200_ctx()
     d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
     h_results.release(); stage.release();
     d_mid.release();
-    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release();
+    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); d_zcodes.release();
     for (WaveSlot& w : slots) {
         w.d_in.release(); w.d_out.release(); w.d_results.release(); w.d_pack.release(); w.d_xin.release(); w.d_xout.release();
         w.h_in.release(); w.h_out.release(); w.h_results.release();
@@ -427,6 +432,9 @@ vbz_b200_ctx::~vbz_b200_ctx()
         if (w.ev_out) cudaEventDestroy(w.ev_out);
         if (w.ev_outs) cudaEventDestroy(w.ev_outs);
     }
+    if (t_begin) cudaEventDestroy(t_begin);
+    if (t_mid) cudaEventDestroy(t_mid);
+    if (t_end) cudaEventDestroy(t_end);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
     if (s_d2hs) cudaStreamDestroy(s_d2hs);
@@ -512,8 +520,10 @@ extern "C" int vbz_b200_compress_device(vbz_b200_ctx* ctx, const void* d_src, co
         set_last_error("invalid options: every read of the batch would be rejected");
         return -1;
     }
-    return compress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0,
-                                (cudaStream_t)stream);
+    if (ctx->stage_timing) { ctx->t_mid_set = false; ctx->t_decode = false; cudaEventRecord(ctx->t_begin, (cudaStream_t)stream); }
+    const int rc = compress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0, (cudaStream_t)stream);
+    if (ctx->stage_timing) cudaEventRecord(ctx->t_end, (cudaStream_t)stream);
+    return rc;
 }
 
 extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, const uint64_t* src_off, const vbz_size_t* src_size,
@@ -539,8 +549,33 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
             else if (dst_size[i] % (unsigned)kind.isz != 0) j.post_code = kErrDestinationSize;
         }
     }
-    return decompress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0,
-                                  (cudaStream_t)stream);
+    if (ctx->stage_timing) { ctx->t_mid_set = false; ctx->t_decode = true; cudaEventRecord(ctx->t_begin, (cudaStream_t)stream); }
+    const int rc = decompress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0, (cudaStream_t)stream);
+    if (ctx->stage_timing) cudaEventRecord(ctx->t_end, (cudaStream_t)stream);
+    return rc;
+}
+
+extern "C" int vbz_b200_set_stage_timing(vbz_b200_ctx* ctx, int on)
+{
+    if (!ctx) return -1;
+    if (on && !ctx->t_begin &&
+        !(cuda_ok(cudaEventCreate(&ctx->t_begin), "cudaEventCreate") && cuda_ok(cudaEventCreate(&ctx->t_mid), "cudaEventCreate") &&
+          cuda_ok(cudaEventCreate(&ctx->t_end), "cudaEventCreate")))
+        return -1;
+    ctx->stage_timing = on != 0;
+    return 0;
+}
+extern "C" int vbz_b200_stage_times(vbz_b200_ctx* ctx, float* stage1_ms, float* zstd_ms)
+{
+    if (!ctx || !ctx->t_begin || !stage1_ms || !zstd_ms) { set_last_error("stage timing is not enabled"); return -1; }
+    if (!cuda_ok(cudaEventSynchronize(ctx->t_end), "cudaEventSynchronize")) return -1;
+    float total = 0.f, first = 0.f;
+    if (!cuda_ok(cudaEventElapsedTime(&total, ctx->t_begin, ctx->t_end), "cudaEventElapsedTime")) return -1;
+    if (!ctx->t_mid_set) { *stage1_ms = total; *zstd_ms = 0.f; return 0; }  // a single stage ran (reported as stage 1)
+    if (!cuda_ok(cudaEventElapsedTime(&first, ctx->t_begin, ctx->t_mid), "cudaEventElapsedTime")) return -1;
+    if (ctx->t_decode) { *zstd_ms = first; *stage1_ms = total - first; }  // decode runs the zstd stage first
+    else { *stage1_ms = first; *zstd_ms = total - first; }
+    return 0;
 }
 
 // ---- host-pointer batches -------------------------------------------------------------------------------------

@@ -52,13 +52,16 @@ struct vbz_b200_ctx {
     cudaStream_t stream = nullptr;
     vbz::StageRing stage;  // pinned descriptor staging
     uint64_t launches = 0;
+    // optional CUDA-event timing of the stages of the last *_device call (vbz_b200_set_stage_timing)
+    bool stage_timing = false, t_mid_set = false, t_decode = false;
+    cudaEvent_t t_begin = nullptr, t_mid = nullptr, t_end = nullptr;
     uint32_t codec_ctas_per_sm = 0;  // != 0 while a host batch runs: room for the transfer kernels (SvbParams::ctas_per_sm)
 
     // descriptors and look-back state (stage 1)
     vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
     vbz::PinBuf h_results;
     // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
-    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zunits, d_zgroups, d_zgeneral;
+    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral;
     // intermediate stage-1 bytes of the two-stage paths
     vbz::DevBuf d_mid;
     // host-pointer API: a batch runs as WAVES through kWaveSlots slots so that the upload of wave w+1, the kernels of

@@ -119,6 +119,7 @@ struct ZstdEncParams {
     const ZstdEncRead* reads;
     const uint32_t* block_read;  // block -> read
     const uint32_t* src_sizes;   // optional per-read content size written by stage 1; >= kErrOutOfMemory is passed through
+    uint8_t* codes;              // n_blocks records of kZGroupCodeBytes: the Huffman code of every group (written by zstd_enc_code_kernel)
     uint64_t* status;            // look-back chain over the blocks of a frame, zeroed before launch
     uint32_t* results;           // per read: bytes written (headers included) or an error code
     uint32_t hdr_bytes;          // 4 = put the "sized" header before the frame
@@ -127,6 +128,7 @@ struct ZstdEncParams {
 };
 constexpr uint32_t kZEncBlock = 128u * 1024u;  // content bytes per GROUP of the encoder: blocks that share one Huffman table
 constexpr uint32_t kZEncSub = 8u * 1024u;     // content bytes per block written by the encoder
+constexpr uint32_t kZGroupCodeBytes = 1200;   // sizeof(ZGroupCode), csrc/zstd_enc_kernels.cuh
 constexpr uint32_t kZBlockMax = 128u * 1024u;
 constexpr int kZdecWarps = 4;
 constexpr uint32_t kZLitStride = kZBlockMax + 32;  // literal scratch per decoding warp

@@ -207,6 +207,10 @@ extern "C" int vbzk_zstd_encode(const VbzkZstdEncParams* params, void* stream)
 {
     const ZstdEncParams& p = *reinterpret_cast<const ZstdEncParams*>(params);
     if (p.n_blocks == 0) return 0;
+    const uint32_t csmem = (uint32_t)(sizeof(ZCode) * kZcodeWarps);
+    if (int e = VBZK_SET_SMEM(zstd_enc_code_kernel, csmem)) return e;
+    VBZ_LAUNCH(zstd_enc_code_kernel, (p.n_blocks + kZcodeWarps - 1) / kZcodeWarps, kZcodeWarps * 32, csmem, (vbz_stream_t)stream, p);
+    if (int e = VBZK_LAST_ERROR()) return e;
     const uint32_t smem = (uint32_t)sizeof(ZEncSmem);
     if (int e = VBZK_SET_SMEM(zstd_encode_kernel, smem)) return e;
     VBZ_LAUNCH(zstd_encode_kernel, p.n_blocks, kZencThreads, smem, (vbz_stream_t)stream, p);

@@ -16,16 +16,21 @@
 // shared table are what lets the DECODER run 64 Huffman streams per table at once (csrc/zstd_dec_kernels.cuh);
 // the table is also built once per 128 KiB here.  The compression level only has to be non-zero.
 //
-// Parallelism: one CTA (8 warps) per group, groups numbered frame-major.
-//   histogram   128-bit loads, per-warp shared-memory histograms (zero bytes counted in a register), merged
-//   code        rank sort of the 256 counts by all threads; the two-queue Huffman construction, the length
-//               limiting and the (small) FSE coding of the weights are serial work of one thread
-//   sizes       a warp per stream, 8 streams after each other: a lane owns a contiguous run of <= 64 symbols, which
+// Parallelism: groups are numbered frame-major; two kernels.
+//   zstd_enc_code_kernel    a WARP per group (8 groups per CTA, no CTA-wide barrier): histogram with 128-bit loads and
+//                           shared-memory atomics (zero bytes counted in a register), rank sort of the 256 counts by the
+//                           warp, then lane 0 runs the inherently serial part - two-queue Huffman construction, length
+//                           limiting, FSE coding of the weights - while the SM's other 31 warps work on their own groups.
+//                           (In the first version this serial part sat in the middle of the 256-thread encode kernel and
+//                           60 % of that kernel's warp samples were the other 255 threads waiting at the barrier behind it.)
+//                           The code, the tree description and the kind of the group go to a 1.2 KB record in global memory.
+//   zstd_encode_kernel      a CTA (8 warps) per group:
+//     sizes     a warp per stream, 8 streams after each other: a lane owns a contiguous run of <= 64 symbols, which
 //               it loads with aligned 128-bit loads and shifts into place in registers; code lengths are summed, a
 //               shuffle scan gives the lane's bit offset (kept for the next pass) and the stream's size
-//   position    one thread sizes the sub-blocks; the group's size is posted, a decoupled look-back over the
+//     position  one thread sizes the sub-blocks; the group's size is posted, a decoupled look-back over the
 //               frame's earlier groups (csrc/svb_kernels.cuh) gives its position
-//   pack        two sub-blocks at a time (4 warps = 4 streams each): codes of two symbols are merged and OR-ed
+//     pack      two sub-blocks at a time (4 warps = 4 streams each): codes of two symbols are merged and OR-ed
 //               into a zeroed shared-memory staging area, which then leaves with aligned 128-bit stores
 #pragma once
 #include "zstd_dec_kernels.cuh"
@@ -38,9 +43,9 @@ constexpr int kZencWarps = kZencThreads / 32;
 constexpr uint32_t kZSubs = kZEncBlock / kZEncSub;   // sub-blocks per group (16)
 constexpr uint32_t kZStreams = kZSubs * 4;           // Huffman streams per group (64)
 
-struct ZEncSmem {
-    uint32_t hist[kZencWarps][256];  // after the histogram: the lanes' bit offsets, uint16_t[kZStreams][32]
-    uint32_t cnt[256];
+// the state of one group's code construction (zstd_enc_code_kernel: one per warp)
+struct ZCode {
+    uint32_t cnt[256];        // the histogram
     uint32_t code[256];       // code | len << 16
     uint8_t order[256];       // symbols by ascending count
     uint8_t len[256];
@@ -51,6 +56,21 @@ struct ZEncSmem {
     uint16_t next[16];
     uint8_t cellidx[13][64];  // per weight value: its cells in table order
     uint8_t weights[256];
+    uint8_t tree[160];        // the Huffman tree description
+    uint32_t max_bits;
+    uint32_t pad[3];
+};
+// what zstd_enc_code_kernel leaves for zstd_encode_kernel, one per group (ZstdEncParams::codes)
+struct ZGroupCode {
+    uint32_t code[256];  // code | len << 16; 0 for symbols that do not occur
+    uint8_t tree[160];
+    uint32_t kind, tree_bytes, nsym, pad;
+};
+static_assert(sizeof(ZGroupCode) == kZGroupCodeBytes, "host and device disagree on the size of a group's code record");
+struct ZEncSmem {
+    uint16_t lane_off[kZStreams][32];  // bit offset of every lane's run inside its stream
+    uint32_t code[256];       // code | len << 16
+    uint8_t len[256];
     uint8_t tree[160];        // the Huffman tree description
     uint32_t v[16];           // scalars shared by the CTA (see the kZv* indices)
     uint64_t excl;
@@ -85,7 +105,7 @@ __device__ __forceinline__ uint32_t zw_close(ZBitW& w, bool marker)  // -> bytes
 
 // ---- Huffman code of one block (one thread; cnt[], order[] are ready) -------------------------------------------
 // -> len[], code[], max_bits.  Returns false if no valid code could be built (the block is then stored raw).
-__device__ bool zenc_build_code(ZEncSmem* s, int nsym)
+__device__ bool zenc_build_code(ZCode* s, int nsym)
 {
     // two-queue construction over the leaves sorted by ascending count: leaves 0..nsym-1, internal nodes nsym..2nsym-2
     const int n = nsym;
@@ -156,14 +176,14 @@ __device__ bool zenc_build_code(ZEncSmem* s, int nsym)
         s->code[sym] = (start[w] >> (w - 1)) | ((uint32_t)L << 16);
         start[w] += 1u << (w - 1);
     }
-    s->v[kZvMaxBits] = (uint32_t)max_len;
+    s->max_bits = (uint32_t)max_len;
     return true;
 }
 
 // ---- tree description (one thread) -> s->tree, returns its size in bytes (0 = cannot be described) -------------------
-__device__ uint32_t zenc_describe_tree(ZEncSmem* s)
+__device__ uint32_t zenc_describe_tree(ZCode* s)
 {
-    const int max_bits = (int)s->v[kZvMaxBits];
+    const int max_bits = (int)s->max_bits;
     int last = 255;
     while (last > 0 && s->len[last] == 0) --last;
     const int nw = last;  // weights of symbols 0..last-1; the last one is implied
@@ -308,6 +328,39 @@ __device__ __forceinline__ void zenc_load_run(const uint8_t* p, uint32_t n, uint
         for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i + 3], w[i + 4], bs);
     }
 }
+// the same in two steps, so that the loads of the next run can be in flight while this one is processed
+struct ZRun { uint4 g[5]; uint32_t sh; };
+__device__ __forceinline__ void zenc_fetch_run(const uint8_t* p, uint32_t n, ZRun& f)
+{
+    const uint4* q = reinterpret_cast<const uint4*>((uintptr_t)p & ~(uintptr_t)15);
+    f.sh = (uint32_t)((uintptr_t)p & 15u);
+    const uint32_t chunks = n ? (f.sh + n + 15) >> 4 : 0;  // 0..5
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        f.g[k] = make_uint4(0, 0, 0, 0);
+        if ((uint32_t)k < chunks) f.g[k] = q[k];
+    }
+}
+__device__ __forceinline__ void zenc_align_run(const ZRun& f, uint32_t (&r)[16])
+{
+    uint32_t w[20];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { w[4 * k] = f.g[k].x; w[4 * k + 1] = f.g[k].y; w[4 * k + 2] = f.g[k].z; w[4 * k + 3] = f.g[k].w; }
+    const uint32_t wo = f.sh >> 2, bs = 8u * (f.sh & 3u);
+    if (wo == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i], w[i + 1], bs);
+    } else if (wo == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i + 1], w[i + 2], bs);
+    } else if (wo == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i + 2], w[i + 3], bs);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __funnelshift_r(w[i + 3], w[i + 4], bs);
+    }
+}
 // Lane l of the stream's warp owns the symbols [count - (l+1) C, count - l C), C = ceil(count / 32) <= 64: the
 // stream is written from its last symbol up, so lane 0 writes the lowest bits.
 __device__ __forceinline__ void zenc_lane_run(uint32_t count, uint32_t lane, uint32_t* lo, uint32_t* n)
@@ -397,6 +450,145 @@ __device__ __forceinline__ ZSub zenc_sub(uint32_t B, uint32_t q)
     return s;
 }
 
+// the lanes of a warp fetch their runs of stream sidx (= 4 * sub-block + stream) of a group of B bytes; n = 0 if there is none
+__device__ __forceinline__ void zenc_fetch_stream(const uint8_t* src, uint32_t B, uint32_t sidx, uint32_t nstreams, uint32_t lane, ZRun& f, uint32_t* n_out)
+{
+    uint32_t n = 0;
+    f.sh = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) f.g[k] = make_uint4(0, 0, 0, 0);
+    if (sidx < nstreams) {
+        const ZSub sb = zenc_sub(B, sidx >> 2);
+        const uint32_t j = sidx & 3u;
+        if (j < sb.streams && sb.bytes >= 32) {
+            const uint32_t cnt = (sb.streams == 4 && j == 3) ? sb.bytes - 3 * sb.seg : sb.seg;
+            uint32_t lo;
+            zenc_lane_run(cnt, lane, &lo, &n);
+            zenc_fetch_run(src + sb.start + j * sb.seg + lo, n, f);
+        }
+    }
+    *n_out = n;
+}
+
+// where group b of the batch lives: false = nothing to encode (rejected read, upstream error, or a group beyond the content)
+struct ZGroupLoc {
+    const uint8_t* src;
+    uint32_t r, gi, ngrp, content, B;
+    bool last;
+};
+__device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, const ZstdEncRead& rd, uint32_t r, ZGroupLoc& g)
+{
+    g.r = r;
+    g.gi = b - rd.first_block;
+    if (rd.rejected) return false;
+    g.content = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
+    if (p.src_sizes && g.content >= kErrOutOfMemory) return false;  // stage 1 reported an error for this read
+    // groups of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'), then the rest
+    const uint32_t split = rd.split < g.content ? rd.split : 0u;
+    const uint32_t n_a = (split + kZEncBlock - 1) / kZEncBlock, n_b = (g.content - split + kZEncBlock - 1) / kZEncBlock;
+    g.ngrp = n_a + n_b ? n_a + n_b : 1u;
+    if (g.gi >= g.ngrp) return false;  // the table was sized for the largest content stage 1 could have produced
+    const uint32_t start = g.gi < n_a ? g.gi * kZEncBlock : split + (g.gi - n_a) * kZEncBlock;
+    const uint32_t region_end = g.gi < n_a ? split : g.content;
+    g.B = region_end - start < kZEncBlock ? region_end - start : kZEncBlock;
+    g.last = g.gi + 1 == g.ngrp;
+    g.src = p.src + rd.src_off + start;
+    return true;
+}
+
+// ---- kernel 1: histogram + Huffman code of every group, a warp per group -------------------------------------------------
+constexpr int kZcodeWarps = 2;
+__global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEncParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ZCode* s = reinterpret_cast<ZCode*>(smem) + wid;
+    const uint32_t b = blockIdx.x * kZcodeWarps + wid;
+    if (b >= p.n_blocks) return;
+    const uint32_t r = p.block_read[b];
+    const ZstdEncRead rd = p.reads[r];
+    ZGroupLoc g;
+    if (!zenc_locate(p, b, rd, r, g)) return;
+    const uint8_t* src = g.src;
+    const uint32_t B = g.B;
+    for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = 0;
+    __syncwarp();
+    // ---- histogram: 128-bit loads over the aligned body (four in flight per lane), bytes at the two ends ----------------
+    {
+        uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
+        if (head > B) head = B;
+        const uint32_t nch = (B - head) >> 4, done = head + (nch << 4);
+        uint32_t* h = s->cnt;
+        uint32_t zeros = 0;
+        if (lane < head) atomicAdd(h + src[lane], 1u);
+        if (lane < B - done) atomicAdd(h + src[done + lane], 1u);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+        for (uint32_t c0 = 0; c0 < nch; c0 += 128) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t c = c0 + 32 * u + lane;
+                q[u] = make_uint4(0, 0, 0, 0);
+                if (c < nch) q[u] = s4[c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t c = c0 + 32 * u + lane;
+                if (c >= nch) continue;
+                const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t v = (w[k] >> (8 * j)) & 0xFFu;
+                        if (v) atomicAdd(h + v, 1u);
+                        else ++zeros;
+                    }
+                }
+            }
+        }
+        if (zeros) atomicAdd(h, zeros);
+    }
+    __syncwarp();
+    // ---- rank sort of the symbols that occur, ascending by (count, symbol): a lane ranks 8 symbols --------------------------
+    uint32_t nsym = 0;
+    {
+        uint32_t c[8], rank[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c[k] = s->cnt[lane * 8 + k]; rank[k] = 0; }
+        for (uint32_t j = 0; j < 256; ++j) {
+            const uint32_t cj = s->cnt[j];
+            if (cj == 0) continue;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rank[k] += (cj < c[k] || (cj == c[k] && j < lane * 8 + k)) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c[k]) { s->order[rank[k]] = (uint8_t)(lane * 8 + k); ++nsym; }
+    }
+    nsym = __reduce_add_sync(0xffffffffu, nsym);
+    __syncwarp();
+    // ---- the code and the kind of group (lane 0) -------------------------------------------------------------------------
+    uint32_t kind = kZKindRaw, tree_bytes = 0;
+    if (lane == 0) {
+        if (B > 0 && nsym == 1) kind = kZKindRle;
+        else if (nsym >= 2 && B >= 32 && zenc_build_code(s, (int)nsym)) {
+            tree_bytes = zenc_describe_tree(s);
+            if (tree_bytes) kind = kZKindHuf;
+        }
+    }
+    kind = __shfl_sync(0xffffffffu, kind, 0);
+    tree_bytes = __shfl_sync(0xffffffffu, tree_bytes, 0);
+    __syncwarp();
+    ZGroupCode* out = reinterpret_cast<ZGroupCode*>(p.codes) + b;
+    if (kind == kZKindHuf) {
+        for (uint32_t i = lane; i < 256; i += 32) out->code[i] = s->code[i];
+        for (uint32_t i = lane; i < 160 / 4; i += 32) reinterpret_cast<uint32_t*>(out->tree)[i] = reinterpret_cast<const uint32_t*>(s->tree)[i];
+    }
+    if (lane == 0) { out->kind = kind; out->tree_bytes = tree_bytes; out->nsym = nsym; }
+}
+
+// ---- kernel 2: sizes, position, pack - a CTA per group --------------------------------------------------------------------
 __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams p)
 {
     VBZ_DYN_SMEM(smem);
@@ -405,29 +597,28 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     const uint32_t b = blockIdx.x;
     const uint32_t r = p.block_read[b];
     const ZstdEncRead rd = p.reads[r];
-    const uint32_t gi = b - rd.first_block;
-    if (rd.rejected) {
-        if (gi == 0 && tid == 0) p.results[r] = rd.preset;
+    ZGroupLoc g;
+    if (!zenc_locate(p, b, rd, r, g)) {
+        if (g.gi == 0 && tid == 0) {
+            if (rd.rejected) p.results[r] = rd.preset;
+            else if (p.src_sizes && g.content >= kErrOutOfMemory) p.results[r] = g.content;
+        }
         return;
     }
-    const uint32_t content = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
-    if (p.src_sizes && content >= kErrOutOfMemory) {  // stage 1 reported an error for this read
-        if (gi == 0 && tid == 0) p.results[r] = content;
-        return;
-    }
-    // groups of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'), then the rest
-    const uint32_t split = rd.split < content ? rd.split : 0u;
-    const uint32_t n_a = (split + kZEncBlock - 1) / kZEncBlock, n_b = (content - split + kZEncBlock - 1) / kZEncBlock;
-    const uint32_t ngrp = n_a + n_b ? n_a + n_b : 1u;
-    if (gi >= ngrp) return;  // the table was sized for the largest content stage 1 could have produced
-    const uint32_t start = gi < n_a ? gi * kZEncBlock : split + (gi - n_a) * kZEncBlock;
-    const uint32_t region_end = gi < n_a ? split : content;
-    const uint32_t B = region_end - start < kZEncBlock ? region_end - start : kZEncBlock;
-    const bool last = gi + 1 == ngrp;
-    const uint8_t* src = p.src + rd.src_off + start;
+    const uint32_t gi = g.gi, content = g.content, B = g.B;
+    const bool last = g.last;
+    const uint8_t* src = g.src;
     const uint32_t nsub = B ? (B + kZEncSub - 1) / kZEncSub : 1u;
-
-    for (uint32_t i = tid; i < kZencWarps * 256; i += kZencThreads) (&s->hist[0][0])[i] = 0;
+    // the group's code, built by zstd_enc_code_kernel
+    const ZGroupCode* gc = reinterpret_cast<const ZGroupCode*>(p.codes) + b;
+    uint32_t kind = gc->kind;
+    const uint32_t tree_bytes = gc->tree_bytes;
+    if (kind == kZKindHuf) {
+        const uint32_t c = gc->code[tid];
+        s->code[tid] = c;
+        s->len[tid] = (uint8_t)(c >> 16);
+        if (tid < 160 / 4) reinterpret_cast<uint32_t*>(s->tree)[tid] = reinterpret_cast<const uint32_t*>(gc->tree)[tid];
+    }
     // bytes before the first block header: the sized header and the frame header, in front of the frame's first group
     uint32_t pre = 0;
     uint8_t prebuf[16];
@@ -441,92 +632,19 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
         pre += 5 + fcs_bytes;
     }
     __syncthreads();
-
-    // ---- histogram: 128-bit loads over the aligned body, bytes at the two ends ----------------------------------------
-    {
-        uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
-        if (head > B) head = B;
-        const uint32_t nch = (B - head) >> 4, done = head + (nch << 4);
-        uint32_t* h = s->hist[wid];
-        uint32_t zeros = 0;
-        if (tid < head) atomicAdd(h + src[tid], 1u);
-        else if (tid >= 32 && tid - 32 < B - done) atomicAdd(h + src[done + tid - 32], 1u);
-        const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
-        for (uint32_t c = tid; c < nch; c += kZencThreads) {
-            const uint4 q = s4[c];
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t v = (w[k] >> (8 * j)) & 0xFFu;
-                    if (v) atomicAdd(h + v, 1u);
-                    else ++zeros;
-                }
-            }
-        }
-        if (zeros) atomicAdd(h, zeros);
-    }
-    __syncthreads();
-    {
-        uint32_t c = 0;
-#pragma unroll
-        for (int w = 0; w < kZencWarps; ++w) c += s->hist[w][tid];
-        s->cnt[tid] = c;
-    }
-    __syncthreads();
-    // rank sort of the symbols that occur, ascending by (count, symbol): thread = symbol
-    uint32_t nsym = 0;
-    {
-        const uint32_t sym = tid, c = s->cnt[sym];
-        if (c) {
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < 256; ++j) {
-                const uint32_t cj = s->cnt[j];
-                rank += (cj != 0 && (cj < c || (cj == c && j < sym))) ? 1u : 0u;
-            }
-            s->order[rank] = (uint8_t)sym;
-            nsym = 1;
-        }
-    }
-    nsym = __reduce_add_sync(0xffffffffu, nsym);
-    if (lane == 0) s->v[8 + wid] = nsym;
-    __syncthreads();
-    nsym = 0;
-#pragma unroll
-    for (int w = 0; w < kZencWarps; ++w) nsym += s->v[8 + w];
-    __syncthreads();
-
-    // ---- the code and the kind of group (one thread) ---------------------------------------------------------------------
-    if (tid == 0) {
-        uint32_t kind = kZKindRaw, tree_bytes = 0;
-        if (B > 0 && nsym == 1) kind = kZKindRle;
-        else if (nsym >= 2 && B >= 32 && zenc_build_code(s, (int)nsym)) {
-            tree_bytes = zenc_describe_tree(s);
-            if (tree_bytes) kind = kZKindHuf;
-        }
-        s->v[kZvKind] = kind;
-        s->v[kZvTreeBytes] = tree_bytes;
-        s->v[kZvNsym] = nsym;
-    }
-    __syncthreads();
-    uint32_t kind = s->v[kZvKind];
-    const uint32_t tree_bytes = s->v[kZvTreeBytes];
-    uint16_t* lane_off = reinterpret_cast<uint16_t*>(&s->hist[0][0]);  // [stream][lane]
+    uint16_t* lane_off = &s->lane_off[0][0];  // [stream][lane]
 
     // ---- sizes: every stream of the group, a warp per stream ----------------------------------------------------------------
     if (kind == kZKindHuf) {
+        ZRun f;
+        uint32_t fn;
+        zenc_fetch_stream(src, B, wid, nsub * 4, lane, f, &fn);
         for (uint32_t sidx = wid; sidx < nsub * 4; sidx += kZencWarps) {
-            const ZSub sb = zenc_sub(B, sidx >> 2);
-            const uint32_t j = sidx & 3u;
-            uint32_t bits = 0;
-            if (j < sb.streams && sb.bytes >= 32) {
-                const uint32_t cnt = (sb.streams == 4 && j == 3) ? sb.bytes - 3 * sb.seg : sb.seg;
-                uint32_t lo, n, run[16];
-                zenc_lane_run(cnt, lane, &lo, &n);
-                zenc_load_run(src + sb.start + j * sb.seg + lo, n, run);
-                bits = zenc_run_bits(s->len, run, n);
-            }
+            uint32_t run[16];
+            const uint32_t n = fn;
+            zenc_align_run(f, run);
+            zenc_fetch_stream(src, B, sidx + kZencWarps, nsub * 4, lane, f, &fn);  // in flight while this stream is summed
+            const uint32_t bits = zenc_run_bits(s->len, run, n);
             const uint32_t incl = warp_scan_u32(bits);
             lane_off[sidx * 32 + lane] = (uint16_t)(incl - bits);
             if (lane == 31) s->sbits[sidx] = incl;
