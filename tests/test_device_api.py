@@ -112,3 +112,32 @@ def test_large_batch_properties():
     assert (d_rd.cpu().numpy().view(np.uint32) == sizes).all()
     mism = int((d_src != d_back).sum().item())
     assert mism == tot_s - int(sizes.astype(np.int64).sum())
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_torch_tensors_zero_copy(level):
+    """SURVEY 8f #1: reads that already live in CUDA tensors are compressed and decompressed where they are."""
+    torch, batch, _ = _setup()
+    from vbz_compression_b200 import CompressionOptions
+    port = ol.port()
+    rng = np.random.default_rng(21 + level)
+    arrs = [data_gen.nanopore_like(int(n), rng) for n in (70_001, 8, 0, 12_345, 300_000)]
+    reads = [torch.from_numpy(a.copy()).cuda() for a in arrs]
+    opts = CompressionOptions(True, 2, level, 1)
+    out, offs, sizes = batch.compress_tensors(reads, opts, sized=True)
+    torch.cuda.synchronize()
+    sz = sizes.cpu().numpy().view(np.uint32)
+    assert (sz < 0xFFFFFFF9).all()
+    o = Options(True, 2, level, 1)
+    chunks = []
+    for a, off, z in zip(arrs, offs, sz):
+        chunk = out[int(off):int(off) + int(z)]
+        if level == 0:
+            rp, bp = port.compress(a, o, sized=True)
+            assert int(z) == rp and chunk.cpu().numpy().tobytes() == bp
+        chunks.append(chunk)
+    back, res = batch.decompress_tensors(chunks, torch.int16, [a.size for a in arrs], opts, sized=True)
+    torch.cuda.synchronize()
+    assert (res.cpu().numpy().view(np.uint32) == np.array([a.nbytes for a in arrs], np.uint32)).all()
+    for a, b in zip(arrs, back):
+        assert np.array_equal(b.cpu().numpy(), a)

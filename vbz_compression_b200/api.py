@@ -133,6 +133,60 @@ class Batch:
         if rc != 0:
             self._fail("vbz_b200_decompress_device")
 
+    # ---- torch tensors that already live on the device: zero-copy ------------------------------------
+    def compress_tensors(self, reads, options, sized=True, stream=None):
+        """reads: list of 1-D contiguous CUDA tensors on this context's device (any integer dtype matching
+        options.integer_size).  Nothing is copied: the kernels read the tensors where they are.  Returns
+        (out, offsets, sizes): `out` one uint8 CUDA tensor, read i's bytes at out[offsets[i] : offsets[i] + sizes[i]],
+        `sizes` an int32 CUDA tensor holding per read what vbz_compress[_sized] would have returned (view as uint32:
+        values >= 0xFFFFFFF9 are VBZ error codes).  Enqueued on the current torch stream; not synchronised."""
+        import torch
+        n = len(reads)
+        dev = torch.device("cuda", self.device)
+        if n == 0:
+            return torch.empty(0, dtype=torch.uint8, device=dev), np.zeros(0, np.uint64), torch.empty(0, dtype=torch.int32, device=dev)
+        for t in reads:
+            if not (t.is_cuda and t.device.index == self.device and t.is_contiguous() and t.data_ptr() % 16 == 0):
+                raise VbzError("compress_tensors needs contiguous, 16-byte aligned CUDA tensors on device %d" % self.device)
+        ptrs = np.array([t.data_ptr() for t in reads], np.uint64)
+        base = int(ptrs.min())
+        src_off = ptrs - np.uint64(base)
+        src_size = np.array([t.numel() * t.element_size() for t in reads], np.uint32)
+        caps = np.array([self.lib.vbz_b200_compress_bound(int(z), ctypes.byref(options), int(sized)) for z in src_size], np.uint64)
+        dst_off = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.uint64)
+        out = torch.empty(int(caps.sum()) + 16, dtype=torch.uint8, device=dev)
+        sizes = torch.zeros(n, dtype=torch.int32, device=dev)
+        st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        self.compress_device(base, src_off, src_size, out.data_ptr(), dst_off, caps.astype(np.uint32), sizes.data_ptr(), options, sized, st)
+        return out, dst_off, sizes
+
+    def decompress_tensors(self, chunks, out_dtype, out_lengths, options, sized=True, stream=None):
+        """chunks: list of 1-D contiguous uint8 CUDA tensors (4-byte aligned) each holding one compressed read (e.g. slices
+        of compress_tensors' output); out_lengths: elements of `out_dtype` per read.  Returns (list of CUDA tensors,
+        results int32 CUDA tensor); enqueued on the current torch stream, not synchronised."""
+        import torch
+        n = len(chunks)
+        dev = torch.device("cuda", self.device)
+        esz = torch.empty(0, dtype=out_dtype).element_size()
+        res = torch.zeros(n, dtype=torch.int32, device=dev)
+        if n == 0:
+            return [], res
+        for t in chunks:
+            if not (t.is_cuda and t.device.index == self.device and t.is_contiguous() and t.data_ptr() % 4 == 0):
+                raise VbzError("decompress_tensors needs contiguous, 4-byte aligned CUDA tensors on device %d" % self.device)
+        ptrs = np.array([t.data_ptr() for t in chunks], np.uint64)
+        base = int(ptrs.min())
+        src_off = ptrs - np.uint64(base)
+        src_size = np.array([t.numel() for t in chunks], np.uint32)
+        dst_size = np.array([int(x) * esz for x in out_lengths], np.uint32)
+        slot = (dst_size.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15)
+        dst_off = np.concatenate([[0], np.cumsum(slot)[:-1]]).astype(np.uint64)
+        out = torch.empty(int(slot.sum()) + 16, dtype=torch.uint8, device=dev)
+        st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        self.decompress_device(base, src_off, src_size, out.data_ptr(), dst_off, dst_size, res.data_ptr(), options, sized, st)
+        outs = [out[int(o):int(o) + int(z)].view(out_dtype) for o, z in zip(dst_off, dst_size)]
+        return outs, res
+
     def synchronize(self):
         if self.lib.vbz_b200_synchronize(self.ctx) != 0:
             self._fail("vbz_b200_synchronize")
