@@ -17,7 +17,9 @@
 // the table is also built once per 128 KiB here.  The compression level only has to be non-zero.
 //
 // Parallelism: groups are numbered frame-major; two kernels.
-//   zstd_enc_code_kernel    a WARP per group (8 groups per CTA, no CTA-wide barrier): histogram with 128-bit loads and
+//   zstd_enc_code_kernel    a WARP per CODE SET - four consecutive groups of a region share one code (every group still carries the
+//                           tree in its first Huffman block, so groups stay independent of each other in the frame) - no CTA-wide
+//                           barrier: histogram with 128-bit loads and
 //                           shared-memory atomics (zero bytes counted in a register), rank sort of the 256 counts by the
 //                           warp, then lane 0 runs the inherently serial part - two-queue Huffman construction, length
 //                           limiting, FSE coding of the weights - while the SM's other 31 warps work on their own groups.
@@ -42,6 +44,7 @@ constexpr int kZencThreads = 256;
 constexpr int kZencWarps = kZencThreads / 32;
 constexpr uint32_t kZSubs = kZEncBlock / kZEncSub;   // sub-blocks per group (16)
 constexpr uint32_t kZStreams = kZSubs * 4;           // Huffman streams per group (64)
+constexpr uint32_t kZCodeSet = 4;                    // consecutive groups of a region that share one Huffman code (built once, over 512 KiB)
 
 // the state of one group's code construction (zstd_enc_code_kernel: one per warp)
 struct ZCode {
@@ -474,6 +477,8 @@ __device__ __forceinline__ void zenc_fetch_stream(const uint8_t* src, uint32_t B
 struct ZGroupLoc {
     const uint8_t* src;
     uint32_t r, gi, ngrp, content, B;
+    uint32_t code_first;  // groups back to the first group of this one's CODE SET (kZCodeSet consecutive groups of a region share one code)
+    uint32_t code_bytes;  // content bytes of the code set, from its first group on
     bool last;
 };
 __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, const ZstdEncRead& rd, uint32_t r, ZGroupLoc& g)
@@ -493,6 +498,10 @@ __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, 
     g.B = region_end - start < kZEncBlock ? region_end - start : kZEncBlock;
     g.last = g.gi + 1 == g.ngrp;
     g.src = p.src + rd.src_off + start;
+    const uint32_t in_region = g.gi < n_a ? g.gi : g.gi - n_a;
+    g.code_first = in_region % kZCodeSet;
+    const uint32_t set_start = start - g.code_first * kZEncBlock;
+    g.code_bytes = region_end - set_start < kZCodeSet * kZEncBlock ? region_end - set_start : kZCodeSet * kZEncBlock;
     return true;
 }
 
@@ -508,9 +517,9 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     const uint32_t r = p.block_read[b];
     const ZstdEncRead rd = p.reads[r];
     ZGroupLoc g;
-    if (!zenc_locate(p, b, rd, r, g)) return;
+    if (!zenc_locate(p, b, rd, r, g) || g.code_first != 0) return;  // the first group of a code set builds the code for all of them
     const uint8_t* src = g.src;
-    const uint32_t B = g.B;
+    const uint32_t B = g.code_bytes;
     for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = 0;
     __syncwarp();
     // ---- histogram: 128-bit loads over the aligned body (four in flight per lane), bytes at the two ends ----------------
@@ -610,7 +619,7 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     const uint8_t* src = g.src;
     const uint32_t nsub = B ? (B + kZEncSub - 1) / kZEncSub : 1u;
     // the group's code, built by zstd_enc_code_kernel
-    const ZGroupCode* gc = reinterpret_cast<const ZGroupCode*>(p.codes) + b;
+    const ZGroupCode* gc = reinterpret_cast<const ZGroupCode*>(p.codes) + (b - g.code_first);
     uint32_t kind = gc->kind;
     const uint32_t tree_bytes = gc->tree_bytes;
     if (kind == kZKindHuf) {
