@@ -506,7 +506,7 @@ __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, 
 }
 
 // ---- kernel 1: histogram + Huffman code of every group, a warp per group -------------------------------------------------
-constexpr int kZcodeWarps = 2;
+constexpr int kZcodeWarps = 1;
 __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEncParams p)
 {
     VBZ_DYN_SMEM(smem);
