@@ -66,7 +66,8 @@ struct S16Ctl {           // control block in shared memory
 struct S16EncSmem {
     static constexpr int kLut = 0;                                   // 96 x u32
     static constexpr int kCtl = 384;
-    static constexpr int kIn = 576;                                  // 16 B left margin + tile + 16 B slack
+    static constexpr int kWin = 576;                                 // look-back windows of the pending tile: kLookWindows x 32 x u64
+    static constexpr int kIn = kWin + kLookWindows * 256;            // 16 B left margin + tile + 16 B slack
     static constexpr int kInBytes = 16 + kS16TileBytes + 16;
     static constexpr int kKeys = kIn + kInBytes;                     // control bytes (+16 phase)
     static constexpr int kData = kKeys + kS16TileKeys + 16;          // 2 x data bytes at tile-local offsets (+64 slack)
@@ -76,7 +77,8 @@ struct S16EncSmem {
 struct S16DecSmem {
     static constexpr int kLut = 0;                                   // 96 x uint2
     static constexpr int kCtl = 768;
-    static constexpr int kKeys = 960;                                // 2 x control bytes (+16 phase)
+    static constexpr int kWin = 960;                                 // look-back windows of the pending tile: kLookWindows x 32 x u64
+    static constexpr int kKeys = kWin + kLookWindows * 256;          // 2 x control bytes (+16 phase)
     static constexpr int kKeysStride = kS16TileKeys + 16;
     static constexpr int kData = kKeys + 2 * kKeysStride;            // data-byte slice (+16 phase, +48 slack)
     static constexpr int kOut = kData + kS16TileBytes + 64;          // 2 x parked samples, thread-private slots
@@ -288,6 +290,27 @@ __device__ __forceinline__ uint64_t s16_prefetch_status(const uint64_t* status, 
     const long long idx = (long long)pend.t - 1 - lane;
     return (pend.valid && idx >= (long long)pend.first_tile) ? vbz_ld_volatile_u64(status + idx) : 0ull;
 }
+// warp 0: start fetching every status word the pending tile's look-back can need (back to the first tile of its read, at most
+// kLookWindows x 32 tiles) into shared memory, asynchronously; s16_resolve_win consumes them a phase later
+__device__ __forceinline__ void s16_prefetch_windows(const uint64_t* status, const S16Pending& pend, uint32_t lane, uint64_t* win)
+{
+#pragma unroll
+    for (int w = 0; w < kLookWindows; ++w) {
+        const long long idx = (long long)pend.t - 1 - 32 * w - lane;
+        if (pend.valid && idx >= (long long)pend.first_tile) vbz_cp_async8(win + w * 32 + lane, status + idx);
+        else win[w * 32 + lane] = 0;
+    }
+    vbz_cp_async_commit();
+}
+__device__ __forceinline__ uint64_t s16_resolve_win(uint64_t* status, const S16Pending& pend, uint64_t mask, uint32_t lane, const uint64_t* win)
+{
+    vbz_cp_async_wait_all();
+    __syncwarp();
+    if (pend.t == pend.first_tile) return 0;  // posted as inclusive right away
+    const uint64_t excl = lookback_exclusive_win(status, pend.t, pend.first_tile, win) & mask;
+    if (lane == 0) vbz_st_volatile_u64(status + pend.t, kStInclusive | ((excl + pend.total) & mask));
+    return excl;
+}
 __device__ __forceinline__ uint64_t s16_resolve(uint64_t* status, const S16Pending& pend, uint64_t mask, uint32_t lane, uint64_t pf = 0, bool have_pf = false)
 {
     if (pend.t == pend.first_tile) return 0;  // posted as inclusive right away
@@ -312,9 +335,9 @@ __device__ __forceinline__ void s16_encode_tile(const SvbParams& p, const SvbRea
     // warp 2 fetches the next tile's load descriptor now and issues the load once this tile's rows are in registers
     uint4 next_load = make_uint4(0, 0, 0, 0);
     if (wid == 2 && t + gridDim.x < p.n_tiles) next_load = s16_fetch_load(p.issue_a + (t + gridDim.x));
-    // warp 0 reads the status words the pending tile's look-back starts from; they are consumed after barrier (1)
-    uint64_t pf = 0;
-    if (wid == 0) pf = s16_prefetch_status(p.status_a, pend, lane);
+    // warp 0 starts fetching the status words of the pending tile's whole look-back; they are consumed after barrier (1)
+    uint64_t* win = reinterpret_cast<uint64_t*>(smem + S16EncSmem::kWin);
+    if (wid == 0) s16_prefetch_windows(p.status_a, pend, lane, win);
 
     // ---- rows: shared -> registers, delta, zigzag, codes -------------------------------------------------------
     uint32_t z[kS16Rows][4], key[kS16Rows], len[kS16Rows], cnt[kS16Rows];
@@ -362,7 +385,7 @@ __device__ __forceinline__ void s16_encode_tile(const SvbParams& p, const SvbRea
         // post this tile's aggregate FIRST, then resolve the tile before it
         if (lane == 0) vbz_st_volatile_u64(p.status_a + t, (ti == 0 ? kStInclusive : kStAggregate) | tile_total);
         if (pend.valid) {
-            const uint64_t excl = s16_resolve(p.status_a, pend, kStValueMask, lane, pf, true);
+            const uint64_t excl = s16_resolve_win(p.status_a, pend, kStValueMask, lane, win);
             if (lane == 0) ctl->excl = excl;
         }
     }
@@ -669,9 +692,9 @@ __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRea
     // warp 2 fetches the next tile's load descriptors now; the loads are issued as the stages become free
     uint4 next_keys = make_uint4(0, 0, 0, 0), next_data = make_uint4(0, 0, 0, 0);
     if (wid == 2 && t + gridDim.x < p.n_tiles) { next_keys = s16_fetch_load(p.issue_a + (t + gridDim.x)); next_data = s16_fetch_load(p.issue_b + (t + gridDim.x)); }
-    // warp 0 reads the status words the pending tile's look-back starts from; they are consumed after barrier (2)
-    uint64_t pf = 0;
-    if (wid == 0) pf = s16_prefetch_status(p.status_b, pend, lane);
+    // warp 0 starts fetching the status words of the pending tile's whole look-back; they are consumed after barrier (2)
+    uint64_t* win = reinterpret_cast<uint64_t*>(smem + S16DecSmem::kWin);
+    if (wid == 0) s16_prefetch_windows(p.status_b, pend, lane, win);
 
     // ---- control bytes -> lengths -> offsets ------------------------------------------------------------------
     uint32_t key[kS16Rows], len[kS16Rows], cnt[kS16Rows];
@@ -774,7 +797,7 @@ __device__ __forceinline__ void s16_decode_tile(const SvbParams& p, const SvbRea
         // post this tile's aggregate FIRST, then resolve the tile before it
         if (lane == 0) vbz_st_volatile_u64(p.status_b + t, (d.ti == 0 ? kStInclusive : kStAggregate) | tile_sum);
         if (pend.valid) {
-            const uint32_t carry = (uint32_t)s16_resolve(p.status_b, pend, 0xFFFFull, lane, pf, true);
+            const uint32_t carry = (uint32_t)s16_resolve_win(p.status_b, pend, 0xFFFFull, lane, win);
             if (lane == 0) ctl->carry = carry;
         }
         if (lane == 0) ctl->flag = 0;

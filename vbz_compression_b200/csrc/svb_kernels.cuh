@@ -73,6 +73,43 @@ __device__ __forceinline__ uint64_t lookback_exclusive_pf(const uint64_t* status
     }
     return excl;
 }
+// The same walk with the first kLookWindows windows (32 tiles each) already sitting in shared memory: win[w * 32 + lane] holds
+// status[tile - 1 - 32 w - lane], or 0 where that index lies before first_tile or the word was still empty when it was fetched.
+// Inside one read nobody can post an INCLUSIVE prefix before the tile in front of it has resolved, so the walk of tile number
+// ti of its read covers ti tiles: fetched one window after the other that was up to four dependent global round trips on
+// the critical path of every tile of a long read; fetched together, ahead of time, it is none (and one for a window that
+// was not complete yet).
+constexpr int kLookWindows = 4;
+__device__ __forceinline__ uint64_t lookback_exclusive_win(const uint64_t* status, uint32_t tile, uint32_t first_tile, const uint64_t* win)
+{
+    const int lane = threadIdx.x & 31;
+    uint64_t excl = 0;
+    long long j = (long long)tile - 1;
+    for (int w = 0;; ++w) {
+        const long long idx = j - lane;
+        const bool valid = idx >= (long long)first_tile;
+        bool have = w < kLookWindows;
+        uint64_t s = 0;
+        unsigned inc, upto;
+        for (;;) {
+            s = valid ? (have ? win[w * 32 + lane] : vbz_ld_volatile_u64(status + idx)) : kStInclusive;
+            have = false;
+            const unsigned st = (unsigned)(s >> 62);
+            const unsigned inv = __ballot_sync(0xffffffffu, st == 0);
+            inc = __ballot_sync(0xffffffffu, st == 2);
+            upto = inc ? ((2u << (__ffs((int)inc) - 1)) - 1u) : 0xffffffffu;
+            if ((inv & upto) == 0) break;
+            VBZ_SPIN_YIELD();
+        }
+        uint64_t v = ((upto >> lane) & 1u) ? (s & kStValueMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (inc) break;
+        j -= 32;
+    }
+    return excl;
+}
 __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, uint32_t tile, uint32_t first_tile)
 {
     return lookback_exclusive_pf(status, tile, first_tile, 0ull, false);

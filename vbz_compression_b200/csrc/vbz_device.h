@@ -63,6 +63,10 @@ static inline void vbz_mbar_wait(uint64_t* bar, uint32_t parity)
     while ((*(volatile uint64_t*)bar >> 32) != 0 || ((uint32_t)*(volatile uint64_t*)bar & 1u) == parity) cpusim::yield();
 }
 static inline void vbz_fence_async_smem() {}
+// 8-byte asynchronous global -> shared copies (cp.async): the emulator copies at once
+static inline void vbz_cp_async8(void* s, const void* g) { memcpy(s, g, 8); }
+static inline void vbz_cp_async_commit() {}
+static inline void vbz_cp_async_wait_all() {}
 static inline void vbz_bulk_store(void* g, const void* s, uint32_t n) { memcpy(g, s, n); }
 static inline void vbz_bulk_store_commit() {}
 static inline void vbz_bulk_store_wait_read() {}
@@ -137,6 +141,13 @@ __device__ __forceinline__ void vbz_mbar_wait(uint64_t* bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register holds the value while it is in flight
+__device__ __forceinline__ void vbz_cp_async8(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vbz_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void vbz_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void vbz_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // make this thread's shared-memory writes visible to the async (TMA) proxy
 __device__ __forceinline__ void vbz_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void vbz_bulk_store(void* gdst, const void* smem_src, uint32_t bytes)
