@@ -101,10 +101,11 @@ __device__ __forceinline__ uint64_t lookback_exclusive_win(const uint64_t* statu
             if ((inv & upto) == 0) break;
             VBZ_SPIN_YIELD();
         }
-        uint64_t v = ((upto >> lane) & 1u) ? (s & kStValueMask) : 0ull;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        excl += v;
+        // at most one INCLUSIVE value (< 2^62) and 31 tile aggregates: two hardware reductions instead of a 64-bit shuffle tree
+        const uint64_t v = ((upto >> lane) & 1u) ? (s & kStValueMask) : 0ull;
+        const uint64_t lo = __reduce_add_sync(0xffffffffu, (uint32_t)(v & 0xFFFFFFu)) , mid = __reduce_add_sync(0xffffffffu, (uint32_t)((v >> 24) & 0xFFFFFFu)),
+                       hi = __reduce_add_sync(0xffffffffu, (uint32_t)(v >> 48));
+        excl += lo + (mid << 24) + (hi << 48);
         if (inc) break;
         j -= 32;
     }
