@@ -65,9 +65,17 @@ bool StageRing::init()
 }
 void* StageRing::take(size_t n)
 {
+    // every block has the size of the largest request so far: a block that grows (cudaFreeHost + cudaMallocHost, which
+    // synchronise the device) in the middle of a run cost one bench step half a second
+    if (n > high_water) {
+        high_water = n + n / 4 + 4096;
+        for (int i = 0; i < kEntries; ++i) {
+            if (!cuda_ok(cudaEventSynchronize(ev[i]), "cudaEventSynchronize")) return nullptr;
+            if (!buf[i].ensure(high_water)) return nullptr;
+        }
+    }
     cur = (cur + 1) % kEntries;
     if (!cuda_ok(cudaEventSynchronize(ev[cur]), "cudaEventSynchronize")) return nullptr;
-    if (!buf[cur].ensure(n ? n : 1)) return nullptr;
     return buf[cur].p;
 }
 bool StageRing::mark(cudaStream_t s) { return cuda_ok(cudaEventRecord(ev[cur], s), "cudaEventRecord"); }

@@ -39,6 +39,7 @@ struct StageRing {
     PinBuf buf[kEntries];
     cudaEvent_t ev[kEntries] = {};
     int cur = 0;
+    size_t high_water = 0;
     bool init();
     void* take(size_t n);          // nullptr on failure (last error set)
     bool mark(cudaStream_t s);     // call after enqueueing the copy that reads the block returned by take()
