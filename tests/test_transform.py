@@ -11,6 +11,7 @@ import golden_data
 import oracle_lib as ol
 import product
 from oracle_lib import Options
+from vbz_compression_b200 import CompressionOptions
 
 port = ol.port()
 
@@ -190,3 +191,23 @@ def test_library_exports_every_declared_symbol():
         syms = subprocess.run(["nm", "-D", "--defined-only", native], capture_output=True, text=True, check=True).stdout
         for s in _lib.EXPORTED_SYMBOLS:
             assert (" T " + s) in syms, s
+
+
+@pytest.mark.parametrize("kind", product.BACKENDS)
+def test_reads_longer_than_the_prefetched_lookback(kind):
+    """A tile's look-back walks back to the first tile of its read; four windows of 32 tiles are prefetched into shared
+    memory (csrc/svb_kernels.cuh: lookback_exclusive_win), longer walks continue with direct loads.  A read of more than
+    128 tiles (> 1,048,576 samples) next to short ones must still come out byte-exact, both ways."""
+    capi, batch, _ = product.get(kind)
+    rng = np.random.default_rng(314)
+    long_n = 1_250_000 if kind == "cpusim" else 5_000_000
+    reads = [data_gen.nanopore_like(n, rng) for n in (30_000, long_n, 9, 70_000)]
+    o = Options(True, 2, 0, 0)
+    opts = CompressionOptions(True, 2, 0, 0)
+    res = batch.compress(reads, opts, sized=True)
+    for arr, (code, blob) in zip(reads, res):
+        rp, bp = port.compress(arr, o, sized=True)
+        assert code == rp and blob == bp
+    back = batch.decompress([b for _, b in res], [a.nbytes for a in reads], opts, sized=True)
+    for arr, (code, blob) in zip(reads, back):
+        assert code == arr.nbytes and blob == arr.tobytes()
