@@ -164,3 +164,61 @@ def test_direct_dma_from_pinned_buffers(level):
                 rp, bpo = port.compress(a, o, sized=True)
                 got = host_c.numpy()[int(coffs[i]): int(coffs[i]) + res_c[i]].tobytes()
                 assert res_c[i] == rp and got == bpo
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [0, 1])
+def test_pinned_and_pageable_reads_in_one_wave(level):
+    """Every read chooses its own way over the link: page-locked buffers are moved in place by the transfer kernels, pageable
+    ones through the wave's pinned staging - in the same wave, next to rejected and empty reads."""
+    import torch
+    _, batch, lib = product.get("gpu")
+    rng = np.random.default_rng(91 + level)
+    lens = [int(x) for x in rng.integers(1_000, 300_000, 40)]
+    lens[3] = 0
+    arrs = [data_gen.nanopore_like(n, rng) for n in lens]
+    opts = CompressionOptions(True, 2, level, 1)
+    o = Options(True, 2, level, 1)
+    n = len(arrs)
+    keep = []
+    srcp, cp, bp, ssz, ccap = [], [], [], [], []
+    for i, a in enumerate(arrs):
+        nbytes = a.nbytes - (1 if i == 7 else 0)  # read 7: odd byte count -> VBZ_INPUT_SIZE_ERROR for it alone
+        cap = int(lib.vbz_max_compressed_size(a.nbytes, ctypes.byref(opts)))
+        if i % 2 == 0:  # page-locked, deliberately misaligned by 2 bytes
+            s = torch.empty(a.nbytes + 16, dtype=torch.uint8).pin_memory()
+            s.numpy()[2:2 + a.nbytes] = a.view(np.uint8)
+            c = torch.zeros(cap + 16, dtype=torch.uint8).pin_memory()
+            b = torch.zeros(a.nbytes + 16, dtype=torch.uint8).pin_memory()
+            keep += [s, c, b]
+            srcp.append(s.data_ptr() + 2); cp.append(c.data_ptr() + 6); bp.append(b.data_ptr() + 2)
+        else:  # pageable numpy memory
+            s = np.ascontiguousarray(a).view(np.uint8).copy() if a.size else np.zeros(1, np.uint8)
+            c = np.zeros(cap + 16, np.uint8)
+            b = np.zeros(a.nbytes + 16, np.uint8)
+            keep += [s, c, b]
+            srcp.append(s.ctypes.data); cp.append(c.ctypes.data); bp.append(b.ctypes.data)
+        ssz.append(nbytes); ccap.append(cap)
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    A = lambda t, v: (t * n)(*v)
+    res_c, res_d = (u32 * n)(), (u32 * n)()
+    os.environ["VBZ_B200_WAVE_MIB"] = "4"
+    try:
+        assert lib.vbz_b200_compress_batch(batch.ctx, A(vp, srcp), A(u32, ssz), A(vp, cp), A(u32, ccap), res_c, n, ctypes.byref(opts), 1) == 0
+        dsz = [a.nbytes for a in arrs]
+        assert lib.vbz_b200_decompress_batch(batch.ctx, A(vp, cp), res_c, A(vp, bp), A(u32, dsz), res_d, n, ctypes.byref(opts), 1) == 0
+    finally:
+        del os.environ["VBZ_B200_WAVE_MIB"]
+    for i, a in enumerate(arrs):
+        if i == 7:
+            assert res_c[i] == (ol.ERR_INPUT_SIZE + 4) & 0xFFFFFFFF
+            continue
+        rp, bpo = port.compress(a, o, sized=True)
+        got = bytes((ctypes.c_uint8 * res_c[i]).from_address(cp[i]))
+        if level == 0:
+            assert res_c[i] == rp and got == bpo, i
+        else:
+            r2, dec = port.decompress(got, o, a.nbytes, sized=True)
+            assert r2 == a.nbytes and dec == a.tobytes(), i
+        assert res_d[i] == a.nbytes
+        assert bytes((ctypes.c_uint8 * a.nbytes).from_address(bp[i])) == a.tobytes(), i
