@@ -523,6 +523,10 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = 0;
     __syncwarp();
     // ---- histogram: 128-bit loads over the aligned body (four in flight per lane), bytes at the two ends ----------------
+    // Large code sets (>= 256 KiB) are SAMPLED: one 512-byte row in four is counted (the shared-memory atomic unit bounds this
+    // kernel), the counts are scaled and every byte value gets a floor of one, so that a value the sample missed still has a code.
+    // A sample that saw a single value is checked against the whole set: constant content stays one RLE block per group.
+    const bool sampled = B >= (256u << 10);
     {
         uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
         if (head > B) head = B;
@@ -532,17 +536,17 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
         if (lane < head) atomicAdd(h + src[lane], 1u);
         if (lane < B - done) atomicAdd(h + src[done + lane], 1u);
         const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
-        for (uint32_t c0 = 0; c0 < nch; c0 += 128) {
+        for (uint32_t c0 = 0; c0 < nch; c0 += 128 * (sampled ? 4u : 1u)) {  // sampled: four rows in flight, from four different 2 KiB stretches
             uint4 q[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t c = c0 + 32 * u + lane;
+                const uint32_t c = c0 + (sampled ? 128u : 32u) * u + lane;
                 q[u] = make_uint4(0, 0, 0, 0);
                 if (c < nch) q[u] = s4[c];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t c = c0 + 32 * u + lane;
+                const uint32_t c = c0 + (sampled ? 128u : 32u) * u + lane;
                 if (c >= nch) continue;
                 const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
@@ -557,6 +561,26 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
             }
         }
         if (zeros) atomicAdd(h, zeros);
+        __syncwarp();
+        if (sampled) {
+            uint32_t seen = 0, which = 0;
+            for (uint32_t i = lane; i < 256; i += 32)
+                if (s->cnt[i]) { ++seen; which = i; }
+            seen = __reduce_add_sync(0xffffffffu, seen);
+            bool constant = false;
+            if (seen == 1) {  // one value in the sample: is it the only one in the whole set?
+                which = __reduce_add_sync(0xffffffffu, which);  // (one lane holds it, the others 0)
+                const uint32_t rep = which * 0x01010101u;
+                uint32_t diff = 0;
+                for (uint32_t c = lane; c < nch; c += 32) {
+                    const uint4 t = s4[c];
+                    diff |= (t.x ^ rep) | (t.y ^ rep) | (t.z ^ rep) | (t.w ^ rep);
+                }
+                constant = !__any_sync(0xffffffffu, diff != 0);  // (the two ends were counted byte by byte)
+            }
+            if (!constant)
+                for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = s->cnt[i] * 4u + 1u;
+        }
     }
     __syncwarp();
     // ---- rank sort of the symbols that occur, ascending by (count, symbol): a lane ranks 8 symbols --------------------------
