@@ -17,7 +17,7 @@
 // the table is also built once per 128 KiB here.  The compression level only has to be non-zero.
 //
 // Parallelism: groups are numbered frame-major; two kernels.
-//   zstd_enc_code_kernel    a WARP per CODE SET - four consecutive groups of a region share one code (every group still carries the
+//   zstd_enc_code_kernel    a WARP per CODE SET - eight consecutive groups of a region share one code (every group still carries the
 //                           tree in its first Huffman block, so groups stay independent of each other in the frame) - no CTA-wide
 //                           barrier: histogram with 128-bit loads and
 //                           shared-memory atomics (zero bytes counted in a register), rank sort of the 256 counts by the
@@ -44,7 +44,7 @@ constexpr int kZencThreads = 256;
 constexpr int kZencWarps = kZencThreads / 32;
 constexpr uint32_t kZSubs = kZEncBlock / kZEncSub;   // sub-blocks per group (16)
 constexpr uint32_t kZStreams = kZSubs * 4;           // Huffman streams per group (64)
-constexpr uint32_t kZCodeSet = 4;                    // consecutive groups of a region that share one Huffman code (built once, over 512 KiB)
+constexpr uint32_t kZCodeSet = 8;                    // consecutive groups of a region that share one Huffman code (built once, over up to 1 MiB)
 
 // the state of one group's code construction (zstd_enc_code_kernel: one per warp)
 struct ZCode {
