@@ -523,10 +523,11 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = 0;
     __syncwarp();
     // ---- histogram: 128-bit loads over the aligned body (four in flight per lane), bytes at the two ends ----------------
-    // Large code sets (>= 256 KiB) are SAMPLED: one 512-byte row in four is counted (the shared-memory atomic unit bounds this
+    // Large code sets are SAMPLED: one 512-byte row in four (from 256 KiB) or in eight (from 512 KiB) is counted (the shared-memory atomic unit bounds this
     // kernel), the counts are scaled and every byte value gets a floor of one, so that a value the sample missed still has a code.
     // A sample that saw a single value is checked against the whole set: constant content stays one RLE block per group.
     const bool sampled = B >= (256u << 10);
+    const uint32_t rate = B >= (512u << 10) ? 8u : 4u;  // one row in `rate`
     {
         uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
         if (head > B) head = B;
@@ -536,17 +537,18 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
         if (lane < head) atomicAdd(h + src[lane], 1u);
         if (lane < B - done) atomicAdd(h + src[done + lane], 1u);
         const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
-        for (uint32_t c0 = 0; c0 < nch; c0 += 128 * (sampled ? 4u : 1u)) {  // sampled: four rows in flight, from four different 2 KiB stretches
+        const uint32_t spacing = sampled ? 32u * rate : 32u;  // chunks between the rows a lane has in flight
+        for (uint32_t c0 = 0; c0 < nch; c0 += 4 * spacing) {
             uint4 q[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t c = c0 + (sampled ? 128u : 32u) * u + lane;
+                const uint32_t c = c0 + spacing * u + lane;
                 q[u] = make_uint4(0, 0, 0, 0);
                 if (c < nch) q[u] = s4[c];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t c = c0 + (sampled ? 128u : 32u) * u + lane;
+                const uint32_t c = c0 + spacing * u + lane;
                 if (c >= nch) continue;
                 const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
                 constant = !__any_sync(0xffffffffu, diff != 0);  // (the two ends were counted byte by byte)
             }
             if (!constant)
-                for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = s->cnt[i] * 4u + 1u;
+                for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = s->cnt[i] * rate + 1u;
         }
     }
     __syncwarp();
