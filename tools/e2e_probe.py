@@ -49,7 +49,8 @@ def main():
         tot += int(src_size[take]); take += 1
     d = torch.empty(tot // 2, dtype=torch.int16, device="cuda")
     bench.nanopore_like_torch(d, bench.SEED)
-    host_in = torch.empty(tot, dtype=torch.uint8).pin_memory()
+    pageable = os.environ.get("PAGEABLE") is not None  # plain malloc'd caller buffers instead of page-locked ones
+    host_in = torch.empty(tot, dtype=torch.uint8) if pageable else torch.empty(tot, dtype=torch.uint8).pin_memory()
     host_in.copy_(d.view(torch.uint8))
     del d
     offs = np.concatenate([[0], np.cumsum(src_size[:take].astype(np.int64))[:-1]])
@@ -57,8 +58,8 @@ def main():
         opts = bench.options_for(wl)
         caps = [int(lib.vbz_max_compressed_size(int(src_size[i]), ctypes.byref(opts))) for i in range(take)]
         coffs = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.int64)
-        host_c = torch.empty(int(sum(caps)), dtype=torch.uint8).pin_memory()
-        host_back = torch.empty(tot, dtype=torch.uint8).pin_memory()
+        host_c = torch.zeros(int(sum(caps)), dtype=torch.uint8) if pageable else torch.empty(int(sum(caps)), dtype=torch.uint8).pin_memory()
+        host_back = torch.zeros(tot, dtype=torch.uint8) if pageable else torch.empty(tot, dtype=torch.uint8).pin_memory()
         vp, u32 = ctypes.c_void_p, ctypes.c_uint32
         srcp = (vp * take)(*[host_in.data_ptr() + int(o) for o in offs])
         cp = (vp * take)(*[host_c.data_ptr() + int(o) for o in coffs])

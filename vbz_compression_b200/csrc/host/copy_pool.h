@@ -58,7 +58,7 @@ private:
     CopyPool()
     {
         unsigned n = std::thread::hardware_concurrency();
-        n = n >= 16 ? 8 : (n >= 4 ? n / 2 : 1);
+        n = n >= 16 ? 12 : (n >= 4 ? n / 2 : 1);  // measured on the 16-core B200 host: 4 threads 17, 8 threads 23, 16 threads 25 GB/s end to end
         if (const char* e = getenv("VBZ_B200_COPY_THREADS")) n = (unsigned)atoi(e);
         if (n < 1) n = 1;
         if (n > 32) n = 32;
