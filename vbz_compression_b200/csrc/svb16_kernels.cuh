@@ -553,16 +553,24 @@ __global__ void __launch_bounds__(kS16Threads) svb16_tile_sums_kernel(SvbParams 
         const uint8_t* keys = p.src + rd.src_off;  // 4-byte aligned (16-byte slots, optional 4-byte header)
         const uint32_t kb0 = ti * kS16TileKeys;
         const uint32_t kb1 = nkeys - kb0 < kS16TileKeys ? nkeys : kb0 + kS16TileKeys;
-        for (uint32_t b = kb0 + lane * 4; b < kb1; b += 128) {
-            uint32_t word;
-            if (b + 4 <= kb1) word = *reinterpret_cast<const uint32_t*>(keys + b);
-            else {
-                word = 0;
-                for (uint32_t i = b; i < kb1; ++i) word |= (uint32_t)keys[i] << (8 * (i - b));
-            }
+        // 2 KiB of control bytes per tile = 16 words per lane: all sixteen loads are issued before the first one is used
+        uint32_t word[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t b = kb0 + (lane + 32u * i) * 4u;
+            word[i] = 0;
+            if (b + 4 <= kb1) word[i] = *reinterpret_cast<const uint32_t*>(keys + b);
+            else if (b < kb1)
+                for (uint32_t k = b; k < kb1; ++k) word[i] |= (uint32_t)keys[k] << (8 * (k - b));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t b = kb0 + (lane + 32u * i) * 4u;
+            if (b >= kb1) continue;
+            uint32_t w = word[i];
             const uint32_t vleft = n - 4 * b;  // values from this word on (>= 1)
-            if (vleft < 16) word &= (1u << (2 * vleft)) - 1u;
-            sum += __popc(word & 0x55555555u) + 2 * __popc(word & 0xAAAAAAAAu);
+            if (vleft < 16) w &= (1u << (2 * vleft)) - 1u;
+            sum += __popc(w & 0x55555555u) + 2 * __popc(w & 0xAAAAAAAAu);
         }
         const uint32_t tv0 = ti * kS16TileValues;
         if (lane == 0) sum += n - tv0 < kS16TileValues ? n - tv0 : kS16TileValues;
