@@ -11,10 +11,44 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__) && !defined(VBZ_CPUSIM)
+#include <emmintrin.h>
+#define VBZ_STREAM_COPY 1
+#endif
 
 namespace vbz {
 
 struct CopyTask { void* dst; const void* src; size_t n; };
+
+// memcpy for pieces that are written once and not read again by this core: non-temporal 16-byte stores skip the
+// read-for-ownership of the destination lines (a third of a plain copy's memory traffic), which is what bounds the staged
+// path (the copy threads together move the batch at ~40 GB/s on the B200 host).
+static inline void stream_copy(void* dst, const void* src, size_t n)
+{
+#ifdef VBZ_STREAM_COPY
+    if (n >= (64u << 10)) {
+        uint8_t* d = static_cast<uint8_t*>(dst);
+        const uint8_t* s = static_cast<const uint8_t*>(src);
+        const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+        if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
+        const size_t blocks = n / 64;
+        for (size_t i = 0; i < blocks; ++i) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16)),
+                          c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+            s += 64;
+            d += 64;
+        }
+        _mm_sfence();
+        memcpy(d, s, n - blocks * 64);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
 
 class CopyPool {
 public:
@@ -29,7 +63,7 @@ public:
         size_t total = 0;
         for (const CopyTask& t : tasks) total += t.n;
         if (workers_.empty() || total < (4u << 20)) {  // small batches: not worth a hand-off
-            for (const CopyTask& t : tasks) if (t.n) memcpy(t.dst, t.src, t.n);
+            for (const CopyTask& t : tasks) if (t.n) stream_copy(t.dst, t.src, t.n);
             return;
         }
         // cut large copies so that the pieces balance
@@ -71,7 +105,7 @@ private:
             const size_t i = next_.fetch_add(1);
             if (i >= pieces.size()) break;
             const CopyTask& t = pieces[i];
-            memcpy(t.dst, t.src, t.n);
+            stream_copy(t.dst, t.src, t.n);
         }
     }
     void loop()
