@@ -252,6 +252,7 @@ def main_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs (its version banner) go to stdout otherwise: stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libvbz_b200 has no CPU path")
