@@ -23,6 +23,7 @@
 #ifndef VBZ_B200_H
 #define VBZ_B200_H
 
+#include <stddef.h>
 #include "vbz.h"
 
 #if defined(__cplusplus)
@@ -50,6 +51,15 @@ VBZ_EXPORT int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src
 VBZ_EXPORT int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* src, const vbz_size_t* src_size,
                                          void* const* dst, const vbz_size_t* dst_size, vbz_size_t* results,
                                          uint32_t n_reads, const struct CompressionOptions* options, int sized);
+
+/* Many HDF5 chunks of one dataset per call: the batch form of the H5Z filter 32020 callback (include/vbz_plugin.h, reference
+ * vbz_plugin/vbz_plugin.cpp:97-229).  flags & 0x0100 (H5Z_FLAG_REVERSE) decodes; cd_values = {version, integer_size, zigzag
+ * [, zstd level = 1]} as stored in the dataset's filter pipeline message.  Chunk i is src[i] (`[u32 size][payload]`, src_size[i]
+ * bytes) -> dst[i] (capacity dst_cap[i]); results[i] = what vbz_decompress_sized / vbz_compress_sized returns for it.  Returns -1
+ * when cd_nelmts < 3 (the filter callback returns 0 for every chunk then). */
+VBZ_EXPORT int vbz_b200_h5z_filter_batch(vbz_b200_ctx* ctx, unsigned int flags, size_t cd_nelmts, const unsigned int cd_values[],
+                                         uint32_t n_chunks, const void* const* src, const vbz_size_t* src_size, void* const* dst,
+                                         const vbz_size_t* dst_cap, vbz_size_t* results);
 
 /* ---- device-resident batches ---------------------------------------------------------------- */
 /* Size of the output slot the device-resident API needs for a read of source_size bytes: a tight

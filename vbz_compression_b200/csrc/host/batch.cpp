@@ -231,7 +231,7 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
 // ---- stage 2 (zstd), encode: content -> frames ----------------------------------------------------------------------
 // reads[i].first_block is set here.
 static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, std::vector<ZstdEncRead>& reads, const uint32_t* d_src_sizes,
-                               uint32_t* d_results, bool sized, cudaStream_t stream)
+                               uint32_t* d_results, bool sized, unsigned level, cudaStream_t stream)
 {
     const uint32_t n = (uint32_t)reads.size();
     if (n == 0) return 0;
@@ -264,26 +264,47 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.err_add = sized ? 4u : 0u;
     p.n_reads = n;
     p.n_blocks = n_blocks;
+    p.level = level;
     e = vbzk_zstd_encode(reinterpret_cast<const VbzkZstdEncParams*>(&p), stream);
     if (e) { cuda_ok((cudaError_t)e, "zstd_encode launch"); return -1; }
     ctx->launches += 3;  // block table, codes, frames
     return 0;
 }
 
-static bool device_path_available(const Stage1Kind& kind, bool decode = false)
+// ---- compress / decompress, device-resident ------------------------------------------------------------------
+// The two-stage paths keep the stage-1 bytes of the reads in flight in an intermediate buffer (d_mid).  A batch is cut into
+// WAVES of consecutive reads whose intermediate slots fit a budget (VBZ_B200_MID_MIB, default 8 GiB): the buffer stays
+// bounded whatever the batch size, so a batch is limited by its own input and output buffers only.  Waves run one after
+// the other on the caller's stream; each is large enough (GiBs) that its dozen launches do not show.
+static uint64_t mid_budget()
 {
-    (void)decode; (void)kind;
-    return true;  // every option combination of the reference has a device path
+    static const uint64_t v = [] {
+        const char* e = getenv("VBZ_B200_MID_MIB");
+        const long m = e ? atol(e) : 0;
+        return (uint64_t)(m > 0 ? m : 8192) << 20;
+    }();
+    return v;
+}
+// format bound of a stage-1 stream of n values: control bytes + 4 data bytes per value (ref streamvbyte.h:33-39 without the padding).
+// A valid stream written by ANY build of the reference fits (the non-SSSE3 builds use 3-byte codes for int16 deltas beyond
+// 16 bits, so the x86 encoder's keys + 2N is not a decode-side bound).
+static inline uint64_t stage1_format_bound(uint32_t n_values) { return ((uint64_t)n_values + 3) / 4 + 4ull * n_values; }
+
+static void stage_mark(vbz_b200_ctx* ctx, cudaStream_t stream)
+{
+    if (!ctx->stage_timing) return;
+    if (ctx->t_used == ctx->t_marks.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        ctx->t_marks.push_back(e);
+    }
+    cudaEventRecord(ctx->t_marks[ctx->t_used++], stream);
 }
 
-// ---- compress / decompress, device-resident ------------------------------------------------------------------
-static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ReadJob>& jobs,
-                                uint32_t* d_results, const Stage1Kind& kind, bool sized, cudaStream_t stream)
+static int compress_wave(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const ReadJob* jobs, uint32_t n, uint32_t* d_results,
+                         const Stage1Kind& kind, bool sized, cudaStream_t stream)
 {
-    if (!device_path_available(kind)) return -1;
-    const uint32_t n = (uint32_t)jobs.size();
     const bool zstd = kind.zstd_level != 0;
-    if (!zstd && kind.isz == 0) { set_last_error("plain copies (integer_size 0, level 0) are not a device operation"); return -1; }
     const uint32_t blk = vbzk_zstd_enc_block_bytes();
     std::vector<uint64_t> mid_off(zstd ? n : 0);
     uint64_t mid_total = 0;
@@ -313,7 +334,7 @@ static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t
         if (!zstd) return enqueue_stage1(ctx, false, kind, d_src, d_dst, reads, sized ? 4u : 0u, d_results, nullptr, stream);
         if (!ctx->d_mid.ensure(mid_total + 16) || !ctx->d_sizes.ensure((size_t)n * 4)) return -1;
         if (enqueue_stage1(ctx, false, kind, d_src, ctx->d_mid.as<uint8_t>(), reads, 0, ctx->d_sizes.as<uint32_t>(), nullptr, stream) != 0) return -1;
-        if (ctx->stage_timing) { cudaEventRecord(ctx->t_mid, stream); ctx->t_mid_set = true; }
+        stage_mark(ctx, stream);
     }
     // stage 2: one zstd frame per read (ref vbz/vbz.cpp:194-204)
     std::vector<ZstdEncRead> zr(n);
@@ -342,16 +363,44 @@ static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t
         z.n_blocks = (uint32_t)std::max<uint64_t>(1, (z.split + blk - 1) / blk + (largest - z.split + blk - 1) / blk);
     }
     return enqueue_zstd_encode(ctx, kind.isz != 0 ? ctx->d_mid.as<uint8_t>() : d_src, d_dst, zr, kind.isz != 0 ? ctx->d_sizes.as<uint32_t>() : nullptr,
-                               d_results, sized, stream);
+                               d_results, sized, kind.zstd_level, stream);
 }
 
-static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ReadJob>& jobs,
-                                  uint32_t* d_results, const Stage1Kind& kind, bool sized, cudaStream_t stream)
+static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ReadJob>& jobs,
+                                uint32_t* d_results, const Stage1Kind& kind, bool sized, cudaStream_t stream)
 {
-    if (!device_path_available(kind, true)) return -1;
-    if (kind.zstd_level == 0 && kind.isz == 0) { set_last_error("plain copies (integer_size 0, level 0) are not a device operation"); return -1; }
-    const uint32_t hdr = sized ? 4u : 0u;
     const uint32_t n = (uint32_t)jobs.size();
+    if (kind.zstd_level == 0 && kind.isz == 0) { set_last_error("plain copies (integer_size 0, level 0) are not a device operation"); return -1; }
+    if (kind.zstd_level == 0 || kind.isz == 0) return compress_wave(ctx, d_src, d_dst, jobs.data(), n, d_results, kind, sized, stream);
+    const uint64_t budget = mid_budget();
+    for (uint32_t a = 0; a < n;) {
+        uint64_t mid = 0;
+        uint32_t b = a;
+        while (b < n) {
+            const uint64_t m = jobs[b].rejected ? 0 : align16(stage1_tight_bound(jobs[b].src_size / (unsigned)kind.isz, kind)) + 16;
+            if (b > a && mid + m > budget) break;
+            mid += m;
+            ++b;
+        }
+        if (a) stage_mark(ctx, stream);  // wave boundary: the previous wave's zstd stage ends here
+        if (compress_wave(ctx, d_src, d_dst, jobs.data() + a, b - a, d_results + a, kind, sized, stream) != 0) return -1;
+        a = b;
+    }
+    return 0;
+}
+
+// intermediate capacity of one read on the decode side
+static inline uint64_t decode_mid_cap(const ReadJob& j, const Stage1Kind& kind)
+{
+    const uint64_t bound = stage1_format_bound(j.dst_size / (unsigned)kind.isz) + 1;  // + 1: a frame one byte too long must not pass for a valid one
+    uint64_t cap = j.mid_cap ? std::min<uint64_t>(j.mid_cap, bound) : bound;         // device-resident frames: the host cannot read the header
+    return std::min<uint64_t>(cap, 0xFFFFFFF0u);
+}
+
+static int decompress_wave(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const ReadJob* jobs, uint32_t n, uint32_t* d_results,
+                           const Stage1Kind& kind, bool sized, cudaStream_t stream)
+{
+    const uint32_t hdr = sized ? 4u : 0u;
     const uint8_t* s1_src = d_src;
     const uint32_t* s1_sizes = nullptr;
     std::vector<uint64_t> mid_off;
@@ -374,9 +423,7 @@ static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8
                 z.dst_off = j.dst_off;
                 z.dst_cap = j.dst_size;
             } else {
-                uint64_t cap = j.mid_cap;
-                if (cap == 0) cap = stage1_tight_bound(j.dst_size / (unsigned)kind.isz, kind) + 16;  // device-resident frames: the host cannot read the header
-                cap = std::min<uint64_t>(cap, 0xFFFFFFF0u);
+                const uint64_t cap = decode_mid_cap(j, kind);
                 mid_off[i] = mid_total;
                 z.dst_off = mid_total;
                 z.dst_cap = (uint32_t)cap;
@@ -391,8 +438,8 @@ static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8
             zdst = ctx->d_mid.as<uint8_t>();
         }
         if (enqueue_zstd_decode(ctx, d_src, zdst, zr, zres, stream) != 0) return -1;
-        if (ctx->stage_timing && kind.isz != 0) { cudaEventRecord(ctx->t_mid, stream); ctx->t_mid_set = true; }
         if (kind.isz == 0) return 0;
+        stage_mark(ctx, stream);
         s1_src = ctx->d_mid.as<uint8_t>();
         s1_sizes = ctx->d_sizes.as<uint32_t>();
     }
@@ -419,9 +466,48 @@ static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8
     return enqueue_stage1(ctx, true, kind, s1_src, d_dst, reads, 0, d_results, s1_sizes, stream);
 }
 
+static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ReadJob>& jobs,
+                                  uint32_t* d_results, const Stage1Kind& kind, bool sized, cudaStream_t stream)
+{
+    const uint32_t n = (uint32_t)jobs.size();
+    if (kind.zstd_level == 0 && kind.isz == 0) { set_last_error("plain copies (integer_size 0, level 0) are not a device operation"); return -1; }
+    if (kind.zstd_level == 0 || kind.isz == 0) return decompress_wave(ctx, d_src, d_dst, jobs.data(), n, d_results, kind, sized, stream);
+    const uint64_t budget = mid_budget();
+    for (uint32_t a = 0; a < n;) {
+        uint64_t mid = 0;
+        uint32_t b = a;
+        while (b < n) {
+            const uint64_t m = jobs[b].rejected ? 0 : align16(decode_mid_cap(jobs[b], kind)) + 16;
+            if (b > a && mid + m > budget) break;
+            mid += m;
+            ++b;
+        }
+        if (a) stage_mark(ctx, stream);
+        if (decompress_wave(ctx, d_src, d_dst, jobs.data() + a, b - a, d_results + a, kind, sized, stream) != 0) return -1;
+        a = b;
+    }
+    return 0;
+}
+
 }  // namespace vbz
 
 using namespace vbz;
+
+// Every entry point runs on the context's device and leaves the caller's current device as it found it (a host process may
+// drive several GPUs, e.g. torch with cuda:1 current while the H5Z filter uses device 0).
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        ok = prev == device || cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+        if (prev == device) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
 
 // ======================================================================================================
 // C ABI (include/vbz_b200.h)
@@ -440,9 +526,7 @@ vbz_b200_ctx::~vbz_b200_ctx()
         if (w.ev_out) cudaEventDestroy(w.ev_out);
         if (w.ev_outs) cudaEventDestroy(w.ev_outs);
     }
-    if (t_begin) cudaEventDestroy(t_begin);
-    if (t_mid) cudaEventDestroy(t_mid);
-    if (t_end) cudaEventDestroy(t_end);
+    for (cudaEvent_t e : t_marks) cudaEventDestroy(e);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
     if (s_d2hs) cudaStreamDestroy(s_d2hs);
@@ -463,7 +547,8 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
         set_last_error("no such CUDA device (" + std::to_string(device) + " of " + std::to_string(n) + "); libvbz_b200 has no CPU fallback");
         return nullptr;
     }
-    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+    DeviceGuard guard(device);
+    if (!guard.ok) return nullptr;
     vbz_b200_ctx* c = new vbz_b200_ctx();
     c->device = device;
     bool ok = cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
@@ -486,7 +571,7 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
 extern "C" void vbz_b200_destroy(vbz_b200_ctx* ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     delete ctx;
 }
@@ -516,7 +601,8 @@ extern "C" int vbz_b200_compress_device(vbz_b200_ctx* ctx, const void* d_src, co
                                         uint32_t n, const CompressionOptions* options, int sized, void* stream)
 {
     if (!ctx || !options) { set_last_error("null context or options"); return -1; }
-    if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return -1;
     const Stage1Kind kind = classify_options(options);
     std::vector<ReadJob> jobs(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -528,9 +614,12 @@ extern "C" int vbz_b200_compress_device(vbz_b200_ctx* ctx, const void* d_src, co
         set_last_error("invalid options: every read of the batch would be rejected");
         return -1;
     }
-    if (ctx->stage_timing) { ctx->t_mid_set = false; ctx->t_decode = false; cudaEventRecord(ctx->t_begin, (cudaStream_t)stream); }
+    ctx->t_used = 0;
+    ctx->t_decode = false;
+    ctx->t_two_stage = kind.zstd_level != 0 && kind.isz != 0;
+    stage_mark(ctx, (cudaStream_t)stream);
     const int rc = compress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0, (cudaStream_t)stream);
-    if (ctx->stage_timing) cudaEventRecord(ctx->t_end, (cudaStream_t)stream);
+    stage_mark(ctx, (cudaStream_t)stream);
     return rc;
 }
 
@@ -539,7 +628,8 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
                                           uint32_t n, const CompressionOptions* options, int sized, void* stream)
 {
     if (!ctx || !options) { set_last_error("null context or options"); return -1; }
-    if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return -1;
     const Stage1Kind kind = classify_options(options);
     if (kind.bad_isz || (kind.isz != 0 && kind.bad_version && kind.zstd_level == 0)) {
         set_last_error("invalid options: every read of the batch would be rejected");
@@ -557,32 +647,36 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
             else if (dst_size[i] % (unsigned)kind.isz != 0) j.post_code = kErrDestinationSize;
         }
     }
-    if (ctx->stage_timing) { ctx->t_mid_set = false; ctx->t_decode = true; cudaEventRecord(ctx->t_begin, (cudaStream_t)stream); }
+    ctx->t_used = 0;
+    ctx->t_decode = true;
+    ctx->t_two_stage = kind.zstd_level != 0 && kind.isz != 0;
+    stage_mark(ctx, (cudaStream_t)stream);
     const int rc = decompress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0, (cudaStream_t)stream);
-    if (ctx->stage_timing) cudaEventRecord(ctx->t_end, (cudaStream_t)stream);
+    stage_mark(ctx, (cudaStream_t)stream);
     return rc;
 }
 
 extern "C" int vbz_b200_set_stage_timing(vbz_b200_ctx* ctx, int on)
 {
     if (!ctx) return -1;
-    if (on && !ctx->t_begin &&
-        !(cuda_ok(cudaEventCreate(&ctx->t_begin), "cudaEventCreate") && cuda_ok(cudaEventCreate(&ctx->t_mid), "cudaEventCreate") &&
-          cuda_ok(cudaEventCreate(&ctx->t_end), "cudaEventCreate")))
-        return -1;
     ctx->stage_timing = on != 0;
+    ctx->t_used = 0;
     return 0;
 }
+// The marks of the last *_device call: begin, then per wave (first stage end, second stage end).  A single-stage call has two marks.
 extern "C" int vbz_b200_stage_times(vbz_b200_ctx* ctx, float* stage1_ms, float* zstd_ms)
 {
-    if (!ctx || !ctx->t_begin || !stage1_ms || !zstd_ms) { set_last_error("stage timing is not enabled"); return -1; }
-    if (!cuda_ok(cudaEventSynchronize(ctx->t_end), "cudaEventSynchronize")) return -1;
-    float total = 0.f, first = 0.f;
-    if (!cuda_ok(cudaEventElapsedTime(&total, ctx->t_begin, ctx->t_end), "cudaEventElapsedTime")) return -1;
-    if (!ctx->t_mid_set) { *stage1_ms = total; *zstd_ms = 0.f; return 0; }  // a single stage ran (reported as stage 1)
-    if (!cuda_ok(cudaEventElapsedTime(&first, ctx->t_begin, ctx->t_mid), "cudaEventElapsedTime")) return -1;
-    if (ctx->t_decode) { *zstd_ms = first; *stage1_ms = total - first; }  // decode runs the zstd stage first
-    else { *stage1_ms = first; *zstd_ms = total - first; }
+    if (!ctx || !stage1_ms || !zstd_ms || ctx->t_used < 2) { set_last_error("stage timing is not enabled"); return -1; }
+    if (!cuda_ok(cudaEventSynchronize(ctx->t_marks[ctx->t_used - 1]), "cudaEventSynchronize")) return -1;
+    float first = 0.f, second = 0.f;
+    for (size_t k = 0; k + 1 < ctx->t_used; ++k) {
+        float ms = 0.f;
+        if (!cuda_ok(cudaEventElapsedTime(&ms, ctx->t_marks[k], ctx->t_marks[k + 1]), "cudaEventElapsedTime")) return -1;
+        if (!ctx->t_two_stage || (k & 1) == 0) first += ms; else second += ms;
+    }
+    if (!ctx->t_two_stage) { *stage1_ms = first; *zstd_ms = 0.f; return 0; }  // a single stage ran (reported as stage 1)
+    if (ctx->t_decode) { *zstd_ms = first; *stage1_ms = second; }  // decode runs the zstd stage first
+    else { *stage1_ms = first; *zstd_ms = second; }
     return 0;
 }
 
@@ -751,6 +845,11 @@ static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
 {
     const uint32_t m = (uint32_t)b.jobs.size();
     if (m == 0) return 0;
+    struct NoStageTiming {  // the stage marks belong to the *_device calls
+        vbz_b200_ctx* c; bool keep;
+        explicit NoStageTiming(vbz_b200_ctx* ctx) : c(ctx), keep(ctx->stage_timing) { c->stage_timing = false; }
+        ~NoStageTiming() { c->stage_timing = keep; }
+    } no_timing(ctx);
     HostTrace tr;
     // ---- plan the waves -------------------------------------------------------------------------------------------
     uint64_t total = 0;
@@ -967,7 +1066,8 @@ extern "C" int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src
 {
     if (!ctx || !o) { set_last_error("null context or options"); return -1; }
     if (n == 0) return 0;
-    if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return -1;
     const bool sized = sized_i != 0;
     const uint32_t hdr = sized ? 4u : 0u;
     HostBatch b;
@@ -999,7 +1099,6 @@ extern "C" int vbz_b200_compress_batch(vbz_b200_ctx* ctx, const void* const* src
         b.jobs.push_back(h);
     }
     if (b.jobs.empty()) return 0;
-    if (!device_path_available(kind)) return -1;
     return run_host_batch(ctx, b);
 }
 
@@ -1008,7 +1107,8 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
 {
     if (!ctx || !o) { set_last_error("null context or options"); return -1; }
     if (n == 0) return 0;
-    if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return -1;
     const bool sized = sized_i != 0;
     const uint32_t hdr = sized ? 4u : 0u;
     HostBatch b;
@@ -1040,7 +1140,10 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
             if (kind.isz == 0) {
                 if (fcs > exact) { results[i] = kErrDestinationSize; continue; }
             } else {
-                if (fcs > (1ull << 31)) { results[i] = kErrOutOfMemory; continue; }  // the reference mallocs the content size here
+                // the reference mallocs the content size here (vbz.cpp:252).  The slot a read gets on the device is capped by what stage 1
+                // can consume for its `exact` output bytes (decode_mid_cap): a header that announces more cannot starve the batch of
+                // memory - the frame then fails to decode into its slot and this read alone reports the error
+                if (fcs > (1ull << 31)) { results[i] = kErrOutOfMemory; continue; }
                 h.j.mid_cap = fcs ? fcs : 1;
                 if (kind.bad_version) h.j.post_code = kErrVersion;
                 else if (exact % (unsigned)kind.isz != 0) h.j.post_code = kErrDestinationSize;
@@ -1055,6 +1158,5 @@ extern "C" int vbz_b200_decompress_batch(vbz_b200_ctx* ctx, const void* const* s
         b.jobs.push_back(h);
     }
     if (b.jobs.empty()) return 0;
-    if (!device_path_available(kind, true)) return -1;
     return run_host_batch(ctx, b);
 }

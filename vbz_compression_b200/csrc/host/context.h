@@ -54,8 +54,9 @@ struct vbz_b200_ctx {
     vbz::StageRing stage;  // pinned descriptor staging
     uint64_t launches = 0;
     // optional CUDA-event timing of the stages of the last *_device call (vbz_b200_set_stage_timing)
-    bool stage_timing = false, t_mid_set = false, t_decode = false;
-    cudaEvent_t t_begin = nullptr, t_mid = nullptr, t_end = nullptr;
+    bool stage_timing = false, t_decode = false, t_two_stage = false;
+    std::vector<cudaEvent_t> t_marks;  // stage boundaries of the last call, in stream order (begin, then two per wave)
+    size_t t_used = 0;
     uint32_t codec_ctas_per_sm = 0;  // != 0 while a host batch runs: room for the transfer kernels (SvbParams::ctas_per_sm)
 
     // descriptors and look-back state (stage 1)

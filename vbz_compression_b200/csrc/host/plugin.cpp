@@ -7,17 +7,37 @@
 #include <cstdlib>
 #include <limits>
 
+#include "../../../include/vbz_b200.h"
 #include "../../../include/vbz_plugin.h"
+
+// cd_values -> CompressionOptions exactly as the filter callback reads them (vbz_plugin.cpp:109-134)
+static bool options_from_cd_values(size_t cd_nelmts, const unsigned int cd_values[], CompressionOptions* options)
+{
+    if (cd_nelmts < 3) return false;  // vbz_plugin.cpp:109-112
+    options->vbz_version = cd_values[FILTER_VBZ_VERSION_OPTION];
+    options->integer_size = cd_values[FILTER_VBZ_INTEGER_SIZE_OPTION];
+    options->perform_delta_zig_zag = cd_values[FILTER_VBZ_USE_DELTA_ZIG_ZAG_COMPRESSION] != 0;
+    options->zstd_compression_level = cd_nelmts > FILTER_VBZ_ZSTD_COMPRESSION_LEVEL_OPTION ? cd_values[FILTER_VBZ_ZSTD_COMPRESSION_LEVEL_OPTION] : 1;
+    return true;
+}
+
+// Many chunks of one dataset per call: what libhdf5 hands the filter one chunk at a time (vbz_plugin.cpp:97-229), as a batch.
+// Chunk buffers are `[u32 size][payload]` (vbz.cpp:302-367); buffers belong to the caller (no malloc/free swap here).
+extern "C" int vbz_b200_h5z_filter_batch(vbz_b200_ctx* ctx, unsigned int flags, size_t cd_nelmts, const unsigned int cd_values[], uint32_t n_chunks,
+                                         const void* const* src, const vbz_size_t* src_size, void* const* dst, const vbz_size_t* dst_cap,
+                                         vbz_size_t* results)
+{
+    CompressionOptions options;
+    if (!options_from_cd_values(cd_nelmts, cd_values, &options)) return -1;
+    if (flags & VBZ_H5Z_FLAG_REVERSE) return vbz_b200_decompress_batch(ctx, src, src_size, dst, dst_cap, results, n_chunks, &options, 1);
+    return vbz_b200_compress_batch(ctx, src, src_size, dst, dst_cap, results, n_chunks, &options, 1);
+}
 
 extern "C" size_t vbz_b200_h5z_filter(unsigned int flags, size_t cd_nelmts, const unsigned int cd_values[], size_t /*nbytes*/,
                                       size_t* buf_size, void** buf)
 {
-    if (cd_nelmts < 3) return 0;  // vbz_plugin.cpp:109-112
     CompressionOptions options;
-    options.vbz_version = cd_values[FILTER_VBZ_VERSION_OPTION];
-    options.integer_size = cd_values[FILTER_VBZ_INTEGER_SIZE_OPTION];
-    options.perform_delta_zig_zag = cd_values[FILTER_VBZ_USE_DELTA_ZIG_ZAG_COMPRESSION] != 0;
-    options.zstd_compression_level = cd_nelmts > FILTER_VBZ_ZSTD_COMPRESSION_LEVEL_OPTION ? cd_values[FILTER_VBZ_ZSTD_COMPRESSION_LEVEL_OPTION] : 1;
+    if (!options_from_cd_values(cd_nelmts, cd_values, &options)) return 0;
 
     void* out = nullptr;
     vbz_size_t out_alloc = 0, used = 0;

@@ -121,15 +121,15 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* status, u
 // within the tile (*warp_excl) and posts, through `cta_slot`, the exclusive prefix of the tile
 // within the read (call chain_wait() to read it when it is finally needed).
 // slots: kSvbWarps words of shared memory, zeroed in the prologue.  mask trims the running value.
-__device__ __forceinline__ void chain_post(volatile uint64_t* slots, volatile uint64_t* cta_slot, uint64_t* status, uint32_t tile,
+__device__ __forceinline__ void chain_post(uint64_t* slots, uint64_t* cta_slot, uint64_t* status, uint32_t tile,
                                            uint32_t first_tile, uint64_t warp_total, uint64_t mask, uint64_t* warp_excl)
 {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) slots[wid] = kSlotReady | (warp_total & mask);
+    if (lane == 0) vbz_slot_post(slots + wid, kSlotReady | (warp_total & mask));
     uint64_t v = 0;
     if (wid > 0) {
         for (;;) {
-            v = lane < wid ? slots[lane] : kSlotReady;
+            v = lane < wid ? vbz_slot_read(slots + lane) : kSlotReady;
             if (__all_sync(0xffffffffu, (v & kSlotReady) != 0)) break;
             VBZ_SPIN_YIELD_SHARED();
         }
@@ -149,14 +149,14 @@ __device__ __forceinline__ void chain_post(volatile uint64_t* slots, volatile ui
             excl = lookback_exclusive(status, tile, first_tile) & mask;
             if (lane == 0) vbz_st_volatile_u64(status + tile, kStInclusive | ((excl + aggregate) & mask));
         }
-        if (lane == 0) *cta_slot = kSlotReady | excl;
+        if (lane == 0) vbz_slot_post(cta_slot, kSlotReady | excl);
     }
 }
-__device__ __forceinline__ uint64_t chain_wait(volatile uint64_t* cta_slot)
+__device__ __forceinline__ uint64_t chain_wait(const uint64_t* cta_slot)
 {
     uint64_t v;
     for (;;) {
-        v = *cta_slot;
+        v = vbz_slot_read(cta_slot);
         if (v & kSlotReady) break;
         VBZ_SPIN_YIELD_SHARED();
     }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kSvbThreads) svb_encode_kernel(SvbParams p)
     constexpr uint32_t TV = kSvbTileBytes / ISZ, WV = kSvbWarpTileBytes / ISZ;
     using L = SvbSmem<ISZ, MODE>;
     VBZ_DYN_SMEM(smem);
-    volatile uint64_t* ctrl = reinterpret_cast<volatile uint64_t*>(smem + L::kCtrlOff);
+    uint64_t* ctrl = reinterpret_cast<uint64_t*>(smem + L::kCtrlOff);
 
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kSvbThreads) svb_decode_kernel(SvbParams p)
     constexpr uint32_t TV = kSvbTileBytes / ISZ, WV = kSvbWarpTileBytes / ISZ;
     using L = SvbSmem<ISZ, MODE>;
     VBZ_DYN_SMEM(smem);
-    volatile uint64_t* ctrl = reinterpret_cast<volatile uint64_t*>(smem + L::kCtrlOff);
+    uint64_t* ctrl = reinterpret_cast<uint64_t*>(smem + L::kCtrlOff);
 
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x;

@@ -125,6 +125,8 @@ struct ZstdEncParams {
     uint32_t hdr_bytes;          // 4 = put the "sized" header before the frame
     uint32_t err_add;            // what the sized entry point adds to error codes (ref vbz/vbz.cpp:329)
     uint32_t n_reads, n_blocks;
+    uint32_t level;              // zstd_compression_level of the call (1, 2, 3 ... select the match finder's effort)
+    uint32_t pad;
 };
 constexpr uint32_t kZEncBlock = 128u * 1024u;  // content bytes per GROUP of the encoder: blocks that share one Huffman table
 constexpr uint32_t kZEncSub = 8u * 1024u;     // content bytes per block written by the encoder

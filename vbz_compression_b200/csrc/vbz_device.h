@@ -26,6 +26,8 @@ template <class T> static inline void vbz_st_stream(T* p, T v) { *p = v; }
 static inline uint64_t vbz_ld_volatile_u64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 static inline void vbz_st_volatile_u64(uint64_t* p, uint64_t v) { *(volatile uint64_t*)p = v; }
 static inline uint32_t vbz_ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+static inline void vbz_slot_post(uint64_t* slot, uint64_t v) { *(volatile uint64_t*)slot = v; }
+static inline uint64_t vbz_slot_read(const uint64_t* slot) { return *(const volatile uint64_t*)slot; }
 
 // packed 16-bit SIMD-in-a-word arithmetic (VIADD.16x2 on sm_100a)
 static inline uint32_t vbz_add16x2(uint32_t a, uint32_t b) { return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16); }
@@ -96,6 +98,18 @@ __device__ __forceinline__ uint32_t vbz_ld_volatile_u32(const uint32_t* p)
 {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// hand-off of one 64-bit word (value + ready bit) between warps of a CTA through shared memory: release store, acquire load
+// (strong operations at CTA scope: defined under the PTX memory model without a barrier in between)
+__device__ __forceinline__ void vbz_slot_post(uint64_t* slot, uint64_t v)
+{
+    asm volatile("st.release.cta.shared.u64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t vbz_slot_read(const uint64_t* slot)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(slot)) : "memory");
     return v;
 }
 // packed 16-bit SIMD-in-a-word arithmetic (VIADD.16x2 on sm_100a)
