@@ -57,7 +57,7 @@ vbzo_size_t vbzo_max_streamvbyte_compressed_size(unsigned integer_size, vbzo_siz
 {
     if (source_size % integer_size != 0) return VBZO_INPUT_SIZE_ERROR;
     uint32_t n = source_size / integer_size;
-    uint64_t cb = ((uint64_t)n + 3) / 4, db = (uint64_t)n * 4;
+    uint64_t cb = (uint32_t)(n + 3u) / 4u, db = (uint64_t)n * 4; /* `length + 3` is uint32 arithmetic in streamvbyte.h:35 */
     return (vbzo_size_t)(cb + db + 16);
 }
 

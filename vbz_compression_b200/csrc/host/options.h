@@ -50,7 +50,7 @@ inline uint32_t max_streamvbyte_size(unsigned isz, uint32_t source_size)
 {
     if (source_size % isz != 0) return kErrInputSize;
     const uint32_t n = source_size / isz;
-    return (uint32_t)(((uint64_t)n + 3) / 4 + (uint64_t)n * 4 + 16);
+    return (uint32_t)((uint64_t)((uint32_t)(n + 3u) / 4u) + (uint64_t)n * 4 + 16);  // `length + 3` wraps in 32 bits there, and so does the result
 }
 // ZSTD_COMPRESSBOUND (zstd.h), the value ZSTD_compressBound returns for sizes in 32-bit range
 inline uint64_t zstd_compress_bound(uint64_t n)
