@@ -87,6 +87,12 @@ VBZ_EXPORT int vbz_b200_synchronize(vbz_b200_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 VBZ_EXPORT uint64_t vbz_b200_kernel_launches(vbz_b200_ctx* ctx);
 
+/* Diagnostics: where the frames of the last zstd-stage decode of this context went (waits for it).  out[0] = blocks listed as units,
+ * out[1] = frames decoded by the general warp-per-frame kernel (checksums, several frames in one buffer, damaged input, pool overflow),
+ * out[2] = frames with sequences decoded block-parallel (sequence kernels), out[3] = sequence records used.  A batch that runs as
+ * several waves reports its last wave. */
+VBZ_EXPORT int vbz_b200_decode_stats(vbz_b200_ctx* ctx, uint32_t out[4]);
+
 /* Optional: time the two stages of each *_device call with CUDA events on the call's stream (bench.py's roofline lines).
  * vbz_b200_stage_times waits for the last call and returns the milliseconds its stage-1 kernels (delta + zigzag + StreamVByte,
  * ref vbz/v0, vbz/v1) and its zstd-stage kernels (ref vbz/vbz.cpp:194-204, 236-272) took, launch overheads included. */

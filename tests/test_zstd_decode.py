@@ -115,3 +115,56 @@ def test_fuzz_corpus_level1_decode(backend):
                     assert a[0] == b[0], (n, ds, sized, o.integer_size, a[0], b[0])
                     if not ol.is_error(b[0]):
                         assert a[1] == b[1]
+
+
+def _decode_stats(backend):
+    import ctypes
+    _, batch, lib = backend
+    out = (ctypes.c_uint32 * 4)()
+    assert lib.vbz_b200_decode_stats(batch.ctx, out) == 0
+    return {"units": out[0], "general": out[1], "seq_frames": out[2], "records": out[3]}
+
+
+def test_frames_with_sequences_take_the_block_parallel_path(backend):
+    """What real fast5 files contain - frames written by the reference's libzstd, whose first block carries sequences - must not
+    fall back to the serial warp-per-frame kernel: the walker lists their blocks, the sequence kernels handle the blocks with
+    sequences (csrc/zstd_dec_kernels.cuh)."""
+    _, batch, _ = backend
+    small = backend[0].path.endswith("cpusim.so")
+    reads = golden_data.fast5_reads()
+    reads = reads[:5] if small else reads
+    o = Options(True, 2, 1, 1)
+    res = batch.decompress([rd["vbz_chunk"] for rd in reads], [rd["samples"].nbytes for rd in reads], o, sized=True)
+    for rd, (code, blob) in zip(reads, res):
+        assert code == rd["samples"].nbytes and blob == rd["samples"].tobytes()
+    st = _decode_stats(backend)
+    assert st["general"] == 0 and st["seq_frames"] == len(reads) and st["records"] > 0, st
+    # libzstd at several levels on inputs with matches of every kind: repeat offsets, long matches, several blocks with sequences
+    rng = np.random.default_rng(5)
+    datas = [bytes(np.repeat(rng.integers(0, 256, 300, dtype=np.uint8), 50)), b"the quick brown fox jumps over the lazy dog. " * 900,
+             bytes(np.arange(60000 if small else 200000, dtype=np.uint32).view(np.uint8)), ol.stage1_encode(data_gen.nanopore_like(60000, rng), 2, True),
+             ol.stage1_encode(np.tile(data_gen.nanopore_like(2000, rng), 40 if small else 150), 2, True)]
+    for level in (1, 3, 9) if small else (1, 2, 3, 5, 9, 19):
+        frames = [ol.zstd_compress_lib(d, level) for d in datas]
+        res = batch.decompress(frames, [len(d) for d in datas], Options(False, 0, level, 0), sized=False)
+        for d, (code, blob) in zip(datas, res):
+            assert code == len(d) and blob == d, (level, len(d), code)
+        st = _decode_stats(backend)
+        assert st["general"] == 0, (level, st)
+
+
+def test_pool_overflow_and_damage_fall_back_to_the_general_kernel(backend):
+    """A frame the sequence kernel cannot vouch for is decided by the general kernel; its neighbours in the batch are not affected."""
+    _, batch, _ = backend
+    rng = np.random.default_rng(6)
+    good = b"abcdefgh" * 4000
+    frame = ol.zstd_compress_lib(good, 3)
+    bad = bytearray(frame)
+    bad[len(bad) // 2] ^= 0x10
+    sig = ol.stage1_encode(data_gen.nanopore_like(30000, rng), 2, True)
+    frames = [frame, bytes(bad), ol.zstd_compress_lib(sig, 1), frame[:-3]]
+    sizes = [len(good), len(good), len(sig), len(good)]
+    res = batch.decompress(frames, sizes, Options(False, 0, 1, 0), sized=False)
+    want = [port.decompress(f, Options(False, 0, 1, 0), s, sized=False) for f, s in zip(frames, sizes)]
+    for (code, blob), (wc, wb) in zip(res, want):
+        assert code == wc and (ol.is_error(wc) or blob == wb)

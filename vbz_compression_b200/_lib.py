@@ -57,6 +57,7 @@ def bind(lib):
     lib.vbz_b200_h5z_filter.restype = ctypes.c_size_t
     lib.vbz_b200_h5z_filter.argtypes = [ctypes.c_uint, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint), ctypes.c_size_t,
                                         ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(vp)]
+    lib.vbz_b200_decode_stats.restype, lib.vbz_b200_decode_stats.argtypes = ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_uint32)]
     lib.vbz_b200_h5z_filter_batch.restype = ctypes.c_int
     lib.vbz_b200_h5z_filter_batch.argtypes = [vp, ctypes.c_uint, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint), u32, ctypes.POINTER(vp), u32p,
                                               ctypes.POINTER(vp), u32p, u32p]
@@ -68,7 +69,7 @@ EXPORTED_SYMBOLS = [
     "vbz_decompress_sized", "vbz_decompressed_size",
     "vbz_b200_device_count", "vbz_b200_create", "vbz_b200_destroy", "vbz_b200_last_error", "vbz_b200_compress_batch",
     "vbz_b200_decompress_batch", "vbz_b200_compress_device", "vbz_b200_decompress_device", "vbz_b200_synchronize",
-    "vbz_b200_kernel_launches", "vbz_b200_compress_bound", "vbz_b200_stream", "vbz_b200_set_stage_timing", "vbz_b200_stage_times",
+    "vbz_b200_kernel_launches", "vbz_b200_compress_bound", "vbz_b200_stream", "vbz_b200_set_stage_timing", "vbz_b200_stage_times", "vbz_b200_decode_stats",
     "H5PLget_plugin_type", "H5PLget_plugin_info", "vbz_plugin_info", "vbz_b200_h5z_filter", "vbz_b200_h5z_filter_batch",
 ]
 

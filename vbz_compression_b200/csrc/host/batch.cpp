@@ -203,6 +203,13 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     for (uint32_t i = 0; i < n; ++i)
         if (!reads[i].rejected) unit_cap += zstd_units_of(reads[i].dst_cap);
     unit_cap = std::min<uint64_t>(std::max<uint64_t>(unit_cap, 8), 0x7FFFFFF0u);
+    // records for the sequences of frames with sequences: one per 32 content bytes on average (a signal frame needs one per ~150; a frame
+    // of a batch that runs the pool dry is decoded by the general kernel instead)
+    uint64_t seq_cap = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!reads[i].rejected) seq_cap += reads[i].dst_cap / 32u + 64u;
+    seq_cap = std::min<uint64_t>(std::max<uint64_t>(seq_cap, 1024), 0x7FFFFFF0u);
+    if (!ctx->d_zseqs.ensure((size_t)seq_cap * sizeof(ZstdSeq)) || !ctx->d_zseqframes.ensure((size_t)n * sizeof(ZstdSeqFrame))) return -1;
     if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes()) ||
         !ctx->d_zunits.ensure((size_t)unit_cap * sizeof(ZstdUnit)) || !ctx->d_zgroups.ensure((size_t)unit_cap * sizeof(ZstdGroup)) ||
         !ctx->d_zgeneral.ensure((size_t)n * 4))
@@ -220,11 +227,16 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.units = ctx->d_zunits.as<ZstdUnit>();
     p.groups = ctx->d_zgroups.as<ZstdGroup>();
     p.general = ctx->d_zgeneral.as<uint32_t>();
+    p.seqs = ctx->d_zseqs.as<ZstdSeq>();
+    p.seq_frames = ctx->d_zseqframes.as<ZstdSeqFrame>();
     p.unit_cap = (uint32_t)unit_cap;
     p.n_reads = n;
+    p.seq_cap = (uint32_t)seq_cap;
+    p.pad = 0;
     const int e = vbzk_zstd_decode(reinterpret_cast<const VbzkZstdDecParams*>(&p), stream);
     if (e) { cuda_ok((cudaError_t)e, "zstd_decode launch"); return -1; }
-    ctx->launches += 3;  // walker, units kernel, general kernel
+    ctx->launches += 5;  // walker, sequence kernel, units kernel, sequence executor, general kernel
+    ctx->last_zdecode_stream = stream;
     return 0;
 }
 
@@ -517,7 +529,7 @@ vbz_b200_ctx::~vbz_b200_ctx()
     d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
     h_results.release(); stage.release();
     d_mid.release();
-    d_zreads.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); d_zcodes.release();
+    d_zreads.release(); d_zseqs.release(); d_zseqframes.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); d_zcodes.release();
     for (WaveSlot& w : slots) {
         w.d_in.release(); w.d_out.release(); w.d_results.release(); w.d_pack.release(); w.d_xin.release(); w.d_xout.release();
         w.h_in.release(); w.h_out.release(); w.h_results.release();
@@ -654,6 +666,21 @@ extern "C" int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, 
     const int rc = decompress_device_impl(ctx, (const uint8_t*)d_src, (uint8_t*)d_dst, jobs, d_results, kind, sized != 0, (cudaStream_t)stream);
     stage_mark(ctx, (cudaStream_t)stream);
     return rc;
+}
+
+// where the frames of the last zstd-stage decode (the last wave of the last call) went: out[0] = units listed, out[1] = frames decoded by
+// the general (warp per frame) kernel, out[2] = frames with sequences decoded block-parallel, out[3] = sequence records used
+extern "C" int vbz_b200_decode_stats(vbz_b200_ctx* ctx, uint32_t out[4])
+{
+    if (!ctx || !out || !ctx->d_zcounter.p) { set_last_error("no zstd-stage decode has run on this context"); return -1; }
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return -1;
+    uint32_t c[16] = {};
+    if (!cuda_ok(cudaStreamSynchronize(ctx->last_zdecode_stream), "cudaStreamSynchronize") ||
+        !cuda_ok(cudaMemcpy(c, ctx->d_zcounter.p, sizeof(c), cudaMemcpyDeviceToHost), "cudaMemcpy"))
+        return -1;
+    out[0] = c[1]; out[1] = c[2]; out[2] = c[6]; out[3] = c[5];
+    return 0;
 }
 
 extern "C" int vbz_b200_set_stage_timing(vbz_b200_ctx* ctx, int on)

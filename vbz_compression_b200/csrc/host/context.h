@@ -57,13 +57,14 @@ struct vbz_b200_ctx {
     bool stage_timing = false, t_decode = false, t_two_stage = false;
     std::vector<cudaEvent_t> t_marks;  // stage boundaries of the last call, in stream order (begin, then two per wave)
     size_t t_used = 0;
+    cudaStream_t last_zdecode_stream = nullptr;
     uint32_t codec_ctas_per_sm = 0;  // != 0 while a host batch runs: room for the transfer kernels (SvbParams::ctas_per_sm)
 
     // descriptors and look-back state (stage 1)
     vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
     vbz::PinBuf h_results;
     // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
-    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral;
+    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral, d_zseqs, d_zseqframes;
     // intermediate stage-1 bytes of the two-stage paths
     vbz::DevBuf d_mid;
     // host-pointer API: a batch runs as WAVES through kWaveSlots slots so that the upload of wave w+1, the kernels of

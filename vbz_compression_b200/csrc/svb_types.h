@@ -73,31 +73,44 @@ struct ZstdRead {
     uint32_t rejected;   // != 0: decided on the host; copy `preset` to results[]
     uint32_t preset;
 };
-// One piece of a "simple" frame (every block Raw, RLE, or Compressed with a literals section and no sequences): the
-// walker (zstd_walk_kernel) lists them, zstd_units_kernel executes them in parallel (csrc/zstd_dec_kernels.cuh).
-enum : uint32_t { kZUnitNop = 0, kZUnitCopy = 1, kZUnitFill = 2, kZUnitHuf = 3 };
+// One block (or piece of a block) of a frame.  The walker (zstd_walk_kernel) lists them; frames whose blocks carry no sequences
+// are executed by zstd_units_kernel alone, in parallel over blocks and Huffman streams.  A block WITH sequences becomes a Seq unit:
+// zstd_seq_kernel decodes its sequences into records (and only then knows how many bytes the block regenerates, i.e. where the
+// blocks after it go), zstd_seqexec_kernel decodes its literals and executes the records (csrc/zstd_dec_kernels.cuh).
+enum : uint32_t { kZUnitNop = 0, kZUnitCopy = 1, kZUnitFill = 2, kZUnitHuf = 3, kZUnitSeq = 4 };
 struct ZstdUnit {
-    uint64_t src_off;    // Copy: the bytes; Fill: the byte; Huf: the literals section (its header first), offsets into ZstdDecParams::src
-    uint64_t dst_off;    // offset into ZstdDecParams::dst
-    uint32_t n;          // Copy / Fill: bytes to produce; Huf: size of the literals section
-    uint32_t tab_back;   // Huf, treeless literals: distance back from src_off to the literals section that carries the tree
+    uint64_t src_off;    // Copy: the bytes; Fill: the byte; Huf / Seq: the literals section (its header first), offsets into ZstdDecParams::src
+    uint64_t dst_off;    // offset into ZstdDecParams::dst (Seq frames: filled in by zstd_seq_kernel)
+    uint32_t n;          // Copy / Fill: bytes to produce; Huf: size of the literals section; Seq: size of the block
+    uint32_t tab_back;   // Huf / Seq, treeless literals: distance back from src_off to the literals section that carries the tree
     uint32_t read;       // whose result becomes kErrZstd if the unit fails
     uint32_t kind;
+    uint32_t regen;      // content bytes the unit produces (Seq: filled in by zstd_seq_kernel)
+    uint32_t nseq;       // Seq: number of sequences
+    uint32_t seq_first;  // Seq: index of its first record in ZstdDecParams::seqs
+    uint32_t pad;
 };
 struct ZstdGroup { uint32_t first, count; };  // units [first, first + count): decoded together by one CTA of zstd_units_kernel
+struct alignas(16) ZstdSeq { uint32_t offset, ll, ml, pad; };  // one decoded sequence: literal run, then a match `offset` back
+struct ZstdSeqFrame { uint32_t read, unit_first, unit_count, pad; };  // a frame with Seq units: its units, in block order
 struct ZstdDecParams {
     const uint8_t* src;
     uint8_t* dst;
     const ZstdRead* reads;
     uint32_t* results;   // per read: content bytes, or kErrZstd
-    uint8_t* lit_scratch;  // 128 KiB + 32 per warp of the general kernel's grid
-    uint32_t* counter;   // 8 words, zeroed before launch: [0] work counter of the general kernel, [1] units listed,
-                         // [2] frames left to the general kernel, [3] work counter of the units kernel, [4] groups listed
+    uint8_t* lit_scratch;  // 128 KiB + 32 per warp of the general kernel's / the sequence executor's grid
+    uint32_t* counter;   // 16 words, zeroed before launch: [0] work counter of the general kernel, [1] units listed,
+                         // [2] frames left to the general kernel, [3] work counter of the units kernel, [4] groups listed,
+                         // [5] sequence records allotted, [6] frames with Seq units, [7] / [8] work counters of the two sequence kernels
     ZstdUnit* units;     // unit_cap entries
     ZstdGroup* groups;   // unit_cap entries
     uint32_t* general;   // n_reads entries: the frames the walker left to the general kernel
+    ZstdSeq* seqs;       // seq_cap records
+    ZstdSeqFrame* seq_frames;  // n_reads entries
     uint32_t unit_cap;
     uint32_t n_reads;
+    uint32_t seq_cap;
+    uint32_t pad;
 };
 VBZ_HD uint32_t zstd_units_of(uint32_t dst_cap) { return dst_cap / 8192u + 6u; }  // unit slots the host reserves per frame
 

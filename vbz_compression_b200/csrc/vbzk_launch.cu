@@ -179,19 +179,33 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     // 1. frames -> units (or the general kernel's list)
     VBZ_LAUNCH(zstd_walk_kernel, (p.n_reads + 127) / 128, 128, 0, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
-    // 2. the groups of units, a CTA of 64 threads each from a work counter; the grid is sized for the most there can be
+    // 2. frames with sequences: decode the sequences into records, which gives every unit of those frames its position
+    {
+        const uint32_t ssmem = (uint32_t)(sizeof(ZSeqWarp) * kZSeqWarps);
+        if (int e = VBZK_SET_SMEM(zstd_seq_kernel, ssmem)) return e;
+        static const uint32_t sgrid_max = persistent_grid(zstd_seq_kernel, kZSeqWarps * 32, ssmem, 0xFFFFFFFFu, 0);
+        const uint32_t sneed = (p.n_reads + kZSeqWarps - 1) / kZSeqWarps;
+        VBZ_LAUNCH(zstd_seq_kernel, sneed < sgrid_max ? sneed : sgrid_max, kZSeqWarps * 32, ssmem, (vbz_stream_t)stream, p);
+        if (int e = VBZK_LAST_ERROR()) return e;
+    }
+    // 3. the groups of units, a CTA of 64 threads each from a work counter; the grid is sized for the most there can be
     const uint32_t usmem = (uint32_t)sizeof(ZGroupSmem);
     if (int e = VBZK_SET_SMEM(zstd_units_kernel, usmem)) return e;
     static const uint32_t ugrid_max = persistent_grid(zstd_units_kernel, kZUnitThreads, usmem, 0xFFFFFFFFu, 0);
     uint32_t ugrid = p.unit_cap < ugrid_max ? p.unit_cap : ugrid_max;
     if (ugrid) VBZ_LAUNCH(zstd_units_kernel, ugrid, kZUnitThreads, usmem, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
-    // 3. whatever the walker left over, a warp per frame
+    // 4. frames with sequences: literals and records of their Seq units, a warp per frame (everything a match can reach back to is in place)
     const uint32_t smem = (uint32_t)(sizeof(ZWarp) * kZdecWarps);
     if (int e = VBZK_SET_SMEM(zstd_decode_kernel, smem)) return e;
     uint32_t grid = vbzk_zstd_decode_grid();
     const uint32_t need = (p.n_reads + kZdecWarps - 1) / kZdecWarps;
     if (need < grid) grid = need;
+    const uint32_t xsmem = (uint32_t)(sizeof(ZExecWarp) * kZExecWarps);
+    if (int e = VBZK_SET_SMEM(zstd_seqexec_kernel, xsmem)) return e;
+    VBZ_LAUNCH(zstd_seqexec_kernel, grid, kZExecWarps * 32, xsmem, (vbz_stream_t)stream, p);  // (same grid bound as the general kernel: they share the literal scratch)
+    if (int e = VBZK_LAST_ERROR()) return e;
+    // 5. whatever the walker and the sequence kernel left over, a warp per frame
     VBZ_LAUNCH(zstd_decode_kernel, grid, kZdecWarps * 32, smem, (vbz_stream_t)stream, p);
     return VBZK_LAST_ERROR();
 }

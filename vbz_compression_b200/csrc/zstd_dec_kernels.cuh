@@ -787,10 +787,24 @@ __device__ __forceinline__ bool z_lit_header(const uint8_t* p, uint32_t n, int* 
     return true;
 }
 
+// number of sequences of a block, from the first bytes of its sequences section (RFC 8878 3.1.1.3.2.1).  *h = bytes used; 0 on truncation
+__device__ __forceinline__ bool z_seq_count(const uint8_t* q, uint32_t left, uint32_t* nseq, uint32_t* h)
+{
+    if (left < 1) return false;
+    const uint32_t b0 = q[0];
+    if (b0 < 128) { *nseq = b0; *h = 1; return true; }
+    if (b0 < 255) { if (left < 2) return false; *nseq = ((b0 - 128) << 8) + q[1]; *h = 2; return true; }
+    if (left < 3) return false;
+    *nseq = z_le16(q + 1) + 0x7F00; *h = 3;
+    return true;
+}
+
 // One pass over a frame.  emit == nullptr: count.  Returns the number of units, or 0xFFFFFFFF if the frame is not for
-// this path.  *total = content bytes.
-__device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_t r, ZstdUnit* emit, uint32_t* total, ZstdGroup* gemit,
-                                 uint32_t unit_base, uint32_t* n_groups)
+// this path.  *total = content bytes (only meaningful when no block carries sequences); *n_seqs = sequences of all Seq units
+// (their records are numbered from seq_base on, block after block).
+struct ZWalk { uint32_t total, groups, seqs; bool deferred; };
+__device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_t r, ZstdUnit* emit, ZstdGroup* gemit, uint32_t unit_base,
+                                 uint32_t seq_base, ZWalk* out)
 {
     const uint32_t kNo = 0xFFFFFFFFu;
     const uint8_t* p = src + rd.src_off;
@@ -803,10 +817,11 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
     n -= h;
     const uint64_t cap = rd.dst_cap;
     uint64_t op = 0;
-    uint32_t units = 0, groups = 0;
+    uint32_t units = 0, groups = 0, seqs = 0;
+    bool deferred = false;         // a block with sequences came by: positions from here on are known after zstd_seq_kernel only
     const uint8_t* tab = nullptr;  // the last literals section that carried a tree
     // a GROUP = up to 16 consecutive Huffman units decoded with the same table (the one that carries the tree and the
-    // treeless ones after it), or a single Raw / RLE piece
+    // treeless ones after it), or a single Raw / RLE piece.  Seq units belong to no group.
     uint32_t g_first = 0, g_count = 0;
     for (;;) {
         if (n < 3) return kNo;
@@ -821,34 +836,49 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
         u.tab_back = 0;
         u.kind = kZUnitNop;
         u.n = 0;
+        u.regen = 0;
+        u.nseq = 0;
+        u.seq_first = 0;
+        u.pad = 0;
         u.src_off = (uint64_t)(p - src);
         uint32_t adv;
         if (type == 0) {
-            if (bs > n || op + bs > cap) return kNo;
-            u.kind = kZUnitCopy; u.n = bs; adv = bs;
+            if (bs > n || (!deferred && op + bs > cap)) return kNo;
+            u.kind = kZUnitCopy; u.n = bs; u.regen = bs; adv = bs;
         } else if (type == 1) {
-            if (n < 1 || op + bs > cap) return kNo;
-            u.kind = kZUnitFill; u.n = bs; adv = 1;
+            if (n < 1 || bs > kZBlockMax || (!deferred && op + bs > cap)) return kNo;
+            u.kind = kZUnitFill; u.n = bs; u.regen = bs; adv = 1;
         } else if (type == 2) {
             if (bs > n || bs >= kZBlockMax) return kNo;
             int lt, streams;
             uint32_t hdr, regen, comp;
             if (!z_lit_header(p, bs, &lt, &hdr, &regen, &comp, &streams)) return kNo;
             const uint32_t sec = lt == 0 ? hdr + regen : lt == 1 ? hdr + 1 : hdr + comp;
-            if ((uint64_t)sec + 1 != bs || p[sec] != 0) return kNo;  // the block must end with "0 sequences"
-            if (regen > kZBlockMax || op + regen > cap) return kNo;
-            if (lt == 0) { u.kind = kZUnitCopy; u.src_off += hdr; u.n = regen; }
-            else if (lt == 1) { u.kind = kZUnitFill; u.src_off += hdr; u.n = regen; }
-            else {
-                if (lt == 2) tab = p;
-                else if (!tab) return kNo;
-                u.kind = kZUnitHuf; u.n = sec; u.tab_back = (uint32_t)(p - tab);
+            if (sec >= bs || regen > kZBlockMax) return kNo;
+            if (lt == 2) tab = p;
+            else if (lt == 3 && !tab) return kNo;
+            if (p[sec] == 0) {  // "0 sequences": the block regenerates exactly its literals
+                if ((uint64_t)sec + 1 != bs || (!deferred && op + regen > cap)) return kNo;
+                if (lt == 0) { u.kind = kZUnitCopy; u.src_off += hdr; u.n = regen; }
+                else if (lt == 1) { u.kind = kZUnitFill; u.src_off += hdr; u.n = regen; }
+                else { u.kind = kZUnitHuf; u.n = sec; u.tab_back = (uint32_t)(p - tab); }
+                u.regen = regen;
+            } else {
+                uint32_t nseq, sh;
+                if (!z_seq_count(p + sec, bs - sec, &nseq, &sh)) return kNo;
+                u.kind = kZUnitSeq; u.n = bs; u.tab_back = lt == 3 ? (uint32_t)(p - tab) : 0u;
+                u.nseq = nseq; u.seq_first = seq_base + seqs;
+                seqs += nseq;
+                deferred = true;
             }
             adv = bs;
-            op += regen;
         } else return kNo;
-        if (type < 2) op += bs;
-        if (u.n != 0) {
+        op += u.regen;
+        if (u.kind == kZUnitSeq) {
+            if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; g_count = 0; }
+            if (emit) emit[units] = u;
+            ++units;
+        } else if (u.n != 0) {
             const bool extend = u.kind == kZUnitHuf && u.tab_back != 0 && g_count != 0 && g_count < 16;  // (an open group is always a Huffman one)
             if (!extend) {
                 if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; }
@@ -868,10 +898,13 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
         n -= adv;
         if (last) break;
     }
-    if (n != 0 || (has && op != fcs) || op > 0xFFFFFFF0ull) return kNo;
+    if (n != 0 || op > 0xFFFFFFF0ull) return kNo;
+    if (!deferred && has && op != fcs) return kNo;
     if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; }
-    *total = (uint32_t)op;
-    *n_groups = groups;
+    out->total = (uint32_t)op;
+    out->groups = groups;
+    out->seqs = seqs;
+    out->deferred = deferred;
     return units;
 }
 
@@ -881,22 +914,28 @@ __global__ void zstd_walk_kernel(ZstdDecParams p)
     if (r >= p.n_reads) return;
     const ZstdRead rd = p.reads[r];
     if (rd.rejected) { p.results[r] = rd.preset; return; }
-    uint32_t total = 0, gcnt = 0;
-    const uint32_t cnt = z_walk_frame(p.src, rd, r, nullptr, &total, nullptr, 0, &gcnt);
+    ZWalk w = {0, 0, 0, false};
+    const uint32_t cnt = z_walk_frame(p.src, rd, r, nullptr, nullptr, 0, 0, &w);
     bool mine = cnt != 0xFFFFFFFFu;
     if (mine && cnt != 0) {
         const uint32_t base = atomicAdd(p.counter + 1, cnt);
-        const uint32_t gbase = atomicAdd(p.counter + 4, gcnt);
-        if (base >= p.unit_cap || cnt > p.unit_cap - base || gbase >= p.unit_cap || gcnt > p.unit_cap - gbase) {
+        const uint32_t gbase = w.groups ? atomicAdd(p.counter + 4, w.groups) : 0u;
+        const uint32_t sbase = w.seqs ? atomicAdd(p.counter + 5, w.seqs) : 0u;
+        const uint32_t gcnt = w.groups;
+        if (base >= p.unit_cap || cnt > p.unit_cap - base || (gcnt && (gbase >= p.unit_cap || gcnt > p.unit_cap - gbase)) ||
+            (w.seqs && (sbase >= p.seq_cap || w.seqs > p.seq_cap - sbase))) {
             // out of slots: the units kernel stops at unit_cap; what was allotted here stays empty
-            for (uint32_t k = gbase; k < p.unit_cap && k - gbase < gcnt; ++k) p.groups[k] = ZstdGroup{0, 0};
+            for (uint32_t k = gbase; gcnt && k < p.unit_cap && k - gbase < gcnt; ++k) p.groups[k] = ZstdGroup{0, 0};
             mine = false;
-        } else z_walk_frame(p.src, rd, r, p.units + base, &total, p.groups + gbase, base, &gcnt);
+        } else {
+            z_walk_frame(p.src, rd, r, p.units + base, p.groups + gbase, base, sbase, &w);
+            if (w.deferred) p.seq_frames[atomicAdd(p.counter + 6, 1u)] = ZstdSeqFrame{r, base, cnt, 0};
+        }
     }
-    if (mine) p.results[r] = total;
+    if (mine) { if (!w.deferred) p.results[r] = w.total; }
     else p.general[atomicAdd(p.counter + 2, 1u)] = r;
 #ifdef VBZ_CPUSIM
-    if (getenv("VBZ_B200_TRACE_WALK")) fprintf(stderr, "walk: read %u -> %s (%u units, %u groups, %u bytes)\n", r, mine ? "units" : "general", mine ? cnt : 0u, mine ? gcnt : 0u, total);
+    if (getenv("VBZ_B200_TRACE_WALK")) fprintf(stderr, "walk: read %u -> %s (%u units, %u groups, %u sequences, %u bytes)\n", r, mine ? (w.deferred ? "units + sequence kernels" : "units") : "general", mine ? cnt : 0u, mine ? w.groups : 0u, mine ? w.seqs : 0u, w.total);
 #endif
 }
 
@@ -1075,6 +1114,292 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
             }
             if (!ok) p.results[un.read] = kErrZstd;
         }
+    }
+}
+
+// ---- frames with sequences: the two sequence kernels ------------------------------------------------------------------------
+// A block with sequences regenerates lit_n + sum(match lengths) bytes - known only once its sequences have been decoded, and
+// the FSE states make that a serial walk.  So the work is split by what it depends on:
+//   zstd_seq_kernel      a WARP per frame with Seq units, its blocks in order: lane 0 builds the sequence tables (they and the three
+//                        repeat offsets persist from block to block) and decodes the sequences into RECORDS {offset, ll, ml} with the
+//                        repeat-offset codes resolved; the block's size follows, and with it the position of every unit of the frame
+//                        (dst_off of ALL its units is written here).  Nothing is copied yet.
+//   zstd_units_kernel    then decodes every block WITHOUT sequences of every frame, as before - including the 20 of 21 blocks of a
+//                        libzstd-written signal frame that follow its one block with sequences.
+//   zstd_seqexec_kernel  a warp per frame again, its Seq units in order: Huffman literals (4 lanes, one per stream) into the warp's
+//                        scratch, then the records: literal runs and matches are warp-wide copies.  Matches may reach back into
+//                        earlier blocks: those are complete (the units kernel ran before; earlier Seq units of the frame were
+//                        executed by this same warp).
+// A frame the sequence kernel cannot vouch for (damaged, more records than the pool holds) goes to the general kernel.
+struct ZSeqWarp {  // zstd_seq_kernel: per-warp shared state
+    uint32_t ll[512], ml[512], of[256];  // sym | nbBits << 8 | base << 16
+    int16_t norm[64];
+    uint16_t next[64];
+};
+struct ZExecWarp {  // zstd_seqexec_kernel: per-warp shared state
+    uint16_t huf[2048];
+    uint32_t wtab[64];
+    uint8_t weights[256];
+    int16_t norm[256];
+    uint16_t next[256];
+};
+
+// One of the three sequence tables, by mode (one lane); norm / next: scratch for 64 symbols.  Returns bytes consumed, 0xFFFFFFFF on error.
+__device__ uint32_t z_seq_table2(int16_t* norm, uint16_t* next, uint32_t* cell, int* al, int mode, const uint8_t* p, uint32_t n, int max_al, int max_sym,
+                                 const int16_t* def, int def_n, int def_al, bool have_prev)
+{
+    if (mode == 0) {
+        for (int i = 0; i < def_n; ++i) norm[i] = def[i];
+        if (!z_fse_build(cell, next, norm, def_n, def_al)) return 0xFFFFFFFFu;
+        *al = def_al;
+        return 0;
+    }
+    if (mode == 1) {
+        if (n < 1 || p[0] > max_sym) return 0xFFFFFFFFu;
+        cell[0] = p[0];
+        *al = 0;
+        return 1;
+    }
+    if (mode == 3) return have_prev ? 0u : 0xFFFFFFFFu;
+    int nsym, a;
+    const uint32_t used = z_fse_read_ncount(p, n, max_al, max_sym, norm, &nsym, &a);
+    if (!used) return 0xFFFFFFFFu;
+    if (!z_fse_build(cell, next, norm, nsym, a)) return 0xFFFFFFFFu;
+    *al = a;
+    return used;
+}
+
+// The sequences of one block -> records (lane 0 does the work; every lane returns the same value).  `pos` = content bytes of the frame
+// before the block.  Returns the bytes the block regenerates, or 0xFFFFFFFF if the block is damaged.
+__device__ uint32_t z_block_sequences(ZSeqWarp* zw, ZFrame& f, const uint8_t* bp, uint32_t bs, uint32_t nseq_expected, ZstdSeq* out, uint64_t pos,
+                                      uint32_t lane)
+{
+    const uint32_t kBad = 0xFFFFFFFFu;
+    int lt, streams;
+    uint32_t hdr, lit_n, comp;
+    if (!z_lit_header(bp, bs, &lt, &hdr, &lit_n, &comp, &streams)) return kBad;
+    const uint32_t sec = lt == 0 ? hdr + lit_n : lt == 1 ? hdr + 1 : hdr + comp;
+    if (sec >= bs || lit_n > kZBlockMax) return kBad;
+    const uint8_t* p = bp + sec;
+    uint32_t n = bs - sec, nseq, h;
+    if (!z_seq_count(p, n, &nseq, &h) || nseq != nseq_expected || nseq == 0) return kBad;
+    if (h + 1 > n) return kBad;
+    const int modes = p[h++];
+    if (modes & 3) return kBad;  // reserved bits (checked by libzstd 1.5.x)
+    uint32_t ok = 1, regen = 0;
+    int al_ll = f.al_ll, al_of = f.al_of, al_ml = f.al_ml;
+    uint32_t rep0 = f.rep0, rep1 = f.rep1, rep2 = f.rep2;
+    if (lane == 0) {
+        uint32_t r;
+        r = z_seq_table2(zw->norm, zw->next, zw->ll, &al_ll, modes >> 6, p + h, n - h, 9, 35, kZ_LL_DEF, 36, 6, f.seq_valid);
+        if (r == kBad) ok = 0; else h += r;
+        if (ok) { r = z_seq_table2(zw->norm, zw->next, zw->of, &al_of, (modes >> 4) & 3, p + h, n - h, 8, 31, kZ_OF_DEF, 29, 5, f.seq_valid); if (r == kBad) ok = 0; else h += r; }
+        if (ok) { r = z_seq_table2(zw->norm, zw->next, zw->ml, &al_ml, (modes >> 2) & 3, p + h, n - h, 9, 52, kZ_ML_DEF, 53, 6, f.seq_valid); if (r == kBad) ok = 0; else h += r; }
+        ZBack b;
+        if (ok && !zb_init(b, p + h, n - h)) ok = 0;
+        if (ok) {
+            uint32_t sl = zb_read(b, (uint32_t)al_ll), so = zb_read(b, (uint32_t)al_of), sm = zb_read(b, (uint32_t)al_ml);
+            if (b.pos < 0) ok = 0;
+            uint64_t at = pos;   // content position (frame-relative) before the sequence's literals
+            uint32_t lits = 0;   // literals consumed so far
+            for (uint32_t i = 0; i < nseq && ok; ++i) {
+                const uint32_t cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
+                const uint32_t llc = cl & 0xFF, ofc = co & 0xFF, mlc = cm & 0xFF;
+                if (llc > 35 || mlc > 52 || ofc > 31) { ok = 0; break; }
+                const uint32_t ofv = (ofc ? (1u << ofc) : 1u) + (ofc ? zb_read(b, ofc) : 0u);
+                const uint32_t mlen = kZ_ML_BASE[mlc] + zb_read(b, kZ_ML_BITS[mlc]);
+                const uint32_t llen = kZ_LL_BASE[llc] + zb_read(b, kZ_LL_BITS[llc]);
+                uint32_t offset;
+                if (ofv > 3) {
+                    offset = ofv - 3;
+                    rep2 = rep1; rep1 = rep0; rep0 = offset;
+                } else {
+                    const uint32_t kk = ofv + (llen == 0 ? 1u : 0u);
+                    if (kk == 1) offset = rep0;
+                    else {
+                        offset = (kk == 4) ? rep0 - 1 : (kk == 2 ? rep1 : rep2);
+                        if (offset == 0) offset = 1;  // libzstd: "0 is not valid; input is corrupted; force offset to 1"
+                        if (kk != 2) rep2 = rep1;
+                        rep1 = rep0;
+                        rep0 = offset;
+                    }
+                }
+                if (i + 1 < nseq) {
+                    sl = (cl >> 16) + zb_read(b, (cl >> 8) & 0xFF);
+                    sm = (cm >> 16) + zb_read(b, (cm >> 8) & 0xFF);
+                    so = (co >> 16) + zb_read(b, (co >> 8) & 0xFF);
+                }
+                lits += llen;
+                at += llen;
+                if (b.pos < 0 || lits > lit_n || (uint64_t)offset > at || regen + llen + mlen > 2u * kZBlockMax) { ok = 0; break; }
+                at += mlen;
+                regen += llen + mlen;
+                out[i] = ZstdSeq{offset, llen, mlen, 0};
+            }
+            if (ok && b.pos != 0) ok = 0;
+            regen += lit_n - lits;  // the literals after the last sequence
+            if (regen > kZBlockMax) ok = 0;
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return kBad;
+    f.al_ll = __shfl_sync(0xffffffffu, al_ll, 0);
+    f.al_of = __shfl_sync(0xffffffffu, al_of, 0);
+    f.al_ml = __shfl_sync(0xffffffffu, al_ml, 0);
+    f.rep0 = __shfl_sync(0xffffffffu, rep0, 0);
+    f.rep1 = __shfl_sync(0xffffffffu, rep1, 0);
+    f.rep2 = __shfl_sync(0xffffffffu, rep2, 0);
+    f.seq_valid = true;
+    return __shfl_sync(0xffffffffu, regen, 0);
+}
+
+constexpr int kZSeqWarps = 4;
+__global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ZSeqWarp* zw = reinterpret_cast<ZSeqWarp*>(smem) + wid;
+    const uint32_t n_frames = p.counter[6];
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(p.counter + 7, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_frames) break;
+        const ZstdSeqFrame sf = p.seq_frames[k];
+        const ZstdRead rd = p.reads[sf.read];
+        uint64_t fcs = 0;
+        bool has = false, ck = false;
+        z_frame_header(p.src + rd.src_off, rd.src_bytes, &fcs, &has, &ck);  // (the walker accepted it)
+        ZFrame f;
+        f.huf_bits = 0;
+        f.al_ll = f.al_of = f.al_ml = 0;
+        f.seq_valid = false;
+        f.rep0 = 1; f.rep1 = 4; f.rep2 = 8;
+        uint64_t op = 0;
+        bool ok = true;
+        for (uint32_t ui = 0; ui < sf.unit_count && ok; ++ui) {
+            ZstdUnit* up = p.units + sf.unit_first + ui;
+            const ZstdUnit u = *up;
+            uint32_t regen = u.regen;
+            if (u.kind == kZUnitSeq) {
+                regen = z_block_sequences(zw, f, p.src + u.src_off, u.n, u.nseq, p.seqs + u.seq_first, op, lane);
+                __syncwarp();
+                if (regen == 0xFFFFFFFFu) { ok = false; break; }
+            }
+            if (op + regen > rd.dst_cap) { ok = false; break; }
+            if (lane == 0) { up->dst_off = rd.dst_off + op; up->regen = regen; }
+            op += regen;
+        }
+        if (ok && has && op != fcs) ok = false;
+        if (ok) {
+            if (lane == 0) p.results[sf.read] = (uint32_t)op;
+        } else {
+            // not for this path after all: its units do nothing, the general kernel decides the frame's result
+            for (uint32_t ui = lane; ui < sf.unit_count; ui += 32) p.units[sf.unit_first + ui].kind = kZUnitNop;
+            if (lane == 0) {
+                p.seq_frames[k].unit_count = 0;
+                p.general[atomicAdd(p.counter + 2, 1u)] = sf.read;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// load the Huffman table described by the literals section at tp (one lane works, all get the result: max_bits, 0 = bad)
+__device__ int z_exec_load_table(ZExecWarp* zw, const uint8_t* tp, uint32_t lane)
+{
+    int bits = 0;
+    if (lane == 0) {
+        int lt = 0, st = 0;
+        uint32_t hdr = 0, regen = 0, comp = 0;
+        if (z_lit_header(tp, 5u, &lt, &hdr, &regen, &comp, &st) && lt == 2) {
+            int nw = 0;
+            const uint32_t t = z_huf_read_weights(zw->weights, zw->wtab, zw->norm, zw->next, tp + hdr, comp, &nw);
+            if (t) bits = z_huf_build(zw->huf, zw->weights, nw);
+        }
+    }
+    return __shfl_sync(0xffffffffu, bits, 0);
+}
+
+constexpr int kZExecWarps = 4;
+__global__ void __launch_bounds__(kZExecWarps * 32) zstd_seqexec_kernel(ZstdDecParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ZExecWarp* zw = reinterpret_cast<ZExecWarp*>(smem) + wid;
+    uint8_t* lit = p.lit_scratch + (uint64_t)(blockIdx.x * kZExecWarps + wid) * kZLitStride;
+    const uint32_t n_frames = p.counter[6];
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(p.counter + 8, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_frames) break;
+        const ZstdSeqFrame sf = p.seq_frames[k];
+        const uint8_t* tab_loaded = nullptr;
+        int bits = 0;
+        bool ok = true;
+        for (uint32_t ui = 0; ui < sf.unit_count && ok; ++ui) {
+            const ZstdUnit u = p.units[sf.unit_first + ui];
+            if (u.kind != kZUnitSeq) continue;
+            const uint8_t* bp = p.src + u.src_off;
+            int lt = 0, streams = 4;
+            uint32_t hdr = 0, lit_n = 0, comp = 0;
+            if (!z_lit_header(bp, u.n, &lt, &hdr, &lit_n, &comp, &streams)) { ok = false; break; }
+            // ---- literals -> the warp's scratch ------------------------------------------------------------------------------------
+            if (lt == 0) z_warp_copy(lit, bp + hdr, lit_n, lane);
+            else if (lt == 1) z_warp_fill(lit, bp[hdr], lit_n, lane);
+            else {
+                const uint8_t* tp = bp - u.tab_back;  // (tab_back is 0 when the block carries its own tree)
+                if (tab_loaded != tp) { bits = z_exec_load_table(zw, tp, lane); tab_loaded = tp; }
+                __syncwarp();
+                if (!bits || (streams == 4 && lit_n < 6)) { ok = false; break; }
+                const uint8_t* q = bp + hdr;
+                uint32_t left = comp;
+                if (lt == 2) {  // skip the tree description: its size is the weights header byte's business
+                    const uint32_t hb = q[0];
+                    const uint32_t t = hb >= 128 ? 1 + (hb - 127 + 1) / 2 : 1 + hb;
+                    if (t > left) { ok = false; break; }
+                    q += t; left -= t;
+                }
+                bool sok = true;
+                if (streams == 1) {
+                    if (lane == 0) sok = z_huf_decode_stream(zw->huf, bits, q, left, lit, lit_n);
+                } else if (left < 10) sok = false;
+                else {
+                    const uint32_t s1 = z_le16(q), s2 = z_le16(q + 2), s3 = z_le16(q + 4);
+                    const uint32_t seg = (lit_n + 3) / 4;
+                    if (6 + s1 + s2 + s3 > left || 3 * seg > lit_n) sok = false;
+                    else if (lane < 4) {
+                        const uint32_t s4 = left - 6 - s1 - s2 - s3;
+                        const uint32_t so = lane == 0 ? 0u : lane == 1 ? s1 : lane == 2 ? s1 + s2 : s1 + s2 + s3;
+                        const uint32_t sn = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : s4;
+                        sok = z_huf_decode_stream(zw->huf, bits, q + 6 + so, sn, lit + lane * seg, lane == 3 ? lit_n - 3 * seg : seg);
+                    }
+                }
+                if (!__all_sync(0xffffffffu, sok)) { ok = false; break; }
+            }
+            __syncwarp();
+            // ---- the records: literal run, match, ... and the literals after the last match -------------------------------------------
+            uint8_t* out = p.dst;
+            uint64_t op = u.dst_off;
+            uint32_t lp = 0;
+            const ZstdSeq* sq = p.seqs + u.seq_first;
+            ZstdSeq cur = u.nseq ? sq[0] : ZstdSeq{0, 0, 0, 0};
+            for (uint32_t i = 0; i < u.nseq; ++i) {
+                const ZstdSeq nxt = i + 1 < u.nseq ? sq[i + 1] : ZstdSeq{0, 0, 0, 0};
+                z_warp_copy(out + op, lit + lp, cur.ll, lane);
+                lp += cur.ll;
+                op += cur.ll;
+                __syncwarp();
+                z_warp_match(out, op, cur.offset, cur.ml, lane);
+                op += cur.ml;
+                __syncwarp();
+                cur = nxt;
+            }
+            z_warp_copy(out + op, lit + lp, lit_n - lp, lane);
+            __syncwarp();
+        }
+        if (!ok && lane == 0) p.results[sf.read] = kErrZstd;
     }
 }
 
