@@ -243,7 +243,7 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
 // ---- stage 2 (zstd), encode: content -> frames ----------------------------------------------------------------------
 // reads[i].first_block is set here.
 static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, std::vector<ZstdEncRead>& reads, const uint32_t* d_src_sizes,
-                               uint32_t* d_results, bool sized, unsigned level, cudaStream_t stream)
+                               uint32_t* d_results, bool sized, unsigned level, uint64_t src_extent, cudaStream_t stream)
 {
     const uint32_t n = (uint32_t)reads.size();
     if (n == 0) return 0;
@@ -256,7 +256,10 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     const uint32_t n_blocks = (uint32_t)blocks;
     const size_t bytes = (size_t)n * sizeof(ZstdEncRead);
     if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zblocks.ensure((size_t)n_blocks * 4) || !ctx->d_zstatus.ensure((size_t)n_blocks * 8) ||
-        !ctx->d_zcodes.ensure((size_t)n_blocks * kZGroupCodeBytes))
+        !ctx->d_zcodes.ensure((size_t)n_blocks * kZGroupCodeBytes) ||
+        // scratch of the match finder: literals of the S groups (at their content offsets), sequence records, per-group meta + histogram
+        !ctx->d_zelits.ensure((size_t)src_extent + 64) || !ctx->d_zeseqs.ensure(((size_t)src_extent / 16 + n_blocks + 2) * 8) ||
+        !ctx->d_zemeta.ensure((size_t)n_blocks * kZGroupMetaBytes) || !ctx->d_zehist.ensure((size_t)n_blocks * 1024))
         return -1;
     if (!upload_descriptors(ctx, ctx->d_zreads.p, reads.data(), bytes, stream) ||
         !zero_device(ctx, ctx->d_zstatus.p, (size_t)n_blocks * 8, stream))
@@ -277,9 +280,14 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.n_reads = n;
     p.n_blocks = n_blocks;
     p.level = level;
+    p.pad = 0;
+    p.lits = ctx->d_zelits.as<uint8_t>();
+    p.seqs = ctx->d_zeseqs.as<uint64_t>();
+    p.meta = ctx->d_zemeta.as<uint8_t>();
+    p.hist = ctx->d_zehist.as<uint32_t>();
     e = vbzk_zstd_encode(reinterpret_cast<const VbzkZstdEncParams*>(&p), stream);
     if (e) { cuda_ok((cudaError_t)e, "zstd_encode launch"); return -1; }
-    ctx->launches += 3;  // block table, codes, frames
+    ctx->launches += 5;  // block table, matches, sequences sections, codes, frames
     return 0;
 }
 
@@ -374,8 +382,14 @@ static int compress_wave(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst
         }
         z.n_blocks = (uint32_t)std::max<uint64_t>(1, (z.split + blk - 1) / blk + (largest - z.split + blk - 1) / blk);
     }
+    uint64_t extent = mid_total + 16;
+    if (kind.isz == 0) {
+        extent = 0;
+        for (uint32_t i = 0; i < n; ++i)
+            if (!jobs[i].rejected) extent = std::max<uint64_t>(extent, jobs[i].src_off + jobs[i].src_size);
+    }
     return enqueue_zstd_encode(ctx, kind.isz != 0 ? ctx->d_mid.as<uint8_t>() : d_src, d_dst, zr, kind.isz != 0 ? ctx->d_sizes.as<uint32_t>() : nullptr,
-                               d_results, sized, kind.zstd_level, stream);
+                               d_results, sized, kind.zstd_level, extent, stream);
 }
 
 static int compress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ReadJob>& jobs,
@@ -529,7 +543,7 @@ vbz_b200_ctx::~vbz_b200_ctx()
     d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
     h_results.release(); stage.release();
     d_mid.release();
-    d_zreads.release(); d_zseqs.release(); d_zseqframes.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); d_zcodes.release();
+    d_zelits.release(); d_zeseqs.release(); d_zemeta.release(); d_zehist.release(); d_zreads.release(); d_zseqs.release(); d_zseqframes.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); d_zcodes.release();
     for (WaveSlot& w : slots) {
         w.d_in.release(); w.d_out.release(); w.d_results.release(); w.d_pack.release(); w.d_xin.release(); w.d_xout.release();
         w.h_in.release(); w.h_out.release(); w.h_results.release();

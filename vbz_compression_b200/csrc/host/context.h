@@ -65,6 +65,7 @@ struct vbz_b200_ctx {
     vbz::PinBuf h_results;
     // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
     vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral, d_zseqs, d_zseqframes;
+    vbz::DevBuf d_zelits, d_zeseqs, d_zemeta, d_zehist;  // the encoder's match finder (csrc/zstd_match_kernels.cuh)
     // intermediate stage-1 bytes of the two-stage paths
     vbz::DevBuf d_mid;
     // host-pointer API: a batch runs as WAVES through kWaveSlots slots so that the upload of wave w+1, the kernels of

@@ -140,9 +140,15 @@ struct ZstdEncParams {
     uint32_t n_reads, n_blocks;
     uint32_t level;              // zstd_compression_level of the call (1, 2, 3 ... select the match finder's effort)
     uint32_t pad;
+    // scratch of the match finder (csrc/zstd_match_kernels.cuh)
+    uint8_t* lits;               // as large as the content buffer: the literals of an S group sit at the group's content offset, its sequences sections behind them
+    uint64_t* seqs;              // sequence records: content extent / 16 + n_blocks + 1
+    uint8_t* meta;               // n_blocks records of kZGroupMetaBytes
+    uint32_t* hist;              // n_blocks x 256: literal histogram of every S group
 };
 constexpr uint32_t kZEncBlock = 128u * 1024u;  // content bytes per GROUP of the encoder: blocks that share one Huffman table
 constexpr uint32_t kZEncSub = 8u * 1024u;     // content bytes per block written by the encoder
+constexpr uint32_t kZGroupMetaBytes = 96;     // sizeof(ZGroupMeta), csrc/zstd_match_kernels.cuh
 constexpr uint32_t kZGroupCodeBytes = 1200;   // sizeof(ZGroupCode), csrc/zstd_enc_kernels.cuh
 constexpr uint32_t kZBlockMax = 128u * 1024u;
 constexpr int kZdecWarps = 4;

@@ -221,6 +221,15 @@ extern "C" int vbzk_zstd_encode(const VbzkZstdEncParams* params, void* stream)
 {
     const ZstdEncParams& p = *reinterpret_cast<const ZstdEncParams*>(params);
     if (p.n_blocks == 0) return 0;
+    // matches first: they decide which bytes are literals (csrc/zstd_match_kernels.cuh), then the sequences sections of the S groups
+    const uint32_t msmem = (uint32_t)(sizeof(ZMatchSmem) * kZMatchWarps);
+    if (int e = VBZK_SET_SMEM(zstd_enc_match_kernel, msmem)) return e;
+    VBZ_LAUNCH(zstd_enc_match_kernel, (p.n_blocks + kZMatchWarps - 1) / kZMatchWarps, kZMatchWarps * 32, msmem, (vbz_stream_t)stream, p);
+    if (int e = VBZK_LAST_ERROR()) return e;
+    const uint32_t qsmem = (uint32_t)(sizeof(ZSeqEncSmem) * kZSeqEncWarps);
+    if (int e = VBZK_SET_SMEM(zstd_enc_seq_kernel, qsmem)) return e;
+    VBZ_LAUNCH(zstd_enc_seq_kernel, (p.n_blocks + kZSeqEncWarps - 1) / kZSeqEncWarps, kZSeqEncWarps * 32, qsmem, (vbz_stream_t)stream, p);
+    if (int e = VBZK_LAST_ERROR()) return e;
     const uint32_t csmem = (uint32_t)(sizeof(ZCode) * kZcodeWarps);
     if (int e = VBZK_SET_SMEM(zstd_enc_code_kernel, csmem)) return e;
     VBZ_LAUNCH(zstd_enc_code_kernel, (p.n_blocks + kZcodeWarps - 1) / kZcodeWarps, kZcodeWarps * 32, csmem, (vbz_stream_t)stream, p);

@@ -312,6 +312,16 @@ __device__ bool z_huf_decode_stream(const uint16_t* huf, int max_bits, const uin
     return (long long)v0 + 32ll * (long long)(wp0 - wp) - nbits == avail;
 }
 
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += x;
+    }
+    return v;
+}
+
 // ---- warp-wide copies -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void z_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
 {
@@ -1133,6 +1143,7 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
 // A frame the sequence kernel cannot vouch for (damaged, more records than the pool holds) goes to the general kernel.
 struct ZSeqWarp {  // zstd_seq_kernel: per-warp shared state
     uint32_t ll[512], ml[512], of[256];  // sym | nbBits << 8 | base << 16
+    uint32_t chunk[512];                 // the part of the sequences stream the reader is in (kZSeqChunkWords)
     int16_t norm[64];
     uint16_t next[64];
 };
@@ -1169,8 +1180,73 @@ __device__ uint32_t z_seq_table2(int16_t* norm, uint16_t* next, uint32_t* cell, 
     return used;
 }
 
-// The sequences of one block -> records (lane 0 does the work; every lane returns the same value).  `pos` = content bytes of the frame
-// before the block.  Returns the bytes the block regenerates, or 0xFFFFFFFF if the block is damaged.
+// Backward bit reader for the sequences section, used by the WHOLE warp in lockstep (every lane holds the same state, so refills
+// can stage the stream through shared memory cooperatively): a 64-bit window whose top bit is the next unread bit, refilled 32 bits
+// at a time from a 2 KiB chunk of the stream in shared memory; the chunk moves towards the start of the stream as the reader does.
+constexpr uint32_t kZSeqChunkWords = 512;
+struct ZSeqBits {
+    const uint32_t* words;  // the aligned word that holds the section's first byte
+    uint32_t* chunk;        // shared memory, kZSeqChunkWords words
+    int c_lo;               // index of the word in chunk[0]
+    int wi;                 // next word to take (counting down; < 0: past the start, reads as zero)
+    uint64_t buf;
+    int nbits;
+    long long left;         // unread bits of the stream proper (negative: the reader ran past the start)
+};
+__device__ __forceinline__ void zsb_stage(ZSeqBits& b, int hi_word, uint32_t lane)
+{
+    // chunk <- words [lo, lo + kZSeqChunkWords) with lo + kZSeqChunkWords - 1 = hi_word (or lo = 0)
+    const int lo = hi_word + 1 > (int)kZSeqChunkWords ? hi_word + 1 - (int)kZSeqChunkWords : 0;
+    __syncwarp();
+    for (int k = (int)lane; k < (int)kZSeqChunkWords && lo + k <= hi_word; k += 32) b.chunk[k] = b.words[lo + k];
+    __syncwarp();
+    b.c_lo = lo;
+}
+__device__ __forceinline__ void zsb_refill(ZSeqBits& b, uint32_t lane)
+{
+    while (b.nbits <= 32) {
+        uint32_t w = 0;
+        if (b.wi >= 0) {
+            if (b.wi < b.c_lo) zsb_stage(b, b.wi, lane);
+            w = b.chunk[b.wi - b.c_lo];
+        }
+        b.buf |= (uint64_t)w << (32 - b.nbits);
+        b.nbits += 32;
+        --b.wi;
+    }
+}
+// p[0 .. n): the stream; false if it is empty or ends with a zero byte
+__device__ __forceinline__ bool zsb_init(ZSeqBits& b, uint32_t* chunk, const uint8_t* p, uint32_t n, uint32_t lane)
+{
+    if (n == 0 || p[n - 1] == 0) return false;
+    const uint32_t phase = (uint32_t)((uintptr_t)p & 3u);
+    b.words = reinterpret_cast<const uint32_t*>(p - phase);
+    b.chunk = chunk;
+    const uint32_t last_byte = phase + n - 1;         // byte index of the stream's last byte, from words[0]
+    b.wi = (int)(last_byte >> 2);
+    b.left = (long long)(n - 1) * 8 + z_highbit(p[n - 1]);
+    zsb_stage(b, b.wi, lane);
+    // the first word: only the bits below the marker count
+    const uint32_t v0 = 8u * (last_byte & 3u) + (uint32_t)z_highbit(p[n - 1]);  // unread bits in that word
+    const uint32_t w = b.chunk[b.wi - b.c_lo];
+    b.buf = v0 ? ((uint64_t)w << (64 - v0)) : 0ull;
+    b.nbits = (int)v0;
+    --b.wi;
+    return true;
+}
+__device__ __forceinline__ uint32_t zsb_read(ZSeqBits& b, uint32_t nb, uint32_t lane)
+{
+    if (nb == 0) return 0;
+    if (b.nbits < (int)nb) zsb_refill(b, lane);
+    const uint32_t v = (uint32_t)(b.buf >> (64 - nb));
+    b.buf <<= nb;
+    b.nbits -= (int)nb;
+    b.left -= nb;
+    return v;
+}
+
+// The sequences of one block -> records.  The whole warp walks the stream in lockstep (lane 0 stores).  `pos` = content bytes of the
+// frame before the block.  Returns the bytes the block regenerates, or 0xFFFFFFFF if the block is damaged.
 __device__ uint32_t z_block_sequences(ZSeqWarp* zw, ZFrame& f, const uint8_t* bp, uint32_t bs, uint32_t nseq_expected, ZstdSeq* out, uint64_t pos,
                                       uint32_t lane)
 {
@@ -1186,71 +1262,70 @@ __device__ uint32_t z_block_sequences(ZSeqWarp* zw, ZFrame& f, const uint8_t* bp
     if (h + 1 > n) return kBad;
     const int modes = p[h++];
     if (modes & 3) return kBad;  // reserved bits (checked by libzstd 1.5.x)
-    uint32_t ok = 1, regen = 0;
+    uint32_t ok = 1;
     int al_ll = f.al_ll, al_of = f.al_of, al_ml = f.al_ml;
-    uint32_t rep0 = f.rep0, rep1 = f.rep1, rep2 = f.rep2;
-    if (lane == 0) {
+    if (lane == 0) {  // the tables: one lane (they are small, and rebuilt once per block at most)
         uint32_t r;
         r = z_seq_table2(zw->norm, zw->next, zw->ll, &al_ll, modes >> 6, p + h, n - h, 9, 35, kZ_LL_DEF, 36, 6, f.seq_valid);
         if (r == kBad) ok = 0; else h += r;
         if (ok) { r = z_seq_table2(zw->norm, zw->next, zw->of, &al_of, (modes >> 4) & 3, p + h, n - h, 8, 31, kZ_OF_DEF, 29, 5, f.seq_valid); if (r == kBad) ok = 0; else h += r; }
         if (ok) { r = z_seq_table2(zw->norm, zw->next, zw->ml, &al_ml, (modes >> 2) & 3, p + h, n - h, 9, 52, kZ_ML_DEF, 53, 6, f.seq_valid); if (r == kBad) ok = 0; else h += r; }
-        ZBack b;
-        if (ok && !zb_init(b, p + h, n - h)) ok = 0;
-        if (ok) {
-            uint32_t sl = zb_read(b, (uint32_t)al_ll), so = zb_read(b, (uint32_t)al_of), sm = zb_read(b, (uint32_t)al_ml);
-            if (b.pos < 0) ok = 0;
-            uint64_t at = pos;   // content position (frame-relative) before the sequence's literals
-            uint32_t lits = 0;   // literals consumed so far
-            for (uint32_t i = 0; i < nseq && ok; ++i) {
-                const uint32_t cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
-                const uint32_t llc = cl & 0xFF, ofc = co & 0xFF, mlc = cm & 0xFF;
-                if (llc > 35 || mlc > 52 || ofc > 31) { ok = 0; break; }
-                const uint32_t ofv = (ofc ? (1u << ofc) : 1u) + (ofc ? zb_read(b, ofc) : 0u);
-                const uint32_t mlen = kZ_ML_BASE[mlc] + zb_read(b, kZ_ML_BITS[mlc]);
-                const uint32_t llen = kZ_LL_BASE[llc] + zb_read(b, kZ_LL_BITS[llc]);
-                uint32_t offset;
-                if (ofv > 3) {
-                    offset = ofv - 3;
-                    rep2 = rep1; rep1 = rep0; rep0 = offset;
-                } else {
-                    const uint32_t kk = ofv + (llen == 0 ? 1u : 0u);
-                    if (kk == 1) offset = rep0;
-                    else {
-                        offset = (kk == 4) ? rep0 - 1 : (kk == 2 ? rep1 : rep2);
-                        if (offset == 0) offset = 1;  // libzstd: "0 is not valid; input is corrupted; force offset to 1"
-                        if (kk != 2) rep2 = rep1;
-                        rep1 = rep0;
-                        rep0 = offset;
-                    }
-                }
-                if (i + 1 < nseq) {
-                    sl = (cl >> 16) + zb_read(b, (cl >> 8) & 0xFF);
-                    sm = (cm >> 16) + zb_read(b, (cm >> 8) & 0xFF);
-                    so = (co >> 16) + zb_read(b, (co >> 8) & 0xFF);
-                }
-                lits += llen;
-                at += llen;
-                if (b.pos < 0 || lits > lit_n || (uint64_t)offset > at || regen + llen + mlen > 2u * kZBlockMax) { ok = 0; break; }
-                at += mlen;
-                regen += llen + mlen;
-                out[i] = ZstdSeq{offset, llen, mlen, 0};
-            }
-            if (ok && b.pos != 0) ok = 0;
-            regen += lit_n - lits;  // the literals after the last sequence
-            if (regen > kZBlockMax) ok = 0;
-        }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) return kBad;
-    f.al_ll = __shfl_sync(0xffffffffu, al_ll, 0);
-    f.al_of = __shfl_sync(0xffffffffu, al_of, 0);
-    f.al_ml = __shfl_sync(0xffffffffu, al_ml, 0);
-    f.rep0 = __shfl_sync(0xffffffffu, rep0, 0);
-    f.rep1 = __shfl_sync(0xffffffffu, rep1, 0);
-    f.rep2 = __shfl_sync(0xffffffffu, rep2, 0);
+    h = __shfl_sync(0xffffffffu, h, 0);
+    al_ll = __shfl_sync(0xffffffffu, al_ll, 0);
+    al_of = __shfl_sync(0xffffffffu, al_of, 0);
+    al_ml = __shfl_sync(0xffffffffu, al_ml, 0);
+    f.al_ll = al_ll; f.al_of = al_of; f.al_ml = al_ml;
     f.seq_valid = true;
-    return __shfl_sync(0xffffffffu, regen, 0);
+    __syncwarp();
+    ZSeqBits b;
+    if (h > n || !zsb_init(b, zw->chunk, p + h, n - h, lane)) return kBad;
+    uint32_t sl = zsb_read(b, (uint32_t)al_ll, lane), so = zsb_read(b, (uint32_t)al_of, lane), sm = zsb_read(b, (uint32_t)al_ml, lane);
+    if (b.left < 0) return kBad;
+    uint32_t rep0 = f.rep0, rep1 = f.rep1, rep2 = f.rep2;
+    uint64_t at = pos;   // content position (frame-relative) before the sequence's literals
+    uint32_t lits = 0, regen = 0;
+    for (uint32_t i = 0; i < nseq; ++i) {
+        const uint32_t cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
+        const uint32_t llc = cl & 0xFF, ofc = co & 0xFF, mlc = cm & 0xFF;
+        if (llc > 35 || mlc > 52 || ofc > 31) return kBad;
+        const uint32_t ofv = (1u << ofc) + zsb_read(b, ofc, lane);
+        const uint32_t mlen = kZ_ML_BASE[mlc] + zsb_read(b, kZ_ML_BITS[mlc], lane);
+        const uint32_t llen = kZ_LL_BASE[llc] + zsb_read(b, kZ_LL_BITS[llc], lane);
+        uint32_t offset;
+        if (ofv > 3) {
+            offset = ofv - 3;
+            rep2 = rep1; rep1 = rep0; rep0 = offset;
+        } else {
+            const uint32_t kk = ofv + (llen == 0 ? 1u : 0u);
+            if (kk == 1) offset = rep0;
+            else {
+                offset = (kk == 4) ? rep0 - 1 : (kk == 2 ? rep1 : rep2);
+                if (offset == 0) offset = 1;  // libzstd: "0 is not valid; input is corrupted; force offset to 1"
+                if (kk != 2) rep2 = rep1;
+                rep1 = rep0;
+                rep0 = offset;
+            }
+        }
+        if (i + 1 < nseq) {
+            sl = (cl >> 16) + zsb_read(b, (cl >> 8) & 0xFF, lane);
+            sm = (cm >> 16) + zsb_read(b, (cm >> 8) & 0xFF, lane);
+            so = (co >> 16) + zsb_read(b, (co >> 8) & 0xFF, lane);
+        }
+        lits += llen;
+        at += llen;
+        if (b.left < 0 || lits > lit_n || (uint64_t)offset > at || regen + llen + mlen > 2u * kZBlockMax) return kBad;
+        at += mlen;
+        regen += llen + mlen;
+        if (lane == 0) out[i] = ZstdSeq{offset, llen, mlen, 0};
+    }
+    if (b.left != 0) return kBad;
+    regen += lit_n - lits;  // the literals after the last sequence
+    if (regen > kZBlockMax) return kBad;
+    f.rep0 = rep0; f.rep1 = rep1; f.rep2 = rep2;
+    return regen;
 }
 
 constexpr int kZSeqWarps = 4;
@@ -1379,22 +1454,57 @@ __global__ void __launch_bounds__(kZExecWarps * 32) zstd_seqexec_kernel(ZstdDecP
                 if (!__all_sync(0xffffffffu, sok)) { ok = false; break; }
             }
             __syncwarp();
-            // ---- the records: literal run, match, ... and the literals after the last match -------------------------------------------
+            // ---- the records, 32 at a time.  A lane owns one sequence: it copies its literal run (from the warp's scratch: no
+            // dependency on anything) and then its match, unless the match reads what an earlier sequence of the same 32 produces or
+            // is long - those are done by the whole warp afterwards, in order.  Everything before the 32 is complete.
             uint8_t* out = p.dst;
             uint64_t op = u.dst_off;
             uint32_t lp = 0;
             const ZstdSeq* sq = p.seqs + u.seq_first;
-            ZstdSeq cur = u.nseq ? sq[0] : ZstdSeq{0, 0, 0, 0};
-            for (uint32_t i = 0; i < u.nseq; ++i) {
-                const ZstdSeq nxt = i + 1 < u.nseq ? sq[i + 1] : ZstdSeq{0, 0, 0, 0};
-                z_warp_copy(out + op, lit + lp, cur.ll, lane);
-                lp += cur.ll;
-                op += cur.ll;
+            for (uint32_t i0 = 0; i0 < u.nseq; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const ZstdSeq rec = i < u.nseq ? sq[i] : ZstdSeq{1, 0, 0, 0};
+                const uint32_t span = rec.ll + rec.ml;
+                const uint32_t incl = warp_incl_scan(span, lane), lincl = warp_incl_scan(rec.ll, lane);
+                const uint64_t my_out = op + incl - span;        // where this sequence's literals go
+                const uint32_t my_lit = lp + lincl - rec.ll;
+                const uint64_t mdst = my_out + rec.ll, msrc = mdst - rec.offset;
+                // literal runs
+                if (rec.ll <= 16) {
+                    for (uint32_t k = 0; k < rec.ll; ++k) out[my_out + k] = lit[my_lit + k];
+                }
+                uint32_t big = __ballot_sync(0xffffffffu, rec.ll > 16);
+                while (big) {
+                    const uint32_t fl = (uint32_t)__ffs((int)big) - 1;
+                    big &= big - 1;
+                    const uint32_t n = __shfl_sync(0xffffffffu, rec.ll, fl), fs = __shfl_sync(0xffffffffu, my_lit, fl);
+                    const uint64_t fd = __shfl_sync(0xffffffffu, my_out, fl);
+                    z_warp_copy(out + fd, lit + fs, n, lane);
+                }
                 __syncwarp();
-                z_warp_match(out, op, cur.offset, cur.ml, lane);
-                op += cur.ml;
+                // matches: short and independent of this round's other sequences -> the lane itself
+                const bool dep = msrc < my_out && msrc + rec.ml > op;
+                const bool self = rec.ml != 0 && rec.ml <= 48 && !dep;
+                if (self) {
+                    if (rec.offset == 1) {
+                        const uint8_t v = out[mdst - 1];
+                        for (uint32_t k = 0; k < rec.ml; ++k) out[mdst + k] = v;
+                    } else {
+                        for (uint32_t k = 0; k < rec.ml; ++k) out[mdst + k] = out[msrc + k];
+                    }
+                }
+                uint32_t rest = __ballot_sync(0xffffffffu, rec.ml != 0 && !self);
                 __syncwarp();
-                cur = nxt;
+                while (rest) {
+                    const uint32_t fl = (uint32_t)__ffs((int)rest) - 1;
+                    rest &= rest - 1;
+                    const uint32_t n = __shfl_sync(0xffffffffu, rec.ml, fl), fo = __shfl_sync(0xffffffffu, rec.offset, fl);
+                    const uint64_t fd = __shfl_sync(0xffffffffu, mdst, fl);
+                    z_warp_match(out, fd, fo, n, lane);
+                    __syncwarp();
+                }
+                op += __shfl_sync(0xffffffffu, incl, 31);
+                lp += __shfl_sync(0xffffffffu, lincl, 31);
             }
             z_warp_copy(out + op, lit + lp, lit_n - lp, lane);
             __syncwarp();

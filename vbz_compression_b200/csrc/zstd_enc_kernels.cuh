@@ -37,6 +37,7 @@
 #pragma once
 #include "zstd_dec_kernels.cuh"
 #include "svb_kernels.cuh"
+#include "zstd_match_kernels.cuh"
 
 namespace vbz {
 
@@ -44,7 +45,6 @@ constexpr int kZencThreads = 256;
 constexpr int kZencWarps = kZencThreads / 32;
 constexpr uint32_t kZSubs = kZEncBlock / kZEncSub;   // sub-blocks per group (16)
 constexpr uint32_t kZStreams = kZSubs * 4;           // Huffman streams per group (64)
-constexpr uint32_t kZCodeSet = 8;                    // consecutive groups of a region that share one Huffman code (built once, over up to 1 MiB)
 
 // the state of one group's code construction (zstd_enc_code_kernel: one per warp)
 struct ZCode {
@@ -79,6 +79,8 @@ struct ZEncSmem {
     uint64_t excl;
     uint32_t sbits[kZStreams];     // bits of every stream of the group
     uint32_t sub_off[kZSubs + 1];  // where each sub-block starts in the group's output
+    uint32_t sub_lit[kZSubs];      // S groups: size of each block's literals section
+    uint32_t seq_off[kZSubs + 1];  // S groups: where each block's sequences section sits in the group's literal slot
     uint8_t sub_kind[kZSubs];      // kZKindRaw / kZKindHuf
     uint8_t sub_tree[kZSubs];      // != 0: this sub-block carries the tree
     alignas(16) uint8_t stage[2][kZEncSub + 96];  // (sized header, frame header,) block header, block payload; slack for the copy
@@ -473,38 +475,6 @@ __device__ __forceinline__ void zenc_fetch_stream(const uint8_t* src, uint32_t B
     *n_out = n;
 }
 
-// where group b of the batch lives: false = nothing to encode (rejected read, upstream error, or a group beyond the content)
-struct ZGroupLoc {
-    const uint8_t* src;
-    uint32_t r, gi, ngrp, content, B;
-    uint32_t code_first;  // groups back to the first group of this one's CODE SET (kZCodeSet consecutive groups of a region share one code)
-    uint32_t code_bytes;  // content bytes of the code set, from its first group on
-    bool last;
-};
-__device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, const ZstdEncRead& rd, uint32_t r, ZGroupLoc& g)
-{
-    g.r = r;
-    g.gi = b - rd.first_block;
-    if (rd.rejected) return false;
-    g.content = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
-    if (p.src_sizes && g.content >= kErrOutOfMemory) return false;  // stage 1 reported an error for this read
-    // groups of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'), then the rest
-    const uint32_t split = rd.split < g.content ? rd.split : 0u;
-    const uint32_t n_a = (split + kZEncBlock - 1) / kZEncBlock, n_b = (g.content - split + kZEncBlock - 1) / kZEncBlock;
-    g.ngrp = n_a + n_b ? n_a + n_b : 1u;
-    if (g.gi >= g.ngrp) return false;  // the table was sized for the largest content stage 1 could have produced
-    const uint32_t start = g.gi < n_a ? g.gi * kZEncBlock : split + (g.gi - n_a) * kZEncBlock;
-    const uint32_t region_end = g.gi < n_a ? split : g.content;
-    g.B = region_end - start < kZEncBlock ? region_end - start : kZEncBlock;
-    g.last = g.gi + 1 == g.ngrp;
-    g.src = p.src + rd.src_off + start;
-    const uint32_t in_region = g.gi < n_a ? g.gi : g.gi - n_a;
-    g.code_first = in_region % kZCodeSet;
-    const uint32_t set_start = start - g.code_first * kZEncBlock;
-    g.code_bytes = region_end - set_start < kZCodeSet * kZEncBlock ? region_end - set_start : kZCodeSet * kZEncBlock;
-    return true;
-}
-
 // ---- kernel 1: histogram + Huffman code of every group, a warp per group -------------------------------------------------
 constexpr int kZcodeWarps = 1;
 __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEncParams p)
@@ -518,71 +488,92 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     const ZstdEncRead rd = p.reads[r];
     ZGroupLoc g;
     if (!zenc_locate(p, b, rd, r, g) || g.code_first != 0) return;  // the first group of a code set builds the code for all of them
-    const uint8_t* src = g.src;
     const uint32_t B = g.code_bytes;
     for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = 0;
     __syncwarp();
-    // ---- histogram: 128-bit loads over the aligned body (four in flight per lane), bytes at the two ends ----------------
+    // ---- histogram of the set's LITERALS.  L groups (no sequences): their bytes, with 128-bit loads over the aligned body (four in
+    // flight per lane) and byte loads at the two ends.  S groups: the match kernel counted their literals (csrc/zstd_match_kernels.cuh).
     // Large code sets are SAMPLED: one 512-byte row in four (from 256 KiB) or in eight (from 512 KiB) is counted (the shared-memory atomic unit bounds this
     // kernel), the counts are scaled and every byte value gets a floor of one, so that a value the sample missed still has a code.
     // A sample that saw a single value is checked against the whole set: constant content stays one RLE block per group.
     const bool sampled = B >= (256u << 10);
     const uint32_t rate = B >= (512u << 10) ? 8u : 4u;  // one row in `rate`
+    const ZGroupMeta* meta = reinterpret_cast<const ZGroupMeta*>(p.meta) + b;
+    const uint32_t set_groups = (B + kZEncBlock - 1) / kZEncBlock;
+    bool any_s = false, any_l = false;
     {
-        uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
-        if (head > B) head = B;
-        const uint32_t nch = (B - head) >> 4, done = head + (nch << 4);
         uint32_t* h = s->cnt;
         uint32_t zeros = 0;
-        if (lane < head) atomicAdd(h + src[lane], 1u);
-        if (lane < B - done) atomicAdd(h + src[done + lane], 1u);
-        const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
-        const uint32_t spacing = sampled ? 32u * rate : 32u;  // chunks between the rows a lane has in flight
-        for (uint32_t c0 = 0; c0 < nch; c0 += 4 * spacing) {
-            uint4 q[4];
+        for (uint32_t j = 0; j < set_groups; ++j) {
+            if (meta[j].mode == kZModeS) { any_s = true; continue; }
+            any_l = true;
+            const uint8_t* src = g.src + j * kZEncBlock;
+            const uint32_t gB = B - j * kZEncBlock < kZEncBlock ? B - j * kZEncBlock : kZEncBlock;
+            uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
+            if (head > gB) head = gB;
+            const uint32_t nch = (gB - head) >> 4, done = head + (nch << 4);
+            if (lane < head) atomicAdd(h + src[lane], 1u);
+            if (lane < gB - done) atomicAdd(h + src[done + lane], 1u);
+            const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+            const uint32_t spacing = sampled ? 32u * rate : 32u;  // chunks between the rows a lane has in flight
+            for (uint32_t c0 = 0; c0 < nch; c0 += 4 * spacing) {
+                uint4 q[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t c = c0 + spacing * u + lane;
-                q[u] = make_uint4(0, 0, 0, 0);
-                if (c < nch) q[u] = s4[c];
-            }
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t c = c0 + spacing * u + lane;
+                    q[u] = make_uint4(0, 0, 0, 0);
+                    if (c < nch) q[u] = s4[c];
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t c = c0 + spacing * u + lane;
-                if (c >= nch) continue;
-                const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t c = c0 + spacing * u + lane;
+                    if (c >= nch) continue;
+                    const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t v = (w[k] >> (8 * j)) & 0xFFu;
-                        if (v) atomicAdd(h + v, 1u);
-                        else ++zeros;
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const uint32_t v = (w[k] >> (8 * jj)) & 0xFFu;
+                            if (v) atomicAdd(h + v, 1u);
+                            else ++zeros;
+                        }
                     }
                 }
             }
         }
         if (zeros) atomicAdd(h, zeros);
         __syncwarp();
-        if (sampled) {
+        if (sampled && any_l) {
             uint32_t seen = 0, which = 0;
             for (uint32_t i = lane; i < 256; i += 32)
                 if (s->cnt[i]) { ++seen; which = i; }
             seen = __reduce_add_sync(0xffffffffu, seen);
             bool constant = false;
-            if (seen == 1) {  // one value in the sample: is it the only one in the whole set?
+            if (seen == 1 && !any_s) {  // one value in the sample: is it the only one in the whole set?
                 which = __reduce_add_sync(0xffffffffu, which);  // (one lane holds it, the others 0)
                 const uint32_t rep = which * 0x01010101u;
                 uint32_t diff = 0;
+                const uint8_t* src = g.src;
+                uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
+                if (head > B) head = B;
+                const uint32_t nch = (B - head) >> 4, done = head + (nch << 4);
+                const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
                 for (uint32_t c = lane; c < nch; c += 32) {
                     const uint4 t = s4[c];
                     diff |= (t.x ^ rep) | (t.y ^ rep) | (t.z ^ rep) | (t.w ^ rep);
                 }
-                constant = !__any_sync(0xffffffffu, diff != 0);  // (the two ends were counted byte by byte)
+                if (lane < head) diff |= src[lane] ^ which;
+                if (lane < B - done) diff |= src[done + lane] ^ which;
+                constant = !__any_sync(0xffffffffu, diff != 0);
             }
             if (!constant)
                 for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] = s->cnt[i] * rate + 1u;
         }
+        __syncwarp();
+        if (any_s)
+            for (uint32_t j = 0; j < set_groups; ++j)
+                if (meta[j].mode == kZModeS)
+                    for (uint32_t i = lane; i < 256; i += 32) s->cnt[i] += p.hist[(uint64_t)(b + j) * 256 + i];
     }
     __syncwarp();
     // ---- rank sort of the symbols that occur, ascending by (count, symbol): a lane ranks 8 symbols --------------------------
@@ -606,7 +597,7 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     // ---- the code and the kind of group (lane 0) -------------------------------------------------------------------------
     uint32_t kind = kZKindRaw, tree_bytes = 0;
     if (lane == 0) {
-        if (B > 0 && nsym == 1) kind = kZKindRle;
+        if (B > 0 && nsym == 1 && !any_s) kind = kZKindRle;
         else if (nsym >= 2 && B >= 32 && zenc_build_code(s, (int)nsym)) {
             tree_bytes = zenc_describe_tree(s);
             if (tree_bytes) kind = kZKindHuf;
@@ -623,7 +614,23 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     if (lane == 0) { out->kind = kind; out->tree_bytes = tree_bytes; out->nsym = nsym; }
 }
 
+// `nthreads` threads copy n bytes between two arbitrarily aligned global addresses (the sequences sections: a few KB at most)
+__device__ __forceinline__ void zenc_copy_global(uint8_t* d, const uint8_t* sp, uint32_t n, uint32_t t, uint32_t nthreads)
+{
+    uint32_t head = (4u - (uint32_t)((uintptr_t)d & 3u)) & 3u;
+    if (head > n) head = n;
+    const uint32_t words = (n - head) >> 2, done = head + 4 * words;
+    if (t < head) d[t] = sp[t];
+    else if (t >= 32 && t - 32 < n - done) d[done + t - 32] = sp[done + t - 32];
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(d + head);
+    const uint8_t* s0 = sp + head;
+    for (uint32_t k = t; k < words; k += nthreads) d4[k] = zm_load32(s0 + 4 * k);
+}
+
 // ---- kernel 2: sizes, position, pack - a CTA per group --------------------------------------------------------------------
+// An S group (csrc/zstd_match_kernels.cuh) runs through the same three steps with its compacted LITERALS as the bytes to code:
+// block q holds literals [8 KiB q, 8 KiB (q + 1)) of the group, as a Huffman or Raw literals section, followed by the block's
+// sequences section, which zstd_enc_seq_kernel left behind the literals in the literal scratch.
 __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams p)
 {
     VBZ_DYN_SMEM(smem);
@@ -640,20 +647,27 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
         }
         return;
     }
-    const uint32_t gi = g.gi, content = g.content, B = g.B;
+    const uint32_t gi = g.gi, content = g.content;
     const bool last = g.last;
-    const uint8_t* src = g.src;
-    const uint32_t nsub = B ? (B + kZEncSub - 1) / kZEncSub : 1u;
+    const ZGroupMeta* meta = reinterpret_cast<const ZGroupMeta*>(p.meta) + b;
+    const bool smode = meta->mode == kZModeS;
+    // the bytes to entropy-code: the group itself, or the literals its matches left over
+    const uint8_t* slot = p.lits + (uint64_t)(g.src - p.src);
+    const uint8_t* src = smode ? slot : g.src;
+    const uint32_t B = smode ? meta->lits : g.B;
+    const uint32_t nsub = smode ? meta->nblk : (B ? (B + kZEncSub - 1) / kZEncSub : 1u);
     // the group's code, built by zstd_enc_code_kernel
     const ZGroupCode* gc = reinterpret_cast<const ZGroupCode*>(p.codes) + (b - g.code_first);
-    uint32_t kind = gc->kind;
+    const bool huf_ok = gc->kind == kZKindHuf;
+    uint32_t kind = smode ? (uint32_t)kZKindHuf : gc->kind;  // (an S group always takes the block-by-block path; its literals may still be stored raw)
     const uint32_t tree_bytes = gc->tree_bytes;
-    if (kind == kZKindHuf) {
+    if (huf_ok) {
         const uint32_t c = gc->code[tid];
         s->code[tid] = c;
         s->len[tid] = (uint8_t)(c >> 16);
         if (tid < 160 / 4) reinterpret_cast<uint32_t*>(s->tree)[tid] = reinterpret_cast<const uint32_t*>(gc->tree)[tid];
     }
+    if (smode && tid <= kZSubs) s->seq_off[tid] = meta->seq_off[tid];
     // bytes before the first block header: the sized header and the frame header, in front of the frame's first group
     uint32_t pre = 0;
     uint8_t prebuf[16];
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     uint16_t* lane_off = &s->lane_off[0][0];  // [stream][lane]
 
     // ---- sizes: every stream of the group, a warp per stream ----------------------------------------------------------------
-    if (kind == kZKindHuf) {
+    if (kind == kZKindHuf && huf_ok) {
         ZRun f;
         uint32_t fn;
         zenc_fetch_stream(src, B, wid, nsub * 4, lane, f, &fn);
@@ -693,16 +707,21 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
             bool tree_out = false, any = false;
             for (uint32_t q = 0; q < nsub; ++q) {
                 const ZSub sb = zenc_sub(B, q);
-                uint32_t payload = sb.bytes;
+                // the literals stored as they are: a Raw block (L), or a Raw literals section with a 1 / 2 / 3-byte header (S)
+                const uint32_t raw_lit = smode ? (sb.bytes < 32 ? 1u : sb.bytes < 4096 ? 2u : 3u) + sb.bytes : sb.bytes;
+                const uint32_t seq_sec = smode && s->seq_off[q + 1] > s->seq_off[q] ? s->seq_off[q + 1] - s->seq_off[q] : 1u;  // 1 = "0 sequences"
+                uint32_t payload = smode ? raw_lit + seq_sec : sb.bytes;
                 s->sub_kind[q] = kZKindRaw;
                 s->sub_tree[q] = 0;
-                if (sb.bytes >= 32) {
+                s->sub_lit[q] = raw_lit;
+                if (huf_ok && sb.bytes >= 32) {
                     uint32_t comp = (tree_out ? 0u : tree_bytes) + (sb.streams == 4 ? 6u : 0u);
                     for (uint32_t j = 0; j < sb.streams; ++j) comp += (s->sbits[q * 4 + j] >> 3) + 1;  // + the marker bit
                     const uint32_t lit_hdr = sb.streams == 1 ? 3u : 4u;  // 4 streams: 1024 <= regenerated size <= 8192 and comp below it
-                    const uint32_t huf = lit_hdr + comp + 1;             // + "0 sequences"
-                    if (huf < sb.bytes && comp < (sb.streams == 1 ? 1024u : 16384u)) {
+                    const uint32_t huf = lit_hdr + comp + seq_sec;
+                    if (huf < payload && comp < (sb.streams == 1 ? 1024u : 16384u)) {
                         payload = huf;
+                        s->sub_lit[q] = lit_hdr + comp;
                         s->sub_kind[q] = kZKindHuf;
                         s->sub_tree[q] = tree_out ? 0 : 1;
                         tree_out = true;
@@ -713,7 +732,7 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
                 off += 3 + payload;
             }
             s->sub_off[nsub] = off;
-            if (!any) { kind = kZKindRaw; off = pre; }  // nothing gained anywhere: one Raw block for the group
+            if (!any && !smode) { kind = kZKindRaw; off = pre; }  // nothing gained anywhere: one Raw block for the group
         }
         if (kind == kZKindRle) off = pre + 3 + 1;
         else if (kind == kZKindRaw) off = pre + 3 + B;
@@ -771,12 +790,13 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
         uint32_t sbytes[4] = {0, 0, 0, 0};
         uint32_t lit_hdr = 0, tb = 0;
         if (live) {
-            const uint32_t out_bytes = s->sub_off[q + 1] - s->sub_off[q] - (q == 0 ? 0u : 0u);
+            const uint32_t out_bytes = s->sub_off[q + 1] - s->sub_off[q];
             const uint32_t payload = out_bytes - 3;
             if (ht == 0) {
                 for (uint32_t k = 0; k < front; ++k) stage[k] = prebuf[k];
                 const bool blast = last && q + 1 == nsub;
-                const uint32_t bh = (blast ? 1u : 0u) | ((skind == kZKindHuf ? 2u : 0u) << 1) | (payload << 3);
+                const uint32_t btype = (smode || skind == kZKindHuf) ? 2u : 0u;  // Compressed / Raw
+                const uint32_t bh = (blast ? 1u : 0u) | (btype << 1) | (payload << 3);
                 blk[0] = (uint8_t)bh; blk[1] = (uint8_t)(bh >> 8); blk[2] = (uint8_t)(bh >> 16);
             }
             if (skind == kZKindHuf) {
@@ -798,8 +818,16 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
                     lit[lit_hdr + tb + 2 * k + 1] = (uint8_t)(sbytes[k] >> 8);
                 }
             } else {
+                uint32_t rh = 0;  // S: Raw literals section header (RFC 8878 3.1.1.3.1.1), L: the block is the bytes
+                if (smode) {
+                    rh = sb.bytes < 32 ? 1u : sb.bytes < 4096 ? 2u : 3u;
+                    if (ht == 0) {
+                        const uint32_t v = rh == 1 ? (sb.bytes << 3) : (rh == 2 ? ((sb.bytes << 4) | (1u << 2)) : ((sb.bytes << 4) | (3u << 2)));
+                        for (uint32_t k = 0; k < rh; ++k) blk[3 + k] = (uint8_t)(v >> (8 * k));
+                    }
+                }
                 const uint8_t* from = src + sb.start;
-                for (uint32_t i = ht; i < sb.bytes; i += 128) blk[3 + i] = from[i];
+                for (uint32_t i = ht; i < sb.bytes; i += 128) blk[3 + rh + i] = from[i];
             }
         }
         __syncthreads();  // byte-wise header writes land before the word-wise stream writes next to them
@@ -824,7 +852,12 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
         __syncthreads();
         if (live) {
             const uint32_t o0 = q == 0 ? 0u : s->sub_off[q], o1 = s->sub_off[q + 1];  // sub-block 0 starts at 0 with the frame's headers
-            if (excl + o1 <= rd.dst_cap) zenc_copy_out(dst + o0, stage, o1 - o0, ht, 128);
+            if (excl + o1 <= rd.dst_cap) {
+                const uint32_t seq_n = smode && s->seq_off[q + 1] > s->seq_off[q] ? s->seq_off[q + 1] - s->seq_off[q] : 0u;
+                // staged: headers, the literals section and - when there are no sequences - the zero byte that says so
+                zenc_copy_out(dst + o0, stage, o1 - o0 - seq_n, ht, 128);
+                if (seq_n) zenc_copy_global(dst + o1 - seq_n, slot + s->seq_off[q], seq_n, ht, 128);
+            }
         }
         __syncthreads();
     }

@@ -1,0 +1,568 @@
+// csrc/zstd_match_kernels.cuh - the sequence half of the zstd frame writer: match finding, and the sequences sections (RFC 8878 3.1.1.3.2).
+//
+// Replaces what ZSTD_compress(level) does beyond entropy-coding literals (ref call site vbz/vbz.cpp:194-204): block splitting,
+// hash-table match finding, FSE table construction for literal lengths / match lengths / offsets and the interleaved sequences
+// bitstream.  On nanopore signal the matches that matter are the runs of zero control bytes at the head of every stage-1 stream
+// (96.9 % of them are 0x00) - Huffman cannot go below one bit per byte there; on repetitive input (the
+// reference's own benchmark tiles one trace, vbz/perf/test_data_generator.h:29-74; numpy.arange in pyvbz's README) matches are everything.
+//
+// Units of work.  The content of a frame is cut into GROUPS of <= 128 KiB (csrc/zstd_enc_kernels.cuh).  A group is written either
+//   L  as up to 16 literal-only blocks of 8 KiB (no sequences: what the block-parallel decoder likes best), or
+//   S  as ceil(literals / 8 KiB) blocks that each hold <= 8 KiB of the group's LITERALS (the bytes no match covers, compacted) plus
+//      the sequences that end inside that stretch of literals - so the literal machinery of the encode kernel (4 Huffman streams per
+//      block, lanes own runs of <= 64 symbols) serves both kinds unchanged.
+// zstd_enc_match_kernel   a WARP per group: greedy parse, 32 positions per step.  Every lane looks at "its" position: a repeat of the
+//                         previous byte (4 bytes equal to the 4 bytes one back: a run) or a candidate from a hash table of 4-byte
+//                         words (2^11 entries per warp in shared memory, seeded with the 8 KiB before the group), verified against
+//                         the data.  The first lane with a match wins, the warp extends it 128 bytes per step, the parse continues
+//                         behind it.  After a few steps without a match only one step in four (level 1) or two (level 2) is examined
+//                         (level >= 3: every step), as libzstd's fast strategy accelerates over incompressible data.  Sequences go
+//                         to a record array as {offset, literal run, match length}; a group becomes S only if its matches pay for
+//                         their sequences (12 bytes of match per sequence - which also bounds every scratch area), and only then are
+//                         its literals compacted and counted (per-group histogram for the Huffman code).
+// zstd_enc_seq_kernel     a warp per S group: sequence codes and their histograms, FSE tables (normalised counts, the table description,
+//                         the encoder's state tables; RLE mode for a lone code, the predefined tables for a handful of sequences),
+//                         then lane 0 writes the sequences section of every block of the group: the first one carries the tables,
+//                         the others repeat them (Repeat_Mode).  Offsets are always explicit (offset + 3): no repeat-offset history
+//                         has to be tracked, blocks stay independent of what precedes them.
+// The sections land behind the group's literals in the literal scratch; zstd_encode_kernel copies them in behind each literals section.
+#pragma once
+#include "zstd_dec_kernels.cuh"
+#include "svb_kernels.cuh"
+
+namespace vbz {
+
+constexpr uint32_t kZCodeSet = 8;  // consecutive groups of a region that share one Huffman code (built once, over up to 1 MiB)
+
+// where group b of the batch lives: false = nothing to encode (rejected read, upstream error, or a group beyond the content)
+struct ZGroupLoc {
+    const uint8_t* src;
+    uint32_t r, gi, ngrp, content, B;
+    uint32_t code_first;  // groups back to the first group of this one's CODE SET (kZCodeSet consecutive groups of a region share one code)
+    uint32_t code_bytes;  // content bytes of the code set, from its first group on
+    uint32_t region_off;  // content bytes of the group's region (control bytes | data bytes) before the group
+    bool last;
+};
+__device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, const ZstdEncRead& rd, uint32_t r, ZGroupLoc& g)
+{
+    g.r = r;
+    g.gi = b - rd.first_block;
+    if (rd.rejected) return false;
+    g.content = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
+    if (p.src_sizes && g.content >= kErrOutOfMemory) return false;  // stage 1 reported an error for this read
+    // groups of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'), then the rest
+    const uint32_t split = rd.split < g.content ? rd.split : 0u;
+    const uint32_t n_a = (split + kZEncBlock - 1) / kZEncBlock, n_b = (g.content - split + kZEncBlock - 1) / kZEncBlock;
+    g.ngrp = n_a + n_b ? n_a + n_b : 1u;
+    if (g.gi >= g.ngrp) return false;  // the table was sized for the largest content stage 1 could have produced
+    const uint32_t start = g.gi < n_a ? g.gi * kZEncBlock : split + (g.gi - n_a) * kZEncBlock;
+    const uint32_t region_end = g.gi < n_a ? split : g.content;
+    g.B = region_end - start < kZEncBlock ? region_end - start : kZEncBlock;
+    g.last = g.gi + 1 == g.ngrp;
+    g.src = p.src + rd.src_off + start;
+    const uint32_t in_region = g.gi < n_a ? g.gi : g.gi - n_a;
+    g.code_first = in_region % kZCodeSet;
+    g.region_off = in_region * kZEncBlock;
+    const uint32_t set_start = start - g.code_first * kZEncBlock;
+    g.code_bytes = region_end - set_start < kZCodeSet * kZEncBlock ? region_end - set_start : kZCodeSet * kZEncBlock;
+    return true;
+}
+
+
+
+constexpr uint32_t kZHashLog = 11;
+constexpr uint32_t kZPreWindow = 8192;       // bytes before the group that seed the hash table
+constexpr uint32_t kZMinRun = 8;             // shortest run (offset 1) worth a sequence
+constexpr uint32_t kZMinMatch = 6;           // shortest match at any other offset
+constexpr int kZMatchWarps = 4;
+
+enum : uint32_t { kZModeL = 0, kZModeS = 1 };
+// what the match kernel (and then the sequence kernel) leaves per group
+struct ZGroupMeta {
+    uint32_t mode;          // kZModeL / kZModeS
+    uint32_t nseq;          // S: sequences of the group
+    uint32_t lits;          // S: literals of the group (compacted in the literal scratch, at the group's content offset)
+    uint32_t nblk;          // S: blocks = max(1, ceil(lits / 8 KiB))
+    uint32_t seq_off[17];   // S: the sequences section of block q = bytes [seq_off[q], seq_off[q + 1]) of the group's literal slot (empty: no sequences)
+    uint32_t pad[3];
+};
+static_assert(sizeof(ZGroupMeta) == 96, "ZGroupMeta layout");
+
+__device__ __forceinline__ uint64_t zm_pack(uint32_t off, uint32_t ll, uint32_t ml) { return (uint64_t)off | ((uint64_t)ll << 18) | ((uint64_t)ml << 36); }
+__device__ __forceinline__ uint32_t zm_off(uint64_t r) { return (uint32_t)r & 0x3FFFFu; }
+__device__ __forceinline__ uint32_t zm_ll(uint64_t r) { return (uint32_t)(r >> 18) & 0x3FFFFu; }
+__device__ __forceinline__ uint32_t zm_ml(uint64_t r) { return (uint32_t)(r >> 36) & 0x3FFFFu; }
+
+// 4 bytes at any address, little-endian, through aligned 32-bit loads
+__device__ __forceinline__ uint32_t zm_load32(const uint8_t* p)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = 8u * (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t a = w[0];
+    return sh ? __funnelshift_r(a, w[1], sh) : a;
+}
+__device__ __forceinline__ uint32_t zm_hash(uint32_t w) { return (w * 2654435761u) >> (32 - kZHashLog); }
+
+// first record of group b in the record scratch, and how many it may hold
+__device__ __forceinline__ uint64_t zm_rec_base(uint64_t content_off, uint32_t b) { return content_off / 16 + b; }
+__device__ __forceinline__ uint32_t zm_rec_cap(uint32_t B) { return B / 16; }
+
+struct ZMatchSmem { uint32_t table[1u << kZHashLog]; uint32_t hist[256]; };
+
+// ---- kernel: greedy parse of every group ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdEncParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ZMatchSmem* sm = reinterpret_cast<ZMatchSmem*>(smem) + wid;
+    const uint32_t b = blockIdx.x * kZMatchWarps + wid;
+    if (b >= p.n_blocks) return;
+    const uint32_t r = p.block_read[b];
+    const ZstdEncRead rd = p.reads[r];
+    ZGroupLoc g;
+    ZGroupMeta* meta = reinterpret_cast<ZGroupMeta*>(p.meta) + b;
+    if (!zenc_locate(p, b, rd, r, g)) return;
+    if (lane == 0) { meta->mode = kZModeL; meta->nseq = 0; meta->lits = g.B; meta->nblk = 0; }
+    const uint32_t B = g.B;
+    if (B < 64) return;
+    const uint8_t* src = g.src;
+    const uint64_t content_off = (uint64_t)(src - p.src);
+    uint64_t* recs = p.seqs + zm_rec_base(content_off, b);
+    const uint32_t rec_cap = zm_rec_cap(B);
+    // how far back a match may reach: the group's region (control bytes | data bytes), at most kZPreWindow before the group
+    const uint32_t pre = g.region_off < kZPreWindow ? g.region_off : kZPreWindow;
+    const uint8_t* win = src - pre;  // window coordinate w <-> byte win[w]; the group starts at w = pre
+    // search effort by level: steps without a match before skipping starts, steps skipped for every step examined
+    const uint32_t miss_limit = p.level >= 3 ? 0xFFFFFFFFu : (p.level == 2 ? 4u : 2u);
+    const uint32_t skip_steps = p.level == 2 ? 1u : 3u;
+
+    for (uint32_t i = lane; i < (1u << kZHashLog); i += 32) sm->table[i] = 0;  // entry = window coordinate + 1, 0 = empty
+    __syncwarp();
+    // seed with the pre-window (every position: it is at most 8 KiB)
+    for (uint32_t w0 = 0; w0 + 4 <= pre; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        if (w + 4 <= pre) atomicMax(&sm->table[zm_hash(zm_load32(win + w))], w + 1);
+    }
+    __syncwarp();
+
+    uint32_t pos = 0, anchor = 0, nseq = 0, matched = 0, miss = 0;
+    while (pos + 4 <= B) {
+        // ---- this step's 32 positions ----------------------------------------------------------------------------------------
+        const uint32_t q = pos + lane;
+        const bool live = q + 4 <= B;
+        uint32_t w = 0, wp = 0;
+        if (live) {
+            w = zm_load32(src + q);
+            wp = (q + pre) ? zm_load32(src + q - 1) : ~w;  // the 4 bytes one back (nothing before the region's first byte)
+        }
+        const bool run = live && w == wp;
+        uint32_t dist = 0;
+        if (live) {
+            const uint32_t h = zm_hash(w), at = q + pre, e = sm->table[h];
+            if (e != 0 && e - 1 < at && zm_load32(win + (e - 1)) == w) dist = at - (e - 1);
+        }
+        __syncwarp();
+        if (live) atomicMax(&sm->table[zm_hash(w)], q + pre + 1);
+        uint32_t cand = __ballot_sync(0xffffffffu, run || dist != 0);
+        bool took = false;
+        while (cand) {
+            const uint32_t f = (uint32_t)__ffs((int)cand) - 1;
+            cand &= cand - 1;
+            const uint32_t off = __shfl_sync(0xffffffffu, run ? 1u : dist, f);
+            const uint32_t mp = pos + f;  // match position
+            // ---- extend: 4 bytes per lane, 128 per round -------------------------------------------------------------------------
+            uint32_t ml = 4;
+            for (;;) {
+                const uint32_t at = mp + ml + 4 * lane;
+                uint32_t eq = 0;
+                if (at < B) {
+                    const uint32_t x = zm_load32(src + at) ^ zm_load32(src + at - off);
+                    eq = x ? ((uint32_t)__ffs((int)x) - 1) >> 3 : 4u;
+                    if (eq > B - at) eq = B - at;
+                }
+                const uint32_t stop = __ballot_sync(0xffffffffu, eq < 4);
+                if (stop) {
+                    const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
+                    ml += 4 * fl + __shfl_sync(0xffffffffu, eq, fl);
+                    break;
+                }
+                ml += 128;
+            }
+            const uint32_t need = off == 1 ? kZMinRun : kZMinMatch;
+            // every sequence must be paid for by 12 bytes of match (that is also what keeps the scratch areas from overflowing)
+            if (ml >= need && nseq < rec_cap && 12ull * (nseq + 1) + 256 <= (uint64_t)matched + ml) {
+                if (lane == 0) recs[nseq] = zm_pack(off, mp - anchor, ml);
+                ++nseq;
+                matched += ml;
+                anchor = mp + ml;
+                pos = anchor;
+                took = true;
+                break;
+            }
+        }
+        if (took) { miss = 0; continue; }
+        pos += 32;
+        if (++miss > miss_limit) pos += 32 * skip_steps;
+    }
+    __syncwarp();
+    // ---- L or S? ----------------------------------------------------------------------------------------------------------------------
+    const uint32_t floor_bytes = B / 32 > 64 ? B / 32 : 64;
+    if (nseq == 0 || matched < floor_bytes || 12ull * nseq + 256 > matched) return;  // stays L
+    // ---- S: compact the literals into the literal scratch, count them --------------------------------------------------------------------
+    uint8_t* lits = p.lits + content_off;
+    for (uint32_t i = lane; i < 256; i += 32) sm->hist[i] = 0;
+    __syncwarp();
+    uint32_t from = 0, to = 0;  // source position / literal count before the records of this round
+    for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint64_t rec = i < nseq ? recs[i] : 0ull;
+        const uint32_t ll = zm_ll(rec), ml = zm_ml(rec);
+        const uint32_t span = warp_scan_u32(ll + ml), lsum = warp_scan_u32(ll);
+        const uint32_t my_from = from + span - (ll + ml), my_to = to + lsum - ll;
+        // short runs: the lane copies its own; long ones: the whole warp, one after the other
+        if (ll <= 16) {
+            for (uint32_t k = 0; k < ll; ++k) {
+                const uint8_t v = src[my_from + k];
+                lits[my_to + k] = v;
+                atomicAdd(&sm->hist[v], 1u);
+            }
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, ll > 16);
+        while (big) {
+            const uint32_t f = (uint32_t)__ffs((int)big) - 1;
+            big &= big - 1;
+            const uint32_t n = __shfl_sync(0xffffffffu, ll, f), sf = __shfl_sync(0xffffffffu, my_from, f), st = __shfl_sync(0xffffffffu, my_to, f);
+            for (uint32_t k = lane; k < n; k += 32) {
+                const uint8_t v = src[sf + k];
+                lits[st + k] = v;
+                atomicAdd(&sm->hist[v], 1u);
+            }
+        }
+        from += __shfl_sync(0xffffffffu, span, 31);
+        to += __shfl_sync(0xffffffffu, lsum, 31);
+    }
+    for (uint32_t k = from + lane; k < B; k += 32) {  // the literals after the last match
+        const uint8_t v = src[k];
+        lits[to + k - from] = v;
+        atomicAdd(&sm->hist[v], 1u);
+    }
+    to += B - from;
+    __syncwarp();
+    uint32_t* gh = p.hist + (uint64_t)b * 256;
+    for (uint32_t i = lane; i < 256; i += 32) gh[i] = sm->hist[i];
+    if (lane == 0) { meta->mode = kZModeS; meta->nseq = nseq; meta->lits = to; meta->nblk = to ? (to + kZEncSub - 1) / kZEncSub : 1u; }
+}
+
+// ---- sequence codes (RFC 8878 3.1.1.3.2.1.1) ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t zm_ll_code(uint32_t ll)
+{
+    if (ll < 16) return ll;
+    if (ll < 64) {
+        if (ll < 24) return 16 + ((ll - 16) >> 1);
+        if (ll < 32) return 20 + ((ll - 24) >> 2);
+        if (ll < 48) return 22 + ((ll - 32) >> 3);
+        return 24;
+    }
+    return (uint32_t)z_highbit(ll) + 19;  // 64 -> 25, 128 -> 26, ...
+}
+__device__ __forceinline__ uint32_t zm_ml_code(uint32_t ml)  // ml >= 3
+{
+    const uint32_t v = ml - 3;
+    if (v < 32) return v;
+    if (v < 128) {
+        if (v < 40) return 32 + ((v - 32) >> 1);
+        if (v < 48) return 36 + ((v - 40) >> 2);
+        if (v < 64) return 38 + ((v - 48) >> 3);
+        if (v < 96) return 40 + ((v - 64) >> 4);
+        return 42;
+    }
+    return (uint32_t)z_highbit(v) + 36;  // 128 -> 43, 256 -> 44, ...
+}
+
+// one lane's FSE encoder for one of the three symbol types
+struct ZFseEnc {
+    uint16_t state[256];  // next state by rank of the symbol's occurrences in table order (accuracy log <= 8)
+    int32_t dnb[56];      // deltaNbBits
+    int16_t dfs[56];      // deltaFindState
+    int16_t norm[56];
+    uint8_t cell[256];    // symbol of every cell
+    uint32_t al, mode, nsym, rle_sym;
+};
+struct ZSeqEncSmem {
+    ZFseEnc t[3];         // 0 = literal lengths, 1 = offsets, 2 = match lengths
+    uint32_t hist[3][56];
+    uint32_t blk_cnt[16];
+    uint8_t desc[3][64];  // table descriptions
+    uint32_t desc_n[3];
+};
+
+// counts -> normalised counts that sum to 2^al, every present symbol >= 1.  false if impossible.
+__device__ bool zm_normalize(const uint32_t* cnt, int nsym, uint32_t total, int al, int16_t* norm)
+{
+    const int T = 1 << al;
+    int sum = 0, big = 0, present = 0;
+    for (int s = 0; s < nsym; ++s) {
+        int v = 0;
+        if (cnt[s]) {
+            v = (int)(((uint64_t)cnt[s] * (uint64_t)T) / total);
+            if (v == 0) v = 1;
+            ++present;
+        }
+        norm[s] = (int16_t)v;
+        sum += v;
+        if (cnt[s] > cnt[big]) big = s;
+    }
+    if (present > T) return false;
+    int diff = T - sum;
+    if (diff > 0 || norm[big] + diff >= 1) { norm[big] = (int16_t)(norm[big] + diff); return true; }
+    while (diff < 0) {  // take the excess from the largest counts, one at a time
+        int pick = -1;
+        for (int s = 0; s < nsym; ++s)
+            if (norm[s] > 1 && (pick < 0 || norm[s] > norm[pick])) pick = s;
+        if (pick < 0) return false;
+        norm[pick]--;
+        diff++;
+    }
+    return true;
+}
+// normalised counts -> table description (forward bit stream, RFC 8878 4.1.1).  Returns its size in bytes, 0 if it does not fit `cap`.
+__device__ uint32_t zm_describe(const int16_t* norm, int nsym, int al, uint8_t* out, uint32_t cap)
+{
+    uint64_t acc = 0;
+    uint32_t nbits = 0, nbytes = 0;
+    auto put = [&](uint32_t v, uint32_t nb) {
+        acc |= (uint64_t)v << nbits;
+        nbits += nb;
+        while (nbits >= 8) { if (nbytes < cap) out[nbytes] = (uint8_t)acc; ++nbytes; acc >>= 8; nbits -= 8; }
+    };
+    put((uint32_t)(al - 5), 4);
+    int remaining = (1 << al) + 1, thr = 1 << al, nb = al + 1, sym = 0;
+    while (remaining > 1 && sym < nsym) {
+        const int c = norm[sym];
+        const int max = (2 * thr - 1) - remaining;
+        int v = c + 1;  // (-1, "less than one", would be written as 0: this writer gives every present symbol at least one cell)
+        if (v < max) put((uint32_t)v, (uint32_t)(nb - 1));
+        else {
+            if (v >= thr) v += max;
+            put((uint32_t)v, (uint32_t)nb);
+        }
+        remaining -= c < 0 ? -c : c;
+        ++sym;
+        if (c == 0) {
+            int zeros = 0;
+            while (sym + zeros < nsym && norm[sym + zeros] == 0) ++zeros;
+            sym += zeros;
+            while (zeros >= 3) { put(3, 2); zeros -= 3; }
+            put((uint32_t)zeros, 2);
+        }
+        while (remaining < thr) { nb--; thr >>= 1; }
+    }
+    if (remaining != 1) return 0;
+    if (nbits) { if (nbytes < cap) out[nbytes] = (uint8_t)acc; ++nbytes; }
+    return nbytes <= cap ? nbytes : 0;
+}
+// normalised counts (-1 = "less than one", as in the predefined tables) -> the encoder's tables
+__device__ void zm_build_enc(ZFseEnc* t, int nsym, int al)
+{
+    const int T = 1 << al;
+    int cumul[57];
+    int high = T - 1;
+    cumul[0] = 0;
+    for (int s = 0; s < nsym; ++s) {
+        const int n = t->norm[s];
+        cumul[s + 1] = cumul[s] + (n == -1 ? 1 : n);
+        if (n == -1) t->cell[high--] = (uint8_t)s;
+    }
+    const int step = (T >> 1) + (T >> 3) + 3;
+    int pos = 0;
+    for (int s = 0; s < nsym; ++s)
+        for (int i = 0; i < t->norm[s]; ++i) {
+            t->cell[pos] = (uint8_t)s;
+            do { pos = (pos + step) & (T - 1); } while (pos > high);
+        }
+    for (int u = 0; u < T; ++u) { const int s = t->cell[u]; t->state[cumul[s]++] = (uint16_t)(T + u); }
+    int total = 0;
+    for (int s = 0; s < nsym; ++s) {
+        const int n = t->norm[s];
+        if (n == 0) { t->dnb[s] = ((al + 1) << 16) - T; t->dfs[s] = 0; }
+        else if (n == -1 || n == 1) { t->dnb[s] = (al << 16) - T; t->dfs[s] = (int16_t)(total - 1); total += 1; }
+        else {
+            const int max_bits_out = al - z_highbit((uint32_t)(n - 1));
+            t->dnb[s] = (max_bits_out << 16) - (n << max_bits_out);
+            t->dfs[s] = (int16_t)(total - n);
+            total += n;
+        }
+    }
+    t->al = (uint32_t)al;
+}
+
+// forward bit writer into global memory (one lane)
+struct ZGBitW { uint8_t* p; uint64_t acc; uint32_t nbits, nbytes; };
+__device__ __forceinline__ void zg_put(ZGBitW& w, uint32_t v, uint32_t nb)
+{
+    w.acc |= (uint64_t)v << w.nbits;
+    w.nbits += nb;
+    while (w.nbits >= 8) { w.p[w.nbytes++] = (uint8_t)w.acc; w.acc >>= 8; w.nbits -= 8; }
+}
+__device__ __forceinline__ void zm_fse_init(const ZFseEnc* t, uint32_t sym, uint32_t* st)
+{
+    if (t->mode == 1) { *st = 0; return; }  // RLE: no state
+    const int32_t d = t->dnb[sym];
+    const uint32_t nb = (uint32_t)(d + (1 << 15)) >> 16;
+    const uint32_t value = (nb << 16) - (uint32_t)d;
+    *st = t->state[(value >> nb) + t->dfs[sym]];
+}
+__device__ __forceinline__ void zm_fse_encode(const ZFseEnc* t, uint32_t sym, uint32_t* st, ZGBitW& w)
+{
+    if (t->mode == 1) return;
+    const uint32_t nb = (uint32_t)((int32_t)*st + t->dnb[sym]) >> 16;
+    zg_put(w, *st & ((1u << nb) - 1u), nb);
+    *st = t->state[(*st >> nb) + t->dfs[sym]];
+}
+__device__ __forceinline__ void zm_fse_flush(const ZFseEnc* t, uint32_t st, ZGBitW& w)
+{
+    if (t->mode == 1) return;
+    zg_put(w, st & ((1u << t->al) - 1u), t->al);
+}
+
+// ---- kernel: the sequences sections of every S group, a warp per group ------------------------------------------------------------------
+constexpr int kZSeqEncWarps = 2;
+__global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEncParams p)
+{
+    VBZ_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ZSeqEncSmem* sm = reinterpret_cast<ZSeqEncSmem*>(smem) + wid;
+    const uint32_t b = blockIdx.x * kZSeqEncWarps + wid;
+    if (b >= p.n_blocks) return;
+    ZGroupMeta* meta = reinterpret_cast<ZGroupMeta*>(p.meta) + b;
+    const uint32_t r = p.block_read[b];
+    const ZstdEncRead rd = p.reads[r];
+    ZGroupLoc g;
+    if (!zenc_locate(p, b, rd, r, g) || meta->mode != kZModeS) return;
+    const uint32_t nseq = meta->nseq, lits = meta->lits, nblk = meta->nblk;
+    const uint64_t content_off = (uint64_t)(g.src - p.src);
+    uint64_t* recs = p.seqs + zm_rec_base(content_off, b);
+    uint8_t* slot = p.lits + content_off;
+
+    for (uint32_t i = lane; i < 3 * 56; i += 32) (&sm->hist[0][0])[i] = 0;
+    if (lane < 16) sm->blk_cnt[lane] = 0;
+    __syncwarp();
+    // ---- pass 1: which block a sequence belongs to, its literal run inside that block, the code histograms -----------------------------
+    uint32_t lit_before = 0;
+    for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint64_t rec = i < nseq ? recs[i] : 0ull;
+        const uint32_t ll = zm_ll(rec), ml = zm_ml(rec), off = zm_off(rec);
+        const uint32_t lsum = warp_scan_u32(ll);
+        if (i < nseq) {
+            const uint32_t c = lit_before + lsum - ll;  // literals of the group before this sequence's run
+            uint32_t blk = (c + ll) >> 13;               // the block in which the run ends (a run that ends on a boundary opens the next block)
+            if (blk >= nblk) blk = nblk - 1;
+            const uint32_t start = blk << 13;
+            const uint32_t ll_in = c + ll - (c > start ? c : start);
+            recs[i] = zm_pack(off, ll_in, ml);
+            atomicAdd(&sm->hist[0][zm_ll_code(ll_in)], 1u);
+            atomicAdd(&sm->hist[1][(uint32_t)z_highbit(off + 3)], 1u);
+            atomicAdd(&sm->hist[2][zm_ml_code(ml)], 1u);
+            atomicAdd(&sm->blk_cnt[blk], 1u);
+        }
+        lit_before += __shfl_sync(0xffffffffu, lsum, 31);
+    }
+    __syncwarp();
+    // ---- the three tables: lanes 0, 1, 2 ---------------------------------------------------------------------------------------------------
+    if (lane < 3) {
+        ZFseEnc* t = &sm->t[lane];
+        const int max_sym = lane == 0 ? 36 : (lane == 1 ? 32 : 53);
+        const uint32_t* h = sm->hist[lane];
+        int nsym = 0, present = 0, only = 0;
+        for (int s = 0; s < max_sym; ++s)
+            if (h[s]) { nsym = s + 1; ++present; only = s; }
+        t->nsym = (uint32_t)nsym;
+        sm->desc_n[lane] = 0;
+        bool done = false;
+        if (present == 1) {  // RLE_Mode: one byte, no bits per sequence
+            t->mode = 1; t->rle_sym = (uint32_t)only; t->al = 0;
+            sm->desc[lane][0] = (uint8_t)only; sm->desc_n[lane] = 1;
+            done = true;
+        }
+        if (!done && nseq >= 48) {  // FSE_Compressed_Mode
+            const int max_al = lane == 1 ? 7 : 8;
+            int al = z_highbit(nseq) - 2;
+            al = al < 5 ? 5 : (al > max_al ? max_al : al);
+            while ((1 << al) < present) ++al;
+            if (al <= max_al && zm_normalize(h, nsym, nseq, al, t->norm)) {
+                const uint32_t n = zm_describe(t->norm, nsym, al, sm->desc[lane], 64);
+                if (n) { sm->desc_n[lane] = n; t->mode = 2; zm_build_enc(t, nsym, al); done = true; }
+            }
+        }
+        if (!done) {  // Predefined_Mode
+            const int16_t* def = lane == 0 ? kZ_LL_DEF : (lane == 1 ? kZ_OF_DEF : kZ_ML_DEF);
+            const int def_n = lane == 0 ? 36 : (lane == 1 ? 29 : 53);
+            for (int s = 0; s < def_n; ++s) t->norm[s] = def[s];
+            t->mode = 0;
+            zm_build_enc(t, def_n, lane == 1 ? 5 : 6);
+        }
+    }
+    __syncwarp();
+    // offsets beyond the predefined table's 29 codes cannot occur: the window is 136 KiB (code <= 17)
+    // ---- the sections: lane 0, block after block ---------------------------------------------------------------------------------------------
+    if (lane == 0) {
+        const ZFseEnc* tl = &sm->t[0];
+        const ZFseEnc* to = &sm->t[1];
+        const ZFseEnc* tm = &sm->t[2];
+        uint32_t at = (lits + 3u) & ~3u;  // behind the literals
+        uint32_t first_rec = 0;
+        bool tables_out = false;
+        for (uint32_t q = 0; q < nblk; ++q) {
+            meta->seq_off[q] = at;
+            const uint32_t n = sm->blk_cnt[q];
+            if (n == 0) continue;
+            uint8_t* o = slot + at;
+            uint32_t hb = 0;
+            if (n < 128) o[hb++] = (uint8_t)n;
+            else if (n < 0x7F00) { o[hb++] = (uint8_t)((n >> 8) + 128); o[hb++] = (uint8_t)n; }
+            else { o[hb++] = 255; o[hb++] = (uint8_t)(n - 0x7F00); o[hb++] = (uint8_t)((n - 0x7F00) >> 8); }
+            if (!tables_out) {
+                o[hb++] = (uint8_t)((tl->mode << 6) | (to->mode << 4) | (tm->mode << 2));
+                for (int k = 0; k < 3; ++k)
+                    for (uint32_t j = 0; j < sm->desc_n[k]; ++j) o[hb++] = sm->desc[k][j];
+                tables_out = true;
+            } else {
+                o[hb++] = (uint8_t)((3u << 6) | (3u << 4) | (3u << 2));  // Repeat_Mode x 3
+            }
+            ZGBitW w = {o + hb, 0, 0, 0};
+            // written last sequence first: the decoder reads the stream from its end
+            uint64_t rec = recs[first_rec + n - 1];
+            uint32_t llv = zm_ll(rec), mlv = zm_ml(rec), ofv = zm_off(rec) + 3;
+            uint32_t llc = zm_ll_code(llv), mlc = zm_ml_code(mlv), ofc = (uint32_t)z_highbit(ofv);
+            uint32_t sl, so, s_m;
+            zm_fse_init(tm, mlc, &s_m);
+            zm_fse_init(to, ofc, &so);
+            zm_fse_init(tl, llc, &sl);
+            zg_put(w, llv - kZ_LL_BASE[llc], kZ_LL_BITS[llc]);
+            zg_put(w, mlv - kZ_ML_BASE[mlc], kZ_ML_BITS[mlc]);
+            zg_put(w, ofv - (1u << ofc), ofc);
+            for (uint32_t k = n - 1; k-- > 0;) {
+                rec = recs[first_rec + k];
+                llv = zm_ll(rec); mlv = zm_ml(rec); ofv = zm_off(rec) + 3;
+                llc = zm_ll_code(llv); mlc = zm_ml_code(mlv); ofc = (uint32_t)z_highbit(ofv);
+                zm_fse_encode(to, ofc, &so, w);
+                zm_fse_encode(tm, mlc, &s_m, w);
+                zm_fse_encode(tl, llc, &sl, w);
+                zg_put(w, llv - kZ_LL_BASE[llc], kZ_LL_BITS[llc]);
+                zg_put(w, mlv - kZ_ML_BASE[mlc], kZ_ML_BITS[mlc]);
+                zg_put(w, ofv - (1u << ofc), ofc);
+            }
+            zm_fse_flush(tm, s_m, w);
+            zm_fse_flush(to, so, w);
+            zm_fse_flush(tl, sl, w);
+            zg_put(w, 1, 1);  // the marker above the last bit
+            if (w.nbits) { w.p[w.nbytes++] = (uint8_t)w.acc; }
+            at += hb + w.nbytes;
+            first_rec += n;
+        }
+        for (uint32_t q = nblk; q <= 16; ++q) meta->seq_off[q] = at;
+    }
+}
+
+}  // namespace vbz
