@@ -127,7 +127,7 @@ def test_ratio_close_to_libzstd_on_signal(backend):
     r, blob = capi.compress(arr, o, sized=True)
     rp, blob_ref = port.compress(arr, o, sized=True)
     assert not ol.is_error(r)
-    assert r <= 1.05 * rp, (r, rp)   # Huffman-only blocks: within a few percent of libzstd level 1 on signal
+    assert r <= 1.01 * rp, (r, rp)   # zero runs of the control bytes as sequences, Huffman literals: what libzstd level 1 reaches on signal
 
 
 def test_fast5_fixture_reencode(backend):
@@ -144,4 +144,56 @@ def test_fast5_fixture_reencode(backend):
         assert rp == want.nbytes and back == want.tobytes()
         tot += r
         tot_ref += len(rd["vbz_chunk"])
-    assert tot <= 1.04 * tot_ref, (tot, tot_ref)
+    assert tot <= 1.006 * tot_ref, (tot, tot_ref)  # the reference's own files: 0.4222 of raw; this writer 0.4231
+
+
+def test_repetitive_inputs_compress_like_libzstd(backend):
+    """Where matches are everything (a Huffman-only writer was 7-90x worse here): the pyvbz README's arange (27 bytes with the
+    reference), the reference benchmark's tiled trace (vbz/perf/test_data_generator.h:29-74), constant signal - sizes next to what the
+    reference writes at the same level, and every frame decodes with the reference."""
+    capi = backend[0]
+    ref = ol.ref() or port
+    rng = np.random.default_rng(3)
+    small = capi.path.endswith("cpusim.so")
+    trace = data_gen.nanopore_like(2000, rng)
+    fixture = golden_data.fast5_reads()[0]["samples"]
+    cases = [("arange", np.arange(1000, dtype=np.int16), 40, None), ("tiled synthetic trace", np.tile(trace, 30 if small else 100), None, 1.5),
+             ("tiled fixture trace", np.tile(fixture[:5000], 10 if small else 30), None, 1.5), ("constant", np.full(60000, 7, np.int16), 64, None),
+             ("zeros", np.zeros(100000, np.int16), 64, None)]
+    for level in (1, 3):
+        o = Options(True, 2, level, 1)
+        for name, arr, max_bytes, max_factor in cases:
+            r, blob = capi.compress(arr, o, sized=True)
+            rr, theirs = ref.compress(arr, o, sized=True)
+            assert not ol.is_error(r) and not ol.is_error(rr)
+            if max_bytes is not None:
+                assert r <= max_bytes, (name, level, r, rr)
+            if max_factor is not None:
+                assert r <= max_factor * rr, (name, level, r, rr)
+            rd, back = ref.decompress(blob, o, arr.nbytes, sized=True)
+            assert rd == arr.nbytes and back == arr.tobytes(), (name, level)
+            r3, back3 = capi.decompress(blob, o, arr.nbytes, sized=True)
+            assert r3 == arr.nbytes and back3 == arr.tobytes(), (name, level)
+
+
+def test_matches_of_every_kind_round_trip(backend):
+    """The match finder on text-like and structured bytes (zstd only, every level the reference maps to a strategy of its own): long and
+    short matches, overlapping ones, matches across the 128 KiB groups and the 8 KiB literal blocks inside them; stock libzstd decodes all."""
+    capi = backend[0]
+    rng = np.random.default_rng(23)
+    small = capi.path.endswith("cpusim.so")
+    words = [bytes(rng.integers(97, 123, int(k), dtype=np.uint8)) for k in rng.integers(2, 12, 300)]
+    text = b" ".join(words[int(i)] for i in rng.integers(0, 300, 20000 if small else 80000))
+    cases = [text, b"ab" * 70000, bytes(rng.integers(0, 256, 5000, dtype=np.uint8)) * (20 if small else 60),
+             bytes(np.arange(50000 if small else 150000, dtype=np.uint32).view(np.uint8)), bytes(200000) + b"x" + bytes(70000),
+             bytes(np.repeat(rng.integers(0, 256, 3000, dtype=np.uint8), rng.integers(1, 40, 3000)))]
+    for level in (1, 2, 3, 19):
+        o = Options(False, 0, level, 0)
+        for data in cases:
+            arr = np.frombuffer(data, np.uint8)
+            r, frame = capi.compress(arr, o, sized=False)
+            assert not ol.is_error(r), (level, len(data), r)
+            _check_frame(frame, data)
+            r2, back = capi.decompress(frame, o, len(data), sized=False)
+            assert r2 == len(data) and back == data
+            assert r <= len(ol.zstd_compress_lib(data, 1)) * 2 + 64, (level, len(data), r)  # within 2x of libzstd level 1 even on text

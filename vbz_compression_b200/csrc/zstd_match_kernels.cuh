@@ -15,8 +15,8 @@
 //                         previous byte (4 bytes equal to the 4 bytes one back: a run) or a candidate from a hash table of 4-byte
 //                         words (2^11 entries per warp in shared memory, seeded with the 8 KiB before the group), verified against
 //                         the data.  The first lane with a match wins, the warp extends it 128 bytes per step, the parse continues
-//                         behind it.  After a few steps without a match only one step in four (level 1) or two (level 2) is examined
-//                         (level >= 3: every step), as libzstd's fast strategy accelerates over incompressible data.  Sequences go
+//                         behind it.  The longer the stretch without a match, the more steps are skipped between examined ones (level 1: up
+//                         to 3 in 4; higher levels later and less), as libzstd's fast strategy accelerates over incompressible data.  Sequences go
 //                         to a record array as {offset, literal run, match length}; a group becomes S only if its matches pay for
 //                         their sequences (12 bytes of match per sequence - which also bounds every scratch area), and only then are
 //                         its literals compacted and counted (per-group histogram for the Huffman code).
@@ -41,6 +41,7 @@ struct ZGroupLoc {
     uint32_t code_first;  // groups back to the first group of this one's CODE SET (kZCodeSet consecutive groups of a region share one code)
     uint32_t code_bytes;  // content bytes of the code set, from its first group on
     uint32_t region_off;  // content bytes of the group's region (control bytes | data bytes) before the group
+    bool keys;            // the group lies in the control-byte region of a stage-1 stream
     bool last;
 };
 __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, const ZstdEncRead& rd, uint32_t r, ZGroupLoc& g)
@@ -63,6 +64,7 @@ __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, 
     const uint32_t in_region = g.gi < n_a ? g.gi : g.gi - n_a;
     g.code_first = in_region % kZCodeSet;
     g.region_off = in_region * kZEncBlock;
+    g.keys = g.gi < n_a;
     const uint32_t set_start = start - g.code_first * kZEncBlock;
     g.code_bytes = region_end - set_start < kZCodeSet * kZEncBlock ? region_end - set_start : kZCodeSet * kZEncBlock;
     return true;
@@ -72,9 +74,15 @@ __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, 
 
 constexpr uint32_t kZHashLog = 11;
 constexpr uint32_t kZPreWindow = 8192;       // bytes before the group that seed the hash table
-constexpr uint32_t kZMinRun = 8;             // shortest run (offset 1) worth a sequence
+constexpr uint32_t kZMinRun = 5;             // shortest run (offset 1) worth a sequence
 constexpr uint32_t kZMinMatch = 6;           // shortest match at any other offset
+constexpr uint32_t kZMinKeyMatch = 32;       // ... among the control bytes of a stage-1 stream
 constexpr int kZMatchWarps = 4;
+#ifdef VBZ_CPUSIM
+static inline uint32_t zm_tune(const char* name, uint32_t dflt) { const char* e = getenv(name); return e ? (uint32_t)atoi(e) : dflt; }  // experiments on the emulator
+#else
+#define zm_tune(name, dflt) (dflt)
+#endif
 
 enum : uint32_t { kZModeL = 0, kZModeS = 1 };
 // what the match kernel (and then the sequence kernel) leaves per group
@@ -101,7 +109,13 @@ __device__ __forceinline__ uint32_t zm_load32(const uint8_t* p)
     const uint32_t a = w[0];
     return sh ? __funnelshift_r(a, w[1], sh) : a;
 }
-__device__ __forceinline__ uint32_t zm_hash(uint32_t w) { return (w * 2654435761u) >> (32 - kZHashLog); }
+// hash of 6 bytes (w = the first four, w2 = the next two): what libzstd's fast strategy hashes at level 1 for inputs of this size -
+// four bytes repeat by chance all the time in a narrow alphabet, and the greedy parse would take those accidents
+__device__ __forceinline__ uint32_t zm_hash(uint32_t w, uint32_t w2)
+{
+    const uint64_t k = ((uint64_t)w | ((uint64_t)(w2 & 0xFFFFu) << 32)) << 16;
+    return (uint32_t)((k * 227718039650203ull) >> (64 - kZHashLog));
+}
 
 // first record of group b in the record scratch, and how many it may hold
 __device__ __forceinline__ uint64_t zm_rec_base(uint64_t content_off, uint32_t b) { return content_off / 16 + b; }
@@ -132,67 +146,92 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     // how far back a match may reach: the group's region (control bytes | data bytes), at most kZPreWindow before the group
     const uint32_t pre = g.region_off < kZPreWindow ? g.region_off : kZPreWindow;
     const uint8_t* win = src - pre;  // window coordinate w <-> byte win[w]; the group starts at w = pre
-    // search effort by level: steps without a match before skipping starts, steps skipped for every step examined
-    const uint32_t miss_limit = p.level >= 3 ? 0xFFFFFFFFu : (p.level == 2 ? 4u : 2u);
-    const uint32_t skip_steps = p.level == 2 ? 1u : 3u;
+    // search effort by level.  As libzstd's fast strategy, the parse speeds up over data without matches: for every 2^shift bytes
+    // since the last match one more step is skipped after each step examined, up to `skip_cap` (level 1: 3 steps in 4 after 768 bytes)
+    const uint32_t skip_shift = p.level >= 3 ? 12u : (p.level == 2 ? 10u : 8u);
+    const uint32_t skip_cap = p.level >= 3 ? 1u : 3u;
 
     for (uint32_t i = lane; i < (1u << kZHashLog); i += 32) sm->table[i] = 0;  // entry = window coordinate + 1, 0 = empty
     __syncwarp();
     // seed with the pre-window (every position: it is at most 8 KiB)
-    for (uint32_t w0 = 0; w0 + 4 <= pre; w0 += 32) {
+    for (uint32_t w0 = 0; w0 + 6 <= pre; w0 += 32) {
         const uint32_t w = w0 + lane;
-        if (w + 4 <= pre) atomicMax(&sm->table[zm_hash(zm_load32(win + w))], w + 1);
+        if (w + 6 <= pre) atomicMax(&sm->table[zm_hash(zm_load32(win + w), zm_load32(win + w + 4))], w + 1);
     }
     __syncwarp();
 
-    uint32_t pos = 0, anchor = 0, nseq = 0, matched = 0, miss = 0;
+    uint32_t pos = 0, anchor = 0, nseq = 0, matched = 0, rep_off = 0;
     while (pos + 4 <= B) {
         // ---- this step's 32 positions ----------------------------------------------------------------------------------------
         const uint32_t q = pos + lane;
         const bool live = q + 4 <= B;
-        uint32_t w = 0, wp = 0;
+        const bool live6 = q + 6 <= B;  // enough bytes for the hash
+        uint32_t w = 0, wp = 0, w2 = 0;
         if (live) {
             w = zm_load32(src + q);
             wp = (q + pre) ? zm_load32(src + q - 1) : ~w;  // the 4 bytes one back (nothing before the region's first byte)
         }
+        // bytes q + 4, q + 5: the first two bytes of the word four lanes up (the last four lanes load them)
+        w2 = __shfl_down_sync(0xffffffffu, w, 4);
+        if (lane >= 28 && live6) w2 = zm_load32(src + q + 4);
+        w2 &= 0xFFFFu;
         const bool run = live && w == wp;
+        // the offset of the last match found through the table, tried again everywhere: once a period has been found the parse stays
+        // on it, whatever more recent (and shorter) repeats the table offers
+        const bool rep = rep_off > 1 && live && q + pre >= rep_off && zm_load32(src + q - rep_off) == w;
         uint32_t dist = 0;
-        if (live) {
-            const uint32_t h = zm_hash(w), at = q + pre, e = sm->table[h];
-            if (e != 0 && e - 1 < at && zm_load32(win + (e - 1)) == w) dist = at - (e - 1);
+        const uint32_t h = zm_hash(w, w2);
+        if (live6) {
+            const uint32_t at = q + pre, e = sm->table[h];
+            if (e != 0 && e - 1 < at && zm_load32(win + (e - 1)) == w && (zm_load32(win + (e - 1) + 4) & 0xFFFFu) == w2) dist = at - (e - 1);
         }
         __syncwarp();
-        if (live) atomicMax(&sm->table[zm_hash(w)], q + pre + 1);
-        uint32_t cand = __ballot_sync(0xffffffffu, run || dist != 0);
+        uint32_t cand = __ballot_sync(0xffffffffu, run || rep || dist != 0);
         bool took = false;
         while (cand) {
             const uint32_t f = (uint32_t)__ffs((int)cand) - 1;
             cand &= cand - 1;
-            const uint32_t off = __shfl_sync(0xffffffffu, run ? 1u : dist, f);
             const uint32_t mp = pos + f;  // match position
-            // ---- extend: 4 bytes per lane, 128 per round -------------------------------------------------------------------------
-            uint32_t ml = 4;
-            for (;;) {
-                const uint32_t at = mp + ml + 4 * lane;
-                uint32_t eq = 0;
-                if (at < B) {
-                    const uint32_t x = zm_load32(src + at) ^ zm_load32(src + at - off);
-                    eq = x ? ((uint32_t)__ffs((int)x) - 1) >> 3 : 4u;
-                    if (eq > B - at) eq = B - at;
+            // the lane may have both a run (offset 1) and a hash candidate: the longer one wins (a period beats the zero runs inside it)
+            const uint32_t f_run = __shfl_sync(0xffffffffu, run ? 1u : 0u, f), f_dist = __shfl_sync(0xffffffffu, dist, f);
+            const uint32_t f_rep = __shfl_sync(0xffffffffu, rep ? rep_off : 0u, f);
+            uint32_t off = 0, ml = 0;
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t o = pass == 0 ? f_run : (pass == 1 ? (f_rep != f_run ? f_rep : 0u) : (f_dist > 1 && f_dist != f_rep ? f_dist : 0u));
+                if (o == 0) continue;
+                // ---- extend: 4 bytes per lane, 128 per round ---------------------------------------------------------------------
+                uint32_t m = 4;
+                for (;;) {
+                    const uint32_t at = mp + m + 4 * lane;
+                    uint32_t eq = 0;
+                    if (at < B) {
+                        const uint32_t x = zm_load32(src + at) ^ zm_load32(src + at - o);
+                        eq = x ? ((uint32_t)__ffs((int)x) - 1) >> 3 : 4u;
+                        if (eq > B - at) eq = B - at;
+                    }
+                    const uint32_t stop = __ballot_sync(0xffffffffu, eq < 4);
+                    if (stop) {
+                        const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
+                        m += 4 * fl + __shfl_sync(0xffffffffu, eq, fl);
+                        break;
+                    }
+                    m += 128;
                 }
-                const uint32_t stop = __ballot_sync(0xffffffffu, eq < 4);
-                if (stop) {
-                    const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
-                    ml += 4 * fl + __shfl_sync(0xffffffffu, eq, fl);
-                    break;
-                }
-                ml += 128;
+                // an offset other than 1 costs a dozen bits more per sequence: it has to buy a clearly longer match
+                if (off == 0 || m > ml + (off == 1 ? 16u : 4u)) { ml = m; off = o; }
             }
-            const uint32_t need = off == 1 ? kZMinRun : kZMinMatch;
-            // every sequence must be paid for by 12 bytes of match (that is also what keeps the scratch areas from overflowing)
-            if (ml >= need && nseq < rec_cap && 12ull * (nseq + 1) + 256 <= (uint64_t)matched + ml) {
+            // what a match must bring.  Control bytes are nearly all zero and cost a bit each as literals: only a long match at a
+            // distance pays for the dozen bits of its offset there; among data bytes (6 to 7 bits each) a short one does
+            const uint32_t need = off == 1 ? zm_tune("VBZ_TUNE_MINRUN", kZMinRun) : (g.keys ? zm_tune("VBZ_TUNE_KEYMATCH", kZMinKeyMatch) : zm_tune("VBZ_TUNE_MINMATCH", kZMinMatch));
+            // every sequence must be paid for by 12 bytes of match (that is also what keeps the scratch areas from overflowing):
+            // a shorter match is taken only on the credit of longer ones before it
+            if (ml >= need && nseq < rec_cap && (ml >= 12 || 12ull * (nseq + 1) <= (uint64_t)matched + ml)) {
                 if (lane == 0) recs[nseq] = zm_pack(off, mp - anchor, ml);
+#ifdef VBZ_CPUSIM
+                if (lane == 0 && getenv("VBZ_B200_TRACE_SEQ") && nseq < 60) fprintf(stderr, "  seq %u: at %u ll %u ml %u off %u (run %u rep %u dist %u)\n", nseq, mp, mp - anchor, ml, off, f_run, f_rep, f_dist);
+#endif
                 ++nseq;
+                if (off > 1) rep_off = off;
                 matched += ml;
                 anchor = mp + ml;
                 pos = anchor;
@@ -200,14 +239,23 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
                 break;
             }
         }
-        if (took) { miss = 0; continue; }
+        // the table learns the positions the parse has passed - not those behind a short match, which the next step looks at again
+        // (their entries would point at themselves)
+        if (live6 && (!took || q < pos)) atomicMax(&sm->table[h], q + pre + 1);
+        __syncwarp();
+        if (took) continue;
         pos += 32;
-        if (++miss > miss_limit) pos += 32 * skip_steps;
+        const uint32_t skip = (pos - anchor) >> skip_shift;
+        pos += 32 * (skip < skip_cap ? skip : skip_cap);
     }
     __syncwarp();
     // ---- L or S? ----------------------------------------------------------------------------------------------------------------------
     const uint32_t floor_bytes = B / 32 > 64 ? B / 32 : 64;
-    if (nseq == 0 || matched < floor_bytes || 12ull * nseq + 256 > matched) return;  // stays L
+#ifdef VBZ_CPUSIM
+    if (lane == 0 && getenv("VBZ_B200_TRACE_MATCH")) fprintf(stderr, "match: group %u B %u nseq %u matched %u rep_off %u\n", b, B, nseq, matched, rep_off);
+#endif
+    // (12 nseq <= matched holds by construction; the sections - at most 10 bytes per sequence and 256 of headers and tables - must fit behind the literals)
+    if (nseq == 0 || matched < floor_bytes || 10ull * nseq + 256 > matched) return;  // stays L
     // ---- S: compact the literals into the literal scratch, count them --------------------------------------------------------------------
     uint8_t* lits = p.lits + content_off;
     for (uint32_t i = lane; i < 256; i += 32) sm->hist[i] = 0;
