@@ -1,7 +1,7 @@
 """the minimal fast5 / HDF5 chunk reader finds every VBZ chunk of a file without libhdf5 and decodes them
 as one batch.  Restates python/test/test_vbz_filter.py:57-73: Raw/Signal must be equal across the gzip, VBZ v0 and VBZ v1
-fixtures.  Needs the reference's test_data (build container only); the chunk payloads themselves are also pinned by
-tests/golden/fast5_chunks.npz (test_oracle.py, test_plugin.py), which travel to the GPU box."""
+fixtures.  The three fixture files (the reference's test_data/*.fast5, reference-held test vectors like the rest of tests/golden/)
+travel with the repo in tests/golden/fast5/, so the GPU tests run on the box, where /root/reference does not exist."""
 import os
 import zlib
 
@@ -11,8 +11,7 @@ import pytest
 import product
 from vbz_compression_b200 import fast5
 
-DATA = "/root/reference/test_data"
-pytestmark = pytest.mark.skipif(not os.path.isdir(DATA), reason="reference fixtures not present")
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fast5")
 
 
 def _zip_signals(path):

@@ -325,7 +325,7 @@ static int compress_wave(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst
                          const Stage1Kind& kind, bool sized, cudaStream_t stream)
 {
     const bool zstd = kind.zstd_level != 0;
-    const uint32_t blk = vbzk_zstd_enc_block_bytes();
+    const uint32_t blk = vbzk_zstd_enc_block_bytes(), kblk = vbzk_zstd_enc_key_block_bytes();
     std::vector<uint64_t> mid_off(zstd ? n : 0);
     uint64_t mid_total = 0;
     if (kind.isz != 0) {
@@ -380,7 +380,7 @@ static int compress_wave(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst
             z.src_off = j.src_off;
             z.src_bytes = j.src_size;
         }
-        z.n_blocks = (uint32_t)std::max<uint64_t>(1, (z.split + blk - 1) / blk + (largest - z.split + blk - 1) / blk);
+        z.n_blocks = (uint32_t)std::max<uint64_t>(1, (z.split + kblk - 1) / kblk + (largest - z.split + blk - 1) / blk);
     }
     uint64_t extent = mid_total + 16;
     if (kind.isz == 0) {

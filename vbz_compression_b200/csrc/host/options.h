@@ -63,7 +63,7 @@ inline bool is_error(uint32_t v) { return v >= kErrOutOfMemory; }
 // Never above ZSTD_compressBound(n).
 inline uint64_t zstd_enc_worst_case(uint64_t n)
 {
-    const uint64_t blocks = n / kZEncSub + 2;
+    const uint64_t blocks = n / kZEncSub + n / kZEncBlockKeys + 4;  // every group may end with a partial block; two regions
     return 9 + 3 * blocks + n;
 }
 

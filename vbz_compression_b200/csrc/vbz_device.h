@@ -26,6 +26,7 @@ template <class T> static inline void vbz_st_stream(T* p, T v) { *p = v; }
 static inline uint64_t vbz_ld_volatile_u64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 static inline void vbz_st_volatile_u64(uint64_t* p, uint64_t v) { *(volatile uint64_t*)p = v; }
 static inline uint32_t vbz_ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+static inline void vbz_prefetch_l2(const void*) {}
 static inline void vbz_slot_post(uint64_t* slot, uint64_t v) { *(volatile uint64_t*)slot = v; }
 static inline uint64_t vbz_slot_read(const uint64_t* slot) { return *(const volatile uint64_t*)slot; }
 
@@ -100,6 +101,8 @@ __device__ __forceinline__ uint32_t vbz_ld_volatile_u32(const uint32_t* p)
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// pull the line that holds p towards the SM ahead of its use (no register, no wait)
+__device__ __forceinline__ void vbz_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // hand-off of one 64-bit word (value + ready bit) between warps of a CTA through shared memory: release store, acquire load
 // (strong operations at CTA scope: defined under the PTX memory model without a barrier in between)
 __device__ __forceinline__ void vbz_slot_post(uint64_t* slot, uint64_t v)

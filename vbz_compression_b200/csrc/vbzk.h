@@ -38,6 +38,7 @@ int vbzk_zstd_decode(const struct VbzkZstdDecParams* params, void* stream);
 struct VbzkZstdEncRead;   /* == vbz::ZstdEncRead */
 struct VbzkZstdEncParams; /* == vbz::ZstdEncParams */
 uint32_t vbzk_zstd_enc_block_bytes(void);
+uint32_t vbzk_zstd_enc_key_block_bytes(void); /* group size inside the control-byte region (ZstdEncRead::split) */
 int vbzk_zstd_enc_fill_blocks(const struct VbzkZstdEncRead* d_reads, uint32_t n_reads, uint32_t* d_block_read, void* stream);
 int vbzk_zstd_encode(const struct VbzkZstdEncParams* params, void* stream);
 

@@ -211,6 +211,7 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
 }
 
 extern "C" uint32_t vbzk_zstd_enc_block_bytes(void) { return kZEncBlock; }
+extern "C" uint32_t vbzk_zstd_enc_key_block_bytes(void) { return kZEncBlockKeys; }
 extern "C" int vbzk_zstd_enc_fill_blocks(const VbzkZstdEncRead* d_reads, uint32_t n_reads, uint32_t* d_block_read, void* stream)
 {
     if (n_reads == 0) return 0;

@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     const bool sampled = B >= (256u << 10);
     const uint32_t rate = B >= (512u << 10) ? 8u : 4u;  // one row in `rate`
     const ZGroupMeta* meta = reinterpret_cast<const ZGroupMeta*>(p.meta) + b;
-    const uint32_t set_groups = (B + kZEncBlock - 1) / kZEncBlock;
+    const uint32_t set_groups = (B + g.gsize - 1) / g.gsize;
     bool any_s = false, any_l = false;
     {
         uint32_t* h = s->cnt;
@@ -507,8 +507,8 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
         for (uint32_t j = 0; j < set_groups; ++j) {
             if (meta[j].mode == kZModeS) { any_s = true; continue; }
             any_l = true;
-            const uint8_t* src = g.src + j * kZEncBlock;
-            const uint32_t gB = B - j * kZEncBlock < kZEncBlock ? B - j * kZEncBlock : kZEncBlock;
+            const uint8_t* src = g.src + j * g.gsize;
+            const uint32_t gB = B - j * g.gsize < g.gsize ? B - j * g.gsize : g.gsize;
             uint32_t head = (16u - (uint32_t)((uintptr_t)src & 15u)) & 15u;
             if (head > gB) head = gB;
             const uint32_t nch = (gB - head) >> 4, done = head + (nch << 4);

@@ -13,7 +13,7 @@
 //      block, lanes own runs of <= 64 symbols) serves both kinds unchanged.
 // zstd_enc_match_kernel   a WARP per group: greedy parse, 32 positions per step.  Every lane looks at "its" position: a repeat of the
 //                         previous byte (4 bytes equal to the 4 bytes one back: a run) or a candidate from a hash table of 4-byte
-//                         words (2^11 entries per warp in shared memory, seeded with the 8 KiB before the group), verified against
+//                         6-byte strings (2^10 tagged entries per warp in shared memory, seeded with the 8 KiB before the group), verified against
 //                         the data.  The first lane with a match wins, the warp extends it 128 bytes per step, the parse continues
 //                         behind it.  The longer the stretch without a match, the more steps are skipped between examined ones (level 1: up
 //                         to 3 in 4; higher levels later and less), as libzstd's fast strategy accelerates over incompressible data.  Sequences go
@@ -42,6 +42,7 @@ struct ZGroupLoc {
     uint32_t code_bytes;  // content bytes of the code set, from its first group on
     uint32_t region_off;  // content bytes of the group's region (control bytes | data bytes) before the group
     bool keys;            // the group lies in the control-byte region of a stage-1 stream
+    uint32_t gsize;       // nominal size of the groups of this region
     bool last;
 };
 __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, const ZstdEncRead& rd, uint32_t r, ZGroupLoc& g)
@@ -51,28 +52,32 @@ __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, 
     if (rd.rejected) return false;
     g.content = p.src_sizes ? p.src_sizes[r] : rd.src_bytes;
     if (p.src_sizes && g.content >= kErrOutOfMemory) return false;  // stage 1 reported an error for this read
-    // groups of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'), then the rest
+    // groups of the first region (stage 1's control bytes: their statistics differ completely from the data bytes'; groups of 32 KiB there:
+    // nearly all of them is matches, so a group is sequences - serial work for one warp in the match finder, the sequence writer and
+    // the decoder's sequence reader alike), then the rest in groups of 128 KiB
     const uint32_t split = rd.split < g.content ? rd.split : 0u;
-    const uint32_t n_a = (split + kZEncBlock - 1) / kZEncBlock, n_b = (g.content - split + kZEncBlock - 1) / kZEncBlock;
+    const uint32_t n_a = (split + kZEncBlockKeys - 1) / kZEncBlockKeys, n_b = (g.content - split + kZEncBlock - 1) / kZEncBlock;
     g.ngrp = n_a + n_b ? n_a + n_b : 1u;
     if (g.gi >= g.ngrp) return false;  // the table was sized for the largest content stage 1 could have produced
-    const uint32_t start = g.gi < n_a ? g.gi * kZEncBlock : split + (g.gi - n_a) * kZEncBlock;
-    const uint32_t region_end = g.gi < n_a ? split : g.content;
-    g.B = region_end - start < kZEncBlock ? region_end - start : kZEncBlock;
+    g.keys = g.gi < n_a;
+    g.gsize = g.keys ? kZEncBlockKeys : kZEncBlock;
+    const uint32_t start = g.keys ? g.gi * kZEncBlockKeys : split + (g.gi - n_a) * kZEncBlock;
+    const uint32_t region_end = g.keys ? split : g.content;
+    g.B = region_end - start < g.gsize ? region_end - start : g.gsize;
     g.last = g.gi + 1 == g.ngrp;
     g.src = p.src + rd.src_off + start;
-    const uint32_t in_region = g.gi < n_a ? g.gi : g.gi - n_a;
+    const uint32_t in_region = g.keys ? g.gi : g.gi - n_a;
     g.code_first = in_region % kZCodeSet;
-    g.region_off = in_region * kZEncBlock;
-    g.keys = g.gi < n_a;
-    const uint32_t set_start = start - g.code_first * kZEncBlock;
-    g.code_bytes = region_end - set_start < kZCodeSet * kZEncBlock ? region_end - set_start : kZCodeSet * kZEncBlock;
+    g.region_off = in_region * g.gsize;
+    const uint32_t set_start = start - g.code_first * g.gsize;
+    g.code_bytes = region_end - set_start < kZCodeSet * g.gsize ? region_end - set_start : kZCodeSet * g.gsize;
     return true;
 }
 
 
 
-constexpr uint32_t kZHashLog = 11;
+constexpr uint32_t kZHashLog = 10;
+constexpr uint32_t kZTagBits = 14;          // a table entry = (window coordinate + 1) << 14 | 14 more bits of the hash: a lane only goes to memory to verify a candidate whose tag agrees
 constexpr uint32_t kZPreWindow = 8192;       // bytes before the group that seed the hash table
 constexpr uint32_t kZMinRun = 5;             // shortest run (offset 1) worth a sequence
 constexpr uint32_t kZMinMatch = 6;           // shortest match at any other offset
@@ -111,17 +116,20 @@ __device__ __forceinline__ uint32_t zm_load32(const uint8_t* p)
 }
 // hash of 6 bytes (w = the first four, w2 = the next two): what libzstd's fast strategy hashes at level 1 for inputs of this size -
 // four bytes repeat by chance all the time in a narrow alphabet, and the greedy parse would take those accidents
+// -> index in the top kZHashLog bits, tag in the kZTagBits below them
 __device__ __forceinline__ uint32_t zm_hash(uint32_t w, uint32_t w2)
 {
     const uint64_t k = ((uint64_t)w | ((uint64_t)(w2 & 0xFFFFu) << 32)) << 16;
-    return (uint32_t)((k * 227718039650203ull) >> (64 - kZHashLog));
+    return (uint32_t)((k * 227718039650203ull) >> (64 - kZHashLog - kZTagBits));
 }
+__device__ __forceinline__ uint32_t zm_index(uint32_t h) { return h >> kZTagBits; }
+__device__ __forceinline__ uint32_t zm_entry(uint32_t h, uint32_t wpos) { return ((wpos + 1) << kZTagBits) | (h & ((1u << kZTagBits) - 1u)); }
 
 // first record of group b in the record scratch, and how many it may hold
 __device__ __forceinline__ uint64_t zm_rec_base(uint64_t content_off, uint32_t b) { return content_off / 16 + b; }
 __device__ __forceinline__ uint32_t zm_rec_cap(uint32_t B) { return B / 16; }
 
-struct ZMatchSmem { uint32_t table[1u << kZHashLog]; uint32_t hist[256]; };
+struct ZMatchSmem { uint32_t table[1u << kZHashLog]; };  // (its first KiB is the literal histogram once the parse is over)
 
 // ---- kernel: greedy parse of every group ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdEncParams p)
@@ -156,13 +164,17 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     // seed with the pre-window (every position: it is at most 8 KiB)
     for (uint32_t w0 = 0; w0 + 6 <= pre; w0 += 32) {
         const uint32_t w = w0 + lane;
-        if (w + 6 <= pre) atomicMax(&sm->table[zm_hash(zm_load32(win + w), zm_load32(win + w + 4))], w + 1);
+        if (w + 6 <= pre) {
+            const uint32_t h = zm_hash(zm_load32(win + w), zm_load32(win + w + 4));
+            atomicMax(&sm->table[zm_index(h)], zm_entry(h, w));
+        }
     }
     __syncwarp();
 
     uint32_t pos = 0, anchor = 0, nseq = 0, matched = 0, rep_off = 0;
     while (pos + 4 <= B) {
         // ---- this step's 32 positions ----------------------------------------------------------------------------------------
+        if (lane < 4 && pos + 512 + 128 * lane < B) vbz_prefetch_l2(src + pos + 512 + 128 * lane);
         const uint32_t q = pos + lane;
         const bool live = q + 4 <= B;
         const bool live6 = q + 6 <= B;  // enough bytes for the hash
@@ -182,25 +194,44 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
         uint32_t dist = 0;
         const uint32_t h = zm_hash(w, w2);
         if (live6) {
-            const uint32_t at = q + pre, e = sm->table[h];
-            if (e != 0 && e - 1 < at && zm_load32(win + (e - 1)) == w && (zm_load32(win + (e - 1) + 4) & 0xFFFFu) == w2) dist = at - (e - 1);
+            const uint32_t at = q + pre, e = sm->table[zm_index(h)], ep = e >> kZTagBits;  // ep = window coordinate + 1, 0 = empty
+            if (ep != 0 && ((e ^ h) & ((1u << kZTagBits) - 1u)) == 0 && ep - 1 < at && zm_load32(win + (ep - 1)) == w &&
+                (zm_load32(win + (ep - 1) + 4) & 0xFFFFu) == w2)
+                dist = at - (ep - 1);
         }
         __syncwarp();
+        // how far a run that starts at each position goes, without touching memory again: bit i of eq1 says "the byte at pos + i equals
+        // the one before it", a run from lane i is the stretch of ones from bit i on (`open`: it reaches the end of the 32 positions)
+        bool same = live && (q + pre) != 0 && (w & 0xFFu) == (wp & 0xFFu);  // (wp's low byte is the byte before q)
+        if (!live && q < B && (q + pre) != 0) same = src[q] == src[q - 1];     // the group's last three positions
+        const uint32_t eq1 = __ballot_sync(0xffffffffu, same);
+        const uint32_t ahead = ~(eq1 >> lane) & (0xFFFFFFFFu >> lane);
+        const uint32_t run_ml = ahead ? (uint32_t)__ffs((int)ahead) - 1 : 32u - lane;
+        const uint32_t mine = (run ? 0x80u : 0u) | (ahead ? 0u : 0x40u) | run_ml;  // run | open | length, for the lane that wins
         uint32_t cand = __ballot_sync(0xffffffffu, run || rep || dist != 0);
+        const uint32_t others = __ballot_sync(0xffffffffu, rep || dist != 0);  // lanes with more than a run to offer
         bool took = false;
         while (cand) {
             const uint32_t f = (uint32_t)__ffs((int)cand) - 1;
-            cand &= cand - 1;
             const uint32_t mp = pos + f;  // match position
-            // the lane may have both a run (offset 1) and a hash candidate: the longer one wins (a period beats the zero runs inside it)
-            const uint32_t f_run = __shfl_sync(0xffffffffu, run ? 1u : 0u, f), f_dist = __shfl_sync(0xffffffffu, dist, f);
+            // the lane may have a run (offset 1), the repeated offset and a hash candidate: the longest wins, by a margin that pays for
+            // the dearer offset (a period beats the zero runs inside it)
+            const uint32_t f_mine = __shfl_sync(0xffffffffu, mine, f), f_dist = __shfl_sync(0xffffffffu, dist, f);
             const uint32_t f_rep = __shfl_sync(0xffffffffu, rep ? rep_off : 0u, f);
+            const uint32_t f_run = f_mine >> 7;
             uint32_t off = 0, ml = 0;
             for (int pass = 0; pass < 3; ++pass) {
                 const uint32_t o = pass == 0 ? f_run : (pass == 1 ? (f_rep != f_run ? f_rep : 0u) : (f_dist > 1 && f_dist != f_rep ? f_dist : 0u));
                 if (o == 0) continue;
-                // ---- extend: 4 bytes per lane, 128 per round ---------------------------------------------------------------------
                 uint32_t m = 4;
+                if (pass == 0) {
+                    m = f_mine & 0x3Fu;                         // known from the bit mask ...
+                    if (!(f_mine & 0x40u)) { ml = m; off = 1; continue; }  // ... all of it, if the run ends among the 32 positions
+                } else if (off != 0) {  // this offset must beat the match in hand by a margin: the four bytes where that is decided first
+                    const uint32_t probe = mp + ml + (off == 1 ? 16u : 4u) - 3;
+                    if (probe + 4 > B || zm_load32(src + probe) != zm_load32(src + probe - o)) continue;
+                }
+                // ---- extend: 4 bytes per lane, 128 per round ---------------------------------------------------------------------
                 for (;;) {
                     const uint32_t at = mp + m + 4 * lane;
                     uint32_t eq = 0;
@@ -227,9 +258,6 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
             // a shorter match is taken only on the credit of longer ones before it
             if (ml >= need && nseq < rec_cap && (ml >= 12 || 12ull * (nseq + 1) <= (uint64_t)matched + ml)) {
                 if (lane == 0) recs[nseq] = zm_pack(off, mp - anchor, ml);
-#ifdef VBZ_CPUSIM
-                if (lane == 0 && getenv("VBZ_B200_TRACE_SEQ") && nseq < 60) fprintf(stderr, "  seq %u: at %u ll %u ml %u off %u (run %u rep %u dist %u)\n", nseq, mp, mp - anchor, ml, off, f_run, f_rep, f_dist);
-#endif
                 ++nseq;
                 if (off > 1) rep_off = off;
                 matched += ml;
@@ -238,10 +266,14 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
                 took = true;
                 break;
             }
+            // not worth a sequence: neither are the runs that start inside it (the same bytes, fewer of them)
+            const uint32_t upto = f + (off == 1 && ml > 1 ? ml : 1u);
+            const uint32_t inside = upto >= 32 ? 0xFFFFFFFFu : (1u << upto) - 1u;
+            cand &= ~(inside & ~others) & ~(1u << f);
         }
         // the table learns the positions the parse has passed - not those behind a short match, which the next step looks at again
         // (their entries would point at themselves)
-        if (live6 && (!took || q < pos)) atomicMax(&sm->table[h], q + pre + 1);
+        if (live6 && (!took || q < pos)) atomicMax(&sm->table[zm_index(h)], zm_entry(h, q + pre));
         __syncwarp();
         if (took) continue;
         pos += 32;
@@ -255,10 +287,12 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     if (lane == 0 && getenv("VBZ_B200_TRACE_MATCH")) fprintf(stderr, "match: group %u B %u nseq %u matched %u rep_off %u\n", b, B, nseq, matched, rep_off);
 #endif
     // (12 nseq <= matched holds by construction; the sections - at most 10 bytes per sequence and 256 of headers and tables - must fit behind the literals)
-    if (nseq == 0 || matched < floor_bytes || 10ull * nseq + 256 > matched) return;  // stays L
+    // and with 96 more (16 blocks, 3 + 3 bytes of headers each) an S group is never larger than the bytes it stands for
+    if (nseq == 0 || matched < floor_bytes || 10ull * nseq + 256 + 96 > matched) return;  // stays L
     // ---- S: compact the literals into the literal scratch, count them --------------------------------------------------------------------
     uint8_t* lits = p.lits + content_off;
-    for (uint32_t i = lane; i < 256; i += 32) sm->hist[i] = 0;
+    uint32_t* hist = sm->table;  // (the parse is over)
+    for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
     __syncwarp();
     uint32_t from = 0, to = 0;  // source position / literal count before the records of this round
     for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
@@ -272,7 +306,7 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
             for (uint32_t k = 0; k < ll; ++k) {
                 const uint8_t v = src[my_from + k];
                 lits[my_to + k] = v;
-                atomicAdd(&sm->hist[v], 1u);
+                atomicAdd(&hist[v], 1u);
             }
         }
         uint32_t big = __ballot_sync(0xffffffffu, ll > 16);
@@ -283,7 +317,7 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
             for (uint32_t k = lane; k < n; k += 32) {
                 const uint8_t v = src[sf + k];
                 lits[st + k] = v;
-                atomicAdd(&sm->hist[v], 1u);
+                atomicAdd(&hist[v], 1u);
             }
         }
         from += __shfl_sync(0xffffffffu, span, 31);
@@ -292,12 +326,12 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     for (uint32_t k = from + lane; k < B; k += 32) {  // the literals after the last match
         const uint8_t v = src[k];
         lits[to + k - from] = v;
-        atomicAdd(&sm->hist[v], 1u);
+        atomicAdd(&hist[v], 1u);
     }
     to += B - from;
     __syncwarp();
     uint32_t* gh = p.hist + (uint64_t)b * 256;
-    for (uint32_t i = lane; i < 256; i += 32) gh[i] = sm->hist[i];
+    for (uint32_t i = lane; i < 256; i += 32) gh[i] = hist[i];
     if (lane == 0) { meta->mode = kZModeS; meta->nseq = nseq; meta->lits = to; meta->nblk = to ? (to + kZEncSub - 1) / kZEncSub : 1u; }
 }
 
