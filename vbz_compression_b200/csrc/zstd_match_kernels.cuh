@@ -79,10 +79,11 @@ __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, 
 constexpr uint32_t kZHashLog = 10;
 constexpr uint32_t kZTagBits = 14;          // a table entry = (window coordinate + 1) << 14 | 14 more bits of the hash: a lane only goes to memory to verify a candidate whose tag agrees
 constexpr uint32_t kZPreWindow = 8192;       // bytes before the group that seed the hash table
-constexpr uint32_t kZMinRun = 5;             // shortest run (offset 1) worth a sequence
+constexpr uint32_t kZMinRun = 12;            // shortest run (offset 1) worth a sequence
 constexpr uint32_t kZMinMatch = 6;           // shortest match at any other offset
 constexpr uint32_t kZMinKeyMatch = 32;       // ... among the control bytes of a stage-1 stream
-constexpr int kZMatchWarps = 4;
+constexpr int kZMatchWarps = 1;  // (a warp per CTA: a group of control bytes is dense steps from end to end, a group of noise a few dozen strided ones -
+                                 // sharing a CTA, the short ones would hold their slots until the long one is done)
 #ifdef VBZ_CPUSIM
 static inline uint32_t zm_tune(const char* name, uint32_t dflt) { const char* e = getenv(name); return e ? (uint32_t)atoi(e) : dflt; }  // experiments on the emulator
 #else
@@ -131,7 +132,88 @@ __device__ __forceinline__ uint32_t zm_rec_cap(uint32_t B) { return B / 16; }
 
 struct ZMatchSmem { uint32_t table[1u << kZHashLog]; };  // (its first KiB is the literal histogram once the parse is over)
 
+// 8 bytes at any address, little-endian, through three aligned 32-bit loads (bytes up to p + 11 - (p & 3) are touched)
+__device__ __forceinline__ void zm_load64(const uint8_t* p, uint32_t& lo, uint32_t& hi)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = 8u * (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t x0 = w[0], x1 = w[1], x2 = w[2];
+    lo = __funnelshift_r(x0, x1, sh);
+    hi = __funnelshift_r(x1, x2, sh);
+}
+__device__ __forceinline__ uint32_t zm_rot8(uint32_t w) { return (w >> 8) | (w << 24); }
+// bytes of w that are not zero
+__device__ __forceinline__ uint32_t zm_nonzero_bytes(uint32_t w)
+{
+    const uint32_t t = (w | (w >> 4));
+    const uint32_t u = (t | (t >> 2));
+    return (uint32_t)__popc((u | (u >> 1)) & 0x01010101u);
+}
+
+// what the parse carries from step to step (the same in every lane)
+struct ZParse {
+    uint32_t pos, anchor, nseq, matched, rep_off;
+};
+
+// one sequence: `ml` bytes at `mp` repeat what lies `off` back.  With `back`, the match first grows towards the anchor as far as the bytes
+// before it agree too (a strided step lands in the middle of a repeat; libzstd's fast strategy "catches up" the same way).  The
+// credit rule: every sequence must be paid for by 12 bytes of match - which also bounds the record and section scratch areas.
+__device__ __forceinline__ bool zm_emit(ZParse& z, uint64_t* recs, uint32_t rec_cap, const uint8_t* src, uint32_t pre, uint32_t mp, uint32_t off,
+                                        uint32_t ml, bool back, uint32_t need, uint32_t lane)
+{
+    if (back) {
+        for (;;) {
+            const uint32_t room = mp - z.anchor;                 // bytes between the anchor and the match
+            uint32_t lim = mp + pre - off;                       // ... and how far back the source may go (window coordinate 0)
+            if (lim > room) lim = room;
+            if (lim == 0) break;
+            const uint8_t* win = src - pre;
+            const bool eq = lane < lim && win[mp + pre - 1 - lane] == win[mp + pre - 1 - lane - off];
+            const uint32_t ne = ~__ballot_sync(0xffffffffu, eq);
+            const uint32_t k = ne ? (uint32_t)__ffs((int)ne) - 1 : 32u;
+            mp -= k;
+            ml += k;
+            if (k < 32) break;
+        }
+    }
+    if (ml < need || z.nseq >= rec_cap || !(ml >= 12 || 12ull * (z.nseq + 1) <= (uint64_t)z.matched + ml)) return false;
+    if (lane == 0) recs[z.nseq] = zm_pack(off, mp - z.anchor, ml);
+    ++z.nseq;
+    z.matched += ml;
+    z.anchor = mp + ml;
+    return true;
+}
+
+// how far the bytes from mp + m on repeat what lies `o` back: 4 bytes per lane, 128 per round (m bytes are known to agree)
+__device__ __forceinline__ uint32_t zm_extend(const uint8_t* src, uint32_t B, uint32_t mp, uint32_t o, uint32_t m, uint32_t lane)
+{
+    for (;;) {
+        const uint32_t at = mp + m + 4 * lane;
+        uint32_t eq = 0;
+        if (at < B) {
+            const uint32_t x = zm_load32(src + at) ^ zm_load32(src + at - o);
+            eq = x ? ((uint32_t)__ffs((int)x) - 1) >> 3 : 4u;
+            if (eq > B - at) eq = B - at;
+        }
+        const uint32_t stop = __ballot_sync(0xffffffffu, eq < 4);
+        if (stop) {
+            const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
+            return m + 4 * fl + __shfl_sync(0xffffffffu, eq, fl);
+        }
+        m += 128;
+    }
+}
+
 // ---- kernel: greedy parse of every group ---------------------------------------------------------------------------------------------
+// A step looks at 32 positions, one per lane, `s` bytes apart.  s = 1 + (bytes since the last match >> skip_shift): over data without
+// matches the parse accelerates exactly as libzstd's fast strategy does (ZSTD_compressBlock_fast: step = 1 + (ip - anchor >> 8)), so a
+// 128 KiB group of noise costs a few dozen steps, and the table learns the positions the steps looked at.
+//   dense steps (s == 1)  bit i of `eq1` says "the byte at pos + i equals the one before it"; a RUN is a stretch of ones, and a run of
+//                         kZMinRun bytes or more is a match at offset 1 - found with no table, no memory access beyond the step's own
+//                         loads, carried from step to step while it lasts.  The other positions (the BREAKS, where a run ends) ask the
+//                         hash table; a verified candidate is extended by the whole warp, forwards and backwards.
+//   strided steps         any candidate (a table hit, the repeated offset, five equal bytes) sends the parse back to dense steps at that
+//                         position; the match then grows backwards over what the stride jumped.
 __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdEncParams p)
 {
     VBZ_DYN_SMEM(smem);
@@ -154,137 +236,154 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     // how far back a match may reach: the group's region (control bytes | data bytes), at most kZPreWindow before the group
     const uint32_t pre = g.region_off < kZPreWindow ? g.region_off : kZPreWindow;
     const uint8_t* win = src - pre;  // window coordinate w <-> byte win[w]; the group starts at w = pre
-    // search effort by level.  As libzstd's fast strategy, the parse speeds up over data without matches: for every 2^shift bytes
-    // since the last match one more step is skipped after each step examined, up to `skip_cap` (level 1: 3 steps in 4 after 768 bytes)
-    const uint32_t skip_shift = p.level >= 3 ? 12u : (p.level == 2 ? 10u : 8u);
-    const uint32_t skip_cap = p.level >= 3 ? 1u : 3u;
+    const uint32_t skip_shift = zm_tune("VBZ_TUNE_SKIPSHIFT", p.level >= 3 ? 10u : (p.level == 2 ? 9u : 8u));
+    const uint32_t min_run = zm_tune("VBZ_TUNE_MINRUN", kZMinRun);
+    // what a match at a distance must bring.  Control bytes are nearly all zero and cost a bit each as literals - and while every
+    // sequence of a group has offset 1 the offsets cost nothing (RLE table): only a long match pays there; among data bytes (6 to 7
+    // bits each) a short one does
+    const uint32_t need = g.keys ? zm_tune("VBZ_TUNE_KEYMATCH", kZMinKeyMatch) : zm_tune("VBZ_TUNE_MINMATCH", kZMinMatch);
+    const uint32_t key_nz = zm_tune("VBZ_TUNE_KEYNZ", 2u);
+    const uint32_t end = B - 11;  // positions q < end are looked at: the loads of a position reach up to q + 10
 
-    for (uint32_t i = lane; i < (1u << kZHashLog); i += 32) sm->table[i] = 0;  // entry = window coordinate + 1, 0 = empty
+    for (uint32_t i = lane; i < (1u << kZHashLog); i += 32) sm->table[i] = 0;  // entry = (window coordinate + 1, tag), 0 = empty
     __syncwarp();
-    // seed with the pre-window (every position: it is at most 8 KiB)
-    for (uint32_t w0 = 0; w0 + 6 <= pre; w0 += 32) {
-        const uint32_t w = w0 + lane;
-        if (w + 6 <= pre) {
-            const uint32_t h = zm_hash(zm_load32(win + w), zm_load32(win + w + 4));
-            atomicMax(&sm->table[zm_index(h)], zm_entry(h, w));
+    // seed with the pre-window, one position in four (a repeat that matters is long: the dense steps at the head of the group look at
+    // every phase of it).  Later positions overwrite earlier ones.
+    for (uint32_t w0 = 0; w0 + 12 <= pre; w0 += 128) {
+        const uint32_t w = w0 + 4 * lane;
+        if (w + 12 <= pre) {
+            uint32_t lo, hi;
+            zm_load64(win + w, lo, hi);
+            const uint32_t h = zm_hash(lo, hi);
+            sm->table[zm_index(h)] = zm_entry(h, w);
         }
+        __syncwarp();
     }
-    __syncwarp();
 
-    uint32_t pos = 0, anchor = 0, nseq = 0, matched = 0, rep_off = 0;
-    while (pos + 4 <= B) {
-        // ---- this step's 32 positions ----------------------------------------------------------------------------------------
-        if (lane < 4 && pos + 512 + 128 * lane < B) vbz_prefetch_l2(src + pos + 512 + 128 * lane);
-        const uint32_t q = pos + lane;
-        const bool live = q + 4 <= B;
-        const bool live6 = q + 6 <= B;  // enough bytes for the hash
-        uint32_t w = 0, wp = 0, w2 = 0;
+    ZParse z = {0, 0, 0, 0, 0};
+    uint32_t carry = 0;        // dense steps: the bytes [pos - carry, pos) each equal their predecessor (a run that is still open)
+    bool dense_next = false;   // the next step is dense whatever the distance from the anchor
+    uint32_t caught_at = 0xFFFFFFFFu;  // where a strided step sent the parse back to dense ones: a run that starts there may have begun earlier
+    while (z.pos < end) {
+        uint32_t s = 1;
+        if (!dense_next && carry == 0) {
+            s += (z.pos - z.anchor) >> skip_shift;
+            if (s > 255) s = 255;
+        }
+        dense_next = false;
+        const uint32_t q = z.pos + lane * s;
+        const bool live = q < end;
+        if (s == 1 && lane < 2 && z.pos + 256 + 128 * lane < B) vbz_prefetch_l2(src + z.pos + 256 + 128 * lane);
+        uint32_t w = 0, w2 = 0, prevb = 0x100;
         if (live) {
-            w = zm_load32(src + q);
-            wp = (q + pre) ? zm_load32(src + q - 1) : ~w;  // the 4 bytes one back (nothing before the region's first byte)
+            uint32_t lo, hi;
+            if (q + pre != 0) {
+                zm_load64(src + q - 1, lo, hi);
+                prevb = lo & 0xFFu;
+                w = __funnelshift_r(lo, hi, 8);
+                w2 = (hi >> 8) & 0xFFFFu;
+            } else {  // nothing before the region's first byte
+                zm_load64(src + q, lo, hi);
+                w = lo;
+                w2 = hi & 0xFFFFu;
+            }
         }
-        // bytes q + 4, q + 5: the first two bytes of the word four lanes up (the last four lanes load them)
-        w2 = __shfl_down_sync(0xffffffffu, w, 4);
-        if (lane >= 28 && live6) w2 = zm_load32(src + q + 4);
-        w2 &= 0xFFFFu;
-        const bool run = live && w == wp;
-        // the offset of the last match found through the table, tried again everywhere: once a period has been found the parse stays
-        // on it, whatever more recent (and shorter) repeats the table offers
-        const bool rep = rep_off > 1 && live && q + pre >= rep_off && zm_load32(src + q - rep_off) == w;
-        uint32_t dist = 0;
+        const bool all4 = w == zm_rot8(w);
+        const bool same = live && (w & 0xFFu) == prevb;
+        // lanes that ask the table: not inside a run (the run logic owns those positions)
+        const bool hl = live && (s > 1 || (!same && !all4));
+        // a match among control bytes must be long to pay for its offset - and four times as long where it starts with "one code byte
+        // and zeros", which repeats all the time there
+        const uint32_t far = !g.keys ? 0u : (zm_nonzero_bytes(w) >= key_nz ? need : 4u * need);
         const uint32_t h = zm_hash(w, w2);
-        if (live6) {
-            const uint32_t at = q + pre, e = sm->table[zm_index(h)], ep = e >> kZTagBits;  // ep = window coordinate + 1, 0 = empty
-            if (ep != 0 && ((e ^ h) & ((1u << kZTagBits) - 1u)) == 0 && ep - 1 < at && zm_load32(win + (ep - 1)) == w &&
-                (zm_load32(win + (ep - 1) + 4) & 0xFFFFu) == w2)
-                dist = at - (ep - 1);
-        }
-        __syncwarp();
-        // how far a run that starts at each position goes, without touching memory again: bit i of eq1 says "the byte at pos + i equals
-        // the one before it", a run from lane i is the stretch of ones from bit i on (`open`: it reaches the end of the 32 positions)
-        bool same = live && (q + pre) != 0 && (w & 0xFFu) == (wp & 0xFFu);  // (wp's low byte is the byte before q)
-        if (!live && q < B && (q + pre) != 0) same = src[q] == src[q - 1];     // the group's last three positions
-        const uint32_t eq1 = __ballot_sync(0xffffffffu, same);
-        const uint32_t ahead = ~(eq1 >> lane) & (0xFFFFFFFFu >> lane);
-        const uint32_t run_ml = ahead ? (uint32_t)__ffs((int)ahead) - 1 : 32u - lane;
-        const uint32_t mine = (run ? 0x80u : 0u) | (ahead ? 0u : 0x40u) | run_ml;  // run | open | length, for the lane that wins
-        uint32_t cand = __ballot_sync(0xffffffffu, run || rep || dist != 0);
-        const uint32_t others = __ballot_sync(0xffffffffu, rep || dist != 0);  // lanes with more than a run to offer
-        bool took = false;
-        while (cand) {
-            const uint32_t f = (uint32_t)__ffs((int)cand) - 1;
-            const uint32_t mp = pos + f;  // match position
-            // the lane may have a run (offset 1), the repeated offset and a hash candidate: the longest wins, by a margin that pays for
-            // the dearer offset (a period beats the zero runs inside it)
-            const uint32_t f_mine = __shfl_sync(0xffffffffu, mine, f), f_dist = __shfl_sync(0xffffffffu, dist, f);
-            const uint32_t f_rep = __shfl_sync(0xffffffffu, rep ? rep_off : 0u, f);
-            const uint32_t f_run = f_mine >> 7;
-            uint32_t off = 0, ml = 0;
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t o = pass == 0 ? f_run : (pass == 1 ? (f_rep != f_run ? f_rep : 0u) : (f_dist > 1 && f_dist != f_rep ? f_dist : 0u));
-                if (o == 0) continue;
-                uint32_t m = 4;
-                if (pass == 0) {
-                    m = f_mine & 0x3Fu;                         // known from the bit mask ...
-                    if (!(f_mine & 0x40u)) { ml = m; off = 1; continue; }  // ... all of it, if the run ends among the 32 positions
-                } else if (off != 0) {  // this offset must beat the match in hand by a margin: the four bytes where that is decided first
-                    const uint32_t probe = mp + ml + (off == 1 ? 16u : 4u) - 3;
-                    if (probe + 4 > B || zm_load32(src + probe) != zm_load32(src + probe - o)) continue;
-                }
-                // ---- extend: 4 bytes per lane, 128 per round ---------------------------------------------------------------------
-                for (;;) {
-                    const uint32_t at = mp + m + 4 * lane;
-                    uint32_t eq = 0;
-                    if (at < B) {
-                        const uint32_t x = zm_load32(src + at) ^ zm_load32(src + at - o);
-                        eq = x ? ((uint32_t)__ffs((int)x) - 1) >> 3 : 4u;
-                        if (eq > B - at) eq = B - at;
-                    }
-                    const uint32_t stop = __ballot_sync(0xffffffffu, eq < 4);
-                    if (stop) {
-                        const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
-                        m += 4 * fl + __shfl_sync(0xffffffffu, eq, fl);
-                        break;
-                    }
-                    m += 128;
-                }
-                // an offset other than 1 costs a dozen bits more per sequence: it has to buy a clearly longer match
-                if (off == 0 || m > ml + (off == 1 ? 16u : 4u)) { ml = m; off = o; }
+        const uint32_t at = q + pre;
+        uint32_t dist = 0;
+        if (hl) {
+            const uint32_t e = sm->table[zm_index(h)], ep = e >> kZTagBits;  // ep = window coordinate + 1, 0 = empty
+            if (ep != 0 && ((e ^ h) & ((1u << kZTagBits) - 1u)) == 0 && ep - 1 < at) {
+                uint32_t lo, hi;
+                zm_load64(win + (ep - 1), lo, hi);
+                if (lo == w && (hi & 0xFFFFu) == w2) dist = at - (ep - 1);
             }
-            // what a match must bring.  Control bytes are nearly all zero and cost a bit each as literals: only a long match at a
-            // distance pays for the dozen bits of its offset there; among data bytes (6 to 7 bits each) a short one does
-            const uint32_t need = off == 1 ? zm_tune("VBZ_TUNE_MINRUN", kZMinRun) : (g.keys ? zm_tune("VBZ_TUNE_KEYMATCH", kZMinKeyMatch) : zm_tune("VBZ_TUNE_MINMATCH", kZMinMatch));
-            // every sequence must be paid for by 12 bytes of match (that is also what keeps the scratch areas from overflowing):
-            // a shorter match is taken only on the credit of longer ones before it
-            if (ml >= need && nseq < rec_cap && (ml >= 12 || 12ull * (nseq + 1) <= (uint64_t)matched + ml)) {
-                if (lane == 0) recs[nseq] = zm_pack(off, mp - anchor, ml);
-                ++nseq;
-                if (off > 1) rep_off = off;
-                matched += ml;
-                anchor = mp + ml;
-                pos = anchor;
-                took = true;
-                break;
-            }
-            // not worth a sequence: neither are the runs that start inside it (the same bytes, fewer of them)
-            const uint32_t upto = f + (off == 1 && ml > 1 ? ml : 1u);
-            const uint32_t inside = upto >= 32 ? 0xFFFFFFFFu : (1u << upto) - 1u;
-            cand &= ~(inside & ~others) & ~(1u << f);
+            // the offset of the last match found through the table, tried again: once a period has been found the parse stays on it
+            if (dist == 0 && z.rep_off > 1 && at >= z.rep_off && zm_load32(src + q - z.rep_off) == w) dist = z.rep_off;
+            // ... look at its far end before the warp spends a round on it
+            if (dist != 0 && far != 0 && !(q + far <= B && zm_load32(src + q + far - 4) == zm_load32(src + q + far - 4 - dist))) dist = 0;
         }
-        // the table learns the positions the parse has passed - not those behind a short match, which the next step looks at again
-        // (their entries would point at themselves)
-        if (live6 && (!took || q < pos)) atomicMax(&sm->table[zm_index(h)], zm_entry(h, q + pre));
+        const uint32_t others = __ballot_sync(0xffffffffu, dist != 0);
+        if (s > 1) {
+            // ---- strided step: any sign of a repeat -> dense steps from there -------------------------------------------------------------
+            const uint32_t cand = others | __ballot_sync(0xffffffffu, same && all4);
+            const uint32_t f = cand ? (uint32_t)__ffs((int)cand) - 1 : 32u;
+            if (hl && lane <= f) sm->table[zm_index(h)] = zm_entry(h, at);
+            __syncwarp();
+            if (cand) { z.pos += f * s; dense_next = true; caught_at = z.pos; }
+            else z.pos += 32 * s;
+            continue;
+        }
+        // ---- dense step: the runs that end in it, the candidates at the breaks, in order --------------------------------------------------
+        // X = the step's 32 "equals its predecessor" bits in the high word, below them the run that was open when the step began (as many
+        // ones as it is long, 32 at most).  Bit j of `longs` says "ones at j .. j + min_run - 1" (erosion by doubling), an END is a one
+        // below a zero: a run worth a sequence is an end whose bit min_run - 1 down is set in `longs` - found without walking the breaks.
+        const uint32_t nlive = end - z.pos < 32 ? end - z.pos : 32u;
+        const uint32_t live_mask = nlive < 32 ? (1u << nlive) - 1u : 0xFFFFFFFFu;
+        const uint32_t eq1 = __ballot_sync(0xffffffffu, same) & live_mask;
+        const uint32_t lowc = carry >= 32 ? 0xFFFFFFFFu : (carry ? ~(0xFFFFFFFFu >> carry) : 0u);
+        const uint64_t X = ((uint64_t)eq1 << 32) | lowc;
+        uint64_t longs = X;
+        {
+            uint32_t len = 1;
+            while (2 * len <= min_run) { longs &= longs >> len; len *= 2; }
+            if (min_run > len) longs &= longs >> (min_run - len);
+        }
+        // ends at window index -1 (the open run stops at the step's first position) .. nlive - 2 (a run that reaches the last live position
+        // stays open); bit i of run_ends: a run worth a sequence ends just before window index i
+        const uint64_t ends = X & ~(X >> 1) & ~(1ull << (31 + nlive));
+        const uint32_t run_ends = (uint32_t)((ends & (longs << (min_run - 1))) >> 31);
+        uint32_t events = run_ends | others;
+        bool moved = false;
+        while (events) {
+            const uint32_t i = (uint32_t)__ffs((int)events) - 1;
+            events &= events - 1;
+            if ((run_ends >> i) & 1u) {
+                // the run's first position: above the highest zero below its end
+                const uint64_t zeros = ~X & ((1ull << (31 + i)) - 1ull);
+                const uint32_t start = zeros ? z.pos + (63u - (uint32_t)__clzll((long long)zeros)) + 1u - 32u : z.pos - carry;
+                zm_emit(z, recs, rec_cap, src, pre, start, 1u, z.pos + i - start, start == caught_at, min_run, lane);
+            }
+            if ((others >> i) & 1u) {
+                const uint32_t o = __shfl_sync(0xffffffffu, dist, i), mp = z.pos + i;
+                const uint32_t ml = zm_extend(src, B, mp, o, 4, lane);
+                const uint32_t need_f = g.keys ? __shfl_sync(0xffffffffu, far, i) : need;
+                if (zm_emit(z, recs, rec_cap, src, pre, mp, o, ml, true, need_f, lane)) {
+                    z.rep_off = o;
+                    moved = true;
+                    break;
+                }
+            }
+        }
+        // the table learns the positions the parse has passed - not those behind a match that ends inside the step, which the next
+        // step looks at again (their entries would point at themselves)
+        if (hl && (!moved || q < z.anchor)) sm->table[zm_index(h)] = zm_entry(h, at);
         __syncwarp();
-        if (took) continue;
-        pos += 32;
-        const uint32_t skip = (pos - anchor) >> skip_shift;
-        pos += 32 * (skip < skip_cap ? skip : skip_cap);
+        if (moved) { z.pos = z.anchor; carry = 0; }
+        else {
+            const uint32_t brk = ~eq1 & live_mask;  // the run that is open at the end of the step: the ones above the last break
+            carry = brk ? nlive - 1u - (31u - (uint32_t)__clz((int)brk)) : carry + nlive;
+            z.pos += nlive;
+        }
     }
+    if (carry) {  // the run that is open at the end: to the group's last byte
+        const uint32_t start = z.pos - carry;
+        const uint32_t ml = zm_extend(src, B, start, 1u, carry, lane);
+        if (ml >= min_run) zm_emit(z, recs, rec_cap, src, pre, start, 1u, ml, start == caught_at, min_run, lane);
+    }
+    const uint32_t nseq = z.nseq, matched = z.matched;
     __syncwarp();
     // ---- L or S? ----------------------------------------------------------------------------------------------------------------------
     const uint32_t floor_bytes = B / 32 > 64 ? B / 32 : 64;
 #ifdef VBZ_CPUSIM
-    if (lane == 0 && getenv("VBZ_B200_TRACE_MATCH")) fprintf(stderr, "match: group %u B %u nseq %u matched %u rep_off %u\n", b, B, nseq, matched, rep_off);
+    if (lane == 0 && getenv("VBZ_B200_TRACE_MATCH")) fprintf(stderr, "match: group %u B %u nseq %u matched %u rep_off %u\n", b, B, nseq, matched, z.rep_off);
 #endif
     // (12 nseq <= matched holds by construction; the sections - at most 10 bytes per sequence and 256 of headers and tables - must fit behind the literals)
     // and with 96 more (16 blocks, 3 + 3 bytes of headers each) an S group is never larger than the bytes it stands for
