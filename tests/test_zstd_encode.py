@@ -176,6 +176,33 @@ def test_repetitive_inputs_compress_like_libzstd(backend):
             assert r3 == arr.nbytes and back3 == arr.tobytes(), (name, level)
 
 
+def test_runs_of_every_length_among_control_bytes(backend):
+    """The run scan of the control-byte groups (csrc/zstd_match_kernels.cuh: zm_runs_line / zm_runs_bytes): flat stretches of every length and
+    alignment - shorter than a lane, whole 128-byte lines of zero control bytes, runs across lines and spans - between bursts of large
+    deltas.  A run that is lost or cut short still decodes, so the size is the check: next to what the reference writes."""
+    capi = backend[0]
+    ref = ol.ref() or port
+    rng = np.random.default_rng(5)
+    small = capi.path.endswith("cpusim.so")
+    for trial in range(2 if small else 6):
+        pieces, level = [], 100
+        for L in rng.integers(8, 9000, 40 if small else 120):
+            pieces.append(np.full(int(L), level, np.int16))
+            burst = rng.integers(-3000, 3000, int(rng.integers(1, 40))).astype(np.int16)
+            pieces.append(burst)
+            level = int(rng.integers(-500, 500))
+        arr = np.concatenate(pieces)
+        o = Options(True, 2, 1, 1)
+        r, blob = capi.compress(arr, o, sized=True)
+        rr, theirs = ref.compress(arr, o, sized=True)
+        assert not ol.is_error(r) and not ol.is_error(rr)
+        assert r <= 1.10 * rr + 16, (trial, r, rr)
+        rd, back = ref.decompress(blob, o, arr.nbytes, sized=True)
+        assert rd == arr.nbytes and back == arr.tobytes()
+        r3, back3 = capi.decompress(blob, o, arr.nbytes, sized=True)
+        assert r3 == arr.nbytes and back3 == arr.tobytes()
+
+
 def test_matches_of_every_kind_round_trip(backend):
     """The match finder on text-like and structured bytes (zstd only, every level the reference maps to a strategy of its own): long and
     short matches, overlapping ones, matches across the 128 KiB groups and the 8 KiB literal blocks inside them; stock libzstd decodes all."""

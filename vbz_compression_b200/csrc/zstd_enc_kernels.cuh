@@ -80,7 +80,7 @@ struct ZEncSmem {
     uint32_t sbits[kZStreams];     // bits of every stream of the group
     uint32_t sub_off[kZSubs + 1];  // where each sub-block starts in the group's output
     uint32_t sub_lit[kZSubs];      // S groups: size of each block's literals section
-    uint32_t seq_off[kZSubs + 1];  // S groups: where each block's sequences section sits in the group's literal slot
+    uint32_t seq_off[kZSubs], seq_len[kZSubs];  // S groups: where each block's sequences section sits in the group's literal slot, its bytes
     uint8_t sub_kind[kZSubs];      // kZKindRaw / kZKindHuf
     uint8_t sub_tree[kZSubs];      // != 0: this sub-block carries the tree
     alignas(16) uint8_t stage[2][kZEncSub + 96];  // (sized header, frame header,) block header, block payload; slack for the copy
@@ -445,25 +445,25 @@ __global__ void zstd_enc_fill_blocks_kernel(const ZstdEncRead* reads, uint32_t n
 
 // geometry of sub-block q of a group of B bytes
 struct ZSub { uint32_t start, bytes, streams, seg; };
-__device__ __forceinline__ ZSub zenc_sub(uint32_t B, uint32_t q)
+__device__ __forceinline__ ZSub zenc_sub(uint32_t B, uint32_t q, uint32_t slice = kZEncSub)
 {
     ZSub s;
-    s.start = q * kZEncSub;
-    s.bytes = B - s.start < kZEncSub ? B - s.start : kZEncSub;
+    s.start = q * slice;
+    s.bytes = B - s.start < slice ? B - s.start : slice;
     s.streams = s.bytes < 1024 ? 1u : 4u;
     s.seg = s.streams == 1 ? s.bytes : (s.bytes + 3) / 4;
     return s;
 }
 
 // the lanes of a warp fetch their runs of stream sidx (= 4 * sub-block + stream) of a group of B bytes; n = 0 if there is none
-__device__ __forceinline__ void zenc_fetch_stream(const uint8_t* src, uint32_t B, uint32_t sidx, uint32_t nstreams, uint32_t lane, ZRun& f, uint32_t* n_out)
+__device__ __forceinline__ void zenc_fetch_stream(const uint8_t* src, uint32_t B, uint32_t sidx, uint32_t nstreams, uint32_t lane, ZRun& f, uint32_t* n_out, uint32_t slice)
 {
     uint32_t n = 0;
     f.sh = 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) f.g[k] = make_uint4(0, 0, 0, 0);
     if (sidx < nstreams) {
-        const ZSub sb = zenc_sub(B, sidx >> 2);
+        const ZSub sb = zenc_sub(B, sidx >> 2, slice);
         const uint32_t j = sidx & 3u;
         if (j < sb.streams && sb.bytes >= 32) {
             const uint32_t cnt = (sb.streams == 4 && j == 3) ? sb.bytes - 3 * sb.seg : sb.seg;
@@ -655,6 +655,7 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     const uint8_t* slot = p.lits + (uint64_t)(g.src - p.src);
     const uint8_t* src = smode ? slot : g.src;
     const uint32_t B = smode ? meta->lits : g.B;
+    const uint32_t slice = smode ? 1u << zm_slice_shift(g.keys) : kZEncSub;  // literals per block
     const uint32_t nsub = smode ? meta->nblk : (B ? (B + kZEncSub - 1) / kZEncSub : 1u);
     // the group's code, built by zstd_enc_code_kernel
     const ZGroupCode* gc = reinterpret_cast<const ZGroupCode*>(p.codes) + (b - g.code_first);
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
         s->len[tid] = (uint8_t)(c >> 16);
         if (tid < 160 / 4) reinterpret_cast<uint32_t*>(s->tree)[tid] = reinterpret_cast<const uint32_t*>(gc->tree)[tid];
     }
-    if (smode && tid <= kZSubs) s->seq_off[tid] = meta->seq_off[tid];
+    if (smode && tid < kZSubs) { s->seq_off[tid] = meta->seq_off[tid]; s->seq_len[tid] = meta->seq_len[tid]; }
     // bytes before the first block header: the sized header and the frame header, in front of the frame's first group
     uint32_t pre = 0;
     uint8_t prebuf[16];
@@ -687,12 +688,12 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     if (kind == kZKindHuf && huf_ok) {
         ZRun f;
         uint32_t fn;
-        zenc_fetch_stream(src, B, wid, nsub * 4, lane, f, &fn);
+        zenc_fetch_stream(src, B, wid, nsub * 4, lane, f, &fn, slice);
         for (uint32_t sidx = wid; sidx < nsub * 4; sidx += kZencWarps) {
             uint32_t run[16];
             const uint32_t n = fn;
             zenc_align_run(f, run);
-            zenc_fetch_stream(src, B, sidx + kZencWarps, nsub * 4, lane, f, &fn);  // in flight while this stream is summed
+            zenc_fetch_stream(src, B, sidx + kZencWarps, nsub * 4, lane, f, &fn, slice);  // in flight while this stream is summed
             const uint32_t bits = zenc_run_bits(s->len, run, n);
             const uint32_t incl = warp_scan_u32(bits);
             lane_off[sidx * 32 + lane] = (uint16_t)(incl - bits);
@@ -706,10 +707,10 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
         if (kind == kZKindHuf) {
             bool tree_out = false, any = false;
             for (uint32_t q = 0; q < nsub; ++q) {
-                const ZSub sb = zenc_sub(B, q);
+                const ZSub sb = zenc_sub(B, q, slice);
                 // the literals stored as they are: a Raw block (L), or a Raw literals section with a 1 / 2 / 3-byte header (S)
                 const uint32_t raw_lit = smode ? (sb.bytes < 32 ? 1u : sb.bytes < 4096 ? 2u : 3u) + sb.bytes : sb.bytes;
-                const uint32_t seq_sec = smode && s->seq_off[q + 1] > s->seq_off[q] ? s->seq_off[q + 1] - s->seq_off[q] : 1u;  // 1 = "0 sequences"
+                const uint32_t seq_sec = smode && s->seq_len[q] ? s->seq_len[q] : 1u;  // 1 = "0 sequences"
                 uint32_t payload = smode ? raw_lit + seq_sec : sb.bytes;
                 s->sub_kind[q] = kZKindRaw;
                 s->sub_tree[q] = 0;
@@ -781,7 +782,7 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
     for (uint32_t q0 = 0; q0 < nsub; q0 += 2) {
         const uint32_t q = q0 + half;
         const bool live = q < nsub;
-        const ZSub sb = zenc_sub(B, live ? q : 0);
+        const ZSub sb = zenc_sub(B, live ? q : 0, slice);
         const uint32_t skind = live ? s->sub_kind[q] : kZKindRaw;
         const uint32_t front = (live && q == 0) ? pre : 0u;  // the frame's headers travel with its first sub-block
         for (uint32_t i = ht; i < (kZEncSub + 96) / 16; i += 128) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0, 0, 0, 0);
@@ -853,7 +854,7 @@ __global__ void __launch_bounds__(kZencThreads) zstd_encode_kernel(ZstdEncParams
         if (live) {
             const uint32_t o0 = q == 0 ? 0u : s->sub_off[q], o1 = s->sub_off[q + 1];  // sub-block 0 starts at 0 with the frame's headers
             if (excl + o1 <= rd.dst_cap) {
-                const uint32_t seq_n = smode && s->seq_off[q + 1] > s->seq_off[q] ? s->seq_off[q + 1] - s->seq_off[q] : 0u;
+                const uint32_t seq_n = smode ? s->seq_len[q] : 0u;
                 // staged: headers, the literals section and - when there are no sequences - the zero byte that says so
                 zenc_copy_out(dst + o0, stage, o1 - o0 - seq_n, ht, 128);
                 if (seq_n) zenc_copy_global(dst + o1 - seq_n, slot + s->seq_off[q], seq_n, ht, 128);

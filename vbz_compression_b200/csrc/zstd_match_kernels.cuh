@@ -96,11 +96,14 @@ struct ZGroupMeta {
     uint32_t mode;          // kZModeL / kZModeS
     uint32_t nseq;          // S: sequences of the group
     uint32_t lits;          // S: literals of the group (compacted in the literal scratch, at the group's content offset)
-    uint32_t nblk;          // S: blocks = max(1, ceil(lits / 8 KiB))
-    uint32_t seq_off[17];   // S: the sequences section of block q = bytes [seq_off[q], seq_off[q + 1]) of the group's literal slot (empty: no sequences)
-    uint32_t pad[3];
+    uint32_t nblk;          // S: blocks = max(1, ceil(lits / slice)), slice = zm_slice(control bytes?)
+    uint32_t seq_off[16];   // S: the sequences section of block q = seq_len[q] bytes at seq_off[q] of the group's literal slot (0 bytes: no sequences)
+    uint32_t seq_len[16];
 };
-static_assert(sizeof(ZGroupMeta) == 96, "ZGroupMeta layout");
+static_assert(sizeof(ZGroupMeta) == kZGroupMetaBytes, "ZGroupMeta layout");
+// literals per block of an S group: 2 KiB among control bytes (a group there is sequences more than anything else, and a block's sequences are
+// serial work for one lane in zstd_enc_seq_kernel and in the decoder alike: 16 blocks = 16 lanes), 8 KiB among data bytes
+__device__ __forceinline__ uint32_t zm_slice_shift(bool keys) { return keys ? 11u : 13u; }
 
 __device__ __forceinline__ uint64_t zm_pack(uint32_t off, uint32_t ll, uint32_t ml) { return (uint64_t)off | ((uint64_t)ll << 18) | ((uint64_t)ml << 36); }
 __device__ __forceinline__ uint32_t zm_off(uint64_t r) { return (uint32_t)r & 0x3FFFFu; }
@@ -204,6 +207,117 @@ __device__ __forceinline__ uint32_t zm_extend(const uint8_t* src, uint32_t B, ui
     }
 }
 
+// ---- runs among control bytes: 128 bytes per step ---------------------------------------------------------------------------------------
+// Nearly every sequence of a signal read is a run of zero control bytes, and there is one for every few dozen bytes: the parse of a
+// control-byte group is therefore a scan for runs that never walks over breaks or runs one at a time.
+//   zm_runs_line   one aligned 128-byte line: a lane holds 4 bytes and the 4 bits "equals its predecessor"; a run of kZMinRun (>= 11) bytes
+//                  covers two whole lanes at least, so runs are stretches of FULL lanes (one ballot) plus the ones at the top of the lane
+//                  before and at the bottom of the lane after.  The lane at the head of a stretch owns the run; owners of finished runs
+//                  write their records side by side (rank by popc).  The run that reaches the end of the line is carried into the next.
+//   zm_runs_bytes  any other range, 32 positions per step (byte loads): heads and tails of spans, and around a match found through the table.
+struct ZRuns { uint32_t carry; };  // bytes [pos - carry, pos) each equal their predecessor: the run that is open at pos
+
+__device__ __forceinline__ void zm_runs_line(ZParse& z, ZRuns& rs, uint64_t* recs, uint32_t rec_cap, const uint8_t* src, uint32_t pre, uint32_t P,
+                                             uint32_t min_run, uint32_t lane, uint32_t W, uint32_t before)
+{
+    // W: the lane's four bytes; before: the byte ahead of the line (0x100: none)
+    uint32_t pb = __shfl_up_sync(0xffffffffu, W, 1) >> 24;
+    if (lane == 0) pb = before < 0x100u ? before : (~W & 0xFFu);
+    const uint32_t x = W ^ ((W << 8) | pb);
+    const uint32_t t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 where a byte of x is zero
+    const uint32_t n = (((t >> 7) * 0x00204081u) >> 21) & 0xFu;                  // bit k: byte 4 * lane + k equals its predecessor
+    const bool full = n == 0xFu;
+    const uint32_t F = __ballot_sync(0xffffffffu, full);
+    const uint32_t low1 = (uint32_t)__ffs((int)~n) - 1;          // ones at the bottom of the lane (0 .. 4)
+    const uint32_t top1 = (uint32_t)__clz((int)~(n << 28));      // ones at its top (0 .. 4)
+    // owners: the first lane of a stretch of full lanes; lane 0 also when the carried run ends inside it
+    const uint32_t below = __shfl_up_sync(0xffffffffu, top1, 1);
+    const bool first = full && (lane == 0 || !((F >> (lane - 1)) & 1u));
+    const uint32_t notf = ~(F >> lane);                                         // (zeros come in at the top: the stretch ends at lane 32 at the latest)
+    const uint32_t nfull = !full ? 0u : (notf ? (uint32_t)__ffs((int)notf) - 1 : 32u);  // (a line of nothing but full lanes: 32)
+    const uint32_t after = lane + nfull;                                           // the lane behind the stretch
+    const uint32_t tail = __shfl_sync(0xffffffffu, low1, after & 31u);
+    const uint32_t head = lane == 0 ? rs.carry : below;
+    const bool owner = first || (lane == 0 && rs.carry != 0);
+    const bool closed = after < 32;
+    const uint32_t len = head + 4 * nfull + (closed ? (full ? tail : low1) : 0u);
+    const uint32_t start = P + 4 * lane - head;
+    const uint32_t Q = __ballot_sync(0xffffffffu, owner && closed && len >= min_run);
+    if (Q && z.nseq + (uint32_t)__popc((int)Q) <= rec_cap) {
+        const uint32_t lower = Q & ((1u << lane) - 1u);
+        const uint32_t prev_lane = lower ? 31u - (uint32_t)__clz((int)lower) : 0u;
+        const uint32_t prev_end = __shfl_sync(0xffffffffu, start + len, prev_lane);
+        const bool mine = (Q >> lane) & 1u;
+        if (mine) recs[z.nseq + (uint32_t)__popc((int)lower)] = zm_pack(1u, start - (lower ? prev_end : z.anchor), len);
+        z.nseq += (uint32_t)__popc((int)Q);
+        z.matched += __reduce_add_sync(0xffffffffu, mine ? len : 0u);
+        z.anchor = __shfl_sync(0xffffffffu, start + len, 31u - (uint32_t)__clz((int)Q));
+    }
+    // what is open at the end of the line: the stretch that reaches lane 31, or the ones at the top of lane 31
+    const uint32_t top_stretch = (uint32_t)__clz((int)~F);  // full lanes at the top
+    const uint32_t own = 32u - top_stretch;                 // its first lane (32: none)
+    const uint32_t open_len = __shfl_sync(0xffffffffu, head + 4 * nfull, own & 31u);
+    const uint32_t top31 = __shfl_sync(0xffffffffu, top1, 31);
+    rs.carry = top_stretch ? open_len : top31;
+}
+
+// [from, to): 32 positions per step.  `ends_run`: the byte at `to` is known to differ from its predecessor (the open run stops there).
+__device__ __forceinline__ void zm_runs_bytes(ZParse& z, ZRuns& rs, uint64_t* recs, uint32_t rec_cap, const uint8_t* src, uint32_t pre, uint32_t from,
+                                              uint32_t to, uint32_t min_run, uint32_t lane)
+{
+    while (from < to) {
+        const uint32_t nlive = to - from < 32 ? to - from : 32u;
+        const uint32_t live_mask = nlive < 32 ? (1u << nlive) - 1u : 0xFFFFFFFFu;
+        const uint32_t q = from + lane;
+        const bool same = lane < nlive && (q + pre) != 0 && src[q] == src[(int)q - 1];
+        const uint32_t eq1 = __ballot_sync(0xffffffffu, same) & live_mask;
+        const uint32_t carry = rs.carry;
+        const uint32_t lowc = carry >= 32 ? 0xFFFFFFFFu : (carry ? ~(0xFFFFFFFFu >> carry) : 0u);
+        const uint64_t X = ((uint64_t)eq1 << 32) | lowc;
+        uint64_t longs = X;
+        {
+            uint32_t len = 1;
+            while (2 * len <= min_run) { longs &= longs >> len; len *= 2; }
+            if (min_run > len) longs &= longs >> (min_run - len);
+        }
+        const uint64_t ends = X & ~(X >> 1) & ~(1ull << (31 + nlive));
+        uint32_t run_ends = (uint32_t)((ends & (longs << (min_run - 1))) >> 31);
+        while (run_ends) {
+            const uint32_t i = (uint32_t)__ffs((int)run_ends) - 1;
+            run_ends &= run_ends - 1;
+            const uint64_t zeros = ~X & ((1ull << (31 + i)) - 1ull);
+            const uint32_t start = zeros ? from + (63u - (uint32_t)__clzll((long long)zeros)) + 1u - 32u : from - carry;
+            zm_emit(z, recs, rec_cap, src, pre, start, 1u, from + i - start, false, min_run, lane);
+        }
+        const uint32_t brk = ~eq1 & live_mask;
+        rs.carry = brk ? nlive - 1u - (31u - (uint32_t)__clz((int)brk)) : carry + nlive;
+        from += nlive;
+    }
+}
+
+// [from, to) by whatever fits: bytes up to the first line boundary, whole lines, bytes
+__device__ __forceinline__ void zm_runs(ZParse& z, ZRuns& rs, uint64_t* recs, uint32_t rec_cap, const uint8_t* src, uint32_t pre, uint32_t from, uint32_t to,
+                                        uint32_t min_run, uint32_t lane)
+{
+    const uint32_t mis = (uint32_t)((uintptr_t)(src + from) & 127u);
+    if (mis && to - from >= 128 + (128 - mis)) {
+        zm_runs_bytes(z, rs, recs, rec_cap, src, pre, from, from + (128 - mis), min_run, lane);
+        from += 128 - mis;
+    }
+    if (((uintptr_t)(src + from) & 127u) == 0 && to - from >= 128 && !zm_tune("VBZ_TUNE_NOLINES", 0u)) {
+        // the next line is on its way while this one is looked at
+        uint32_t W = reinterpret_cast<const uint32_t*>(src + from)[lane];
+        uint32_t before = (from + pre) ? src[(int)from - 1] : 0x100u;
+        for (; to - from >= 128; from += 128) {
+            const uint32_t Wn = to - from >= 256 ? reinterpret_cast<const uint32_t*>(src + from + 128)[lane] : 0u;
+            zm_runs_line(z, rs, recs, rec_cap, src, pre, from, min_run, lane, W, before);
+            before = __shfl_sync(0xffffffffu, W, 31) >> 24;
+            W = Wn;
+        }
+    }
+    zm_runs_bytes(z, rs, recs, rec_cap, src, pre, from, to, min_run, lane);
+}
+
 // ---- kernel: greedy parse of every group ---------------------------------------------------------------------------------------------
 // A step looks at 32 positions, one per lane, `s` bytes apart.  s = 1 + (bytes since the last match >> skip_shift): over data without
 // matches the parse accelerates exactly as libzstd's fast strategy does (ZSTD_compressBlock_fast: step = 1 + (ip - anchor >> 8)), so a
@@ -243,6 +357,7 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     // bits each) a short one does
     const uint32_t need = g.keys ? zm_tune("VBZ_TUNE_KEYMATCH", kZMinKeyMatch) : zm_tune("VBZ_TUNE_MINMATCH", kZMinMatch);
     const uint32_t key_nz = zm_tune("VBZ_TUNE_KEYNZ", 2u);
+    const uint32_t key_stride = zm_tune("VBZ_TUNE_KEYSTRIDE", 255u);
     const uint32_t end = B - 11;  // positions q < end are looked at: the loads of a position reach up to q + 10
 
     for (uint32_t i = lane; i < (1u << kZHashLog); i += 32) sm->table[i] = 0;  // entry = (window coordinate + 1, tag), 0 = empty
@@ -261,10 +376,87 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     }
 
     ZParse z = {0, 0, 0, 0, 0};
+    if (g.keys) {
+        // ---- control bytes: runs by zm_runs over every byte; the table is asked at 32 positions per SPAN, `s` bytes apart, s growing with
+        // the distance from the last match found through the table (runs do not count: there is one every few dozen bytes)
+        ZRuns rs = {0};
+        uint32_t hanchor = 0;
+        static_assert(kZMinRun >= 11, "zm_runs_line: a run must cover two whole lanes");
+        const uint32_t kmin_run = min_run < 11 ? 11u : min_run;
+        while (z.pos < B) {
+            uint32_t st = 1 + ((z.pos - hanchor) >> skip_shift);
+            if (st > key_stride) st = key_stride;
+            uint32_t span_end = z.pos + 32 * st;
+            span_end += (128u - (uint32_t)((uintptr_t)(src + span_end) & 127u)) & 127u;  // spans end on line boundaries
+            if (span_end > B) span_end = B;
+            const uint32_t q = z.pos + lane * st;
+            const bool live = q < end && q < span_end;
+            uint32_t w = 0, w2 = 0, prevb = 0x100;
+            if (live) {
+                uint32_t lo, hi;
+                if (q + pre != 0) {
+                    zm_load64(src + q - 1, lo, hi);
+                    prevb = lo & 0xFFu;
+                    w = __funnelshift_r(lo, hi, 8);
+                    w2 = (hi >> 8) & 0xFFFFu;
+                } else {
+                    zm_load64(src + q, lo, hi);
+                    w = lo;
+                    w2 = hi & 0xFFFFu;
+                }
+            }
+            // a position inside a run belongs to the run; a match must be long to pay for its offset (while every sequence of a group
+            // has offset 1 the offsets cost nothing: RLE table) - four times as long where it starts with "one code byte and zeros"
+            const bool hl = live && (w & 0xFFu) != prevb && w != zm_rot8(w);
+            const uint32_t far = zm_nonzero_bytes(w) >= key_nz ? need : 4u * need;
+            const uint32_t h = zm_hash(w, w2);
+            const uint32_t at = q + pre;
+            uint32_t dist = 0;
+            if (hl) {
+                const uint32_t e = sm->table[zm_index(h)], ep = e >> kZTagBits;
+                if (ep != 0 && ((e ^ h) & ((1u << kZTagBits) - 1u)) == 0 && ep - 1 < at) {
+                    uint32_t lo, hi;
+                    zm_load64(win + (ep - 1), lo, hi);
+                    if (lo == w && (hi & 0xFFFFu) == w2) dist = at - (ep - 1);
+                }
+                if (dist == 0 && z.rep_off > 1 && at >= z.rep_off && zm_load32(src + q - z.rep_off) == w) dist = z.rep_off;
+                // ... look at its far end and its middle before the warp spends a round on it
+                if (dist != 0 && !(q + far <= B && zm_load32(src + q + far - 4) == zm_load32(src + q + far - 4 - dist) &&
+                                   zm_load32(src + q + far / 2) == zm_load32(src + q + far / 2 - dist)))
+                    dist = 0;
+            }
+            uint32_t others = __ballot_sync(0xffffffffu, dist != 0);
+            uint32_t cur = z.pos;
+            bool moved = false;
+            while (others) {
+                const uint32_t f = (uint32_t)__ffs((int)others) - 1;
+                others &= others - 1;
+                const uint32_t mp = z.pos + f * st;
+                zm_runs(z, rs, recs, rec_cap, src, pre, cur, mp, kmin_run, lane);
+                if (rs.carry >= kmin_run) zm_emit(z, recs, rec_cap, src, pre, mp - rs.carry, 1u, rs.carry, false, kmin_run, lane);  // (the byte at mp differs from its predecessor)
+                rs.carry = 0;
+                cur = mp;
+                const uint32_t o = __shfl_sync(0xffffffffu, dist, f);
+                const uint32_t ml = zm_extend(src, B, mp, o, 4, lane);
+                if (zm_emit(z, recs, rec_cap, src, pre, mp, o, ml, true, __shfl_sync(0xffffffffu, far, f), lane)) {
+                    z.rep_off = o;
+                    hanchor = z.anchor;
+                    moved = true;
+                    break;
+                }
+            }
+            if (hl && (!moved || q < z.anchor)) sm->table[zm_index(h)] = zm_entry(h, at);
+            __syncwarp();
+            if (moved) { z.pos = z.anchor; continue; }
+            zm_runs(z, rs, recs, rec_cap, src, pre, cur, span_end, kmin_run, lane);
+            z.pos = span_end;
+        }
+        if (rs.carry >= kmin_run) zm_emit(z, recs, rec_cap, src, pre, B - rs.carry, 1u, rs.carry, false, kmin_run, lane);
+    }
     uint32_t carry = 0;        // dense steps: the bytes [pos - carry, pos) each equal their predecessor (a run that is still open)
     bool dense_next = false;   // the next step is dense whatever the distance from the anchor
     uint32_t caught_at = 0xFFFFFFFFu;  // where a strided step sent the parse back to dense ones: a run that starts there may have begun earlier
-    while (z.pos < end) {
+    while (!g.keys && z.pos < end) {
         uint32_t s = 1;
         if (!dense_next && carry == 0) {
             s += (z.pos - z.anchor) >> skip_shift;
@@ -373,7 +565,7 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
             z.pos += nlive;
         }
     }
-    if (carry) {  // the run that is open at the end: to the group's last byte
+    if (!g.keys && carry) {  // the run that is open at the end: to the group's last byte
         const uint32_t start = z.pos - carry;
         const uint32_t ml = zm_extend(src, B, start, 1u, carry, lane);
         if (ml >= min_run) zm_emit(z, recs, rec_cap, src, pre, start, 1u, ml, start == caught_at, min_run, lane);
@@ -387,51 +579,60 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
 #endif
     // (12 nseq <= matched holds by construction; the sections - at most 10 bytes per sequence and 256 of headers and tables - must fit behind the literals)
     // and with 96 more (16 blocks, 3 + 3 bytes of headers each) an S group is never larger than the bytes it stands for
-    if (nseq == 0 || matched < floor_bytes || 10ull * nseq + 256 + 96 > matched) return;  // stays L
+    if (nseq == 0 || matched < floor_bytes || 10ull * nseq + 256 + 96 + 16 * 8 + 16 > matched) return;  // stays L
     // ---- S: compact the literals into the literal scratch, count them --------------------------------------------------------------------
     uint8_t* lits = p.lits + content_off;
     uint32_t* hist = sm->table;  // (the parse is over)
     for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
     __syncwarp();
     uint32_t from = 0, to = 0;  // source position / literal count before the records of this round
+    uint32_t zeros = 0;         // literals that are 0x00 (most of them among control bytes: counted by ballot, not by 32 atomics on one word)
     for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
         const uint32_t i = i0 + lane;
         const uint64_t rec = i < nseq ? recs[i] : 0ull;
         const uint32_t ll = zm_ll(rec), ml = zm_ml(rec);
         const uint32_t span = warp_scan_u32(ll + ml), lsum = warp_scan_u32(ll);
-        const uint32_t my_from = from + span - (ll + ml), my_to = to + lsum - ll;
-        // short runs: the lane copies its own; long ones: the whole warp, one after the other
-        if (ll <= 16) {
-            for (uint32_t k = 0; k < ll; ++k) {
-                const uint8_t v = src[my_from + k];
-                lits[my_to + k] = v;
-                atomicAdd(&hist[v], 1u);
+        const uint32_t my_from = from + span - (ll + ml);
+        const uint32_t total = __shfl_sync(0xffffffffu, lsum, 31);
+        // a gather: literal o of the round belongs to the first record whose inclusive count exceeds o (binary search over the lanes)
+        for (uint32_t o0 = 0; o0 < total; o0 += 32) {
+            const uint32_t o = o0 + lane;
+            uint32_t j = 0;
+#pragma unroll
+            for (uint32_t step = 16; step != 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, lsum, j + step - 1);
+                if (v <= o) j += step;
             }
-        }
-        uint32_t big = __ballot_sync(0xffffffffu, ll > 16);
-        while (big) {
-            const uint32_t f = (uint32_t)__ffs((int)big) - 1;
-            big &= big - 1;
-            const uint32_t n = __shfl_sync(0xffffffffu, ll, f), sf = __shfl_sync(0xffffffffu, my_from, f), st = __shfl_sync(0xffffffffu, my_to, f);
-            for (uint32_t k = lane; k < n; k += 32) {
-                const uint8_t v = src[sf + k];
-                lits[st + k] = v;
-                atomicAdd(&hist[v], 1u);
+            j &= 31u;
+            const uint32_t fj = __shfl_sync(0xffffffffu, my_from, j), ej = __shfl_sync(0xffffffffu, lsum - ll, j);
+            uint32_t v = 0x100;
+            if (o < total) {
+                v = src[fj + (o - ej)];
+                lits[to + o] = (uint8_t)v;
+                if (v) atomicAdd(&hist[v], 1u);
             }
+            zeros += (uint32_t)__popc((int)__ballot_sync(0xffffffffu, v == 0));
         }
         from += __shfl_sync(0xffffffffu, span, 31);
-        to += __shfl_sync(0xffffffffu, lsum, 31);
+        to += total;
     }
-    for (uint32_t k = from + lane; k < B; k += 32) {  // the literals after the last match
-        const uint8_t v = src[k];
-        lits[to + k - from] = v;
-        atomicAdd(&hist[v], 1u);
+    for (uint32_t k0 = from; k0 < B; k0 += 32) {  // the literals after the last match
+        const uint32_t k = k0 + lane;
+        uint32_t v = 0x100;
+        if (k < B) {
+            v = src[k];
+            lits[to + k - from] = (uint8_t)v;
+            if (v) atomicAdd(&hist[v], 1u);
+        }
+        zeros += (uint32_t)__popc((int)__ballot_sync(0xffffffffu, v == 0));
     }
+    __syncwarp();
+    if (lane == 0) hist[0] = zeros;
     to += B - from;
     __syncwarp();
     uint32_t* gh = p.hist + (uint64_t)b * 256;
     for (uint32_t i = lane; i < 256; i += 32) gh[i] = hist[i];
-    if (lane == 0) { meta->mode = kZModeS; meta->nseq = nseq; meta->lits = to; meta->nblk = to ? (to + kZEncSub - 1) / kZEncSub : 1u; }
+    if (lane == 0) { meta->mode = kZModeS; meta->nseq = nseq; meta->lits = to; meta->nblk = to ? (to + (1u << zm_slice_shift(g.keys)) - 1) >> zm_slice_shift(g.keys) : 1u; }
 }
 
 // ---- sequence codes (RFC 8878 3.1.1.3.2.1.1) ----------------------------------------------------------------------------------------
@@ -628,6 +829,7 @@ __global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEn
     for (uint32_t i = lane; i < 3 * 56; i += 32) (&sm->hist[0][0])[i] = 0;
     if (lane < 16) sm->blk_cnt[lane] = 0;
     __syncwarp();
+    const uint32_t shift = zm_slice_shift(g.keys);
     // ---- pass 1: which block a sequence belongs to, its literal run inside that block, the code histograms -----------------------------
     uint32_t lit_before = 0;
     for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
@@ -637,9 +839,9 @@ __global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEn
         const uint32_t lsum = warp_scan_u32(ll);
         if (i < nseq) {
             const uint32_t c = lit_before + lsum - ll;  // literals of the group before this sequence's run
-            uint32_t blk = (c + ll) >> 13;               // the block in which the run ends (a run that ends on a boundary opens the next block)
+            uint32_t blk = (c + ll) >> shift;            // the block in which the run ends (a run that ends on a boundary opens the next block)
             if (blk >= nblk) blk = nblk - 1;
-            const uint32_t start = blk << 13;
+            const uint32_t start = blk << shift;
             const uint32_t ll_in = c + ll - (c > start ? c : start);
             recs[i] = zm_pack(off, ll_in, ml);
             atomicAdd(&sm->hist[0][zm_ll_code(ll_in)], 1u);
@@ -686,28 +888,30 @@ __global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEn
     }
     __syncwarp();
     // offsets beyond the predefined table's 29 codes cannot occur: the window is 136 KiB (code <= 17)
-    // ---- the sections: lane 0, block after block ---------------------------------------------------------------------------------------------
-    if (lane == 0) {
+    // ---- the sections: a lane per block.  Every block's section has its own place behind the literals, sized for the worst case
+    // (10 bytes per sequence: 26 bits of states, 50 of extra bits at most; headers and table descriptions in the first one) --------------
+    {
         const ZFseEnc* tl = &sm->t[0];
         const ZFseEnc* to = &sm->t[1];
         const ZFseEnc* tm = &sm->t[2];
-        uint32_t at = (lits + 3u) & ~3u;  // behind the literals
-        uint32_t first_rec = 0;
-        bool tables_out = false;
-        for (uint32_t q = 0; q < nblk; ++q) {
-            meta->seq_off[q] = at;
-            const uint32_t n = sm->blk_cnt[q];
-            if (n == 0) continue;
+        const uint32_t n = lane < nblk ? sm->blk_cnt[lane] : 0u;
+        const uint32_t with = __ballot_sync(0xffffffffu, n != 0);
+        const bool tables = with && lane == (uint32_t)__ffs((int)with) - 1;  // the first block with sequences carries the tables, the others repeat them
+        const uint32_t cap = n ? 8u + 10u * n + (tables ? 200u : 0u) : 0u;
+        const uint32_t cap_incl = warp_scan_u32(cap), n_incl = warp_scan_u32(n);
+        const uint32_t at = ((lits + 3u) & ~3u) + cap_incl - cap;
+        const uint32_t first_rec = n_incl - n;
+        uint32_t bytes = 0;
+        if (n) {
             uint8_t* o = slot + at;
             uint32_t hb = 0;
             if (n < 128) o[hb++] = (uint8_t)n;
             else if (n < 0x7F00) { o[hb++] = (uint8_t)((n >> 8) + 128); o[hb++] = (uint8_t)n; }
             else { o[hb++] = 255; o[hb++] = (uint8_t)(n - 0x7F00); o[hb++] = (uint8_t)((n - 0x7F00) >> 8); }
-            if (!tables_out) {
+            if (tables) {
                 o[hb++] = (uint8_t)((tl->mode << 6) | (to->mode << 4) | (tm->mode << 2));
                 for (int k = 0; k < 3; ++k)
                     for (uint32_t j = 0; j < sm->desc_n[k]; ++j) o[hb++] = sm->desc[k][j];
-                tables_out = true;
             } else {
                 o[hb++] = (uint8_t)((3u << 6) | (3u << 4) | (3u << 2));  // Repeat_Mode x 3
             }
@@ -739,10 +943,9 @@ __global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEn
             zm_fse_flush(tl, sl, w);
             zg_put(w, 1, 1);  // the marker above the last bit
             if (w.nbits) { w.p[w.nbytes++] = (uint8_t)w.acc; }
-            at += hb + w.nbytes;
-            first_rec += n;
+            bytes = hb + w.nbytes;
         }
-        for (uint32_t q = nblk; q <= 16; ++q) meta->seq_off[q] = at;
+        if (lane < 16) { meta->seq_off[lane] = at; meta->seq_len[lane] = bytes; }
     }
 }
 
