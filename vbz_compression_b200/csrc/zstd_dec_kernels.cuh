@@ -1143,9 +1143,8 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
 // A frame the sequence kernel cannot vouch for (damaged, more records than the pool holds) goes to the general kernel.
 struct ZSeqWarp {  // zstd_seq_kernel: per-warp shared state
     uint32_t ll[512], ml[512], of[256];  // sym | nbBits << 8 | base << 16
-    uint32_t chunk[512];                 // the part of the sequences stream the reader is in (kZSeqChunkWords)
-    int16_t norm[64];
-    uint16_t next[64];
+    int16_t norm[3][64];                 // scratch of the three table builders (lanes 0 - 2)
+    uint16_t next[3][64];
 };
 struct ZExecWarp {  // zstd_seqexec_kernel: per-warp shared state
     uint16_t huf[2048];
@@ -1180,64 +1179,42 @@ __device__ uint32_t z_seq_table2(int16_t* norm, uint16_t* next, uint32_t* cell, 
     return used;
 }
 
-// Backward bit reader for the sequences section, used by the WHOLE warp in lockstep (every lane holds the same state, so refills
-// can stage the stream through shared memory cooperatively): a 64-bit window whose top bit is the next unread bit, refilled 32 bits
-// at a time from a 2 KiB chunk of the stream in shared memory; the chunk moves towards the start of the stream as the reader does.
-constexpr uint32_t kZSeqChunkWords = 512;
-struct ZSeqBits {
+// Backward bit reader for a sequences section, one per lane: a 64-bit window whose top bit is the next unread bit, refilled 32 bits at a
+// time through aligned word loads (a lane walks down its own stream; the lines it touches stay in L1).
+struct ZLaneBits {
     const uint32_t* words;  // the aligned word that holds the section's first byte
-    uint32_t* chunk;        // shared memory, kZSeqChunkWords words
-    int c_lo;               // index of the word in chunk[0]
     int wi;                 // next word to take (counting down; < 0: past the start, reads as zero)
     uint64_t buf;
     int nbits;
     long long left;         // unread bits of the stream proper (negative: the reader ran past the start)
 };
-__device__ __forceinline__ void zsb_stage(ZSeqBits& b, int hi_word, uint32_t lane)
-{
-    // chunk <- words [lo, lo + kZSeqChunkWords) with lo + kZSeqChunkWords - 1 = hi_word (or lo = 0)
-    const int lo = hi_word + 1 > (int)kZSeqChunkWords ? hi_word + 1 - (int)kZSeqChunkWords : 0;
-    __syncwarp();
-    for (int k = (int)lane; k < (int)kZSeqChunkWords && lo + k <= hi_word; k += 32) b.chunk[k] = b.words[lo + k];
-    __syncwarp();
-    b.c_lo = lo;
-}
-__device__ __forceinline__ void zsb_refill(ZSeqBits& b, uint32_t lane)
-{
-    while (b.nbits <= 32) {
-        uint32_t w = 0;
-        if (b.wi >= 0) {
-            if (b.wi < b.c_lo) zsb_stage(b, b.wi, lane);
-            w = b.chunk[b.wi - b.c_lo];
-        }
-        b.buf |= (uint64_t)w << (32 - b.nbits);
-        b.nbits += 32;
-        --b.wi;
-    }
-}
 // p[0 .. n): the stream; false if it is empty or ends with a zero byte
-__device__ __forceinline__ bool zsb_init(ZSeqBits& b, uint32_t* chunk, const uint8_t* p, uint32_t n, uint32_t lane)
+__device__ __forceinline__ bool zlb_init(ZLaneBits& b, const uint8_t* p, uint32_t n)
 {
     if (n == 0 || p[n - 1] == 0) return false;
     const uint32_t phase = (uint32_t)((uintptr_t)p & 3u);
     b.words = reinterpret_cast<const uint32_t*>(p - phase);
-    b.chunk = chunk;
-    const uint32_t last_byte = phase + n - 1;         // byte index of the stream's last byte, from words[0]
+    const uint32_t last_byte = phase + n - 1;  // byte index of the stream's last byte, from words[0]
     b.wi = (int)(last_byte >> 2);
     b.left = (long long)(n - 1) * 8 + z_highbit(p[n - 1]);
-    zsb_stage(b, b.wi, lane);
-    // the first word: only the bits below the marker count
-    const uint32_t v0 = 8u * (last_byte & 3u) + (uint32_t)z_highbit(p[n - 1]);  // unread bits in that word
-    const uint32_t w = b.chunk[b.wi - b.c_lo];
+    const uint32_t v0 = 8u * (last_byte & 3u) + (uint32_t)z_highbit(p[n - 1]);  // unread bits in the last word: those below the marker
+    const uint32_t w = b.words[b.wi];
     b.buf = v0 ? ((uint64_t)w << (64 - v0)) : 0ull;
     b.nbits = (int)v0;
     --b.wi;
     return true;
 }
-__device__ __forceinline__ uint32_t zsb_read(ZSeqBits& b, uint32_t nb, uint32_t lane)
+__device__ __forceinline__ uint32_t zlb_read(ZLaneBits& b, uint32_t nb)
 {
     if (nb == 0) return 0;
-    if (b.nbits < (int)nb) zsb_refill(b, lane);
+    if (b.nbits < (int)nb) {
+        while (b.nbits <= 32) {
+            const uint32_t w = b.wi >= 0 ? b.words[b.wi] : 0u;
+            b.buf |= (uint64_t)w << (32 - b.nbits);
+            b.nbits += 32;
+            --b.wi;
+        }
+    }
     const uint32_t v = (uint32_t)(b.buf >> (64 - nb));
     b.buf <<= nb;
     b.nbits -= (int)nb;
@@ -1245,59 +1222,63 @@ __device__ __forceinline__ uint32_t zsb_read(ZSeqBits& b, uint32_t nb, uint32_t 
     return v;
 }
 
-// The sequences of one block -> records.  The whole warp walks the stream in lockstep (lane 0 stores).  `pos` = content bytes of the
-// frame before the block.  Returns the bytes the block regenerates, or 0xFFFFFFFF if the block is damaged.
-__device__ uint32_t z_block_sequences(ZSeqWarp* zw, ZFrame& f, const uint8_t* bp, uint32_t bs, uint32_t nseq_expected, ZstdSeq* out, uint64_t pos,
-                                      uint32_t lane)
+// what a lane knows about "its" Seq unit before the sequences are decoded
+struct ZSeqHead {
+    const uint8_t* sec;  // the sequences section behind its count: the modes byte first
+    uint32_t n;          // bytes from there to the end of the block
+    uint32_t nseq, lit_n;
+    int modes;           // -1: the block is damaged
+};
+__device__ __forceinline__ ZSeqHead z_seq_head(const uint8_t* bp, uint32_t bs, uint32_t nseq_expected)
 {
-    const uint32_t kBad = 0xFFFFFFFFu;
+    ZSeqHead h = {nullptr, 0, 0, 0, -1};
     int lt, streams;
     uint32_t hdr, lit_n, comp;
-    if (!z_lit_header(bp, bs, &lt, &hdr, &lit_n, &comp, &streams)) return kBad;
+    if (!z_lit_header(bp, bs, &lt, &hdr, &lit_n, &comp, &streams)) return h;
     const uint32_t sec = lt == 0 ? hdr + lit_n : lt == 1 ? hdr + 1 : hdr + comp;
-    if (sec >= bs || lit_n > kZBlockMax) return kBad;
-    const uint8_t* p = bp + sec;
-    uint32_t n = bs - sec, nseq, h;
-    if (!z_seq_count(p, n, &nseq, &h) || nseq != nseq_expected || nseq == 0) return kBad;
-    if (h + 1 > n) return kBad;
-    const int modes = p[h++];
-    if (modes & 3) return kBad;  // reserved bits (checked by libzstd 1.5.x)
-    uint32_t ok = 1;
-    int al_ll = f.al_ll, al_of = f.al_of, al_ml = f.al_ml;
-    if (lane == 0) {  // the tables: one lane (they are small, and rebuilt once per block at most)
-        uint32_t r;
-        r = z_seq_table2(zw->norm, zw->next, zw->ll, &al_ll, modes >> 6, p + h, n - h, 9, 35, kZ_LL_DEF, 36, 6, f.seq_valid);
-        if (r == kBad) ok = 0; else h += r;
-        if (ok) { r = z_seq_table2(zw->norm, zw->next, zw->of, &al_of, (modes >> 4) & 3, p + h, n - h, 8, 31, kZ_OF_DEF, 29, 5, f.seq_valid); if (r == kBad) ok = 0; else h += r; }
-        if (ok) { r = z_seq_table2(zw->norm, zw->next, zw->ml, &al_ml, (modes >> 2) & 3, p + h, n - h, 9, 52, kZ_ML_DEF, 53, 6, f.seq_valid); if (r == kBad) ok = 0; else h += r; }
-    }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    if (!ok) return kBad;
-    h = __shfl_sync(0xffffffffu, h, 0);
-    al_ll = __shfl_sync(0xffffffffu, al_ll, 0);
-    al_of = __shfl_sync(0xffffffffu, al_of, 0);
-    al_ml = __shfl_sync(0xffffffffu, al_ml, 0);
-    f.al_ll = al_ll; f.al_of = al_of; f.al_ml = al_ml;
-    f.seq_valid = true;
-    __syncwarp();
-    ZSeqBits b;
-    if (h > n || !zsb_init(b, zw->chunk, p + h, n - h, lane)) return kBad;
-    uint32_t sl = zsb_read(b, (uint32_t)al_ll, lane), so = zsb_read(b, (uint32_t)al_of, lane), sm = zsb_read(b, (uint32_t)al_ml, lane);
+    if (sec >= bs || lit_n > kZBlockMax) return h;
+    uint32_t nseq, used;
+    if (!z_seq_count(bp + sec, bs - sec, &nseq, &used) || nseq != nseq_expected || nseq == 0) return h;
+    if (sec + used + 1 > bs) return h;
+    const int modes = bp[sec + used];
+    if (modes & 3) return h;  // reserved bits (checked by libzstd 1.5.x)
+    h.sec = bp + sec + used;
+    h.n = bs - sec - used;
+    h.nseq = nseq;
+    h.lit_n = lit_n;
+    h.modes = modes;
+    return h;
+}
+
+// The sequences of one block -> records, one lane.  The bitstream is p[0 .. n).  With `track` the lane knows the repeat offsets the block
+// starts with (rep[]) and resolves the repeat codes as it goes; without, an offset value of 1 .. 3 is left in the record as 0x80000000 | value
+// (*raw says whether there was any) for z_resolve_repeats.  Returns the bytes the block regenerates, 0xFFFFFFFF if it is damaged.
+// *back: a match may reach back beyond the start of the block.
+__device__ uint32_t z_lane_sequences(const ZSeqWarp* zw, int al_ll, int al_of, int al_ml, const uint8_t* p, uint32_t n, uint32_t nseq, uint32_t lit_n,
+                                     ZstdSeq* out, bool track, uint32_t* rep, bool* raw, bool* back)
+{
+    const uint32_t kBad = 0xFFFFFFFFu;
+    ZLaneBits b;
+    if (!zlb_init(b, p, n)) return kBad;
+    uint32_t sl = zlb_read(b, (uint32_t)al_ll), so = zlb_read(b, (uint32_t)al_of), sm = zlb_read(b, (uint32_t)al_ml);
     if (b.left < 0) return kBad;
-    uint32_t rep0 = f.rep0, rep1 = f.rep1, rep2 = f.rep2;
-    uint64_t at = pos;   // content position (frame-relative) before the sequence's literals
+    uint32_t rep0 = rep[0], rep1 = rep[1], rep2 = rep[2];
     uint32_t lits = 0, regen = 0;
+    bool any_raw = false, reach = false;
     for (uint32_t i = 0; i < nseq; ++i) {
         const uint32_t cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
         const uint32_t llc = cl & 0xFF, ofc = co & 0xFF, mlc = cm & 0xFF;
         if (llc > 35 || mlc > 52 || ofc > 31) return kBad;
-        const uint32_t ofv = (1u << ofc) + zsb_read(b, ofc, lane);
-        const uint32_t mlen = kZ_ML_BASE[mlc] + zsb_read(b, kZ_ML_BITS[mlc], lane);
-        const uint32_t llen = kZ_LL_BASE[llc] + zsb_read(b, kZ_LL_BITS[llc], lane);
+        const uint32_t ofv = (1u << ofc) + zlb_read(b, ofc);
+        const uint32_t mlen = kZ_ML_BASE[mlc] + zlb_read(b, kZ_ML_BITS[mlc]);
+        const uint32_t llen = kZ_LL_BASE[llc] + zlb_read(b, kZ_LL_BITS[llc]);
         uint32_t offset;
         if (ofv > 3) {
             offset = ofv - 3;
             rep2 = rep1; rep1 = rep0; rep0 = offset;
+        } else if (!track) {
+            offset = 0x80000000u | ofv;
+            any_raw = true;
         } else {
             const uint32_t kk = ofv + (llen == 0 ? 1u : 0u);
             if (kk == 1) offset = rep0;
@@ -1310,24 +1291,49 @@ __device__ uint32_t z_block_sequences(ZSeqWarp* zw, ZFrame& f, const uint8_t* bp
             }
         }
         if (i + 1 < nseq) {
-            sl = (cl >> 16) + zsb_read(b, (cl >> 8) & 0xFF, lane);
-            sm = (cm >> 16) + zsb_read(b, (cm >> 8) & 0xFF, lane);
-            so = (co >> 16) + zsb_read(b, (co >> 8) & 0xFF, lane);
+            sl = (cl >> 16) + zlb_read(b, (cl >> 8) & 0xFF);
+            sm = (cm >> 16) + zlb_read(b, (cm >> 8) & 0xFF);
+            so = (co >> 16) + zlb_read(b, (co >> 8) & 0xFF);
         }
         lits += llen;
-        at += llen;
-        if (b.left < 0 || lits > lit_n || (uint64_t)offset > at || regen + llen + mlen > 2u * kZBlockMax) return kBad;
-        at += mlen;
+        if (b.left < 0 || lits > lit_n || regen + llen + mlen > 2u * kZBlockMax) return kBad;
+        if (offset > regen + llen) reach = true;  // (an unresolved code counts: its value has the top bit set)
         regen += llen + mlen;
-        if (lane == 0) out[i] = ZstdSeq{offset, llen, mlen, 0};
+        out[i] = ZstdSeq{offset, llen, mlen, 0};
     }
     if (b.left != 0) return kBad;
     regen += lit_n - lits;  // the literals after the last sequence
     if (regen > kZBlockMax) return kBad;
-    f.rep0 = rep0; f.rep1 = rep1; f.rep2 = rep2;
+    rep[0] = rep0; rep[1] = rep1; rep[2] = rep2;
+    *raw = any_raw;
+    *back = reach;
     return regen;
 }
+// the repeat codes a lane left in the records of a block, resolved in order from the offsets the block starts with (one lane)
+__device__ void z_resolve_repeats(ZstdSeq* sq, uint32_t nseq, uint32_t* rep)
+{
+    uint32_t rep0 = rep[0], rep1 = rep[1], rep2 = rep[2];
+    for (uint32_t i = 0; i < nseq; ++i) {
+        uint32_t offset = sq[i].offset;
+        if (!(offset & 0x80000000u)) { rep2 = rep1; rep1 = rep0; rep0 = offset; continue; }
+        const uint32_t kk = (offset & 3u) + (sq[i].ll == 0 ? 1u : 0u);
+        if (kk == 1) offset = rep0;
+        else {
+            offset = (kk == 4) ? rep0 - 1 : (kk == 2 ? rep1 : rep2);
+            if (offset == 0) offset = 1;
+            if (kk != 2) rep2 = rep1;
+            rep1 = rep0;
+            rep0 = offset;
+        }
+        sq[i].offset = offset;
+    }
+    rep[0] = rep0; rep[1] = rep1; rep[2] = rep2;
+}
 
+// zstd_seq_kernel: a WARP per frame with Seq units.  Its Seq units are taken in SETS: a unit whose block brings tables (or names the
+// predefined / RLE ones) and the units after it that repeat all three (Repeat_Mode x 3: what the writer of csrc/zstd_match_kernels.cuh
+// gives every block of a group but the first).  Lanes 0 - 2 build the set's tables, then every unit of the set is decoded by a lane of
+// its own - sequences are serial work per block, not per frame.  libzstd's frames have sets of one.
 constexpr int kZSeqWarps = 4;
 __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams p)
 {
@@ -1335,6 +1341,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     ZSeqWarp* zw = reinterpret_cast<ZSeqWarp*>(smem) + wid;
     const uint32_t n_frames = p.counter[6];
+    const uint32_t kBad = 0xFFFFFFFFu;
     for (;;) {
         uint32_t k = 0;
         if (lane == 0) k = atomicAdd(p.counter + 7, 1u);
@@ -1345,32 +1352,137 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
         uint64_t fcs = 0;
         bool has = false, ck = false;
         z_frame_header(p.src + rd.src_off, rd.src_bytes, &fcs, &has, &ck);  // (the walker accepted it)
-        ZFrame f;
-        f.huf_bits = 0;
-        f.al_ll = f.al_of = f.al_ml = 0;
-        f.seq_valid = false;
-        f.rep0 = 1; f.rep1 = 4; f.rep2 = 8;
-        uint64_t op = 0;
+        int al[3] = {0, 0, 0};  // literal lengths, offsets, match lengths
+        bool tables_valid = false;
+        uint32_t rep[3] = {1, 4, 8};  // the repeat offsets before the next Seq unit (all lanes hold them)
         bool ok = true;
-        for (uint32_t ui = 0; ui < sf.unit_count && ok; ++ui) {
-            ZstdUnit* up = p.units + sf.unit_first + ui;
-            const ZstdUnit u = *up;
-            uint32_t regen = u.regen;
-            if (u.kind == kZUnitSeq) {
-                regen = z_block_sequences(zw, f, p.src + u.src_off, u.n, u.nseq, p.seqs + u.seq_first, op, lane);
-                __syncwarp();
-                if (regen == 0xFFFFFFFFu) { ok = false; break; }
+        uint32_t ui = 0;
+        while (ui < sf.unit_count && ok) {
+            // ---- the next 32 units: which are Seq, what their blocks say ---------------------------------------------------------------
+            const uint32_t mine = ui + lane;
+            ZstdUnit u = {};
+            u.kind = kZUnitNop;
+            if (mine < sf.unit_count) u = p.units[sf.unit_first + mine];
+            const bool is_seq = u.kind == kZUnitSeq;
+            const uint32_t seqmask = __ballot_sync(0xffffffffu, is_seq);
+            if (!seqmask) { ui += 32; continue; }
+            const uint32_t head_lane = (uint32_t)__ffs((int)seqmask) - 1;
+            ZSeqHead h = {nullptr, 0, 0, 0, -1};
+            if (is_seq) h = z_seq_head(p.src + u.src_off, u.n, u.nseq);
+            if (__ballot_sync(0xffffffffu, is_seq && h.modes < 0)) { ok = false; break; }
+            // the set: the head and the Seq units behind it (among these 32) that repeat all three tables
+            const uint32_t stop = __ballot_sync(0xffffffffu, is_seq && lane > head_lane && h.modes != 0xFC);
+            const uint32_t upto = stop ? (uint32_t)__ffs((int)stop) - 1 : 32u;
+            const uint32_t members = seqmask & (upto < 32 ? (1u << upto) - 1u : 0xFFFFFFFFu);
+            const bool member = (members >> lane) & 1u;
+            // ---- the head's tables: lanes 0, 1, 2 build one each ---------------------------------------------------------------------------
+            const int hmodes = __shfl_sync(0xffffffffu, h.modes, head_lane);
+            const uint64_t hsec = __shfl_sync(0xffffffffu, (uint64_t)(uintptr_t)h.sec, head_lane);
+            const uint32_t hn = __shfl_sync(0xffffffffu, h.n, head_lane);
+            const uint8_t* tp = reinterpret_cast<const uint8_t*>((uintptr_t)hsec) + 1;  // behind the modes byte
+            uint32_t tn = hn - 1;
+            uint32_t used_all = 0;
+            {
+                // the descriptions follow each other: a lane must know the sizes of those before its own.  Sizes first (lane 0 reads the
+                // counts of all three - cheap next to the table builds), then the builds side by side.
+                uint32_t off3[3] = {0, 0, 0}, bad = 0;
+                if (lane == 0) {
+                    uint32_t at = 0;
+                    for (int t = 0; t < 3 && !bad; ++t) {
+                        const int mode = (hmodes >> (6 - 2 * t)) & 3;
+                        off3[t] = at;
+                        if (mode == 1) { if (at + 1 > tn) bad = 1; else at += 1; }
+                        else if (mode == 2) {
+                            int nsym, a;
+                            const uint32_t used = at <= tn ? z_fse_read_ncount(tp + at, tn - at, t == 1 ? 8 : 9, t == 0 ? 35 : (t == 1 ? 31 : 52), zw->norm[0], &nsym, &a) : 0u;
+                            if (!used) bad = 1; else at += used;
+                        } else if (mode == 3 && !tables_valid) bad = 1;
+                    }
+                    used_all = at;
+                }
+                bad = __shfl_sync(0xffffffffu, bad, 0);
+                if (bad) { ok = false; break; }
+                used_all = __shfl_sync(0xffffffffu, used_all, 0);
+                const uint32_t o0 = __shfl_sync(0xffffffffu, off3[0], 0), o1 = __shfl_sync(0xffffffffu, off3[1], 0), o2 = __shfl_sync(0xffffffffu, off3[2], 0);
+                uint32_t tbad = 0;
+                int my_al = 0;
+                if (lane < 3) {
+                    const int mode = (hmodes >> (6 - 2 * (int)lane)) & 3;
+                    const uint32_t at = lane == 0 ? o0 : (lane == 1 ? o1 : o2);
+                    uint32_t* cell = lane == 0 ? zw->ll : (lane == 1 ? zw->of : zw->ml);
+                    my_al = al[lane];
+                    const uint32_t r = z_seq_table2(zw->norm[lane], zw->next[lane], cell, &my_al, mode, tp + at, tn - at, lane == 1 ? 8 : 9,
+                                                    lane == 0 ? 35 : (lane == 1 ? 31 : 52), lane == 0 ? kZ_LL_DEF : (lane == 1 ? kZ_OF_DEF : kZ_ML_DEF),
+                                                    lane == 0 ? 36 : (lane == 1 ? 29 : 53), lane == 1 ? 5 : 6, tables_valid);
+                    if (r == kBad) tbad = 1;
+                }
+                if (__ballot_sync(0xffffffffu, tbad != 0)) { ok = false; break; }
+                al[0] = __shfl_sync(0xffffffffu, my_al, 0);
+                al[1] = __shfl_sync(0xffffffffu, my_al, 1);
+                al[2] = __shfl_sync(0xffffffffu, my_al, 2);
+                tables_valid = true;
             }
-            if (op + regen > rd.dst_cap) { ok = false; break; }
-            if (lane == 0) { up->dst_off = rd.dst_off + op; up->regen = regen; }
-            op += regen;
+            __syncwarp();
+            // ---- every member decodes its block.  The head knows the repeat offsets it starts with; the others leave repeat codes raw ------
+            uint32_t regen = 0, my_rep[3] = {rep[0], rep[1], rep[2]};
+            bool raw = false, back = false;
+            if (member) {
+                const bool is_head = lane == head_lane;
+                const uint8_t* bits = is_head ? h.sec + 1 + used_all : h.sec + 1;
+                const uint32_t nbits = is_head ? (h.n >= 1 + used_all ? h.n - 1 - used_all : 0u) : h.n - 1;
+                regen = (u.seq_first >= p.seq_cap || u.nseq > p.seq_cap - u.seq_first)
+                            ? kBad
+                            : z_lane_sequences(zw, al[0], al[1], al[2], bits, nbits, h.nseq, h.lit_n, p.seqs + u.seq_first, is_head, my_rep, &raw, &back);
+            }
+            if (__ballot_sync(0xffffffffu, member && regen == kBad)) { ok = false; break; }
+            // ---- the repeat offsets behind the set: member after member (what a block without repeat codes leaves behind is its last three
+            // offsets; one with codes is walked by a lane) ----------------------------------------------------------------------------------------
+            {
+                uint32_t mm = members;
+                while (mm) {
+                    const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
+                    mm &= mm - 1;
+                    if (m == head_lane) {
+                        rep[0] = __shfl_sync(0xffffffffu, my_rep[0], m); rep[1] = __shfl_sync(0xffffffffu, my_rep[1], m); rep[2] = __shfl_sync(0xffffffffu, my_rep[2], m);
+                        continue;
+                    }
+                    const bool m_raw = __shfl_sync(0xffffffffu, raw ? 1u : 0u, m) != 0;
+                    const uint32_t m_nseq = __shfl_sync(0xffffffffu, h.nseq, m), m_first = __shfl_sync(0xffffffffu, u.seq_first, m);
+                    if (m_raw) {
+                        if (lane == 0) z_resolve_repeats(p.seqs + m_first, m_nseq, rep);
+                        rep[0] = __shfl_sync(0xffffffffu, rep[0], 0); rep[1] = __shfl_sync(0xffffffffu, rep[1], 0); rep[2] = __shfl_sync(0xffffffffu, rep[2], 0);
+                    } else {  // the lane started from the wrong offsets but pushed only explicit ones: its last min(nseq, 3) are right
+                        const uint32_t r0 = __shfl_sync(0xffffffffu, my_rep[0], m), r1 = __shfl_sync(0xffffffffu, my_rep[1], m), r2 = __shfl_sync(0xffffffffu, my_rep[2], m);
+                        if (m_nseq >= 3) { rep[0] = r0; rep[1] = r1; rep[2] = r2; }
+                        else if (m_nseq == 2) { rep[2] = rep[0]; rep[0] = r0; rep[1] = r1; }
+                        else { rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = r0; }
+                    }
+                }
+            }
+            if (member) {
+                ZstdUnit* up = p.units + sf.unit_first + mine;
+                up->regen = regen;
+                up->pad = back || raw ? 1u : 0u;  // a match may reach back beyond the block: the executor waits for the units before it
+            }
+            __syncwarp();
+            ui += upto;  // (upto >= head_lane + 1: the units before the head are not Seq)
+        }
+        // ---- positions: every unit of the frame, 32 at a time ----------------------------------------------------------------------------
+        uint64_t op = 0;
+        for (uint32_t u0 = 0; u0 < sf.unit_count && ok; u0 += 32) {
+            const uint32_t mine = u0 + lane;
+            const uint32_t regen = mine < sf.unit_count ? p.units[sf.unit_first + mine].regen : 0u;
+            const uint32_t incl = warp_incl_scan(regen, lane);
+            if (mine < sf.unit_count) p.units[sf.unit_first + mine].dst_off = rd.dst_off + op + incl - regen;
+            op += __shfl_sync(0xffffffffu, incl, 31);
+            if (op > rd.dst_cap) ok = false;
         }
         if (ok && has && op != fcs) ok = false;
         if (ok) {
             if (lane == 0) p.results[sf.read] = (uint32_t)op;
         } else {
             // not for this path after all: its units do nothing, the general kernel decides the frame's result
-            for (uint32_t ui = lane; ui < sf.unit_count; ui += 32) p.units[sf.unit_first + ui].kind = kZUnitNop;
+            for (uint32_t ui2 = lane; ui2 < sf.unit_count; ui2 += 32) p.units[sf.unit_first + ui2].kind = kZUnitNop;
             if (lane == 0) {
                 p.seq_frames[k].unit_count = 0;
                 p.general[atomicAdd(p.counter + 2, 1u)] = sf.read;
@@ -1410,6 +1522,7 @@ __global__ void __launch_bounds__(kZExecWarps * 32) zstd_seqexec_kernel(ZstdDecP
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_frames) break;
         const ZstdSeqFrame sf = p.seq_frames[k];
+        const uint64_t frame_off = p.reads[sf.read].dst_off;
         const uint8_t* tab_loaded = nullptr;
         int bits = 0;
         bool ok = true;
@@ -1469,6 +1582,8 @@ __global__ void __launch_bounds__(kZExecWarps * 32) zstd_seqexec_kernel(ZstdDecP
                 const uint64_t my_out = op + incl - span;        // where this sequence's literals go
                 const uint32_t my_lit = lp + lincl - rec.ll;
                 const uint64_t mdst = my_out + rec.ll, msrc = mdst - rec.offset;
+                // an offset beyond the frame's first byte: damaged (checked here: the sequence kernel decodes blocks side by side and does not know positions)
+                if (__ballot_sync(0xffffffffu, rec.ml != 0 && (uint64_t)rec.offset > mdst - frame_off)) { ok = false; break; }
                 // literal runs
                 if (rec.ll <= 16) {
                     for (uint32_t k = 0; k < rec.ll; ++k) out[my_out + k] = lit[my_lit + k];
