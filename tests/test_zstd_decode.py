@@ -153,6 +153,24 @@ def test_frames_with_sequences_take_the_block_parallel_path(backend):
         assert st["general"] == 0, (level, st)
 
 
+def test_own_frames_take_the_block_parallel_path_one_at_a_time(backend):
+    """A read decoded on its own (the H5Z filter's case: one chunk per call) has no neighbours whose unit slots it could borrow: the slots
+    reserved per frame (csrc/svb_types.h: zstd_units_of) must cover what this library's writer cuts - 2 KiB literal blocks in the S groups
+    of the control-byte region included.  A frame that ends up in the general kernel costs 20 ms instead of 0.2."""
+    capi, batch, _ = backend
+    rng = np.random.default_rng(8)
+    small = capi.path.endswith("cpusim.so")
+    o = Options(True, 2, 1, 1)
+    for n in (140000, 200000) if small else (140000, 300000, 700000, 1000000):
+        arr = data_gen.nanopore_like(n, rng)
+        (code, blob), = batch.compress([arr], o, sized=True)
+        assert code == len(blob)
+        (rc, back), = batch.decompress([blob], [arr.nbytes], o, sized=True)
+        assert rc == arr.nbytes and back == arr.tobytes()
+        st = _decode_stats(backend)
+        assert st["general"] == 0 and st["seq_frames"] == 1, (n, st)
+
+
 def test_pool_overflow_and_damage_fall_back_to_the_general_kernel(backend):
     """A frame the sequence kernel cannot vouch for is decided by the general kernel; its neighbours in the batch are not affected."""
     _, batch, _ = backend

@@ -64,7 +64,7 @@ struct vbz_b200_ctx {
     vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
     vbz::PinBuf h_results;
     // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
-    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral, d_zseqs, d_zseqframes;
+    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral, d_zseqs, d_zseqframes, d_zseqlist;
     vbz::DevBuf d_zelits, d_zeseqs, d_zemeta, d_zehist;  // the encoder's match finder (csrc/zstd_match_kernels.cuh)
     // intermediate stage-1 bytes of the two-stage paths
     vbz::DevBuf d_mid;

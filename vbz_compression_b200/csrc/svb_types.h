@@ -101,18 +101,23 @@ struct ZstdDecParams {
     uint8_t* lit_scratch;  // 128 KiB + 32 per warp of the general kernel's / the sequence executor's grid
     uint32_t* counter;   // 16 words, zeroed before launch: [0] work counter of the general kernel, [1] units listed,
                          // [2] frames left to the general kernel, [3] work counter of the units kernel, [4] groups listed,
-                         // [5] sequence records allotted, [6] frames with Seq units, [7] / [8] work counters of the two sequence kernels
+                         // [5] sequence records allotted, [6] frames with Seq units, [7] / [8] work counters of the two sequence kernels,
+                         // [9] entries of seq_list
     ZstdUnit* units;     // unit_cap entries
     ZstdGroup* groups;   // unit_cap entries
     uint32_t* general;   // n_reads entries: the frames the walker left to the general kernel
     ZstdSeq* seqs;       // seq_cap records
     ZstdSeqFrame* seq_frames;  // n_reads entries
+    uint32_t* seq_list;  // unit_cap entries: the Seq units of the frames the sequence kernel vouches for, in block order (the executor's work list)
     uint32_t unit_cap;
     uint32_t n_reads;
     uint32_t seq_cap;
     uint32_t pad;
 };
-VBZ_HD uint32_t zstd_units_of(uint32_t dst_cap) { return dst_cap / 8192u + 6u; }  // unit slots the host reserves per frame
+// unit slots the host reserves per frame.  This library's writer: a block per 8 KiB of content, per 2 KiB of literals in the S groups of the
+// control-byte region (a fifth of a stage-1 stream) - content / 5 KiB at most; libzstd: a block per 128 KiB.  A frame of a batch that runs
+// the pool dry (other writers may cut blocks of any size) is decoded by the general kernel.
+VBZ_HD uint32_t zstd_units_of(uint32_t dst_cap) { return dst_cap / 4096u + 8u; }
 
 struct ZstdEncRead {
     uint64_t src_off;     // the content: bytes [src_off, src_off + size) of ZstdEncParams::src

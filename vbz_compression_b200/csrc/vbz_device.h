@@ -27,6 +27,8 @@ static inline uint64_t vbz_ld_volatile_u64(const uint64_t* p) { return *(const v
 static inline void vbz_st_volatile_u64(uint64_t* p, uint64_t v) { *(volatile uint64_t*)p = v; }
 static inline uint32_t vbz_ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 static inline void vbz_prefetch_l2(const void*) {}
+static inline uint32_t vbz_ld_acquire_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+static inline void vbz_st_release_u32(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 static inline void vbz_slot_post(uint64_t* slot, uint64_t v) { *(volatile uint64_t*)slot = v; }
 static inline uint64_t vbz_slot_read(const uint64_t* slot) { return *(const volatile uint64_t*)slot; }
 
@@ -101,6 +103,14 @@ __device__ __forceinline__ uint32_t vbz_ld_volatile_u32(const uint32_t* p)
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// hand-off of data through global memory between CTAs: everything written before the release store is visible to whoever sees its value
+__device__ __forceinline__ uint32_t vbz_ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void vbz_st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 // pull the line that holds p towards the SM ahead of its use (no register, no wait)
 __device__ __forceinline__ void vbz_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // hand-off of one 64-bit word (value + ready bit) between warps of a CTA through shared memory: release store, acquire load

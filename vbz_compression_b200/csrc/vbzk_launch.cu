@@ -195,15 +195,17 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     uint32_t ugrid = p.unit_cap < ugrid_max ? p.unit_cap : ugrid_max;
     if (ugrid) VBZ_LAUNCH(zstd_units_kernel, ugrid, kZUnitThreads, usmem, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
-    // 4. frames with sequences: literals and records of their Seq units, a warp per frame (everything a match can reach back to is in place)
+    // 4. frames with sequences: the records of their Seq units, a warp per unit (the literals are in place, and so is everything the units kernel wrote)
     const uint32_t smem = (uint32_t)(sizeof(ZWarp) * kZdecWarps);
     if (int e = VBZK_SET_SMEM(zstd_decode_kernel, smem)) return e;
     uint32_t grid = vbzk_zstd_decode_grid();
     const uint32_t need = (p.n_reads + kZdecWarps - 1) / kZdecWarps;
     if (need < grid) grid = need;
-    const uint32_t xsmem = (uint32_t)(sizeof(ZExecWarp) * kZExecWarps);
-    if (int e = VBZK_SET_SMEM(zstd_seqexec_kernel, xsmem)) return e;
-    VBZ_LAUNCH(zstd_seqexec_kernel, grid, kZExecWarps * 32, xsmem, (vbz_stream_t)stream, p);  // (same grid bound as the general kernel: they share the literal scratch)
+    {
+        static const uint32_t xgrid_max = persistent_grid(zstd_seqexec_kernel, kZExecWarps * 32, 0, 0xFFFFFFFFu, 0);
+        const uint64_t xneed = ((uint64_t)p.unit_cap + kZExecWarps - 1) / kZExecWarps;
+        VBZ_LAUNCH(zstd_seqexec_kernel, (uint32_t)(xneed < xgrid_max ? xneed : xgrid_max), kZExecWarps * 32, 0, (vbz_stream_t)stream, p);
+    }
     if (int e = VBZK_LAST_ERROR()) return e;
     // 5. whatever the walker and the sequence kernel left over, a warp per frame
     VBZ_LAUNCH(zstd_decode_kernel, grid, kZdecWarps * 32, smem, (vbz_stream_t)stream, p);

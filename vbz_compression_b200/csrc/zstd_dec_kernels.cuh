@@ -852,6 +852,7 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
         u.pad = 0;
         u.src_off = (uint64_t)(p - src);
         uint32_t adv;
+        int seq_lt = 0;  // Seq units: type of the literals section
         if (type == 0) {
             if (bs > n || (!deferred && op + bs > cap)) return kNo;
             u.kind = kZUnitCopy; u.n = bs; u.regen = bs; adv = bs;
@@ -877,6 +878,7 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
                 uint32_t nseq, sh;
                 if (!z_seq_count(p + sec, bs - sec, &nseq, &sh)) return kNo;
                 u.kind = kZUnitSeq; u.n = bs; u.tab_back = lt == 3 ? (uint32_t)(p - tab) : 0u;
+                seq_lt = lt;
                 u.nseq = nseq; u.seq_first = seq_base + seqs;
                 seqs += nseq;
                 deferred = true;
@@ -884,12 +886,11 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
             adv = bs;
         } else return kNo;
         op += u.regen;
-        if (u.kind == kZUnitSeq) {
-            if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; g_count = 0; }
-            if (emit) emit[units] = u;
-            ++units;
-        } else if (u.n != 0) {
-            const bool extend = u.kind == kZUnitHuf && u.tab_back != 0 && g_count != 0 && g_count < 16;  // (an open group is always a Huffman one)
+        if (u.kind == kZUnitSeq || u.n != 0) {
+            // a Seq unit's literals are decoded by the units kernel like any other literals section (to the END of the block's place in the
+            // output, csrc: zstd_seqexec_kernel): with Huffman literals it joins the groups, with Raw / RLE ones it stands alone
+            const bool huf = u.kind == kZUnitHuf || (u.kind == kZUnitSeq && seq_lt >= 2);
+            const bool extend = huf && u.tab_back != 0 && g_count != 0 && g_count < 16;  // (an open group is always a Huffman one)
             if (!extend) {
                 if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; }
                 g_first = units;
@@ -898,7 +899,7 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
             if (emit) emit[units] = u;
             ++units;
             ++g_count;
-            if (u.kind != kZUnitHuf) {  // Raw / RLE pieces stand alone
+            if (!huf) {  // Raw / RLE pieces stand alone
                 if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count};
                 ++groups;
                 g_count = 0;
@@ -1060,7 +1061,18 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
             }
             continue;
         }
-        if (u0.kind != kZUnitHuf) continue;
+        if (u0.kind == kZUnitSeq) {  // Raw / RLE literals of a block with sequences: to the end of the block's place (the Huffman ones: below)
+            int lt0 = 0, st0 = 0;
+            uint32_t hdr0 = 0, lit0 = 0, comp0 = 0;
+            if (z_lit_header(p.src + u0.src_off, u0.n, &lt0, &hdr0, &lit0, &comp0, &st0) && lt0 < 2 && lit0 <= u0.regen) {
+                uint8_t* d = p.dst + u0.dst_off + (u0.regen - lit0);
+                const uint8_t* sp = p.src + u0.src_off + hdr0;
+                if (lt0 == 1) { const uint8_t v = sp[0]; for (uint32_t k = tid; k < lit0; k += kZUnitThreads) d[k] = v; }
+                else for (uint32_t k = tid; k < lit0; k += kZUnitThreads) d[k] = sp[k];
+                continue;
+            }
+        }
+        if (u0.kind != kZUnitHuf && u0.kind != kZUnitSeq) continue;
         // ---- the group's table: the tree sits in the literals section tab_back bytes before the first unit's ----------------------
         int bits = 0;
         {
@@ -1096,8 +1108,9 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
             const uint8_t* lp = p.src + un.src_off;
             int lt = 0, streams = 4;
             uint32_t hdr = 0, regen = 0, comp = 0;
-            bool ok = bits != 0 && un.kind == kZUnitHuf && z_lit_header(lp, un.n, &lt, &hdr, &regen, &comp, &streams) && lt >= 2 && regen <= kZBlockMax &&
-                      hdr + comp <= un.n && !(streams == 4 && regen < 6);
+            if (un.kind == kZUnitNop) continue;
+            bool ok = bits != 0 && (un.kind == kZUnitHuf || un.kind == kZUnitSeq) && z_lit_header(lp, un.n, &lt, &hdr, &regen, &comp, &streams) && lt >= 2 &&
+                      regen <= kZBlockMax && hdr + comp <= un.n && !(streams == 4 && regen < 6) && (un.kind == kZUnitHuf || regen <= un.regen);
             if (ok) {
                 const uint8_t* q = lp + hdr;
                 uint32_t left = comp;
@@ -1105,7 +1118,7 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
                     if (t > left) ok = false;
                     else { q += t; left -= t; }
                 }
-                uint8_t* dst = p.dst + un.dst_off;
+                uint8_t* dst = p.dst + un.dst_off + (un.kind == kZUnitSeq && ok ? un.regen - regen : 0u);  // Seq: the literals wait at the end of the block's place
                 if (!ok) {
                 } else if (streams == 1) {
                     if (j == 0) ok = z_huf_decode_stream(sm->huf, bits, q, left, dst, regen);
@@ -1141,19 +1154,13 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
 //                        earlier blocks: those are complete (the units kernel ran before; earlier Seq units of the frame were
 //                        executed by this same warp).
 // A frame the sequence kernel cannot vouch for (damaged, more records than the pool holds) goes to the general kernel.
+// entries of ZstdDecParams::seq_list: a unit index, whether the unit is the first Seq unit of its frame, and - set by the executor - done
+constexpr uint32_t kZListIndexMask = 0x3FFFFFFFu, kZListFirst = 0x40000000u, kZListDone = 0x80000000u;
 struct ZSeqWarp {  // zstd_seq_kernel: per-warp shared state
     uint32_t ll[512], ml[512], of[256];  // sym | nbBits << 8 | base << 16
     int16_t norm[3][64];                 // scratch of the three table builders (lanes 0 - 2)
     uint16_t next[3][64];
 };
-struct ZExecWarp {  // zstd_seqexec_kernel: per-warp shared state
-    uint16_t huf[2048];
-    uint32_t wtab[64];
-    uint8_t weights[256];
-    int16_t norm[256];
-    uint16_t next[256];
-};
-
 // One of the three sequence tables, by mode (one lane); norm / next: scratch for 64 symbols.  Returns bytes consumed, 0xFFFFFFFF on error.
 __device__ uint32_t z_seq_table2(int16_t* norm, uint16_t* next, uint32_t* cell, int* al, int mode, const uint8_t* p, uint32_t n, int max_al, int max_sym,
                                  const int16_t* def, int def_n, int def_al, bool have_prev)
@@ -1356,7 +1363,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
         bool tables_valid = false;
         uint32_t rep[3] = {1, 4, 8};  // the repeat offsets before the next Seq unit (all lanes hold them)
         bool ok = true;
-        uint32_t ui = 0;
+        uint32_t ui = 0, n_seq_units = 0;
         while (ui < sf.unit_count && ok) {
             // ---- the next 32 units: which are Seq, what their blocks say ---------------------------------------------------------------
             const uint32_t mine = ui + lane;
@@ -1465,6 +1472,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                 up->pad = back || raw ? 1u : 0u;  // a match may reach back beyond the block: the executor waits for the units before it
             }
             __syncwarp();
+            n_seq_units += (uint32_t)__popc((int)members);
             ui += upto;  // (upto >= head_lane + 1: the units before the head are not Seq)
         }
         // ---- positions: every unit of the frame, 32 at a time ----------------------------------------------------------------------------
@@ -1478,8 +1486,22 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
             if (op > rd.dst_cap) ok = false;
         }
         if (ok && has && op != fcs) ok = false;
+        if (ok && (uint64_t)sf.unit_first + sf.unit_count >= kZListIndexMask) ok = false;
         if (ok) {
             if (lane == 0) p.results[sf.read] = (uint32_t)op;
+            // the executor's work list: the frame's Seq units in block order, side by side (a unit only ever waits for entries before its own)
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(p.counter + 9, n_seq_units);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t done = 0;
+            for (uint32_t u0 = 0; u0 < sf.unit_count; u0 += 32) {
+                const uint32_t mine = u0 + lane;
+                const bool is_seq = mine < sf.unit_count && p.units[sf.unit_first + mine].kind == kZUnitSeq;
+                const uint32_t m = __ballot_sync(0xffffffffu, is_seq);
+                const uint32_t rank = done + (uint32_t)__popc((int)(m & ((1u << lane) - 1u)));
+                if (is_seq) p.seq_list[base + rank] = (sf.unit_first + mine) | (rank == 0 ? kZListFirst : 0u);
+                done += (uint32_t)__popc((int)m);
+            }
         } else {
             // not for this path after all: its units do nothing, the general kernel decides the frame's result
             for (uint32_t ui2 = lane; ui2 < sf.unit_count; ui2 += 32) p.units[sf.unit_first + ui2].kind = kZUnitNop;
@@ -1492,120 +1514,97 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
     }
 }
 
-// load the Huffman table described by the literals section at tp (one lane works, all get the result: max_bits, 0 = bad)
-__device__ int z_exec_load_table(ZExecWarp* zw, const uint8_t* tp, uint32_t lane)
-{
-    int bits = 0;
-    if (lane == 0) {
-        int lt = 0, st = 0;
-        uint32_t hdr = 0, regen = 0, comp = 0;
-        if (z_lit_header(tp, 5u, &lt, &hdr, &regen, &comp, &st) && lt == 2) {
-            int nw = 0;
-            const uint32_t t = z_huf_read_weights(zw->weights, zw->wtab, zw->norm, zw->next, tp + hdr, comp, &nw);
-            if (t) bits = z_huf_build(zw->huf, zw->weights, nw);
-        }
-    }
-    return __shfl_sync(0xffffffffu, bits, 0);
-}
-
+// zstd_seqexec_kernel: a WARP per Seq unit, taken from the list in order.  The unit's literals already sit at the END of the block's place in
+// the output (the units kernel put them there); the records are executed from the front: a literal run moves down to where it belongs,
+// a match copies what lies `offset` back.  What a sequence writes ends at or below where the literals of the next one wait, so nothing
+// is overwritten before it is read - the block expands in place, and the literals behind the last sequence are where they belong already.
+// A unit with a match that may reach back beyond its block first waits until the frame's Seq units before it are done (the entries of the
+// list before its own; everything else was written by the units kernel).  Units are taken in list order: what a unit waits for is running or done.
 constexpr int kZExecWarps = 4;
+// wait until every Seq unit of the frame before list entry k is done: the entries from k - 1 down to the one that carries the First mark,
+// 32 per look (lane 0 holds the nearest)
+__device__ __forceinline__ void z_exec_wait(const uint32_t* list, uint32_t k, uint32_t lane)
+{
+    long long hi = (long long)k;
+    for (;;) {
+        const long long idx = hi - 1 - (long long)lane;
+        bool found;
+        for (;;) {
+            const uint32_t e = idx >= 0 ? vbz_ld_acquire_u32(list + idx) : (kZListDone | kZListFirst);
+            const uint32_t firsts = __ballot_sync(0xffffffffu, (e & kZListFirst) != 0);
+            const uint32_t upto = firsts ? (2u << ((uint32_t)__ffs((int)firsts) - 1)) - 1u : 0xFFFFFFFFu;  // the lanes that hold entries of this frame
+            const uint32_t open = __ballot_sync(0xffffffffu, !(e & kZListDone)) & upto;
+            found = firsts != 0;
+            if (!open) break;
+            VBZ_SPIN_YIELD();
+        }
+        if (found) break;
+        hi -= 32;
+    }
+    __syncwarp();
+}
 __global__ void __launch_bounds__(kZExecWarps * 32) zstd_seqexec_kernel(ZstdDecParams p)
 {
-    VBZ_DYN_SMEM(smem);
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    ZExecWarp* zw = reinterpret_cast<ZExecWarp*>(smem) + wid;
-    uint8_t* lit = p.lit_scratch + (uint64_t)(blockIdx.x * kZExecWarps + wid) * kZLitStride;
-    const uint32_t n_frames = p.counter[6];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_list = p.counter[9];
+    uint8_t* out = p.dst;
     for (;;) {
         uint32_t k = 0;
         if (lane == 0) k = atomicAdd(p.counter + 8, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= n_frames) break;
-        const ZstdSeqFrame sf = p.seq_frames[k];
-        const uint64_t frame_off = p.reads[sf.read].dst_off;
-        const uint8_t* tab_loaded = nullptr;
-        int bits = 0;
-        bool ok = true;
-        for (uint32_t ui = 0; ui < sf.unit_count && ok; ++ui) {
-            const ZstdUnit u = p.units[sf.unit_first + ui];
-            if (u.kind != kZUnitSeq) continue;
-            const uint8_t* bp = p.src + u.src_off;
-            int lt = 0, streams = 4;
-            uint32_t hdr = 0, lit_n = 0, comp = 0;
-            if (!z_lit_header(bp, u.n, &lt, &hdr, &lit_n, &comp, &streams)) { ok = false; break; }
-            // ---- literals -> the warp's scratch ------------------------------------------------------------------------------------
-            if (lt == 0) z_warp_copy(lit, bp + hdr, lit_n, lane);
-            else if (lt == 1) z_warp_fill(lit, bp[hdr], lit_n, lane);
-            else {
-                const uint8_t* tp = bp - u.tab_back;  // (tab_back is 0 when the block carries its own tree)
-                if (tab_loaded != tp) { bits = z_exec_load_table(zw, tp, lane); tab_loaded = tp; }
-                __syncwarp();
-                if (!bits || (streams == 4 && lit_n < 6)) { ok = false; break; }
-                const uint8_t* q = bp + hdr;
-                uint32_t left = comp;
-                if (lt == 2) {  // skip the tree description: its size is the weights header byte's business
-                    const uint32_t hb = q[0];
-                    const uint32_t t = hb >= 128 ? 1 + (hb - 127 + 1) / 2 : 1 + hb;
-                    if (t > left) { ok = false; break; }
-                    q += t; left -= t;
-                }
-                bool sok = true;
-                if (streams == 1) {
-                    if (lane == 0) sok = z_huf_decode_stream(zw->huf, bits, q, left, lit, lit_n);
-                } else if (left < 10) sok = false;
-                else {
-                    const uint32_t s1 = z_le16(q), s2 = z_le16(q + 2), s3 = z_le16(q + 4);
-                    const uint32_t seg = (lit_n + 3) / 4;
-                    if (6 + s1 + s2 + s3 > left || 3 * seg > lit_n) sok = false;
-                    else if (lane < 4) {
-                        const uint32_t s4 = left - 6 - s1 - s2 - s3;
-                        const uint32_t so = lane == 0 ? 0u : lane == 1 ? s1 : lane == 2 ? s1 + s2 : s1 + s2 + s3;
-                        const uint32_t sn = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : s4;
-                        sok = z_huf_decode_stream(zw->huf, bits, q + 6 + so, sn, lit + lane * seg, lane == 3 ? lit_n - 3 * seg : seg);
-                    }
-                }
-                if (!__all_sync(0xffffffffu, sok)) { ok = false; break; }
-            }
-            __syncwarp();
-            // ---- the records, 32 at a time.  A lane owns one sequence: it copies its literal run (from the warp's scratch: no
-            // dependency on anything) and then its match, unless the match reads what an earlier sequence of the same 32 produces or
-            // is long - those are done by the whole warp afterwards, in order.  Everything before the 32 is complete.
-            uint8_t* out = p.dst;
+        if (k >= n_list) break;
+        const uint32_t entry = p.seq_list[k];
+        const bool first = (entry & kZListFirst) != 0;
+        const ZstdUnit u = p.units[entry & kZListIndexMask];
+        const uint64_t frame_off = p.reads[u.read].dst_off;
+        const uint8_t* bp = p.src + u.src_off;
+        int lt = 0, streams = 4;
+        uint32_t hdr = 0, lit_n = 0, comp = 0;
+        bool ok = z_lit_header(bp, u.n, &lt, &hdr, &lit_n, &comp, &streams) && lit_n <= u.regen;
+        if (ok && !first && (u.pad & 1u)) z_exec_wait(p.seq_list, k, lane);
+        if (ok) {
+            const uint8_t* lit = out + u.dst_off + (u.regen - lit_n);  // literal i of the block waits at lit[i]
             uint64_t op = u.dst_off;
             uint32_t lp = 0;
             const ZstdSeq* sq = p.seqs + u.seq_first;
-            for (uint32_t i0 = 0; i0 < u.nseq; i0 += 32) {
+            for (uint32_t i0 = 0; i0 < u.nseq && ok; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 const ZstdSeq rec = i < u.nseq ? sq[i] : ZstdSeq{1, 0, 0, 0};
                 const uint32_t span = rec.ll + rec.ml;
                 const uint32_t incl = warp_incl_scan(span, lane), lincl = warp_incl_scan(rec.ll, lane);
                 const uint64_t my_out = op + incl - span;        // where this sequence's literals go
-                const uint32_t my_lit = lp + lincl - rec.ll;
                 const uint64_t mdst = my_out + rec.ll, msrc = mdst - rec.offset;
-                // an offset beyond the frame's first byte: damaged (checked here: the sequence kernel decodes blocks side by side and does not know positions)
+                // an offset beyond the frame's first byte: damaged (checked here: the sequence kernel decodes blocks side by side and knows no positions)
                 if (__ballot_sync(0xffffffffu, rec.ml != 0 && (uint64_t)rec.offset > mdst - frame_off)) { ok = false; break; }
-                // literal runs
-                if (rec.ll <= 16) {
-                    for (uint32_t k = 0; k < rec.ll; ++k) out[my_out + k] = lit[my_lit + k];
-                }
-                uint32_t big = __ballot_sync(0xffffffffu, rec.ll > 16);
-                while (big) {
-                    const uint32_t fl = (uint32_t)__ffs((int)big) - 1;
-                    big &= big - 1;
-                    const uint32_t n = __shfl_sync(0xffffffffu, rec.ll, fl), fs = __shfl_sync(0xffffffffu, my_lit, fl);
-                    const uint64_t fd = __shfl_sync(0xffffffffu, my_out, fl);
-                    z_warp_copy(out + fd, lit + fs, n, lane);
+                // ---- literal runs, in literal order, 32 bytes per step: literal o of the round belongs to the first sequence whose inclusive
+                // count exceeds o.  Reads come before the writes of a step, and a step writes below what later steps read.
+                const uint32_t total = __shfl_sync(0xffffffffu, lincl, 31);
+                for (uint32_t o0 = 0; o0 < total; o0 += 32) {
+                    const uint32_t o = o0 + lane;
+                    uint32_t j = 0;
+#pragma unroll
+                    for (uint32_t step = 16; step != 0; step >>= 1) {
+                        const uint32_t v = __shfl_sync(0xffffffffu, lincl, j + step - 1);
+                        if (v <= o) j += step;
+                    }
+                    j &= 31u;
+                    const uint32_t ej = __shfl_sync(0xffffffffu, lincl - rec.ll, j);
+                    const uint32_t oj_lo = __shfl_sync(0xffffffffu, (uint32_t)my_out, j), oj_hi = __shfl_sync(0xffffffffu, (uint32_t)(my_out >> 32), j);
+                    uint8_t v = 0;
+                    if (o < total) v = lit[lp + o];
+                    __syncwarp();
+                    if (o < total) out[(((uint64_t)oj_hi << 32) | oj_lo) + (o - ej)] = v;
                 }
                 __syncwarp();
-                // matches: short and independent of this round's other sequences -> the lane itself
+                // ---- matches: short and independent of this round's other sequences -> the lane itself; the others by the whole warp, in order
                 const bool dep = msrc < my_out && msrc + rec.ml > op;
                 const bool self = rec.ml != 0 && rec.ml <= 48 && !dep;
                 if (self) {
                     if (rec.offset == 1) {
                         const uint8_t v = out[mdst - 1];
-                        for (uint32_t k = 0; k < rec.ml; ++k) out[mdst + k] = v;
+                        for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = v;
                     } else {
-                        for (uint32_t k = 0; k < rec.ml; ++k) out[mdst + k] = out[msrc + k];
+                        for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = out[msrc + q];
                     }
                 }
                 uint32_t rest = __ballot_sync(0xffffffffu, rec.ml != 0 && !self);
@@ -1614,17 +1613,21 @@ __global__ void __launch_bounds__(kZExecWarps * 32) zstd_seqexec_kernel(ZstdDecP
                     const uint32_t fl = (uint32_t)__ffs((int)rest) - 1;
                     rest &= rest - 1;
                     const uint32_t n = __shfl_sync(0xffffffffu, rec.ml, fl), fo = __shfl_sync(0xffffffffu, rec.offset, fl);
-                    const uint64_t fd = __shfl_sync(0xffffffffu, mdst, fl);
-                    z_warp_match(out, fd, fo, n, lane);
+                    const uint32_t fd_lo = __shfl_sync(0xffffffffu, (uint32_t)mdst, fl), fd_hi = __shfl_sync(0xffffffffu, (uint32_t)(mdst >> 32), fl);
+                    z_warp_match(out, ((uint64_t)fd_hi << 32) | fd_lo, fo, n, lane);
                     __syncwarp();
                 }
                 op += __shfl_sync(0xffffffffu, incl, 31);
-                lp += __shfl_sync(0xffffffffu, lincl, 31);
+                lp += total;
             }
-            z_warp_copy(out + op, lit + lp, lit_n - lp, lane);
-            __syncwarp();
+            if (ok && (lp > lit_n || op + (lit_n - lp) != u.dst_off + u.regen)) ok = false;  // (the sequence kernel's sums say otherwise: not reached)
         }
-        if (!ok && lane == 0) p.results[sf.read] = kErrZstd;
+        if (!ok && lane == 0) p.results[u.read] = kErrZstd;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            vbz_st_release_u32(p.seq_list + k, entry | kZListDone);
+        }
     }
 }
 
