@@ -541,10 +541,8 @@ struct DeviceGuard {
 // ======================================================================================================
 vbz_b200_ctx::~vbz_b200_ctx()
 {
-    d_reads.release(); d_tiles.release(); d_status.release(); d_wtoff.release(); d_issue.release(); d_results.release(); d_sizes.release();
+    release_all(); alt.release_all();
     h_results.release(); stage.release();
-    d_mid.release();
-    d_zelits.release(); d_zeseqs.release(); d_zemeta.release(); d_zehist.release(); d_zreads.release(); d_zseqs.release(); d_zseqframes.release(); d_zcounter.release(); d_zlit.release(); d_zunits.release(); d_zgroups.release(); d_zgeneral.release(); d_zblocks.release(); d_zstatus.release(); d_zcodes.release();
     for (WaveSlot& w : slots) {
         w.d_in.release(); w.d_out.release(); w.d_results.release(); w.d_pack.release(); w.d_xin.release(); w.d_xout.release();
         w.h_in.release(); w.h_out.release(); w.h_results.release();
@@ -558,6 +556,7 @@ vbz_b200_ctx::~vbz_b200_ctx()
     if (s_d2h) cudaStreamDestroy(s_d2h);
     if (s_d2hs) cudaStreamDestroy(s_d2hs);
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
 }
 
 extern "C" int vbz_b200_device_count(void)
@@ -579,6 +578,7 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
     vbz_b200_ctx* c = new vbz_b200_ctx();
     c->device = device;
     bool ok = cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              cuda_ok(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_d2hs, cudaStreamNonBlocking), "cudaStreamCreate") &&
@@ -600,6 +600,7 @@ extern "C" void vbz_b200_destroy(vbz_b200_ctx* ctx)
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     delete ctx;
 }
 
@@ -956,6 +957,14 @@ static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
         if ((max_in_staged && !sl.h_in.ensure(max_in_staged + 16)) || (max_out_staged && !sl.h_out.ensure(max_out_staged + 16))) return -1;
     }
     cudaStream_t sk = ctx->stream, sh = ctx->s_h2d, sd = ctx->s_d2h, sds = ctx->s_d2hs;
+    // the kernels of odd waves run on the second stream with the second set of scratch buffers (VBZ_B200_STREAMS=1: all on one)
+    const bool two_streams = W > 2 && env_u32("VBZ_B200_STREAMS", 2) >= 2;
+    struct ScratchParity {
+        vbz_b200_ctx* c; int cur = 0;
+        explicit ScratchParity(vbz_b200_ctx* ctx) : c(ctx) {}
+        void set(int par) { if (par != cur) { c->swap_scratch(); cur = par; } }
+        ~ScratchParity() { set(0); }
+    } parity(ctx);
     struct CtaCap {  // the codec shares the SMs with the transfer kernels for the duration of the batch
         vbz_b200_ctx* c;
         CtaCap(vbz_b200_ctx* ctx, uint32_t v) : c(ctx) { c->codec_ctas_per_sm = v; }
@@ -975,6 +984,7 @@ static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
             vbz_b200_ctx::WaveSlot& sl = ctx->slots[it % S];
             uint8_t* d_in = sl.d_in.as<uint8_t>();
             uint8_t* d_out = sl.d_out.as<uint8_t>();
+            if (two_streams) { parity.set((int)(it & 1u)); sk = (it & 1u) ? ctx->stream2 : ctx->stream; }
             tr.mark(sh);
             if (w.in_staged) {
                 copies.clear();
@@ -1096,7 +1106,7 @@ static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
     tr.report(m, W, dma_in, dma_out, xfers);
     if (rc == 0) tr.timeline();
     if (rc != 0) {  // leave nothing in flight that still points at the caller's buffers
-        cudaStreamSynchronize(sh); cudaStreamSynchronize(sk); cudaStreamSynchronize(sd); cudaStreamSynchronize(sds);
+        cudaStreamSynchronize(sh); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2); cudaStreamSynchronize(sd); cudaStreamSynchronize(sds);
     }
     return rc;
 }

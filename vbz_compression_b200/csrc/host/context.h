@@ -1,6 +1,8 @@
 // csrc/host/context.h - per-device state of the host layer: a stream, grow-only scratch in HBM,
 // pinned staging.  One context is used by one thread at a time.
 #pragma once
+#include <utility>
+#include <initializer_list>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -46,9 +48,26 @@ struct StageRing {
     void release();
 };
 
+// Everything the kernels of one wave (or one *_device call) scribble on, besides the caller's buffers.
+struct ScratchSet {
+    // descriptors and look-back state (stage 1)
+    DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
+    // stage 2 (zstd): descriptors, work counters, units / groups / sequence records of the decoder, literal scratch of the general kernel
+    DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral, d_zseqs, d_zseqframes, d_zseqlist;
+    DevBuf d_zelits, d_zeseqs, d_zemeta, d_zehist;  // the encoder's match finder (csrc/zstd_match_kernels.cuh)
+    // intermediate stage-1 bytes of the two-stage paths
+    DevBuf d_mid;
+    void release_all()
+    {
+        for (DevBuf* b : {&d_reads, &d_tiles, &d_status, &d_wtoff, &d_issue, &d_results, &d_sizes, &d_zreads, &d_zcounter, &d_zlit, &d_zblocks, &d_zstatus, &d_zcodes,
+                          &d_zunits, &d_zgroups, &d_zgeneral, &d_zseqs, &d_zseqframes, &d_zseqlist, &d_zelits, &d_zeseqs, &d_zemeta, &d_zehist, &d_mid})
+            b->release();
+    }
+};
+
 }  // namespace vbz
 
-struct vbz_b200_ctx {
+struct vbz_b200_ctx : vbz::ScratchSet {
     int device = 0;
     cudaStream_t stream = nullptr;
     vbz::StageRing stage;  // pinned descriptor staging
@@ -59,15 +78,13 @@ struct vbz_b200_ctx {
     size_t t_used = 0;
     cudaStream_t last_zdecode_stream = nullptr;
     uint32_t codec_ctas_per_sm = 0;  // != 0 while a host batch runs: room for the transfer kernels (SvbParams::ctas_per_sm)
-
-    // descriptors and look-back state (stage 1)
-    vbz::DevBuf d_reads, d_tiles, d_status, d_wtoff, d_issue, d_results, d_sizes;
     vbz::PinBuf h_results;
-    // stage 2 (zstd): descriptors, work counter, literal scratch of the decoding warps
-    vbz::DevBuf d_zreads, d_zcounter, d_zlit, d_zblocks, d_zstatus, d_zcodes, d_zunits, d_zgroups, d_zgeneral, d_zseqs, d_zseqframes, d_zseqlist;
-    vbz::DevBuf d_zelits, d_zeseqs, d_zemeta, d_zehist;  // the encoder's match finder (csrc/zstd_match_kernels.cuh)
-    // intermediate stage-1 bytes of the two-stage paths
-    vbz::DevBuf d_mid;
+    // a second set of scratch buffers and a second kernel stream: the waves of a host batch alternate between the two, so that the
+    // launch-latency-bound head and tail of one wave's kernels overlap with the next wave's (csrc/host/batch.cpp: run_host_batch)
+    vbz::ScratchSet alt;
+    cudaStream_t stream2 = nullptr;
+    void swap_scratch() { std::swap(static_cast<vbz::ScratchSet&>(*this), alt); }
+
     // host-pointer API: a batch runs as WAVES through kWaveSlots slots so that the upload of wave w+1, the kernels of
     // wave w and the download of wave w-1 overlap (csrc/host/batch.cpp: run_host_batch)
     static constexpr int kWaveSlots = 5;
