@@ -143,28 +143,29 @@ __device__ uint32_t z_fse_read_ncount(const uint8_t* p, uint32_t n, int max_al, 
     *al_out = al;
     return used;
 }
-// normalised counts -> decoding table (cells: sym | nb << 8 | base << 16)
+// normalised counts -> decoding table (cells: sym | nb << 8 | base << 16; cell u lives at cell[u * STRIDE])
+template <int STRIDE = 1>
 __device__ bool z_fse_build(uint32_t* cell, uint16_t* next, const int16_t* norm, int nsym, int al)
 {
     const int T = 1 << al;
     int high = T - 1;
     for (int s = 0; s < nsym; ++s) {
-        if (norm[s] == -1) { cell[high--] = (uint32_t)s; next[s] = 1; }
+        if (norm[s] == -1) { cell[(high--) * STRIDE] = (uint32_t)s; next[s] = 1; }
         else next[s] = (uint16_t)norm[s];
     }
     const int step = (T >> 1) + (T >> 3) + 3;
     int pos = 0;
     for (int s = 0; s < nsym; ++s)
         for (int i = 0; i < norm[s]; ++i) {
-            cell[pos] = (uint32_t)s;
+            cell[pos * STRIDE] = (uint32_t)s;
             do { pos = (pos + step) & (T - 1); } while (pos > high);
         }
     if (pos != 0) return false;
     for (int u = 0; u < T; ++u) {
-        const uint32_t s = cell[u] & 0xFFu;
+        const uint32_t s = cell[u * STRIDE] & 0xFFu;
         const uint32_t x = next[s]++;
         const uint32_t nb = (uint32_t)(al - z_highbit(x));
-        cell[u] = s | (nb << 8) | ((((x << nb) - (uint32_t)T) & 0xFFFFu) << 16);
+        cell[u * STRIDE] = s | (nb << 8) | ((((x << nb) - (uint32_t)T) & 0xFFFFu) << 16);
     }
     return true;
 }
@@ -1157,17 +1158,33 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
 // entries of ZstdDecParams::seq_list: a unit index, whether the unit is the first Seq unit of its frame, and - set by the executor - done
 constexpr uint32_t kZListIndexMask = 0x3FFFFFFFu, kZListFirst = 0x40000000u, kZListDone = 0x80000000u;
 struct ZSeqWarp {  // zstd_seq_kernel: per-warp shared state
-    uint32_t ll[512], ml[512], of[256];  // sym | nbBits << 8 | base << 16
+    // packed cells: x = next-state base | state bits << 16 | extra bits << 24, y = value base (a sequence is three look-ups, nothing else)
+    uint2 ll[512], ml[512], of[256];
     int16_t norm[3][64];                 // scratch of the three table builders (lanes 0 - 2)
     uint16_t next[3][64];
 };
-// One of the three sequence tables, by mode (one lane); norm / next: scratch for 64 symbols.  Returns bytes consumed, 0xFFFFFFFF on error.
+// cells as z_fse_build leaves them (sym | nb << 8 | base << 16 in x) -> packed cells; which: 0 literal lengths, 1 offsets, 2 match lengths
+__device__ __forceinline__ void z_seq_pack(uint2* cell, int al, int which, uint32_t lane)
+{
+    const uint32_t T = 1u << al;  // (RLE: al = 0, one cell)
+    for (uint32_t u = lane; u < T; u += 32) {
+        const uint32_t x = cell[u].x, sym = x & 0xFFu;
+        uint32_t extra, base;
+        if (which == 0) { extra = sym < 36 ? kZ_LL_BITS[sym] : 0u; base = sym < 36 ? kZ_LL_BASE[sym] : 0u; }
+        else if (which == 1) { extra = sym & 31u; base = 1u << (sym & 31u); }
+        else { extra = sym < 53 ? kZ_ML_BITS[sym] : 0u; base = sym < 53 ? kZ_ML_BASE[sym] : 0u; }
+        cell[u] = make_uint2((x >> 16) | (((x >> 8) & 0xFFu) << 16) | (extra << 24), base);
+    }
+}
+
+// One of the three sequence tables, by mode (one lane); norm / next: scratch for 64 symbols.  The cells go to every other word of `cell`
+// (the x words of the packed table, see z_seq_pack).  Returns bytes consumed, 0xFFFFFFFF on error.
 __device__ uint32_t z_seq_table2(int16_t* norm, uint16_t* next, uint32_t* cell, int* al, int mode, const uint8_t* p, uint32_t n, int max_al, int max_sym,
                                  const int16_t* def, int def_n, int def_al, bool have_prev)
 {
     if (mode == 0) {
         for (int i = 0; i < def_n; ++i) norm[i] = def[i];
-        if (!z_fse_build(cell, next, norm, def_n, def_al)) return 0xFFFFFFFFu;
+        if (!z_fse_build<2>(cell, next, norm, def_n, def_al)) return 0xFFFFFFFFu;
         *al = def_al;
         return 0;
     }
@@ -1181,52 +1198,9 @@ __device__ uint32_t z_seq_table2(int16_t* norm, uint16_t* next, uint32_t* cell, 
     int nsym, a;
     const uint32_t used = z_fse_read_ncount(p, n, max_al, max_sym, norm, &nsym, &a);
     if (!used) return 0xFFFFFFFFu;
-    if (!z_fse_build(cell, next, norm, nsym, a)) return 0xFFFFFFFFu;
+    if (!z_fse_build<2>(cell, next, norm, nsym, a)) return 0xFFFFFFFFu;
     *al = a;
     return used;
-}
-
-// Backward bit reader for a sequences section, one per lane: a 64-bit window whose top bit is the next unread bit, refilled 32 bits at a
-// time through aligned word loads (a lane walks down its own stream; the lines it touches stay in L1).
-struct ZLaneBits {
-    const uint32_t* words;  // the aligned word that holds the section's first byte
-    int wi;                 // next word to take (counting down; < 0: past the start, reads as zero)
-    uint64_t buf;
-    int nbits;
-    long long left;         // unread bits of the stream proper (negative: the reader ran past the start)
-};
-// p[0 .. n): the stream; false if it is empty or ends with a zero byte
-__device__ __forceinline__ bool zlb_init(ZLaneBits& b, const uint8_t* p, uint32_t n)
-{
-    if (n == 0 || p[n - 1] == 0) return false;
-    const uint32_t phase = (uint32_t)((uintptr_t)p & 3u);
-    b.words = reinterpret_cast<const uint32_t*>(p - phase);
-    const uint32_t last_byte = phase + n - 1;  // byte index of the stream's last byte, from words[0]
-    b.wi = (int)(last_byte >> 2);
-    b.left = (long long)(n - 1) * 8 + z_highbit(p[n - 1]);
-    const uint32_t v0 = 8u * (last_byte & 3u) + (uint32_t)z_highbit(p[n - 1]);  // unread bits in the last word: those below the marker
-    const uint32_t w = b.words[b.wi];
-    b.buf = v0 ? ((uint64_t)w << (64 - v0)) : 0ull;
-    b.nbits = (int)v0;
-    --b.wi;
-    return true;
-}
-__device__ __forceinline__ uint32_t zlb_read(ZLaneBits& b, uint32_t nb)
-{
-    if (nb == 0) return 0;
-    if (b.nbits < (int)nb) {
-        while (b.nbits <= 32) {
-            const uint32_t w = b.wi >= 0 ? b.words[b.wi] : 0u;
-            b.buf |= (uint64_t)w << (32 - b.nbits);
-            b.nbits += 32;
-            --b.wi;
-        }
-    }
-    const uint32_t v = (uint32_t)(b.buf >> (64 - nb));
-    b.buf <<= nb;
-    b.nbits -= (int)nb;
-    b.left -= nb;
-    return v;
 }
 
 // what a lane knows about "its" Seq unit before the sequences are decoded
@@ -1261,24 +1235,76 @@ __device__ __forceinline__ ZSeqHead z_seq_head(const uint8_t* bp, uint32_t bs, u
 // starts with (rep[]) and resolves the repeat codes as it goes; without, an offset value of 1 .. 3 is left in the record as 0x80000000 | value
 // (*raw says whether there was any) for z_resolve_repeats.  Returns the bytes the block regenerates, 0xFFFFFFFF if it is damaged.
 // *back: a match may reach back beyond the start of the block.
+// A sequence is a serial step (the three states of sequence i + 1 come out of the bits behind those of sequence i), so the step is
+// kept short: `bp` counts the unread bits, the 64 bits below it come from three aligned words, and the packed cells say how many bits
+// each of the six fields takes - no refill tests, no second look-up between the cell and the value.
 __device__ uint32_t z_lane_sequences(const ZSeqWarp* zw, int al_ll, int al_of, int al_ml, const uint8_t* p, uint32_t n, uint32_t nseq, uint32_t lit_n,
                                      ZstdSeq* out, bool track, uint32_t* rep, bool* raw, bool* back)
 {
     const uint32_t kBad = 0xFFFFFFFFu;
-    ZLaneBits b;
-    if (!zlb_init(b, p, n)) return kBad;
-    uint32_t sl = zlb_read(b, (uint32_t)al_ll), so = zlb_read(b, (uint32_t)al_of), sm = zlb_read(b, (uint32_t)al_ml);
-    if (b.left < 0) return kBad;
+    if (n == 0 || p[n - 1] == 0 || n > (1u << 24)) return kBad;
+    const uint32_t phase = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(p - phase);  // stream bit k = bit 8 * phase + k of this array of words
+    const uint32_t lead = 8u * phase, wlast = (phase + n - 1) >> 2;
+    long long left = (long long)(n - 1) * 8 + z_highbit(p[n - 1]);  // unread bits (negative: the reader ran past the start)
+    // n bits below bit position lead + left (n <= 32); bits before the stream read as zero
+    auto slow_read = [&](uint32_t nb) -> uint32_t {
+        if (nb == 0) return 0u;
+        left -= nb;
+        uint64_t v = 0;
+        const long long from = left;  // stream bit index of the field's lowest bit (may be negative)
+        const long long lo = from < 0 ? 0 : from;
+        const long long hi = from + nb;  // exclusive
+        if (hi > 0) {
+            const uint32_t a = lead + (uint32_t)lo, wi = a >> 5, sh = a & 31u;
+            const uint64_t two = (uint64_t)words[wi] | ((uint64_t)(((a + (uint32_t)(hi - lo) - 1) >> 5) > wi ? words[wi + 1] : 0u) << 32);
+            v = (two >> sh) & ((1ull << (uint32_t)(hi - lo)) - 1ull);
+            v <<= (uint32_t)(lo - from);
+        }
+        return (uint32_t)v;
+    };
+    uint32_t sl = slow_read((uint32_t)al_ll), so = slow_read((uint32_t)al_of), sm = slow_read((uint32_t)al_ml);
+    if (left < 0) return kBad;
     uint32_t rep0 = rep[0], rep1 = rep[1], rep2 = rep[2];
     uint32_t lits = 0, regen = 0;
     bool any_raw = false, reach = false;
+    // the window: hi:lo = the 64 stream bits below bit position `wtop` (top bit first), of which the top `wtop - left` are spent already.
+    // It is reloaded from three aligned words whenever fewer than 64 - spent bits could be needed; between reloads fields are cut out
+    // of the pair at their offsets - six independent extractions, no chain through a shifting window.
+    uint32_t lo = 0, hi = 0;
+    long long wtop = -1;  // (no window yet)
     for (uint32_t i = 0; i < nseq; ++i) {
-        const uint32_t cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
-        const uint32_t llc = cl & 0xFF, ofc = co & 0xFF, mlc = cm & 0xFF;
-        if (llc > 35 || mlc > 52 || ofc > 31) return kBad;
-        const uint32_t ofv = (1u << ofc) + zlb_read(b, ofc);
-        const uint32_t mlen = kZ_ML_BASE[mlc] + zlb_read(b, kZ_ML_BITS[mlc]);
-        const uint32_t llen = kZ_LL_BASE[llc] + zlb_read(b, kZ_LL_BITS[llc]);
+        const uint2 cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
+        const uint32_t ofb = co.x >> 24, mlb = cm.x >> 24, llb = cl.x >> 24;
+        const bool more = i + 1 < nseq;
+        const uint32_t nls = more ? (cl.x >> 16) & 0xFFu : 0u, nms = more ? (cm.x >> 16) & 0xFFu : 0u, nos = more ? (co.x >> 16) & 0xFFu : 0u;
+        const uint32_t c1 = ofb, c2 = c1 + mlb, c3 = c2 + llb, c4 = c3 + nls, c5 = c4 + nms, need = c5 + nos;
+        uint32_t ofx, mlx, llx, xl, xm, xo;
+        if (left >= 96 && need <= 64) {
+            uint32_t spent = (uint32_t)(wtop - left);
+            if (wtop < 0 || spent + need > 64) {
+                const uint32_t a = lead + (uint32_t)left - 64u, wi = a >> 5, sh = a & 31u;
+                const uint32_t w0 = words[wi], w1 = words[wi + 1], w2 = words[wi + 2 < wlast ? wi + 2 : wlast];  // (with sh = 0 the third word is not part of the 64 bits)
+                lo = __funnelshift_r(w0, w1, sh);
+                hi = __funnelshift_r(w1, w2, sh);
+                wtop = left;
+                spent = 0;
+            }
+            // nb bits that start t bits below the top of hi:lo (t + nb <= 64, nb <= 31)
+#define Z_CUT(dst, t, nb) { const uint32_t t_ = spent + (t); const uint32_t x_ = t_ < 32 ? __funnelshift_l(lo, hi, t_) : lo << (t_ - 32); dst = (x_ >> 1) >> (31u - (nb)); }
+            Z_CUT(ofx, 0u, ofb) Z_CUT(mlx, c1, mlb) Z_CUT(llx, c2, llb) Z_CUT(xl, c3, nls) Z_CUT(xm, c4, nms) Z_CUT(xo, c5, nos)
+#undef Z_CUT
+            left -= need;
+        } else {
+            ofx = slow_read(ofb); mlx = slow_read(mlb); llx = slow_read(llb);
+            xl = slow_read(nls); xm = slow_read(nms); xo = slow_read(nos);
+            if (left < 0) return kBad;
+            wtop = -1;
+        }
+        const uint32_t ofv = co.y + ofx, mlen = cm.y + mlx, llen = cl.y + llx;
+        sl = (cl.x & 0xFFFFu) + xl;
+        sm = (cm.x & 0xFFFFu) + xm;
+        so = (co.x & 0xFFFFu) + xo;
         uint32_t offset;
         if (ofv > 3) {
             offset = ofv - 3;
@@ -1297,18 +1323,13 @@ __device__ uint32_t z_lane_sequences(const ZSeqWarp* zw, int al_ll, int al_of, i
                 rep0 = offset;
             }
         }
-        if (i + 1 < nseq) {
-            sl = (cl >> 16) + zlb_read(b, (cl >> 8) & 0xFF);
-            sm = (cm >> 16) + zlb_read(b, (cm >> 8) & 0xFF);
-            so = (co >> 16) + zlb_read(b, (co >> 8) & 0xFF);
-        }
         lits += llen;
-        if (b.left < 0 || lits > lit_n || regen + llen + mlen > 2u * kZBlockMax) return kBad;
+        if (lits > lit_n || regen + llen + mlen > 2u * kZBlockMax) return kBad;
         if (offset > regen + llen) reach = true;  // (an unresolved code counts: its value has the top bit set)
         regen += llen + mlen;
         out[i] = ZstdSeq{offset, llen, mlen, 0};
     }
-    if (b.left != 0) return kBad;
+    if (left != 0) return kBad;
     regen += lit_n - lits;  // the literals after the last sequence
     if (regen > kZBlockMax) return kBad;
     rep[0] = rep0; rep[1] = rep1; rep[2] = rep2;
@@ -1416,7 +1437,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                 if (lane < 3) {
                     const int mode = (hmodes >> (6 - 2 * (int)lane)) & 3;
                     const uint32_t at = lane == 0 ? o0 : (lane == 1 ? o1 : o2);
-                    uint32_t* cell = lane == 0 ? zw->ll : (lane == 1 ? zw->of : zw->ml);
+                    uint32_t* cell = reinterpret_cast<uint32_t*>(lane == 0 ? zw->ll : (lane == 1 ? zw->of : zw->ml));  // (the x words)
                     my_al = al[lane];
                     const uint32_t r = z_seq_table2(zw->norm[lane], zw->next[lane], cell, &my_al, mode, tp + at, tn - at, lane == 1 ? 8 : 9,
                                                     lane == 0 ? 35 : (lane == 1 ? 31 : 52), lane == 0 ? kZ_LL_DEF : (lane == 1 ? kZ_OF_DEF : kZ_ML_DEF),
@@ -1428,6 +1449,11 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                 al[1] = __shfl_sync(0xffffffffu, my_al, 1);
                 al[2] = __shfl_sync(0xffffffffu, my_al, 2);
                 tables_valid = true;
+                __syncwarp();
+                // the tables that were (re)built: cells -> packed cells, all lanes
+                if (((hmodes >> 6) & 3) != 3) z_seq_pack(zw->ll, al[0], 0, lane);
+                if (((hmodes >> 4) & 3) != 3) z_seq_pack(zw->of, al[1], 1, lane);
+                if (((hmodes >> 2) & 3) != 3) z_seq_pack(zw->ml, al[2], 2, lane);
             }
             __syncwarp();
             // ---- every member decodes its block.  The head knows the repeat offsets it starts with; the others leave repeat codes raw ------
@@ -1489,18 +1515,29 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
         if (ok && (uint64_t)sf.unit_first + sf.unit_count >= kZListIndexMask) ok = false;
         if (ok) {
             if (lane == 0) p.results[sf.read] = (uint32_t)op;
-            // the executor's work list: the frame's Seq units in block order, side by side (a unit only ever waits for entries before its own)
+            // the executor's work list: the frame's CHAINS in block order, side by side.  A chain = a Seq unit that needs nothing from the
+            // Seq units before it (or the frame's first) and the Seq units behind it that do (pad & 1): one warp runs it from end to end
+            uint32_t heads = 0;
+            for (uint32_t u0 = 0; u0 < sf.unit_count; u0 += 32) {
+                const uint32_t mine = u0 + lane;
+                const bool is_seq = mine < sf.unit_count && p.units[sf.unit_first + mine].kind == kZUnitSeq;
+                const uint32_t m = __ballot_sync(0xffffffffu, is_seq);
+                const bool head = is_seq && ((heads == 0 && !(m & ((1u << lane) - 1u))) || !(p.units[sf.unit_first + mine].pad & 1u));
+                heads += (uint32_t)__popc((int)__ballot_sync(0xffffffffu, head));
+            }
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(p.counter + 9, n_seq_units);
+            if (lane == 0) base = atomicAdd(p.counter + 9, heads);
             base = __shfl_sync(0xffffffffu, base, 0);
             uint32_t done = 0;
             for (uint32_t u0 = 0; u0 < sf.unit_count; u0 += 32) {
                 const uint32_t mine = u0 + lane;
                 const bool is_seq = mine < sf.unit_count && p.units[sf.unit_first + mine].kind == kZUnitSeq;
                 const uint32_t m = __ballot_sync(0xffffffffu, is_seq);
-                const uint32_t rank = done + (uint32_t)__popc((int)(m & ((1u << lane) - 1u)));
-                if (is_seq) p.seq_list[base + rank] = (sf.unit_first + mine) | (rank == 0 ? kZListFirst : 0u);
-                done += (uint32_t)__popc((int)m);
+                const bool head = is_seq && ((done == 0 && !(m & ((1u << lane) - 1u))) || !(p.units[sf.unit_first + mine].pad & 1u));
+                const uint32_t hm = __ballot_sync(0xffffffffu, head);
+                const uint32_t rank = done + (uint32_t)__popc((int)(hm & ((1u << lane) - 1u)));
+                if (head) p.seq_list[base + rank] = (sf.unit_first + mine) | (rank == 0 ? kZListFirst : 0u);
+                done += (uint32_t)__popc((int)hm);
             }
         } else {
             // not for this path after all: its units do nothing, the general kernel decides the frame's result
@@ -1514,12 +1551,14 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
     }
 }
 
-// zstd_seqexec_kernel: a WARP per Seq unit, taken from the list in order.  The unit's literals already sit at the END of the block's place in
+// zstd_seqexec_kernel: a WARP per chain of Seq units, taken from the list in order.  The unit's literals already sit at the END of the block's place in
 // the output (the units kernel put them there); the records are executed from the front: a literal run moves down to where it belongs,
 // a match copies what lies `offset` back.  What a sequence writes ends at or below where the literals of the next one wait, so nothing
 // is overwritten before it is read - the block expands in place, and the literals behind the last sequence are where they belong already.
-// A unit with a match that may reach back beyond its block first waits until the frame's Seq units before it are done (the entries of the
-// list before its own; everything else was written by the units kernel).  Units are taken in list order: what a unit waits for is running or done.
+// The list holds CHAINS: a unit that needs nothing from the frame's Seq units before it, and the units behind it with a match that may
+// reach back beyond their block - those run behind it in the same warp.  Before the first such unit the warp waits until the frame's
+// earlier chains are done (the entries of the list before its own; everything else was written by the units kernel).  Chains are taken in
+// list order: what a chain waits for is running or done.
 constexpr int kZExecWarps = 4;
 // wait until every Seq unit of the frame before list entry k is done: the entries from k - 1 down to the one that carries the First mark,
 // 32 per look (lane 0 holds the nearest)
@@ -1543,86 +1582,107 @@ __device__ __forceinline__ void z_exec_wait(const uint32_t* list, uint32_t k, ui
     }
     __syncwarp();
 }
+// the records of one Seq unit (all lanes); false: the block is damaged
+__device__ bool z_exec_unit(const ZstdDecParams& p, const ZstdUnit& u, uint64_t frame_off, uint32_t lane)
+{
+    uint8_t* out = p.dst;
+    const uint8_t* bp = p.src + u.src_off;
+    int lt = 0, streams = 4;
+    uint32_t hdr = 0, lit_n = 0, comp = 0;
+    if (!z_lit_header(bp, u.n, &lt, &hdr, &lit_n, &comp, &streams) || lit_n > u.regen) return false;
+    const uint8_t* lit = out + u.dst_off + (u.regen - lit_n);  // literal i of the block waits at lit[i]
+    uint64_t op = u.dst_off;
+    uint32_t lp = 0;
+    const ZstdSeq* sq = p.seqs + u.seq_first;
+    for (uint32_t i0 = 0; i0 < u.nseq; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const ZstdSeq rec = i < u.nseq ? sq[i] : ZstdSeq{1, 0, 0, 0};
+        const uint32_t span = rec.ll + rec.ml;
+        const uint32_t incl = warp_incl_scan(span, lane), lincl = warp_incl_scan(rec.ll, lane);
+        const uint64_t my_out = op + incl - span;        // where this sequence's literals go
+        const uint64_t mdst = my_out + rec.ll, msrc = mdst - rec.offset;
+        // an offset beyond the frame's first byte: damaged (checked here: the sequence kernel decodes blocks side by side and knows no positions)
+        if (__ballot_sync(0xffffffffu, rec.ml != 0 && (uint64_t)rec.offset > mdst - frame_off)) return false;
+        // ---- literal runs, in literal order, 32 bytes per step: literal o of the round belongs to the first sequence whose inclusive
+        // count exceeds o.  Reads come before the writes of a step, and a step writes below what later steps read.
+        const uint32_t total = __shfl_sync(0xffffffffu, lincl, 31);
+        for (uint32_t o0 = 0; o0 < total; o0 += 32) {
+            const uint32_t o = o0 + lane;
+            uint32_t j = 0;
+#pragma unroll
+            for (uint32_t step = 16; step != 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, lincl, j + step - 1);
+                if (v <= o) j += step;
+            }
+            j &= 31u;
+            const uint32_t ej = __shfl_sync(0xffffffffu, lincl - rec.ll, j);
+            const uint32_t oj_lo = __shfl_sync(0xffffffffu, (uint32_t)my_out, j), oj_hi = __shfl_sync(0xffffffffu, (uint32_t)(my_out >> 32), j);
+            uint8_t v = 0;
+            if (o < total) v = lit[lp + o];
+            __syncwarp();
+            if (o < total) out[(((uint64_t)oj_hi << 32) | oj_lo) + (o - ej)] = v;
+        }
+        __syncwarp();
+        // ---- matches: short and independent of this round's other sequences -> the lane itself; the others by the whole warp, in order
+        const bool dep = msrc < my_out && msrc + rec.ml > op;
+        const bool self = rec.ml != 0 && rec.ml <= 48 && !dep;
+        if (self) {
+            if (rec.offset == 1) {
+                const uint8_t v = out[mdst - 1];
+                for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = v;
+            } else {
+                for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = out[msrc + q];
+            }
+        }
+        uint32_t rest = __ballot_sync(0xffffffffu, rec.ml != 0 && !self);
+        __syncwarp();
+        while (rest) {
+            const uint32_t fl = (uint32_t)__ffs((int)rest) - 1;
+            rest &= rest - 1;
+            const uint32_t n = __shfl_sync(0xffffffffu, rec.ml, fl), fo = __shfl_sync(0xffffffffu, rec.offset, fl);
+            const uint32_t fd_lo = __shfl_sync(0xffffffffu, (uint32_t)mdst, fl), fd_hi = __shfl_sync(0xffffffffu, (uint32_t)(mdst >> 32), fl);
+            z_warp_match(out, ((uint64_t)fd_hi << 32) | fd_lo, fo, n, lane);
+            __syncwarp();
+        }
+        op += __shfl_sync(0xffffffffu, incl, 31);
+        lp += total;
+    }
+    return lp <= lit_n && op + (lit_n - lp) == u.dst_off + u.regen;  // (the sequence kernel's sums say so)
+}
+
 __global__ void __launch_bounds__(kZExecWarps * 32) zstd_seqexec_kernel(ZstdDecParams p)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_list = p.counter[9];
-    uint8_t* out = p.dst;
+    uint32_t n_units = p.counter[1];
+    if (n_units > p.unit_cap) n_units = p.unit_cap;
     for (;;) {
         uint32_t k = 0;
         if (lane == 0) k = atomicAdd(p.counter + 8, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_list) break;
         const uint32_t entry = p.seq_list[k];
-        const bool first = (entry & kZListFirst) != 0;
-        const ZstdUnit u = p.units[entry & kZListIndexMask];
-        const uint64_t frame_off = p.reads[u.read].dst_off;
-        const uint8_t* bp = p.src + u.src_off;
-        int lt = 0, streams = 4;
-        uint32_t hdr = 0, lit_n = 0, comp = 0;
-        bool ok = z_lit_header(bp, u.n, &lt, &hdr, &lit_n, &comp, &streams) && lit_n <= u.regen;
-        if (ok && !first && (u.pad & 1u)) z_exec_wait(p.seq_list, k, lane);
-        if (ok) {
-            const uint8_t* lit = out + u.dst_off + (u.regen - lit_n);  // literal i of the block waits at lit[i]
-            uint64_t op = u.dst_off;
-            uint32_t lp = 0;
-            const ZstdSeq* sq = p.seqs + u.seq_first;
-            for (uint32_t i0 = 0; i0 < u.nseq && ok; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                const ZstdSeq rec = i < u.nseq ? sq[i] : ZstdSeq{1, 0, 0, 0};
-                const uint32_t span = rec.ll + rec.ml;
-                const uint32_t incl = warp_incl_scan(span, lane), lincl = warp_incl_scan(rec.ll, lane);
-                const uint64_t my_out = op + incl - span;        // where this sequence's literals go
-                const uint64_t mdst = my_out + rec.ll, msrc = mdst - rec.offset;
-                // an offset beyond the frame's first byte: damaged (checked here: the sequence kernel decodes blocks side by side and knows no positions)
-                if (__ballot_sync(0xffffffffu, rec.ml != 0 && (uint64_t)rec.offset > mdst - frame_off)) { ok = false; break; }
-                // ---- literal runs, in literal order, 32 bytes per step: literal o of the round belongs to the first sequence whose inclusive
-                // count exceeds o.  Reads come before the writes of a step, and a step writes below what later steps read.
-                const uint32_t total = __shfl_sync(0xffffffffu, lincl, 31);
-                for (uint32_t o0 = 0; o0 < total; o0 += 32) {
-                    const uint32_t o = o0 + lane;
-                    uint32_t j = 0;
-#pragma unroll
-                    for (uint32_t step = 16; step != 0; step >>= 1) {
-                        const uint32_t v = __shfl_sync(0xffffffffu, lincl, j + step - 1);
-                        if (v <= o) j += step;
-                    }
-                    j &= 31u;
-                    const uint32_t ej = __shfl_sync(0xffffffffu, lincl - rec.ll, j);
-                    const uint32_t oj_lo = __shfl_sync(0xffffffffu, (uint32_t)my_out, j), oj_hi = __shfl_sync(0xffffffffu, (uint32_t)(my_out >> 32), j);
-                    uint8_t v = 0;
-                    if (o < total) v = lit[lp + o];
-                    __syncwarp();
-                    if (o < total) out[(((uint64_t)oj_hi << 32) | oj_lo) + (o - ej)] = v;
-                }
-                __syncwarp();
-                // ---- matches: short and independent of this round's other sequences -> the lane itself; the others by the whole warp, in order
-                const bool dep = msrc < my_out && msrc + rec.ml > op;
-                const bool self = rec.ml != 0 && rec.ml <= 48 && !dep;
-                if (self) {
-                    if (rec.offset == 1) {
-                        const uint8_t v = out[mdst - 1];
-                        for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = v;
-                    } else {
-                        for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = out[msrc + q];
-                    }
-                }
-                uint32_t rest = __ballot_sync(0xffffffffu, rec.ml != 0 && !self);
-                __syncwarp();
-                while (rest) {
-                    const uint32_t fl = (uint32_t)__ffs((int)rest) - 1;
-                    rest &= rest - 1;
-                    const uint32_t n = __shfl_sync(0xffffffffu, rec.ml, fl), fo = __shfl_sync(0xffffffffu, rec.offset, fl);
-                    const uint32_t fd_lo = __shfl_sync(0xffffffffu, (uint32_t)mdst, fl), fd_hi = __shfl_sync(0xffffffffu, (uint32_t)(mdst >> 32), fl);
-                    z_warp_match(out, ((uint64_t)fd_hi << 32) | fd_lo, fo, n, lane);
-                    __syncwarp();
-                }
-                op += __shfl_sync(0xffffffffu, incl, 31);
-                lp += total;
+        uint32_t idx = entry & kZListIndexMask;
+        ZstdUnit u = p.units[idx];
+        const uint32_t read = u.read;
+        const uint64_t frame_off = p.reads[read].dst_off;
+        bool ok = true, waited = (entry & kZListFirst) != 0;
+        // the chain: this unit, then the Seq units of the frame behind it that need what lies before them
+        for (;;) {
+            if (!z_exec_unit(p, u, frame_off, lane)) { ok = false; break; }
+            __syncwarp();
+            bool more = false;
+            while (++idx < n_units) {
+                u = p.units[idx];
+                if (u.read != read) break;
+                if (u.kind != kZUnitSeq) continue;
+                more = (u.pad & 1u) != 0;
+                break;
             }
-            if (ok && (lp > lit_n || op + (lit_n - lp) != u.dst_off + u.regen)) ok = false;  // (the sequence kernel's sums say otherwise: not reached)
+            if (!more) break;
+            if (!waited) { z_exec_wait(p.seq_list, k, lane); waited = true; }  // the chains of the frame before this one
         }
-        if (!ok && lane == 0) p.results[u.read] = kErrZstd;
+        if (!ok && lane == 0) p.results[read] = kErrZstd;
         __syncwarp();
         if (lane == 0) {
             __threadfence();
