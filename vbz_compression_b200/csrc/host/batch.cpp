@@ -541,7 +541,8 @@ struct DeviceGuard {
 // ======================================================================================================
 vbz_b200_ctx::~vbz_b200_ctx()
 {
-    release_all(); alt.release_all();
+    release_all();
+    for (vbz::ScratchSet& a : alt) a.release_all();
     h_results.release(); stage.release();
     for (WaveSlot& w : slots) {
         w.d_in.release(); w.d_out.release(); w.d_results.release(); w.d_pack.release(); w.d_xin.release(); w.d_xout.release();
@@ -555,8 +556,9 @@ vbz_b200_ctx::~vbz_b200_ctx()
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
     if (s_d2hs) cudaStreamDestroy(s_d2hs);
+    for (int k = 1; k < kKernelStreams; ++k)
+        if (kstream[k]) cudaStreamDestroy(kstream[k]);
     if (stream) cudaStreamDestroy(stream);
-    if (stream2) cudaStreamDestroy(stream2);
 }
 
 extern "C" int vbz_b200_device_count(void)
@@ -578,11 +580,12 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
     vbz_b200_ctx* c = new vbz_b200_ctx();
     c->device = device;
     bool ok = cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
-              cuda_ok(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->s_d2hs, cudaStreamNonBlocking), "cudaStreamCreate") &&
               c->stage.init();
+    c->kstream[0] = c->stream;
+    for (int k = 1; ok && k < vbz_b200_ctx::kKernelStreams; ++k) ok = cuda_ok(cudaStreamCreateWithFlags(&c->kstream[k], cudaStreamNonBlocking), "cudaStreamCreate");
     for (vbz_b200_ctx::WaveSlot& w : c->slots)
         ok = ok && cuda_ok(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming), "cudaEventCreate") &&
              cuda_ok(cudaEventCreateWithFlags(&w.ev_k, cudaEventDisableTiming), "cudaEventCreate") &&
@@ -599,8 +602,8 @@ extern "C" void vbz_b200_destroy(vbz_b200_ctx* ctx)
 {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    for (cudaStream_t ks : ctx->kstream)
+        if (ks) cudaStreamSynchronize(ks);
     delete ctx;
 }
 
@@ -957,14 +960,13 @@ static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
         if ((max_in_staged && !sl.h_in.ensure(max_in_staged + 16)) || (max_out_staged && !sl.h_out.ensure(max_out_staged + 16))) return -1;
     }
     cudaStream_t sk = ctx->stream, sh = ctx->s_h2d, sd = ctx->s_d2h, sds = ctx->s_d2hs;
-    // the kernels of odd waves run on the second stream with the second set of scratch buffers (VBZ_B200_STREAMS=1: all on one)
-    const bool two_streams = W > 2 && env_u32("VBZ_B200_STREAMS", 2) >= 2;
-    struct ScratchParity {
-        vbz_b200_ctx* c; int cur = 0;
-        explicit ScratchParity(vbz_b200_ctx* ctx) : c(ctx) {}
-        void set(int par) { if (par != cur) { c->swap_scratch(); cur = par; } }
-        ~ScratchParity() { set(0); }
-    } parity(ctx);
+    // the kernels of wave w run on stream w mod n with scratch set w mod n (VBZ_B200_STREAMS=1: everything on one)
+    const uint32_t n_streams = W > 2 ? std::min<uint32_t>(env_u32("VBZ_B200_STREAMS", vbz_b200_ctx::kKernelStreams), vbz_b200_ctx::kKernelStreams) : 1;
+    struct ScratchTurn {
+        vbz_b200_ctx* c;
+        explicit ScratchTurn(vbz_b200_ctx* ctx) : c(ctx) {}
+        ~ScratchTurn() { c->use_scratch(0); }
+    } turn(ctx);
     struct CtaCap {  // the codec shares the SMs with the transfer kernels for the duration of the batch
         vbz_b200_ctx* c;
         CtaCap(vbz_b200_ctx* ctx, uint32_t v) : c(ctx) { c->codec_ctas_per_sm = v; }
@@ -984,7 +986,7 @@ static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
             vbz_b200_ctx::WaveSlot& sl = ctx->slots[it % S];
             uint8_t* d_in = sl.d_in.as<uint8_t>();
             uint8_t* d_out = sl.d_out.as<uint8_t>();
-            if (two_streams) { parity.set((int)(it & 1u)); sk = (it & 1u) ? ctx->stream2 : ctx->stream; }
+            if (n_streams > 1) { ctx->use_scratch((int)(it % n_streams)); sk = ctx->kstream[it % n_streams]; }
             tr.mark(sh);
             if (w.in_staged) {
                 copies.clear();
@@ -1106,7 +1108,7 @@ static int run_host_batch(vbz_b200_ctx* ctx, HostBatch& b)
     tr.report(m, W, dma_in, dma_out, xfers);
     if (rc == 0) tr.timeline();
     if (rc != 0) {  // leave nothing in flight that still points at the caller's buffers
-        cudaStreamSynchronize(sh); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2); cudaStreamSynchronize(sd); cudaStreamSynchronize(sds);
+        cudaStreamSynchronize(sh); for (cudaStream_t ks : ctx->kstream) cudaStreamSynchronize(ks); cudaStreamSynchronize(sd); cudaStreamSynchronize(sds);
     }
     return rc;
 }

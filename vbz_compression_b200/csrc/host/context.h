@@ -79,15 +79,24 @@ struct vbz_b200_ctx : vbz::ScratchSet {
     cudaStream_t last_zdecode_stream = nullptr;
     uint32_t codec_ctas_per_sm = 0;  // != 0 while a host batch runs: room for the transfer kernels (SvbParams::ctas_per_sm)
     vbz::PinBuf h_results;
-    // a second set of scratch buffers and a second kernel stream: the waves of a host batch alternate between the two, so that the
-    // launch-latency-bound head and tail of one wave's kernels overlap with the next wave's (csrc/host/batch.cpp: run_host_batch)
-    vbz::ScratchSet alt;
-    cudaStream_t stream2 = nullptr;
-    void swap_scratch() { std::swap(static_cast<vbz::ScratchSet&>(*this), alt); }
+    // more sets of scratch buffers and more kernel streams: the waves of a host batch take them in turn, so that the latency-bound
+    // head and tail of one wave's kernel chain (a frame's sequences are serial work for one lane) overlap with the waves next to it
+    // (csrc/host/batch.cpp: run_host_batch).  The base class holds the set in use; use_scratch(k) swaps set k in.
+    static constexpr int kKernelStreams = 4;
+    vbz::ScratchSet alt[kKernelStreams - 1];
+    cudaStream_t kstream[kKernelStreams] = {};  // [0] == stream
+    int scratch_in_use = 0;
+    void use_scratch(int k)
+    {
+        if (k == scratch_in_use) return;
+        if (scratch_in_use != 0) std::swap(static_cast<vbz::ScratchSet&>(*this), alt[scratch_in_use - 1]);
+        if (k != 0) std::swap(static_cast<vbz::ScratchSet&>(*this), alt[k - 1]);
+        scratch_in_use = k;
+    }
 
     // host-pointer API: a batch runs as WAVES through kWaveSlots slots so that the upload of wave w+1, the kernels of
     // wave w and the download of wave w-1 overlap (csrc/host/batch.cpp: run_host_batch)
-    static constexpr int kWaveSlots = 5;
+    static constexpr int kWaveSlots = 7;
     struct WaveSlot {
         vbz::DevBuf d_in, d_out, d_results;
         vbz::DevBuf d_pack;         // host-contiguous runs of reads land here by DMA before they are spread to their slots

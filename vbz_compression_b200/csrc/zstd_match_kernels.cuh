@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
             uint32_t lo, hi;
             zm_load64(win + w, lo, hi);
             const uint32_t h = zm_hash(lo, hi);
-            sm->table[zm_index(h)] = zm_entry(h, w);
+            atomicMax(&sm->table[zm_index(h)], zm_entry(h, w));  // (lanes of a step may share an entry: the latest position stays, whatever the order)
         }
         __syncwarp();
     }
@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
                     break;
                 }
             }
-            if (hl && (!moved || q < z.anchor)) sm->table[zm_index(h)] = zm_entry(h, at);
+            __syncwarp();  // (the step's look-ups are done)
+            if (hl && (!moved || q < z.anchor)) atomicMax(&sm->table[zm_index(h)], zm_entry(h, at));
             __syncwarp();
             if (moved) { z.pos = z.anchor; continue; }
             zm_runs(z, rs, recs, rec_cap, src, pre, cur, span_end, kmin_run, lane);
@@ -507,7 +508,8 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
             // ---- strided step: any sign of a repeat -> dense steps from there -------------------------------------------------------------
             const uint32_t cand = others | __ballot_sync(0xffffffffu, same && all4);
             const uint32_t f = cand ? (uint32_t)__ffs((int)cand) - 1 : 32u;
-            if (hl && lane <= f) sm->table[zm_index(h)] = zm_entry(h, at);
+            __syncwarp();  // (the step's look-ups are done)
+            if (hl && lane <= f) atomicMax(&sm->table[zm_index(h)], zm_entry(h, at));
             __syncwarp();
             if (cand) { z.pos += f * s; dense_next = true; caught_at = z.pos; }
             else z.pos += 32 * s;
@@ -556,7 +558,8 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
         }
         // the table learns the positions the parse has passed - not those behind a match that ends inside the step, which the next
         // step looks at again (their entries would point at themselves)
-        if (hl && (!moved || q < z.anchor)) sm->table[zm_index(h)] = zm_entry(h, at);
+        __syncwarp();  // (the step's look-ups are done)
+        if (hl && (!moved || q < z.anchor)) atomicMax(&sm->table[zm_index(h)], zm_entry(h, at));
         __syncwarp();
         if (moved) { z.pos = z.anchor; carry = 0; }
         else {
