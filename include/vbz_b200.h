@@ -74,8 +74,10 @@ VBZ_EXPORT int vbz_b200_compress_device(vbz_b200_ctx* ctx, const void* d_src, co
                                         const vbz_size_t* src_size, void* d_dst, const uint64_t* dst_off,
                                         const vbz_size_t* dst_cap, vbz_size_t* d_results, uint32_t n_reads,
                                         const struct CompressionOptions* options, int sized, void* stream);
-/* dst_size[i] is the exact decompressed size of read i (the caller allocated it, so it knows it);
- * with sized != 0 the 4-byte header at the start of each read is checked against it. */
+/* dst_size[i] is the exact decompressed size of read i (the caller allocated it, so it knows it).  With sized != 0 each read starts with
+ * the 4-byte size header of vbz_compress_sized; it is SKIPPED here (the host cannot read device memory without a round trip): dst_size[i]
+ * must be the value it holds, or the read fails with a stream error.  The host-pointer batches and vbz_decompress_sized read the header
+ * and apply the reference's rules (vbz/vbz.cpp:350-366). */
 VBZ_EXPORT int vbz_b200_decompress_device(vbz_b200_ctx* ctx, const void* d_src, const uint64_t* src_off,
                                           const vbz_size_t* src_size, void* d_dst, const uint64_t* dst_off,
                                           const vbz_size_t* dst_size, vbz_size_t* d_results, uint32_t n_reads,
