@@ -590,31 +590,40 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     __syncwarp();
     uint32_t from = 0, to = 0;  // source position / literal count before the records of this round
     uint32_t zeros = 0;         // literals that are 0x00 (most of them among control bytes: counted by ballot, not by 32 atomics on one word)
+    uint64_t rec_next = lane < nseq ? recs[lane] : 0ull;  // (the next round's records are on their way while this round's literals move)
     for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const uint64_t rec = i < nseq ? recs[i] : 0ull;
+        const uint64_t rec = rec_next;
+        rec_next = i0 + 32 + lane < nseq ? recs[i0 + 32 + lane] : 0ull;
         const uint32_t ll = zm_ll(rec), ml = zm_ml(rec);
         const uint32_t span = warp_scan_u32(ll + ml), lsum = warp_scan_u32(ll);
         const uint32_t my_from = from + span - (ll + ml);
         const uint32_t total = __shfl_sync(0xffffffffu, lsum, 31);
-        // a gather: literal o of the round belongs to the first record whose inclusive count exceeds o (binary search over the lanes)
-        for (uint32_t o0 = 0; o0 < total; o0 += 32) {
-            const uint32_t o = o0 + lane;
-            uint32_t j = 0;
+        // a gather: literal o of the round belongs to the first record whose inclusive count exceeds o (binary search over the lanes);
+        // two steps of 32 literals at a time, both loads in flight before the first store
+        for (uint32_t o0 = 0; o0 < total; o0 += 64) {
+            uint32_t v[2], at[2];
 #pragma unroll
-            for (uint32_t step = 16; step != 0; step >>= 1) {
-                const uint32_t v = __shfl_sync(0xffffffffu, lsum, j + step - 1);
-                if (v <= o) j += step;
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t o = o0 + 32 * h + lane;
+                uint32_t j = 0;
+#pragma unroll
+                for (uint32_t step = 16; step != 0; step >>= 1) {
+                    const uint32_t c = __shfl_sync(0xffffffffu, lsum, j + step - 1);
+                    if (c <= o) j += step;
+                }
+                j &= 31u;
+                const uint32_t fj = __shfl_sync(0xffffffffu, my_from, j), ej = __shfl_sync(0xffffffffu, lsum - ll, j);
+                at[h] = o;
+                v[h] = o < total ? (uint32_t)__ldg(src + fj + (o - ej)) : 0x100u;
             }
-            j &= 31u;
-            const uint32_t fj = __shfl_sync(0xffffffffu, my_from, j), ej = __shfl_sync(0xffffffffu, lsum - ll, j);
-            uint32_t v = 0x100;
-            if (o < total) {
-                v = src[fj + (o - ej)];
-                lits[to + o] = (uint8_t)v;
-                if (v) atomicAdd(&hist[v], 1u);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (at[h] < total) {
+                    lits[to + at[h]] = (uint8_t)v[h];
+                    if (v[h]) atomicAdd(&hist[v[h]], 1u);
+                }
+                zeros += (uint32_t)__popc((int)__ballot_sync(0xffffffffu, v[h] == 0));
             }
-            zeros += (uint32_t)__popc((int)__ballot_sync(0xffffffffu, v == 0));
         }
         from += __shfl_sync(0xffffffffu, span, 31);
         to += total;
@@ -781,13 +790,25 @@ __device__ void zm_build_enc(ZFseEnc* t, int nsym, int al)
     t->al = (uint32_t)al;
 }
 
-// forward bit writer into global memory (one lane)
+// forward bit writer into global memory (one lane): fewer than 32 bits wait in `acc` between calls, four bytes leave at a time
 struct ZGBitW { uint8_t* p; uint64_t acc; uint32_t nbits, nbytes; };
-__device__ __forceinline__ void zg_put(ZGBitW& w, uint32_t v, uint32_t nb)
+__device__ __forceinline__ void zg_put(ZGBitW& w, uint32_t v, uint32_t nb)  // nb <= 32
 {
     w.acc |= (uint64_t)v << w.nbits;
     w.nbits += nb;
-    while (w.nbits >= 8) { w.p[w.nbytes++] = (uint8_t)w.acc; w.acc >>= 8; w.nbits -= 8; }
+    if (w.nbits >= 32) {
+        const uint32_t x = (uint32_t)w.acc;
+        uint8_t* o = w.p + w.nbytes;
+        o[0] = (uint8_t)x; o[1] = (uint8_t)(x >> 8); o[2] = (uint8_t)(x >> 16); o[3] = (uint8_t)(x >> 24);
+        w.nbytes += 4;
+        w.acc >>= 32;
+        w.nbits -= 32;
+    }
+}
+// what is left, the last partial byte included
+__device__ __forceinline__ void zg_flush(ZGBitW& w)
+{
+    while (w.nbits > 0) { w.p[w.nbytes++] = (uint8_t)w.acc; w.acc >>= 8; w.nbits = w.nbits > 8 ? w.nbits - 8 : 0; }
 }
 __device__ __forceinline__ void zm_fse_init(const ZFseEnc* t, uint32_t sym, uint32_t* st)
 {
@@ -930,8 +951,10 @@ __global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEn
             zg_put(w, llv - kZ_LL_BASE[llc], kZ_LL_BITS[llc]);
             zg_put(w, mlv - kZ_ML_BASE[mlc], kZ_ML_BITS[mlc]);
             zg_put(w, ofv - (1u << ofc), ofc);
+            uint64_t rec_ahead = n >= 2 ? recs[first_rec + n - 2] : 0ull;  // (one record ahead of the one being written)
             for (uint32_t k = n - 1; k-- > 0;) {
-                rec = recs[first_rec + k];
+                rec = rec_ahead;
+                if (k) rec_ahead = recs[first_rec + k - 1];
                 llv = zm_ll(rec); mlv = zm_ml(rec); ofv = zm_off(rec) + 3;
                 llc = zm_ll_code(llv); mlc = zm_ml_code(mlv); ofc = (uint32_t)z_highbit(ofv);
                 zm_fse_encode(to, ofc, &so, w);
@@ -945,7 +968,7 @@ __global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEn
             zm_fse_flush(to, so, w);
             zm_fse_flush(tl, sl, w);
             zg_put(w, 1, 1);  // the marker above the last bit
-            if (w.nbits) { w.p[w.nbytes++] = (uint8_t)w.acc; }
+            zg_flush(w);
             bytes = hb + w.nbytes;
         }
         if (lane < 16) { meta->seq_off[lane] = at; meta->seq_len[lane] = bytes; }
