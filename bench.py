@@ -364,7 +364,7 @@ def main_reference(args):
     if args.workload == "h5z-decode":
         pool = reference_pool(args, opts, SEED)
         if pool is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cpu_bench could not be built or run"}))
+            emit_line(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cpu_bench could not be built or run"}))
             return
         raw, lens_b, chunks, csz = pool
         take, tot = sample_prefix(lens_b, int(args.cpu_sample_gib * (1 << 30)))
@@ -373,7 +373,7 @@ def main_reference(args):
         for i in range(total):
             r = run_cpu_decode(chunks[:ctake], csz[:take], raw[:tot], lens_b[:take], opts, reps=1)
             if r is None or r["errors"]:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cpu_bench --decode failed"}))
+                emit_line(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cpu_bench --decode failed"}))
                 return
             if i >= args.warmup:
                 dec.append(r["decode_s"])
@@ -386,7 +386,7 @@ def main_reference(args):
                 "data": "synthetic", "config": workload_config(args, opts), "decode_gbs": val, "ratio": last["ratio"],
                 "cpu_baseline": {"value": val, "unit": "GB/s", "cores": last["threads"], "kind": "reference", "sample": sample},
                 "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit_line(json.dumps(line))
         return
     lens = value_counts(args.workload, read_lengths(args.reads, SEED))
     isz = opts.integer_size
@@ -398,7 +398,7 @@ def main_reference(args):
     for i in range(total):
         r = run_cpu_bench(raw, lens_b, opts, reps=1)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cpu_bench could not be built or run"}))
+            emit_line(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cpu_bench could not be built or run"}))
             return
         if i >= args.warmup:
             enc.append(r["encode_s"]); dec.append(r["decode_s"])
@@ -416,7 +416,7 @@ def main_reference(args):
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -685,7 +685,7 @@ def main_codec(args):
         "raw_bytes_per_gpu": raw_bytes, "roofline": roofline, "transform_stage": transform_stage, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(all_launches), "host_affinity": numa,
     }
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     D.close()
 
 
@@ -883,7 +883,7 @@ def main_h5z(args):
         "job": {"reads": args.reads, "raw_bytes": int(all_raw), "pool_chunks": P, "this_rank": {"first": int(lo), "last": int(hi), "raw_bytes": shard_raw, "calls": len(calls)}},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(all_launches), "host_affinity": numa,
     }
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     D.close()
 
 
@@ -943,7 +943,22 @@ def run_e2e_h5z(args, D, batch, chunks, csz, c_off, lens_b, raw, raw_off, calls,
                       "wall clock, bytes summed over ranks, time = max over ranks" % (D.world, budget_calls, len(calls))}
 
 
+_JSON_OUT = None
+
+
+def emit_line(text):
+    """The one JSON line goes to the process's ORIGINAL stdout (see the guard in __main__)."""
+    out = _JSON_OUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    # stdout carries the JSON line and nothing else: file descriptor 1 is pointed at stderr for the duration of the run, so that whatever a
+    # library prints there (NCCL's version banner does not honour NCCL_DEBUG_FILE in every build) cannot end up in front of the line
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = default_reads(parse_args())
     if a.impl == "reference":
         main_reference(a)
