@@ -99,6 +99,37 @@ def test_damaged_frames_report_like_the_oracle(backend):
                 assert a[1] == b[1]
 
 
+def test_bit_flips_in_own_frames_never_decode_to_something_else(backend):
+    """Single-bit damage anywhere in a frame of this library's own writer (S groups: sequences sections, FSE tables, Repeat_Mode blocks,
+    treeless literals): the block-parallel decoder (sets of blocks a lane each, literals expanded in place, chains handed from warp to
+    warp) must end - with an error, or with exactly what the oracle makes of the same bytes.  Never more lenient than the oracle."""
+    capi, batch, _ = backend
+    rng = np.random.default_rng(9)
+    small = capi.path.endswith("cpusim.so")
+    arr = np.concatenate([data_gen.nanopore_like(9000, rng), np.full(3000, 417, np.int16), data_gen.nanopore_like(4000, rng)])
+    o = Options(True, 2, 1, 1)
+    (code, good), = batch.compress([arr], o, sized=True)
+    assert code == len(good)
+    nbits = 8 * len(good)
+    flips = list(range(32, nbits, 97 if small else 13))
+    blobs = []
+    for bit in flips:
+        bad = bytearray(good)
+        bad[bit >> 3] ^= 1 << (bit & 7)
+        blobs.append(bytes(bad))
+    res = batch.decompress(blobs, [arr.nbytes] * len(blobs), o, sized=True)  # one batch: a damaged read must not touch its neighbours either
+    lenient = 0
+    for bit, blob, (rc, out) in zip(flips, blobs, res):
+        rp, want = port.decompress(blob, o, arr.nbytes, sized=True)
+        if ol.is_error(rc):
+            continue
+        assert not ol.is_error(rp), (bit, rc, rp)
+        assert rc == rp and out == want, (bit, rc, rp)
+        lenient += 1
+    (rc, out), = batch.decompress([good], [arr.nbytes], o, sized=True)
+    assert rc == arr.nbytes and out == arr.tobytes()
+
+
 def test_fuzz_corpus_level1_decode(backend):
     """Restates the decode half of vbz/fuzzing/vbz_fuzz.cpp:138-161 at zstd level 1: arbitrary bytes must be rejected
     (or decoded) exactly as the oracle does."""
