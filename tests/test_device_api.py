@@ -141,3 +141,38 @@ def test_torch_tensors_zero_copy(level):
     assert (res.cpu().numpy().view(np.uint32) == np.array([a.nbytes for a in arrs], np.uint32)).all()
     for a, b in zip(arrs, back):
         assert np.array_equal(b.cpu().numpy(), a)
+
+
+@pytest.mark.parametrize("lookahead", ["0", "1"])
+def test_device_batches_in_waves(lookahead, monkeypatch):
+    """A device-resident batch larger than the intermediate budget runs as waves; on the decode side the walker and the sequence kernel of
+    wave w + 1 run on a second stream beside the kernels that write wave w's output (csrc/host/batch.cpp: decompress_device_impl).
+    Results, the order with respect to the caller's stream and the per-stage timers must not depend on that."""
+    torch, batch, lib = _setup()
+    import ctypes
+    from vbz_compression_b200 import CompressionOptions
+    monkeypatch.setenv("VBZ_B200_MID_MIB", "1")  # a wave per one or two reads
+    monkeypatch.setenv("VBZ_B200_DECODE_LOOKAHEAD", lookahead)
+    rng = np.random.default_rng(33)
+    arrs = [data_gen.nanopore_like(int(n), rng) for n in (260_000, 310_000, 5, 150_000, 401_000, 90_000, 222_222, 0, 333_333, 120_000, 64)]
+    reads = [torch.from_numpy(a.copy()).cuda() for a in arrs]
+    opts = CompressionOptions(True, 2, 1, 1)
+    assert lib.vbz_b200_set_stage_timing(batch.ctx, 1) == 0
+    out, offs, sizes = batch.compress_tensors(reads, opts, sized=True)
+    sz = sizes.cpu().numpy().view(np.uint32)     # (the copy is queued behind the call on the same stream)
+    assert (sz < 0xFFFFFFF9).all()
+    t1, t2 = ctypes.c_float(), ctypes.c_float()
+    assert lib.vbz_b200_stage_times(batch.ctx, ctypes.byref(t1), ctypes.byref(t2)) == 0 and t1.value > 0 and t2.value > 0
+    chunks = [out[int(off):int(off) + int(z)] for off, z in zip(offs, sz)]
+    port = ol.port()
+    o = Options(True, 2, 1, 1)
+    for a, c in zip(arrs, chunks):               # every frame decodes with the oracle
+        rd, back = port.decompress(c.cpu().numpy().tobytes(), o, a.nbytes, sized=True)
+        assert rd == a.nbytes and back == a.tobytes()
+    for _ in range(2):                           # twice: the second call finds both sets of buffers in place
+        back, res = batch.decompress_tensors(chunks, torch.int16, [a.size for a in arrs], opts, sized=True)
+        assert (res.cpu().numpy().view(np.uint32) == np.array([a.nbytes for a in arrs], np.uint32)).all()
+        assert lib.vbz_b200_stage_times(batch.ctx, ctypes.byref(t1), ctypes.byref(t2)) == 0 and t1.value > 0 and t2.value > 0
+        for a, b in zip(arrs, back):
+            assert np.array_equal(b.cpu().numpy(), a)
+    lib.vbz_b200_set_stage_timing(batch.ctx, 0)

@@ -193,11 +193,22 @@ static int enqueue_stage1(vbz_b200_ctx* ctx, bool decode, const Stage1Kind& kind
 }
 
 // ---- stage 2 (zstd), decode: frames -> content --------------------------------------------------------------------
+// `phase`: 0 = everything on `stream`; 1 = the front half only (descriptors, walker, sequence kernel; *keep receives the launch parameters);
+// 2 = the back half with the parameters phase 1 left in *keep (units kernel, executor, general kernel: what writes d_dst)
 static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const std::vector<ZstdRead>& reads, uint32_t* d_results,
-                               cudaStream_t stream)
+                               cudaStream_t stream, int phase = 0, ZstdDecParams* keep = nullptr)
 {
     const uint32_t n = (uint32_t)reads.size();
     if (n == 0) return 0;
+    if (phase == 2) {
+        if (!ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes())) return -1;
+        keep->lit_scratch = ctx->d_zlit.as<uint8_t>();
+        const int e = vbzk_zstd_decode_back(reinterpret_cast<const VbzkZstdDecParams*>(keep), stream);
+        if (e) { cuda_ok((cudaError_t)e, "zstd_decode launch"); return -1; }
+        ctx->launches += 3;
+        ctx->last_zdecode_stream = stream;
+        return 0;
+    }
     const size_t bytes = (size_t)n * sizeof(ZstdRead);
     uint64_t unit_cap = 0;
     for (uint32_t i = 0; i < n; ++i)
@@ -210,7 +221,7 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
         if (!reads[i].rejected) seq_cap += reads[i].dst_cap / 32u + 64u;
     seq_cap = std::min<uint64_t>(std::max<uint64_t>(seq_cap, 1024), 0x7FFFFFF0u);
     if (!ctx->d_zseqs.ensure((size_t)seq_cap * sizeof(ZstdSeq)) || !ctx->d_zseqframes.ensure((size_t)n * sizeof(ZstdSeqFrame))) return -1;
-    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes()) ||
+    if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || (phase == 0 && !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes())) ||
         !ctx->d_zunits.ensure((size_t)unit_cap * sizeof(ZstdUnit)) || !ctx->d_zgroups.ensure((size_t)unit_cap * sizeof(ZstdGroup)) ||
         !ctx->d_zgeneral.ensure((size_t)n * 4) || !ctx->d_zseqlist.ensure((size_t)unit_cap * 4))
         return -1;
@@ -234,6 +245,13 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     p.n_reads = n;
     p.seq_cap = (uint32_t)seq_cap;
     p.pad = 0;
+    if (phase == 1) {
+        *keep = p;
+        const int e = vbzk_zstd_decode_front(reinterpret_cast<const VbzkZstdDecParams*>(&p), stream);
+        if (e) { cuda_ok((cudaError_t)e, "zstd_decode launch"); return -1; }
+        ctx->launches += 2;
+        return 0;
+    }
     const int e = vbzk_zstd_decode(reinterpret_cast<const VbzkZstdDecParams*>(&p), stream);
     if (e) { cuda_ok((cudaError_t)e, "zstd_decode launch"); return -1; }
     ctx->launches += 5;  // walker, sequence kernel, units kernel, sequence executor, general kernel
@@ -299,12 +317,9 @@ static int enqueue_zstd_encode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
 // the other on the caller's stream; each is large enough (GiBs) that its dozen launches do not show.
 static uint64_t mid_budget()
 {
-    static const uint64_t v = [] {
-        const char* e = getenv("VBZ_B200_MID_MIB");
-        const long m = e ? atol(e) : 0;
-        return (uint64_t)(m > 0 ? m : 8192) << 20;
-    }();
-    return v;
+    const char* e = getenv("VBZ_B200_MID_MIB");  // (read per call: tests change it)
+    const long m = e ? atol(e) : 0;
+    return (uint64_t)(m > 0 ? m : 8192) << 20;
 }
 // format bound of a stage-1 stream of n values: control bytes + 4 data bytes per value (ref streamvbyte.h:33-39 without the padding).
 // A valid stream written by ANY build of the reference fits (the non-SSSE3 builds use 3-byte codes for int16 deltas beyond
@@ -424,14 +439,25 @@ static inline uint64_t decode_mid_cap(const ReadJob& j, const Stage1Kind& kind)
     return std::min<uint64_t>(cap, 0xFFFFFFF0u);
 }
 
+// what the front half of a two-stage wave leaves for its back half (decoder look-ahead)
+struct DecodeAhead { ZstdDecParams p; std::vector<uint64_t> mid_off; uint32_t* sizes = nullptr; };
+
+// `phase` / `ahead`: as enqueue_zstd_decode - 1 = the zstd stage's front half only, 2 = its back half and stage 1 (two-stage calls only)
 static int decompress_wave(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const ReadJob* jobs, uint32_t n, uint32_t* d_results,
-                           const Stage1Kind& kind, bool sized, cudaStream_t stream)
+                           const Stage1Kind& kind, bool sized, cudaStream_t stream, int phase = 0, DecodeAhead* ahead = nullptr)
 {
     const uint32_t hdr = sized ? 4u : 0u;
     const uint8_t* s1_src = d_src;
     const uint32_t* s1_sizes = nullptr;
     std::vector<uint64_t> mid_off;
-    if (kind.zstd_level != 0) {
+    if (phase == 2) {
+        std::vector<ZstdRead> none(n);  // (only its size is looked at)
+        if (enqueue_zstd_decode(ctx, d_src, nullptr, none, nullptr, stream, 2, &ahead->p) != 0) return -1;
+        stage_mark(ctx, stream);
+        mid_off.swap(ahead->mid_off);
+        s1_src = ctx->d_mid.as<uint8_t>();
+        s1_sizes = ahead->sizes;
+    } else if (kind.zstd_level != 0) {
         // stage 2 first (ref vbz/vbz.cpp:234-273): each frame decodes into its slot of the intermediate buffer - or
         // straight into the destination when there is no stage 1
         std::vector<ZstdRead> zr(n);
@@ -463,6 +489,12 @@ static int decompress_wave(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t* d_d
             if (!ctx->d_mid.ensure(mid_total + 16) || !ctx->d_sizes.ensure((size_t)n * 4)) return -1;
             zres = ctx->d_sizes.as<uint32_t>();
             zdst = ctx->d_mid.as<uint8_t>();
+        }
+        if (phase == 1) {
+            if (enqueue_zstd_decode(ctx, d_src, zdst, zr, zres, stream, 1, &ahead->p) != 0) return -1;
+            ahead->mid_off.swap(mid_off);
+            ahead->sizes = zres;
+            return 0;
         }
         if (enqueue_zstd_decode(ctx, d_src, zdst, zr, zres, stream) != 0) return -1;
         if (kind.isz == 0) return 0;
@@ -500,6 +532,8 @@ static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8
     if (kind.zstd_level == 0 && kind.isz == 0) { set_last_error("plain copies (integer_size 0, level 0) are not a device operation"); return -1; }
     if (kind.zstd_level == 0 || kind.isz == 0) return decompress_wave(ctx, d_src, d_dst, jobs.data(), n, d_results, kind, sized, stream);
     const uint64_t budget = mid_budget();
+    std::vector<std::pair<uint32_t, uint32_t>> waves;
+    uint64_t mid_max = 0;
     for (uint32_t a = 0; a < n;) {
         uint64_t mid = 0;
         uint32_t b = a;
@@ -509,11 +543,49 @@ static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8
             mid += m;
             ++b;
         }
-        if (a) stage_mark(ctx, stream);
-        if (decompress_wave(ctx, d_src, d_dst, jobs.data() + a, b - a, d_results + a, kind, sized, stream) != 0) return -1;
+        waves.push_back({a, b});
+        mid_max = std::max(mid_max, mid);
         a = b;
     }
-    return 0;
+    // Look-ahead: the walker and the sequence kernel of wave w + 1 (latency-bound: a thread per frame hops over block headers, a frame's
+    // sequences are serial work per block) run on the context's second stream while the kernels that write wave w's output keep the SMs busy.
+    // They write units, records and per-frame sizes only, so those exist twice (ZDecSet); the intermediate buffer is one, sized up front.
+    const char* la = getenv("VBZ_B200_DECODE_LOOKAHEAD");  // "0": one stream, wave after wave
+    const bool lookahead_allowed = !(la && atoi(la) == 0);
+    const bool ahead_ok = lookahead_allowed && waves.size() > 1 && ctx->scratch_in_use == 0 && ctx->zdec_in_use == 0 && stream != ctx->kstream[1] && ctx->ev_fork;
+    if (!ahead_ok) {
+        for (size_t w = 0; w < waves.size(); ++w) {
+            if (w) stage_mark(ctx, stream);
+            if (decompress_wave(ctx, d_src, d_dst, jobs.data() + waves[w].first, waves[w].second - waves[w].first, d_results + waves[w].first, kind, sized, stream) != 0) return -1;
+        }
+        return 0;
+    }
+    if (!ctx->d_mid.ensure(mid_max + 32)) return -1;  // (never reallocated while a wave is in flight)
+    struct Restore { vbz_b200_ctx* c; ~Restore() { c->use_zdec(0); } } restore{ctx};
+    cudaStream_t s2 = ctx->kstream[1];
+    DecodeAhead st[2];
+    int rc = 0;
+    auto front = [&](size_t w) {
+        ctx->use_zdec((int)(w & 1));
+        if (w >= 2) cudaStreamWaitEvent(s2, ctx->ev_back[w & 1], 0);  // the set's previous user (wave w - 2) is done with it
+        const int e = decompress_wave(ctx, d_src, d_dst, jobs.data() + waves[w].first, waves[w].second - waves[w].first, d_results + waves[w].first, kind, sized, s2, 1, &st[w & 1]);
+        cudaEventRecord(ctx->ev_front[w & 1], s2);
+        return e;
+    };
+    cudaEventRecord(ctx->ev_fork, stream);  // the second stream starts behind whatever the caller has queued before this call
+    cudaStreamWaitEvent(s2, ctx->ev_fork, 0);
+    rc = front(0);
+    for (size_t w = 0; w < waves.size() && rc == 0; ++w) {
+        if (w + 1 < waves.size()) rc = front(w + 1);
+        if (rc != 0) break;
+        if (w) stage_mark(ctx, stream);
+        ctx->use_zdec((int)(w & 1));
+        cudaStreamWaitEvent(stream, ctx->ev_front[w & 1], 0);
+        rc = decompress_wave(ctx, d_src, d_dst, jobs.data() + waves[w].first, waves[w].second - waves[w].first, d_results + waves[w].first, kind, sized, stream, 2, &st[w & 1]);
+        cudaEventRecord(ctx->ev_back[w & 1], stream);
+    }
+    if (rc != 0) { cudaStreamSynchronize(s2); cudaStreamSynchronize(stream); }
+    return rc;
 }
 
 }  // namespace vbz
@@ -553,6 +625,11 @@ vbz_b200_ctx::~vbz_b200_ctx()
         if (w.ev_outs) cudaEventDestroy(w.ev_outs);
     }
     for (cudaEvent_t e : t_marks) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ev_fork, ev_front[0], ev_front[1], ev_back[0], ev_back[1]})
+        if (e) cudaEventDestroy(e);
+    for (vbz::DevBuf* b : {&zdec_alt.d_zreads, &zdec_alt.d_zcounter, &zdec_alt.d_zunits, &zdec_alt.d_zgroups, &zdec_alt.d_zgeneral, &zdec_alt.d_zseqs,
+                           &zdec_alt.d_zseqframes, &zdec_alt.d_zseqlist, &zdec_alt.d_sizes})
+        b->release();
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
     if (s_d2hs) cudaStreamDestroy(s_d2hs);
@@ -585,6 +662,10 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
               cuda_ok(cudaStreamCreateWithFlags(&c->s_d2hs, cudaStreamNonBlocking), "cudaStreamCreate") &&
               c->stage.init();
     c->kstream[0] = c->stream;
+    ok = ok && cuda_ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+    for (int k = 0; ok && k < 2; ++k)
+        ok = cuda_ok(cudaEventCreateWithFlags(&c->ev_front[k], cudaEventDisableTiming), "cudaEventCreate") &&
+             cuda_ok(cudaEventCreateWithFlags(&c->ev_back[k], cudaEventDisableTiming), "cudaEventCreate");
     for (int k = 1; ok && k < vbz_b200_ctx::kKernelStreams; ++k) ok = cuda_ok(cudaStreamCreateWithFlags(&c->kstream[k], cudaStreamNonBlocking), "cudaStreamCreate");
     for (vbz_b200_ctx::WaveSlot& w : c->slots)
         ok = ok && cuda_ok(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming), "cudaEventCreate") &&

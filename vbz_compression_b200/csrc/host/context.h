@@ -86,6 +86,19 @@ struct vbz_b200_ctx : vbz::ScratchSet {
     vbz::ScratchSet alt[kKernelStreams - 1];
     cudaStream_t kstream[kKernelStreams] = {};  // [0] == stream
     int scratch_in_use = 0;
+    // the decoder's look-ahead (csrc/host/batch.cpp: decompress_device_impl): the walker and the sequence kernel of the NEXT wave of a
+    // device-resident call run on kstream[1] beside the kernels that write this wave's output, so what they write exists twice
+    struct ZDecSet { vbz::DevBuf d_zreads, d_zcounter, d_zunits, d_zgroups, d_zgeneral, d_zseqs, d_zseqframes, d_zseqlist, d_sizes; } zdec_alt;
+    int zdec_in_use = 0;
+    cudaEvent_t ev_front[2] = {}, ev_back[2] = {}, ev_fork = nullptr;
+    void use_zdec(int k)
+    {
+        if (k == zdec_in_use) return;
+        std::swap(d_zreads, zdec_alt.d_zreads); std::swap(d_zcounter, zdec_alt.d_zcounter); std::swap(d_zunits, zdec_alt.d_zunits);
+        std::swap(d_zgroups, zdec_alt.d_zgroups); std::swap(d_zgeneral, zdec_alt.d_zgeneral); std::swap(d_zseqs, zdec_alt.d_zseqs);
+        std::swap(d_zseqframes, zdec_alt.d_zseqframes); std::swap(d_zseqlist, zdec_alt.d_zseqlist); std::swap(d_sizes, zdec_alt.d_sizes);
+        zdec_in_use = k;
+    }
     void use_scratch(int k)
     {
         if (k == scratch_in_use) return;

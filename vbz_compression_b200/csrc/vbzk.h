@@ -32,7 +32,9 @@ int vbzk_svb_half_decode(int zigzag, const struct VbzkSvbParams* params, void* s
 struct VbzkZstdDecParams; /* == vbz::ZstdDecParams (csrc/svb_types.h) */
 uint32_t vbzk_zstd_decode_grid(void);
 uint64_t vbzk_zstd_decode_scratch_bytes(void);
-int vbzk_zstd_decode(const struct VbzkZstdDecParams* params, void* stream);
+int vbzk_zstd_decode(const struct VbzkZstdDecParams* params, void* stream);       /* = front, then back */
+int vbzk_zstd_decode_front(const struct VbzkZstdDecParams* params, void* stream); /* walker + sequence kernel: nothing of the output is written */
+int vbzk_zstd_decode_back(const struct VbzkZstdDecParams* params, void* stream);  /* units kernel, executor, general kernel */
 
 /* stage 2, encode: one zstd frame per read (csrc/zstd_enc_kernels.cuh); one CTA per 32 KiB block */
 struct VbzkZstdEncRead;   /* == vbz::ZstdEncRead */

@@ -172,7 +172,10 @@ extern "C" uint32_t vbzk_zstd_decode_grid(void)
     return g;
 }
 extern "C" uint64_t vbzk_zstd_decode_scratch_bytes(void) { return (uint64_t)vbzk_zstd_decode_grid() * kZdecWarps * kZLitStride; }
-extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
+// The decode of a batch in two halves (csrc/host/batch.cpp runs the first half of the next wave beside the second half of this one):
+//   front  walker + sequence kernel: reads the frames, writes units / groups / records / positions / per-frame results - nothing of the output
+//   back   units kernel + executor + general kernel: writes the output
+extern "C" int vbzk_zstd_decode_front(const VbzkZstdDecParams* params, void* stream)
 {
     const ZstdDecParams& p = *reinterpret_cast<const ZstdDecParams*>(params);
     if (p.n_reads == 0) return 0;
@@ -180,14 +183,17 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     VBZ_LAUNCH(zstd_walk_kernel, (p.n_reads + 127) / 128, 128, 0, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
     // 2. frames with sequences: decode the sequences into records, which gives every unit of those frames its position
-    {
-        const uint32_t ssmem = (uint32_t)(sizeof(ZSeqWarp) * kZSeqWarps);
-        if (int e = VBZK_SET_SMEM(zstd_seq_kernel, ssmem)) return e;
-        static const uint32_t sgrid_max = persistent_grid(zstd_seq_kernel, kZSeqWarps * 32, ssmem, 0xFFFFFFFFu, 0);
-        const uint32_t sneed = (p.n_reads + kZSeqWarps - 1) / kZSeqWarps;
-        VBZ_LAUNCH(zstd_seq_kernel, sneed < sgrid_max ? sneed : sgrid_max, kZSeqWarps * 32, ssmem, (vbz_stream_t)stream, p);
-        if (int e = VBZK_LAST_ERROR()) return e;
-    }
+    const uint32_t ssmem = (uint32_t)(sizeof(ZSeqWarp) * kZSeqWarps);
+    if (int e = VBZK_SET_SMEM(zstd_seq_kernel, ssmem)) return e;
+    static const uint32_t sgrid_max = persistent_grid(zstd_seq_kernel, kZSeqWarps * 32, ssmem, 0xFFFFFFFFu, 0);
+    const uint32_t sneed = (p.n_reads + kZSeqWarps - 1) / kZSeqWarps;
+    VBZ_LAUNCH(zstd_seq_kernel, sneed < sgrid_max ? sneed : sgrid_max, kZSeqWarps * 32, ssmem, (vbz_stream_t)stream, p);
+    return VBZK_LAST_ERROR();
+}
+extern "C" int vbzk_zstd_decode_back(const VbzkZstdDecParams* params, void* stream)
+{
+    const ZstdDecParams& p = *reinterpret_cast<const ZstdDecParams*>(params);
+    if (p.n_reads == 0) return 0;
     // 3. the groups of units, a CTA of 64 threads each from a work counter; the grid is sized for the most there can be
     const uint32_t usmem = (uint32_t)sizeof(ZGroupSmem);
     if (int e = VBZK_SET_SMEM(zstd_units_kernel, usmem)) return e;
@@ -195,12 +201,7 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     uint32_t ugrid = p.unit_cap < ugrid_max ? p.unit_cap : ugrid_max;
     if (ugrid) VBZ_LAUNCH(zstd_units_kernel, ugrid, kZUnitThreads, usmem, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
-    // 4. frames with sequences: the records of their Seq units, a warp per unit (the literals are in place, and so is everything the units kernel wrote)
-    const uint32_t smem = (uint32_t)(sizeof(ZWarp) * kZdecWarps);
-    if (int e = VBZK_SET_SMEM(zstd_decode_kernel, smem)) return e;
-    uint32_t grid = vbzk_zstd_decode_grid();
-    const uint32_t need = (p.n_reads + kZdecWarps - 1) / kZdecWarps;
-    if (need < grid) grid = need;
+    // 4. frames with sequences: the records of their Seq units, a warp per chain (the literals are in place, and so is everything the units kernel wrote)
     {
         static const uint32_t xgrid_max = persistent_grid(zstd_seqexec_kernel, kZExecWarps * 32, 0, 0xFFFFFFFFu, 0);
         const uint64_t xneed = ((uint64_t)p.unit_cap + kZExecWarps - 1) / kZExecWarps;
@@ -208,8 +209,18 @@ extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
     }
     if (int e = VBZK_LAST_ERROR()) return e;
     // 5. whatever the walker and the sequence kernel left over, a warp per frame
+    const uint32_t smem = (uint32_t)(sizeof(ZWarp) * kZdecWarps);
+    if (int e = VBZK_SET_SMEM(zstd_decode_kernel, smem)) return e;
+    uint32_t grid = vbzk_zstd_decode_grid();
+    const uint32_t need = (p.n_reads + kZdecWarps - 1) / kZdecWarps;
+    if (need < grid) grid = need;
     VBZ_LAUNCH(zstd_decode_kernel, grid, kZdecWarps * 32, smem, (vbz_stream_t)stream, p);
     return VBZK_LAST_ERROR();
+}
+extern "C" int vbzk_zstd_decode(const VbzkZstdDecParams* params, void* stream)
+{
+    if (int e = vbzk_zstd_decode_front(params, stream)) return e;
+    return vbzk_zstd_decode_back(params, stream);
 }
 
 extern "C" uint32_t vbzk_zstd_enc_block_bytes(void) { return kZEncBlock; }
