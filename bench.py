@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W                 (N > 1: launched under torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W
-    python bench.py --workload {full,transform,uint32,h5z-decode} ...
+    python bench.py --workload {full,transform,uint32,int8,tiled,h5z-decode} ...
 
 Workloads (BASELINE.json configs):
   full        (default, configs[2]) full VBZ {zigzag, int16, zstd 1, v1} - the options the reference's users run (pyvbz and
@@ -14,6 +14,9 @@ Workloads (BASELINE.json configs):
               the same batch (`transform_stage`).
   transform   (configs[1]) the transform stage as the whole benchmark.
   uint32      (configs[3]) {no zigzag, 4-byte integers, zstd 3, v0}: values U[0, 2^20), reads of half as many values.
+  int8        {zigzag, 1-byte integers, zstd 1, v1}: the nibble-packed path of vbz/v1; the signal >> 3, reads of twice as many values.
+  tiled       the full options on the reference benchmark's kind of input (vbz/perf/test_data_generator.h): reads of U[30000, 200000]
+              samples that repeat one 15,643-sample trace - where the zstd stage's matches are everything.
   h5z-decode  (configs[4]) decode-only: 1,000,000 reads presented as H5Z chunk buffers `[u32 size][zstd frame]` WRITTEN BY THE
               REFERENCE (oracle/_ref, outside the timed region), sharded by read index over the ranks with byte-balanced
               contiguous ranges (vbz_compression_b200/shard.py), decoded through the batch form of the filter 32020 callback
@@ -45,7 +48,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SEED = 20261017
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-WORKLOADS = ("full", "transform", "uint32", "h5z-decode")
+WORKLOADS = ("full", "transform", "uint32", "int8", "tiled", "h5z-decode")
 
 
 def parse_args():
@@ -74,6 +77,8 @@ def options_for(workload):
         return CompressionOptions(True, 2, 0, 0)
     if workload == "uint32":
         return CompressionOptions(False, 4, 3, 0)
+    if workload == "int8":
+        return CompressionOptions(True, 1, 1, 1)
     return CompressionOptions(True, 2, 1, 1)
 
 
@@ -81,17 +86,29 @@ def workload_name(workload):
     return {"full": "full VBZ int16 zigzag + zstd level 1 (v1)",
             "transform": "transform-only VBZ (delta+zigzag+StreamVByte, zstd level 0), int16",
             "uint32": "uint32 no-zigzag + zstd level 3 (4-byte integer path, v0)",
+            "int8": "int8 zigzag + zstd level 1, v1: the nibble-packed 1-byte path (ref vbz/v1/vbz_streamvbyte_impl.h:20-301)",
+            "tiled": "full VBZ int16 zigzag + zstd level 1 (v1) on the reference benchmark's kind of input: reads that tile one 15,643-sample trace (ref vbz/perf/test_data_generator.h:29-74)",
             "h5z-decode": "decode-only: reference-written H5Z chunk buffers (int16 zigzag zstd 1, cd_values (0,2,1,1) and (1,2,1,1)) sharded by read index"}[workload]
 
 
-def read_lengths(n_reads, seed):
+def read_lengths(n_reads, seed, workload="full"):
     rng = np.random.default_rng(seed)
+    if workload == "tiled":  # the reference's SignalGenerator: U[30000, 200000] samples per read
+        return rng.integers(30000, 200001, n_reads).astype(np.int64)
     return np.floor(np.exp(rng.uniform(np.log(1e4), np.log(1e6), n_reads))).astype(np.int64)
+
+
+TILE_SAMPLES = 15643  # length of the trace the reference's benchmark tiles (vbz/test/test_data.h)
+
+
+def tile_trace():
+    """the trace the `tiled` workload repeats: nanopore-like, as long as the reference's (its samples stay where they are: test vectors, not bench input)"""
+    return nanopore_like_numpy(TILE_SAMPLES, np.random.default_rng(5))
 
 
 def value_counts(workload, lens):
     """values per read: the uint32 workload uses half as many (4-byte) values, so a read has the same bytes"""
-    return lens // 2 if workload == "uint32" else lens
+    return lens // 2 if workload == "uint32" else (lens * 2 if workload == "int8" else lens)
 
 
 def default_reads(args):
@@ -104,8 +121,10 @@ def workload_config(args, opts):
     c = {"workload": workload_name(args.workload),
          "options": {"perform_delta_zig_zag": bool(opts.perform_delta_zig_zag), "integer_size": opts.integer_size,
                      "zstd_compression_level": opts.zstd_compression_level, "vbz_version": opts.vbz_version},
-         "read_length_samples": "floor(exp(U[ln 1e4, ln 1e6]))" + (" / 2 values of 4 bytes" if args.workload == "uint32" else ""),
-         "signal": "uniform U[0, 2^20) uint32" if args.workload == "uint32" else "nanopore-like random walk (BASELINE.md section 3)",
+         "read_length_samples": "U[30000, 200000]" if args.workload == "tiled" else
+                                "floor(exp(U[ln 1e4, ln 1e6]))" + (" / 2 values of 4 bytes" if args.workload == "uint32" else " x 2 values of 1 byte" if args.workload == "int8" else ""),
+         "signal": {"uint32": "uniform U[0, 2^20) uint32", "int8": "nanopore-like random walk (BASELINE.md section 3) >> 3, as int8",
+                    "tiled": "every read = one nanopore-like trace of 15,643 samples repeated from its first sample on"}.get(args.workload, "nanopore-like random walk (BASELINE.md section 3)"),
          "l2": "inputs (GBs per launch) far larger than the 126 MB L2; no flush needed",
          "cpu_arm_sample_gib": args.cpu_sample_gib}
     if args.workload == "h5z-decode":
@@ -129,10 +148,16 @@ def nanopore_like_numpy(n, rng):
     return np.clip(np.rint(x), -4096, 4095).astype(np.int16)
 
 
-def signal_numpy(workload, n_values, rng):
-    """host-side signal of the workload's model, as bytes"""
+def signal_numpy(workload, lens, rng):
+    """host-side signal of the workload's model for reads of `lens` values, back to back, as bytes"""
+    n_values = int(np.sum(lens))
     if workload == "uint32":
         return rng.integers(0, 1 << 20, n_values, dtype=np.uint32).view(np.uint8)
+    if workload == "int8":
+        return (nanopore_like_numpy(n_values, rng) >> 3).astype(np.int8).view(np.uint8)
+    if workload == "tiled":
+        t = tile_trace()
+        return np.concatenate([np.resize(t, int(n)) for n in lens]).view(np.uint8)
     return nanopore_like_numpy(n_values, rng).view(np.uint8)
 
 
@@ -156,8 +181,21 @@ def nanopore_like_torch(out, seed):
         del change, seg, levels, x
 
 
-def fill_device_signal(workload, d_src, seed):
+def fill_device_signal(workload, d_src, seed, src_off=None, lens=None):
     import torch
+    if workload == "tiled":  # every read starts at the trace's first sample
+        longest = int(max(lens))
+        t = torch.from_numpy(np.resize(tile_trace(), longest)).to(d_src.device)
+        v = d_src.view(torch.int16)
+        v.zero_()
+        for o, n in zip(src_off, lens):
+            v[int(o) // 2:int(o) // 2 + int(n)] = t[:int(n)]
+        return
+    if workload == "int8":
+        tmp = torch.empty(d_src.numel(), dtype=torch.int16, device=d_src.device)
+        nanopore_like_torch(tmp, seed)
+        d_src.view(torch.int8).copy_((tmp >> 3).to(torch.int8))
+        return
     if workload == "uint32":
         g = torch.Generator(device=d_src.device)
         g.manual_seed(seed)
@@ -388,11 +426,11 @@ def main_reference(args):
                 "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit_line(json.dumps(line))
         return
-    lens = value_counts(args.workload, read_lengths(args.reads, SEED))
+    lens = value_counts(args.workload, read_lengths(args.reads, SEED, args.workload))
     isz = opts.integer_size
     take, tot = sample_prefix(lens * isz, int(args.cpu_sample_gib * (1 << 30)))
     rng = np.random.default_rng(SEED + 7)
-    raw = signal_numpy(args.workload, int(lens[:take].sum()), rng)
+    raw = signal_numpy(args.workload, lens[:take], rng)
     lens_b = lens[:take] * isz
     enc, dec, last = [], [], None
     for i in range(total):
@@ -409,7 +447,7 @@ def main_reference(args):
     line = {
         "impl": "reference", "metric": "raw int16 GB/s encode+decode", "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": (e + d) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "uint32" if args.workload == "uint32" else "int16", "data": "synthetic",
+        "dtype": {"uint32": "uint32", "int8": "int8"}.get(args.workload, "int16"), "data": "synthetic",
         "config": workload_config(args, opts),
         "encode_gbs": raw.nbytes / e / 1e9, "decode_gbs": raw.nbytes / d / 1e9, "ratio": last["ratio"],
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": last["threads"], "kind": "reference", "sample": sample},
@@ -484,10 +522,10 @@ def main_codec(args):
     opts = options_for(args.workload)
     isz = opts.integer_size
     two_stage = opts.zstd_compression_level != 0
-    s1_name = "svb16" if args.workload != "uint32" else "svb<4,nozz>"
+    s1_name = {"uint32": "svb<4,nozz>", "int8": "svb_half<zz>"}.get(args.workload, "svb16")
 
     # ---- the batch, resident in HBM ---------------------------------------------------------------------
-    lens = value_counts(args.workload, read_lengths(args.reads, SEED + rank))
+    lens = value_counts(args.workload, read_lengths(args.reads, SEED + rank, args.workload))
     n = len(lens)
     src_size = (lens * isz).astype(np.uint32)
     a16 = lambda v: (v + 15) & ~np.uint64(15)
@@ -498,7 +536,7 @@ def main_codec(args):
     raw_bytes = int(src_size.astype(np.int64).sum())
     total_src, total_dst = int(src_slot.sum()), int(caps.sum())
     d_src = torch.empty(total_src, dtype=torch.uint8, device=dev)
-    fill_device_signal(args.workload, d_src, SEED + rank)
+    fill_device_signal(args.workload, d_src, SEED + rank, src_off, lens)
     d_cmp = torch.empty(total_dst, dtype=torch.uint8, device=dev)
     d_back = torch.empty(total_src, dtype=torch.uint8, device=dev)
     d_res_c = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -592,7 +630,7 @@ def main_codec(args):
     if two_stage:
         # BASELINE configs[1] on the same resident batch: the same options with zstd level 0
         from vbz_compression_b200 import CompressionOptions
-        t_opts = CompressionOptions(bool(opts.perform_delta_zig_zag), isz, 0, 0)
+        t_opts = CompressionOptions(bool(opts.perform_delta_zig_zag), isz, 0, opts.vbz_version)
         t_caps = np.array([lib.vbz_b200_compress_bound(int(s), ctypes.byref(t_opts), 1) for s in src_size], np.uint32)
         assert (t_caps.astype(np.uint64) <= caps).all()
         t_size = [None]
@@ -676,7 +714,7 @@ def main_codec(args):
             if x:
                 cpu["reference_decode_of_gpu_frames_gbs"] = x["decode_gbs"]
 
-    dtype = "uint32" if args.workload == "uint32" else "int16"
+    dtype = {"uint32": "uint32", "int8": "int8"}.get(args.workload, "int16")
     line = {
         "metric": "raw %s GB/s encode+decode" % dtype, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",

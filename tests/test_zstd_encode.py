@@ -159,6 +159,8 @@ def test_repetitive_inputs_compress_like_libzstd(backend):
     fixture = golden_data.fast5_reads()[0]["samples"]
     cases = [("arange", np.arange(1000, dtype=np.int16), 40, None), ("tiled synthetic trace", np.tile(trace, 30 if small else 100), None, 1.5),
              ("tiled fixture trace", np.tile(fixture[:5000], 10 if small else 30), None, 1.5), ("constant", np.full(60000, 7, np.int16), 64, None),
+             # a period as long as the reference benchmark's trace (15,643 samples = 16 KB of data bytes: the look-back into the group before)
+             ("long period", np.resize(data_gen.nanopore_like(15643, rng), 90000 if small else 190000), None, 1.15),
              ("zeros", np.zeros(100000, np.int16), 64, None)]
     for level in (1, 3):
         o = Options(True, 2, level, 1)

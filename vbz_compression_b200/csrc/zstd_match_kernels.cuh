@@ -78,7 +78,8 @@ __device__ __forceinline__ bool zenc_locate(const ZstdEncParams& p, uint32_t b, 
 
 constexpr uint32_t kZHashLog = 10;
 constexpr uint32_t kZTagBits = 14;          // a table entry = (window coordinate + 1) << 14 | 14 more bits of the hash: a lane only goes to memory to verify a candidate whose tag agrees
-constexpr uint32_t kZPreWindow = 8192;       // bytes before the group that seed the hash table
+constexpr uint32_t kZPreWindow = 65536;      // bytes before the group that seed the hash table (a period of the reference benchmark's tiled trace is 16 KB of data bytes)
+constexpr uint32_t kZPreDense = 4096;        // ... the nearest of them one position in four, the rest one in sixteen
 constexpr uint32_t kZMinRun = 12;            // shortest run (offset 1) worth a sequence
 constexpr uint32_t kZMinMatch = 6;           // shortest match at any other offset
 constexpr uint32_t kZMinKeyMatch = 32;       // ... among the control bytes of a stage-1 stream
@@ -362,15 +363,28 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
 
     for (uint32_t i = lane; i < (1u << kZHashLog); i += 32) sm->table[i] = 0;  // entry = (window coordinate + 1, tag), 0 = empty
     __syncwarp();
-    // seed with the pre-window, one position in four (a repeat that matters is long: the dense steps at the head of the group look at
-    // every phase of it).  Later positions overwrite earlier ones.
-    for (uint32_t w0 = 0; w0 + 12 <= pre; w0 += 128) {
-        const uint32_t w = w0 + 4 * lane;
-        if (w + 12 <= pre) {
-            uint32_t lo, hi;
-            zm_load64(win + w, lo, hi);
-            const uint32_t h = zm_hash(lo, hi);
-            atomicMax(&sm->table[zm_index(h)], zm_entry(h, w));  // (lanes of a step may share an entry: the latest position stays, whatever the order)
+    // seed with the pre-window: one position in sixteen, one in four over the nearest 4 KiB (a repeat that matters is long: the dense steps
+    // at the head of the group look at every phase of it, one hit is enough).  Later positions replace earlier ones.
+    {
+        const uint32_t far_end = pre > kZPreDense ? (pre - kZPreDense) & ~15u : 0u;
+        for (uint32_t w0 = 0; w0 < far_end; w0 += 512) {
+            const uint32_t w = w0 + 16 * lane;
+            if (w < far_end) {
+                uint32_t lo, hi;
+                zm_load64(win + w, lo, hi);
+                const uint32_t h = zm_hash(lo, hi);
+                atomicMax(&sm->table[zm_index(h)], zm_entry(h, w));  // (lanes of a step may share an entry: the latest position stays, whatever the order)
+            }
+        }
+        __syncwarp();
+        for (uint32_t w0 = far_end; w0 + 12 <= pre; w0 += 128) {
+            const uint32_t w = w0 + 4 * lane;
+            if (w + 12 <= pre) {
+                uint32_t lo, hi;
+                zm_load64(win + w, lo, hi);
+                const uint32_t h = zm_hash(lo, hi);
+                atomicMax(&sm->table[zm_index(h)], zm_entry(h, w));
+            }
         }
         __syncwarp();
     }
