@@ -1246,15 +1246,15 @@ __device__ uint32_t z_lane_sequences(const ZSeqWarp* zw, int al_ll, int al_of, i
     const uint32_t phase = (uint32_t)((uintptr_t)p & 3u);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(p - phase);  // stream bit k = bit 8 * phase + k of this array of words
     const uint32_t lead = 8u * phase, wlast = (phase + n - 1) >> 2;
-    long long left = (long long)(n - 1) * 8 + z_highbit(p[n - 1]);  // unread bits (negative: the reader ran past the start)
+    int32_t left = (int32_t)((n - 1) * 8) + z_highbit(p[n - 1]);  // unread bits (n <= 2^24; negative: the reader ran past the start)
     // n bits below bit position lead + left (n <= 32); bits before the stream read as zero
     auto slow_read = [&](uint32_t nb) -> uint32_t {
         if (nb == 0) return 0u;
         left -= nb;
         uint64_t v = 0;
-        const long long from = left;  // stream bit index of the field's lowest bit (may be negative)
-        const long long lo = from < 0 ? 0 : from;
-        const long long hi = from + nb;  // exclusive
+        const int32_t from = left;  // stream bit index of the field's lowest bit (may be negative)
+        const int32_t lo = from < 0 ? 0 : from;
+        const int32_t hi = from + (int32_t)nb;  // exclusive
         if (hi > 0) {
             const uint32_t a = lead + (uint32_t)lo, wi = a >> 5, sh = a & 31u;
             const uint64_t two = (uint64_t)words[wi] | ((uint64_t)(((a + (uint32_t)(hi - lo) - 1) >> 5) > wi ? words[wi + 1] : 0u) << 32);
@@ -1272,7 +1272,7 @@ __device__ uint32_t z_lane_sequences(const ZSeqWarp* zw, int al_ll, int al_of, i
     // It is reloaded from three aligned words whenever fewer than 64 - spent bits could be needed; between reloads fields are cut out
     // of the pair at their offsets - six independent extractions, no chain through a shifting window.
     uint32_t lo = 0, hi = 0;
-    long long wtop = -1;  // (no window yet)
+    int32_t wtop = -1;  // (no window yet)
     for (uint32_t i = 0; i < nseq; ++i) {
         const uint2 cl = zw->ll[sl], co = zw->of[so], cm = zw->ml[sm];
         const uint32_t ofb = co.x >> 24, mlb = cm.x >> 24, llb = cl.x >> 24;
