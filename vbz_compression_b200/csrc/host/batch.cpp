@@ -666,7 +666,14 @@ extern "C" vbz_b200_ctx* vbz_b200_create(int device)
     for (int k = 0; ok && k < 2; ++k)
         ok = cuda_ok(cudaEventCreateWithFlags(&c->ev_front[k], cudaEventDisableTiming), "cudaEventCreate") &&
              cuda_ok(cudaEventCreateWithFlags(&c->ev_back[k], cudaEventDisableTiming), "cudaEventCreate");
-    for (int k = 1; ok && k < vbz_b200_ctx::kKernelStreams; ++k) ok = cuda_ok(cudaStreamCreateWithFlags(&c->kstream[k], cudaStreamNonBlocking), "cudaStreamCreate");
+    {
+        // kstream[1] carries the decoder's look-ahead (the walker and the sequence kernel of the next wave): highest priority, so that its
+        // CTAs are placed before the persistent grids of the wave that is being written fill the SMs
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        for (int k = 1; ok && k < vbz_b200_ctx::kKernelStreams; ++k)
+            ok = cuda_ok(cudaStreamCreateWithPriority(&c->kstream[k], cudaStreamNonBlocking, k == 1 ? hi_prio : lo_prio), "cudaStreamCreate");
+    }
     for (vbz_b200_ctx::WaveSlot& w : c->slots)
         ok = ok && cuda_ok(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming), "cudaEventCreate") &&
              cuda_ok(cudaEventCreateWithFlags(&w.ev_k, cudaEventDisableTiming), "cudaEventCreate") &&
