@@ -147,6 +147,12 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v)
     for (unsigned i = 0; i < cpusim::g_cur->warp->nlanes; ++i) s += cpusim::warp_exchange(v, i);
     return s;
 }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v)
+{
+    unsigned s = 0;
+    for (unsigned i = 0; i < cpusim::g_cur->warp->nlanes; ++i) s |= cpusim::warp_exchange(v, i);
+    return s;
+}
 static inline unsigned __activemask() { return cpusim::g_cur->warp->nlanes == 32 ? 0xffffffffu : ((1u << cpusim::g_cur->warp->nlanes) - 1); }
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
