@@ -153,6 +153,18 @@ static inline unsigned __reduce_or_sync(unsigned, unsigned v)
     for (unsigned i = 0; i < cpusim::g_cur->warp->nlanes; ++i) s |= cpusim::warp_exchange(v, i);
     return s;
 }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v)
+{
+    unsigned s = 0;
+    for (unsigned i = 0; i < cpusim::g_cur->warp->nlanes; ++i) { const unsigned x = cpusim::warp_exchange(v, i); if (x > s) s = x; }
+    return s;
+}
+static inline unsigned __match_any_sync(unsigned, int v)
+{
+    unsigned m = 0;
+    for (unsigned i = 0; i < cpusim::g_cur->warp->nlanes; ++i) if (cpusim::warp_exchange((unsigned)v, i) == (unsigned)v) m |= 1u << i;
+    return m;
+}
 static inline unsigned __activemask() { return cpusim::g_cur->warp->nlanes == 32 ? 0xffffffffu : ((1u << cpusim::g_cur->warp->nlanes) - 1); }
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -110,97 +110,150 @@ __device__ __forceinline__ uint32_t zw_close(ZBitW& w, bool marker)  // -> bytes
 
 // ---- Huffman code of one block (one thread; cnt[], order[] are ready) -------------------------------------------
 // -> len[], code[], max_bits.  Returns false if no valid code could be built (the block is then stored raw).
-__device__ bool zenc_build_code(ZCode* s, int nsym)
+// All lanes call.  The two-queue merge and the depth chain are serial (lane 0: ~2 n dependent steps); everything that is a map or a
+// reduction over the symbols - leaf lengths, Kraft sum, the census of lengths, the canonical codes - is spread over the warp.
+__device__ bool zenc_build_code(ZCode* s, int nsym, uint32_t lane)
 {
-    // two-queue construction over the leaves sorted by ascending count: leaves 0..nsym-1, internal nodes nsym..2nsym-2
     const int n = nsym;
-    int li = 0, ii = 0, made = 0;
-    for (made = 0; made < n - 1; ++made) {
-        uint32_t w = 0;
-        for (int k = 0; k < 2; ++k) {
-            const bool leaf_ok = li < n, int_ok = ii < made;
-            bool take_leaf;
-            if (leaf_ok && int_ok) take_leaf = s->cnt[s->order[li]] <= s->nodew[ii];
-            else take_leaf = leaf_ok;
-            if (take_leaf) { w += s->cnt[s->order[li]]; s->parent[li] = (uint16_t)(n + made); ++li; }
-            else { w += s->nodew[ii]; s->parent[n + ii] = (uint16_t)(n + made); ++ii; }
+    uint32_t* scratch = s->nodew + 224;  // 32 words at the end of nodew: census of lengths [0..12], first cell per weight [16..28] (n <= 256 nodes use [0, n - 1))
+    if (lane == 0) {
+        // two-queue construction over the leaves sorted by ascending count: leaves 0..nsym-1, internal nodes nsym..2nsym-2
+        int li = 0, ii = 0, made = 0;
+        for (made = 0; made < n - 1; ++made) {
+            uint32_t w = 0;
+            for (int k = 0; k < 2; ++k) {
+                const bool leaf_ok = li < n, int_ok = ii < made;
+                bool take_leaf;
+                if (leaf_ok && int_ok) take_leaf = s->cnt[s->order[li]] <= s->nodew[ii];
+                else take_leaf = leaf_ok;
+                if (take_leaf) { w += s->cnt[s->order[li]]; s->parent[li] = (uint16_t)(n + made); ++li; }
+                else { w += s->nodew[ii]; s->parent[n + ii] = (uint16_t)(n + made); ++ii; }
+            }
+            s->nodew[made] = w;
         }
-        s->nodew[made] = w;
+        // depths: the root is node 2n-2; a parent always has a larger index than its children
+        // (the depth of an internal node is kept in nodew, whose weights are no longer needed)
+        s->nodew[n - 2] = 0;
+        for (int k = n - 3; k >= 0; --k) s->nodew[k] = s->nodew[s->parent[n + k] - n] + 1;
     }
-    // depths: the root is node 2n-2; a parent always has a larger index than its children
-    // (the depth of an internal node is kept in the low byte of nodew, which is no longer needed)
-    s->nodew[n - 2] = 0;
-    for (int k = n - 3; k >= 0; --k) s->nodew[k] = s->nodew[s->parent[n + k] - n] + 1;
-    int max_len = 0;
-    for (int i = 0; i < n; ++i) {
+    __syncwarp();
+    // leaf lengths (limit 11) and the Kraft sum in units of 2^-11
+    int kraft = 0;
+    for (int i = (int)lane; i < n; i += 32) {
         int d = (int)s->nodew[s->parent[i] - n] + 1;
         if (d > 11) d = 11;
         s->len[s->order[i]] = (uint8_t)d;
-        if (d > max_len) max_len = d;
+        kraft += 1 << (11 - d);
     }
-    // length limit 11: repair the Kraft sum (in units of 2^-11).  Too large -> lengthen the rarest symbols that can
-    // still grow; too small -> shorten, each time the most frequent symbol whose gain fits.
-    int kraft = 0;
-    for (int i = 0; i < n; ++i) kraft += 1 << (11 - s->len[s->order[i]]);
-    int guard = 0;
-    // order[] is ascending by count and a symbol only ever grows to 11, so "the rarest symbol that can still grow" is a
-    // pointer that moves one way: everything before it has reached 11 bits
-    for (int pick = 0; kraft > 2048;) {
-        while (pick < n && s->len[s->order[pick]] >= 11) ++pick;
-        if (pick >= n) return false;
-        const int sym = s->order[pick];
-        kraft -= 1 << (10 - s->len[sym]);
-        s->len[sym]++;
-    }
-    while (kraft < 2048) {
-        const int slack = 2048 - kraft;
-        int pick = -1;
-        for (int i = n - 1; i >= 0; --i) {  // most frequent first
-            const int L = s->len[s->order[i]];
-            if (L > 1 && (1 << (11 - L)) <= slack) { pick = i; break; }
+    kraft = (int)__reduce_add_sync(0xffffffffu, (uint32_t)kraft);
+    __syncwarp();
+    if (kraft != 2048) {
+        // length limit 11: repair the Kraft sum.  Too large -> lengthen the rarest symbols that can still grow; too small -> shorten, each
+        // time the most frequent symbol whose gain fits (lane 0: a few steps, each depends on the one before)
+        uint32_t ok = 1;
+        if (lane == 0) {
+            int guard = 0;
+            // order[] is ascending by count and a symbol only ever grows to 11, so "the rarest symbol that can still grow" is a
+            // pointer that moves one way: everything before it has reached 11 bits
+            for (int pick = 0; kraft > 2048 && ok;) {
+                while (pick < n && s->len[s->order[pick]] >= 11) ++pick;
+                if (pick >= n) { ok = 0; break; }
+                const int sym = s->order[pick];
+                kraft -= 1 << (10 - s->len[sym]);
+                s->len[sym]++;
+            }
+            while (kraft < 2048 && ok) {
+                const int slack = 2048 - kraft;
+                int pick = -1;
+                for (int i = n - 1; i >= 0; --i) {  // most frequent first
+                    const int L = s->len[s->order[i]];
+                    if (L > 1 && (1 << (11 - L)) <= slack) { pick = i; break; }
+                }
+                if (pick < 0 || ++guard > 4096) { ok = 0; break; }
+                const int sym = s->order[pick];
+                kraft += 1 << (11 - s->len[sym]);
+                s->len[sym]--;
+            }
         }
-        if (pick < 0 || ++guard > 4096) return false;
-        const int sym = s->order[pick];
-        kraft += 1 << (11 - s->len[sym]);
-        s->len[sym]--;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) return false;
+        __syncwarp();
     }
-    max_len = 0;
-    for (int i = 0; i < n; ++i)
-        if (s->len[s->order[i]] > max_len) max_len = s->len[s->order[i]];
+    // the longest code, the census of lengths
+    uint32_t longest = 0;
+    for (int i = (int)lane; i < n; i += 32) { const uint32_t L = s->len[s->order[i]]; if (L > longest) longest = L; }
+    const int max_len = (int)__reduce_max_sync(0xffffffffu, longest);
+    scratch[lane] = 0;
+    __syncwarp();
+    for (int i = (int)lane; i < n; i += 32) atomicAdd(&scratch[max_len + 1 - s->len[s->order[i]]], 1u);
+    __syncwarp();
     // canonical code in the decoder's table order: longest codes (weight 1) first, symbols ascending within a weight
-    uint32_t rank[13], start[13];
-    for (int w = 0; w < 13; ++w) rank[w] = 0;
-    for (int i = 0; i < n; ++i) rank[max_len + 1 - s->len[s->order[i]]]++;
-    uint32_t acc = 0;
-    for (int w = 1; w <= max_len; ++w) { start[w] = acc; acc += rank[w] << (w - 1); }
-    if (acc != (1u << max_len)) return false;
-    for (int sym = 0; sym < 256; ++sym) {
-        const int L = s->cnt[sym] ? s->len[sym] : 0;
-        if (!L) { s->code[sym] = 0; s->len[sym] = 0; continue; }
-        const int w = max_len + 1 - L;
-        s->code[sym] = (start[w] >> (w - 1)) | ((uint32_t)L << 16);
-        start[w] += 1u << (w - 1);
+    uint32_t ok = 1;
+    if (lane == 0) {
+        uint32_t acc = 0;
+        for (int w = 1; w <= max_len; ++w) { scratch[16 + w] = acc; acc += scratch[w] << (w - 1); }
+        if (acc != (1u << max_len)) ok = 0;
     }
-    s->max_bits = (uint32_t)max_len;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return false;
+    __syncwarp();
+    // a row of 32 consecutive symbols at a time: a symbol's place among those of its weight = what earlier rows used up (kept in
+    // scratch[16 + w]) + the lanes before it in the row with the same weight
+    for (int row = 0; row < 8; ++row) {
+        const int sym = row * 32 + (int)lane;
+        const int L = s->cnt[sym] ? s->len[sym] : 0;
+        const int w = L ? max_len + 1 - L : 0;
+        const uint32_t peers = __match_any_sync(0xffffffffu, w);
+        if (!L) { s->code[sym] = 0; s->len[sym] = 0; }
+        else {
+            const uint32_t idx = (uint32_t)__popc((int)(peers & ((1u << lane) - 1u)));
+            const uint32_t first = scratch[16 + w];
+            s->code[sym] = ((first >> (w - 1)) + idx) | ((uint32_t)L << 16);
+        }
+        __syncwarp();
+        if (L && lane == (uint32_t)__ffs((int)peers) - 1) scratch[16 + w] += (uint32_t)__popc((int)peers) << (w - 1);
+        __syncwarp();
+    }
+    if (lane == 0) s->max_bits = (uint32_t)max_len;
+    __syncwarp();
     return true;
 }
 
 // ---- tree description (one thread) -> s->tree, returns its size in bytes (0 = cannot be described) -------------------
-__device__ uint32_t zenc_describe_tree(ZCode* s)
+// All lanes call: the weights and their census are spread over the warp; the description proper - a few dozen values, then a chain of FSE
+// states - is lane 0's.  Returns (in every lane) the size in bytes, 0 = cannot be described.
+__device__ uint32_t zenc_describe_tree_lane0(ZCode* s, int nw, const uint32_t* census);
+__device__ uint32_t zenc_describe_tree(ZCode* s, uint32_t lane)
 {
     const int max_bits = (int)s->max_bits;
-    int last = 255;
-    while (last > 0 && s->len[last] == 0) --last;
+    uint32_t top = 0;
+    for (int k = 0; k < 8; ++k) { const uint32_t sym = (uint32_t)k * 32 + lane; if (s->len[sym]) top = sym; }
+    int last = (int)__reduce_max_sync(0xffffffffu, top);
     const int nw = last;  // weights of symbols 0..last-1; the last one is implied
-    for (int i = 0; i < nw; ++i) s->weights[i] = s->len[i] ? (uint8_t)(max_bits + 1 - s->len[i]) : 0;
+    uint32_t* census = s->nodew + 224;  // (the code is built: nodew is free)
+    census[lane] = 0;
+    __syncwarp();
+    for (int i = (int)lane; i < nw; i += 32) {
+        const uint8_t w = s->len[i] ? (uint8_t)(max_bits + 1 - s->len[i]) : 0;
+        s->weights[i] = w;
+        atomicAdd(&census[w], 1u);
+    }
+    __syncwarp();
+    uint32_t bytes = 0;
+    if (lane == 0) bytes = zenc_describe_tree_lane0(s, nw, census);
+    bytes = __shfl_sync(0xffffffffu, bytes, 0);
+    __syncwarp();
+    return bytes;
+}
+__device__ uint32_t zenc_describe_tree_lane0(ZCode* s, int nw, const uint32_t* census)
+{
     uint32_t direct = 0;
     if (nw <= 128) direct = 1 + (uint32_t)(nw + 1) / 2;
     uint32_t fse_bytes = 0;
     if (nw >= 2) {
         // FSE-compress the weights: accuracy log 6, every present value gets at least one cell
         int hist[13];
-        for (int w = 0; w < 13; ++w) hist[w] = 0;
-        for (int i = 0; i < nw; ++i) hist[s->weights[i]]++;
+        for (int w = 0; w < 13; ++w) hist[w] = (int)census[w];
         int maxw = 12;
         while (maxw > 0 && hist[maxw] == 0) --maxw;
         int distinct = 0;
@@ -596,15 +649,11 @@ __global__ void __launch_bounds__(kZcodeWarps * 32) zstd_enc_code_kernel(ZstdEnc
     __syncwarp();
     // ---- the code and the kind of group (lane 0) -------------------------------------------------------------------------
     uint32_t kind = kZKindRaw, tree_bytes = 0;
-    if (lane == 0) {
-        if (B > 0 && nsym == 1 && !any_s) kind = kZKindRle;
-        else if (nsym >= 2 && B >= 32 && zenc_build_code(s, (int)nsym)) {
-            tree_bytes = zenc_describe_tree(s);
-            if (tree_bytes) kind = kZKindHuf;
-        }
+    if (B > 0 && nsym == 1 && !any_s) kind = kZKindRle;
+    else if (nsym >= 2 && B >= 32 && zenc_build_code(s, (int)nsym, lane)) {
+        tree_bytes = zenc_describe_tree(s, lane);
+        if (tree_bytes) kind = kZKindHuf;
     }
-    kind = __shfl_sync(0xffffffffu, kind, 0);
-    tree_bytes = __shfl_sync(0xffffffffu, tree_bytes, 0);
     __syncwarp();
     ZGroupCode* out = reinterpret_cast<ZGroupCode*>(p.codes) + b;
     if (kind == kZKindHuf) {
