@@ -250,7 +250,10 @@ __device__ uint32_t zenc_describe_tree_lane0(ZCode* s, int nw, const uint32_t* c
     uint32_t direct = 0;
     if (nw <= 128) direct = 1 + (uint32_t)(nw + 1) / 2;
     uint32_t fse_bytes = 0;
-    if (nw >= 2) {
+    // An alphabet of up to 128 symbols (control bytes, literals of S groups) sends its weights as they are, 4 bits each: some 30 bytes more
+    // per tree than FSE-compressed ones (+0.03 % on signal), but neither this lane nor the decoder's has to walk a chain of FSE states for
+    // it - and half of all trees are of this kind (encode 88.8 -> 86.4 ms, decode 66.9 -> 65.1 ms per 100,000 reads).
+    if (nw >= 2 && !(direct && zm_tune("VBZ_TUNE_DIRECTW", 1u))) {
         // FSE-compress the weights: accuracy log 6, every present value gets at least one cell
         int hist[13];
         for (int w = 0; w < 13; ++w) hist[w] = (int)census[w];
