@@ -569,6 +569,9 @@ static int decompress_device_impl(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8
         ctx->use_zdec((int)(w & 1));
         if (w >= 2) cudaStreamWaitEvent(s2, ctx->ev_back[w & 1], 0);  // the set's previous user (wave w - 2) is done with it
         const int e = decompress_wave(ctx, d_src, d_dst, jobs.data() + waves[w].first, waves[w].second - waves[w].first, d_results + waves[w].first, kind, sized, s2, 1, &st[w & 1]);
+        // the units kernel of this wave leaves a seventh of its persistent grid out: room for the look-ahead of the wave behind it to start
+        // at once instead of behind it (measured: 100 % -> 414 GB/s over the step, 87 % -> 421-423, 75 % -> 416)
+        st[w & 1].p.pad = 86;
         cudaEventRecord(ctx->ev_front[w & 1], s2);
         return e;
     };

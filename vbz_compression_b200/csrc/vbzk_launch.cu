@@ -198,7 +198,10 @@ extern "C" int vbzk_zstd_decode_back(const VbzkZstdDecParams* params, void* stre
     const uint32_t usmem = (uint32_t)sizeof(ZGroupSmem);
     if (int e = VBZK_SET_SMEM(zstd_units_kernel, usmem)) return e;
     static const uint32_t ugrid_max = persistent_grid(zstd_units_kernel, kZUnitThreads, usmem, 0xFFFFFFFFu, 0);
-    uint32_t ugrid = p.unit_cap < ugrid_max ? p.unit_cap : ugrid_max;
+    // (ZstdDecParams::pad = per cent of the persistent grid to use, 0 = all: with the next wave's walker and sequence kernel waiting on a second
+    // stream, a grid that fills every SM to the last thread keeps them out until it retires - csrc/host/batch.cpp: decompress_device_impl)
+    const uint32_t ucap = p.pad > 0 && p.pad < 100 ? (uint32_t)((uint64_t)ugrid_max * p.pad / 100) : ugrid_max;
+    uint32_t ugrid = p.unit_cap < ucap ? p.unit_cap : ucap;
     if (ugrid) VBZ_LAUNCH(zstd_units_kernel, ugrid, kZUnitThreads, usmem, (vbz_stream_t)stream, p);
     if (int e = VBZK_LAST_ERROR()) return e;
     // 4. frames with sequences: the records of their Seq units, a warp per chain (the literals are in place, and so is everything the units kernel wrote)
