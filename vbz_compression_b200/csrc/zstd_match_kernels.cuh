@@ -877,7 +877,9 @@ __global__ void __launch_bounds__(kZSeqEncWarps * 32) zstd_enc_seq_kernel(ZstdEn
         const uint32_t lsum = warp_scan_u32(ll);
         if (i < nseq) {
             const uint32_t c = lit_before + lsum - ll;  // literals of the group before this sequence's run
-            uint32_t blk = (c + ll) >> shift;            // the block in which the run ends (a run that ends on a boundary opens the next block)
+            // the block that holds the last literal in front of the match (none: block 0).  A run that ends on a slice boundary stays with the
+            // block it fills: no block starts with a match, so only a genuine long offset makes a block wait for the one before it in the decoder
+            uint32_t blk = c + ll ? (c + ll - 1) >> shift : 0u;
             if (blk >= nblk) blk = nblk - 1;
             const uint32_t start = blk << shift;
             const uint32_t ll_in = c + ll - (c > start ? c : start);
