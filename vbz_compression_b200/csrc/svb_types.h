@@ -152,7 +152,7 @@ struct ZstdEncParams {
     uint32_t* hist;              // n_blocks x 256: literal histogram of every S group
 };
 constexpr uint32_t kZEncBlock = 128u * 1024u;  // content bytes per GROUP of the encoder: blocks that share one Huffman table
-constexpr uint32_t kZEncBlockKeys = 32u * 1024u;  // ... in the control-byte region of a stage-1 stream (csrc/zstd_match_kernels.cuh: zenc_locate)
+constexpr uint32_t kZEncBlockKeys = 64u * 1024u;  // ... in the control-byte region of a stage-1 stream (csrc/zstd_match_kernels.cuh: zenc_locate)
 constexpr uint32_t kZEncSub = 8u * 1024u;     // content bytes per block written by the encoder
 constexpr uint32_t kZGroupMetaBytes = 144;    // sizeof(ZGroupMeta), csrc/zstd_match_kernels.cuh
 constexpr uint32_t kZGroupCodeBytes = 1200;   // sizeof(ZGroupCode), csrc/zstd_enc_kernels.cuh

@@ -104,7 +104,7 @@ struct ZGroupMeta {
 static_assert(sizeof(ZGroupMeta) == kZGroupMetaBytes, "ZGroupMeta layout");
 // literals per block of an S group: 2 KiB among control bytes (a group there is sequences more than anything else, and a block's sequences are
 // serial work for one lane in zstd_enc_seq_kernel and in the decoder alike: 16 blocks = 16 lanes), 8 KiB among data bytes
-__device__ __forceinline__ uint32_t zm_slice_shift(bool keys) { return keys ? 11u : 13u; }
+__device__ __forceinline__ uint32_t zm_slice_shift(bool keys) { return keys ? 12u : 13u; }
 
 __device__ __forceinline__ uint64_t zm_pack(uint32_t off, uint32_t ll, uint32_t ml) { return (uint64_t)off | ((uint64_t)ll << 18) | ((uint64_t)ml << 36); }
 __device__ __forceinline__ uint32_t zm_off(uint64_t r) { return (uint32_t)r & 0x3FFFFu; }
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kZMatchWarps * 32) zstd_enc_match_kernel(ZstdE
     // bits each) a short one does
     const uint32_t need = g.keys ? zm_tune("VBZ_TUNE_KEYMATCH", kZMinKeyMatch) : zm_tune("VBZ_TUNE_MINMATCH", kZMinMatch);
     const uint32_t key_nz = zm_tune("VBZ_TUNE_KEYNZ", 2u);
-    const uint32_t key_stride = zm_tune("VBZ_TUNE_KEYSTRIDE", 255u);
+    const uint32_t key_stride = zm_tune("VBZ_TUNE_KEYSTRIDE", 32u);
     const uint32_t end = B - 11;  // positions q < end are looked at: the loads of a position reach up to q + 10
 
     for (uint32_t i = lane; i < (1u << kZHashLog); i += 32) sm->table[i] = 0;  // entry = (window coordinate + 1, tag), 0 = empty
