@@ -54,3 +54,125 @@ def test_whole_file_decodes_as_one_batch(backend, name):
     assert set(got) == set(want) and len(got) == 10
     for k in want:
         assert got[k].dtype == np.int16 and np.array_equal(got[k], want[k]), k
+
+
+# ---- the writer half (python/fast5compress/fast5vbz.py:17-55) ------------------------------------------------------------------------------
+
+def _signal_header(f, which=0):
+    """(dataset, {message type: body bytes}) of one /read_*/Raw/Signal as libhdf5 wrote it."""
+    name = sorted(p for p in f.objects() if fast5.is_read_signal(p))[which]
+    msgs = f._messages(f.objects()[name])
+    return f._dataset(name, msgs), {t: bytes(f.b[d:d + size]) for t, d, size in msgs}
+
+
+def test_written_structures_equal_what_libhdf5_writes():
+    """The pieces the transcoder generates, byte for byte against the same pieces in the reference's files (written by h5py/libhdf5)."""
+    v1 = fast5.Fast5File.open(os.path.join(DATA, "multi_fast5_vbz_v1.fast5"))
+    ds, msgs = _signal_header(v1)
+    assert fast5.vbz_pipeline(1, 2, True, 1) == msgs[0x000B]
+    layout = msgs[0x0008]
+    tree = int.from_bytes(layout[3:11], "little")
+    assert fast5.chunked_layout_message(v1, tree, ds.shape[0], 2) == layout
+    c = ds.chunks[0]
+    assert fast5.chunk_btree_node(v1, [(c.size, 0, 0, c.address)], ds.shape[0], 2) == bytes(v1.b[tree:tree + v1.chunk_node_size(1)])
+    assert v1.chunk_node_size(1) == 2096
+    z = fast5.Fast5File.open(os.path.join(DATA, "multi_fast5_zip.fast5"))
+    zds, zmsgs = _signal_header(z)
+    assert fast5.gzip_pipeline(1) == zmsgs[0x000B]
+    # a whole header: the zip fixture's Signal header has no padding message, so it must come out identical
+    name = zds.name
+    hdr = z.objects()[name]
+    raw = [(t, z.b[d - 4], bytes(z.b[d:d + size])) for t, d, size in z._messages(hdr)]
+    size = 16 + z._u(hdr + 8, 4)
+    assert fast5.object_header(raw, 1) == bytes(z.b[hdr:hdr + size])
+
+
+@pytest.mark.parametrize("backend", product.BACKENDS)
+@pytest.mark.parametrize("vbz_version", [0, 1])
+def test_transcode_gzip_to_vbz_and_back(backend, vbz_version):
+    capi, batch, _ = product.get(backend)
+    src = open(os.path.join(DATA, "multi_fast5_zip.fast5"), "rb").read()
+    want = _zip_signals(os.path.join(DATA, "multi_fast5_zip.fast5"))
+    l0 = batch.kernel_launches
+    out = fast5.transcode(src, batch, vbz_version=vbz_version)
+    assert batch.kernel_launches > l0
+    f, g = fast5.Fast5File(src), fast5.Fast5File(out)
+    # the signal: through this library, and every chunk through the unmodified reference
+    got = fast5.read_vbz_signals(out, batch)
+    assert set(got) == set(want)
+    ref = product.oracle_lib.ref() or product.oracle_lib.port()
+    for d in g.datasets():
+        assert np.array_equal(got[d.name], want[d.name]), d.name
+        assert d.vbz_cd_values == [vbz_version, 2, 1, 1] and d.chunk_shape == d.shape and len(d.chunks) == 1
+        opts = product.oracle_lib.Options(True, 2, 1, vbz_version)
+        code, raw = ref.decompress(np.frombuffer(g.chunk_bytes(d.chunks[0]), np.uint8), opts, 2 * d.shape[0], sized=True)
+        assert code == 2 * d.shape[0] and np.array_equal(np.frombuffer(raw, np.int16), want[d.name])
+    # everything else: same objects, same attributes (variable-length strings followed into the global heap)
+    fo, go = f.objects(), g.objects()
+    assert set(fo) == set(go) and len(go) == 151
+    assert sum(len(f.attributes(h)) for h in fo.values()) == 701
+    for p in fo:
+        assert f.attributes(fo[p]) == g.attributes(go[p]), p
+    # the file shrank by what the chunks shrank, give or take the new headers, and says so itself
+    saved = sum(c.size for d in f.datasets() for c in d.chunks) - sum(c.size for d in g.datasets() for c in d.chunks)
+    assert abs((len(src) - len(out)) - saved) < 4096
+    assert g._off(g.eof_pos) == len(out)
+    assert len(out) <= len(open(os.path.join(DATA, "multi_fast5_vbz.fast5"), "rb").read())  # the reference's file with the same objects
+    # without compaction: same content, the size of the source
+    holes = fast5.transcode(src, batch, vbz_version=vbz_version, compact_file=False)
+    assert len(holes) == len(src)
+    assert all(np.array_equal(v, want[k]) for k, v in fast5.read_vbz_signals(holes, batch).items())
+    # and back to gzip (-d): what the zip fixture holds, chunk for chunk
+    back = fast5.transcode(out, batch, decompress=True)
+    b = fast5.Fast5File(back)
+    for d in b.datasets():
+        assert [fid for fid, _ in d.filters] == [1] and len(d.chunks) == 1
+        assert np.array_equal(np.frombuffer(zlib.decompress(bytes(b.chunk_bytes(d.chunks[0]))), np.int16), want[d.name])
+    assert len(back) == len(src)
+    bo = b.objects()
+    for p in fo:
+        assert f.attributes(fo[p]) == b.attributes(bo[p]), p
+
+
+def test_compact_moves_every_address():
+    """Cutting nothing changes nothing; cutting a hole in front of everything (a dead region made by hand) moves all
+    addresses - and an address into a hole is refused."""
+    src = open(os.path.join(DATA, "multi_fast5_vbz_v1.fast5"), "rb").read()
+    assert fast5.compact(src, []) == src
+    f = fast5.Fast5File(src)
+    d = sorted(f.datasets(), key=lambda d: d.chunks[0].address)[0]
+    c = d.chunks[0]
+    with pytest.raises(fast5.Fast5FormatError):
+        fast5.compact(src, [(c.address, c.address + 16)])
+    # give the first chunk's space up by pointing its dataset at a copy behind the end of the file
+    grown = bytearray(src) + bytes(f.chunk_bytes(c))
+    sites = [p for p in fast5._address_sites(f) if f._off(p) == c.address]
+    assert len(sites) == 1
+    grown[sites[0]:sites[0] + 8] = len(src).to_bytes(8, "little")
+    out = fast5.compact(bytes(grown), [(c.address, c.address + c.size)])
+    assert len(out) == len(src)
+    g = fast5.Fast5File(out)
+    a, b = {x.name: x for x in f.datasets()}, {x.name: x for x in g.datasets()}
+    for k in a:
+        assert bytes(f.chunk_bytes(a[k].chunks[0])) == bytes(g.chunk_bytes(b[k].chunks[0])), k
+    fo, go = f.objects(), g.objects()
+    assert all(f.attributes(fo[p]) == g.attributes(go[p]) for p in fo)
+
+
+def test_fast5compress_command_line(tmp_path, capsys):
+    """The reference script's interface: files in, '<file><suffix>' out, names printed (fast5vbz.py:58-76)."""
+    import shutil
+    from vbz_compression_b200 import fast5compress
+    _, batch, lib = product.get("cpusim")
+    src = tmp_path / "reads.fast5"
+    shutil.copy(os.path.join(DATA, "multi_fast5_zip.fast5"), src)
+    fast5compress.Batch = lambda device: product.Batch(device, lib=lib)
+    fast5compress.main([str(src), "-s", ".vbz", "--vbz-version", "0"])
+    printed = capsys.readouterr().out.strip()
+    assert printed == str(src) + ".vbz"
+    want = _zip_signals(str(src))
+    got = fast5.read_vbz_signals(printed, batch)
+    assert all(np.array_equal(got[k], want[k]) for k in want) and len(got) == 10
+    fast5compress.main([printed, "-d", "-s", ".gz"])
+    back = _zip_signals(printed + ".gz")
+    assert all(np.array_equal(back[k], want[k]) for k in want)
