@@ -18,7 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'svb
 python tools/ncu_summary.py raw gpurun_out/${T}_full.ncu-rep gpurun_out/${T}_ncu_kernels.txt
 timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/${T}_bench_full.json 2> gpurun_out/${T}_bench_full.err; echo "full rc=$?"
 timeout 1200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref_full.json 2> gpurun_out/${T}_bench_ref_full.err; echo "ref rc=$?"
-timeout 1200 python bench.py --workload h5z-decode --steps 3 --warmup 2 > gpurun_out/${T}_bench_h5z.json 2> gpurun_out/${T}_bench_h5z.err; echo "h5z rc=$?"
+timeout 1200 python bench.py --workload h5z-decode --pool-gib 8 --steps 3 --warmup 2 > gpurun_out/${T}_bench_h5z.json 2> gpurun_out/${T}_bench_h5z.err; echo "h5z rc=$?"
 timeout 1200 python bench.py --workload uint32 --steps 3 --warmup 2 > gpurun_out/${T}_bench_uint32.json 2> gpurun_out/${T}_bench_uint32.err; echo "uint32 rc=$?"
 python - <<PY
 import json
