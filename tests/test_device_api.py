@@ -143,6 +143,34 @@ def test_torch_tensors_zero_copy(level):
         assert np.array_equal(b.cpu().numpy(), a)
 
 
+@pytest.mark.parametrize("level", [0, 1])
+def test_chunks_of_non_x86_writers_decode_where_they_lie(level):
+    """The reference built without SSSE3 (ARM, generic) writes 3-byte codes for int16 deltas beyond 16 bits: valid chunks whose stage-1
+    payload exceeds the x86 encoder's keys + 2N.  The device-resident decoder cannot read frame headers on the host, so its
+    intermediate slots must be sized by the format's bound (keys + 4N), not by what this library's own encoder would have written.
+    What comes out is what the x86 reference makes of such a chunk (its 16-bit arithmetic wraps where the writer's 32-bit did not:
+    full-range deltas do not survive the trip between the two builds of the reference either)."""
+    torch, batch, _ = _setup()
+    from vbz_compression_b200 import CompressionOptions
+    gen = ol.ref(generic=True)
+    if gen is None:
+        pytest.skip("oracle/_ref/libvbz_ref_generic.so is not built")
+    rng = np.random.default_rng(77 + level)
+    arrs = [data_gen.uniform_full_range(n, np.int16, rng) for n in (9000, 33, 70_000)] + [data_gen.nanopore_like(20_000, rng)]
+    o = Options(True, 2, level, 0)
+    blobs = [gen.compress(a, o, sized=True)[1] for a in arrs]
+    x86 = ol.ref()
+    assert blobs[0] != x86.compress(arrs[0], o, sized=True)[1]  # (the two builds do write different streams for full-range deltas)
+    want = [x86.decompress(b, o, a.nbytes, sized=True) for a, b in zip(arrs, blobs)]
+    assert all(code == a.nbytes for (code, _), a in zip(want, arrs)) and want[3][1] == arrs[3].tobytes()
+    chunks = [torch.from_numpy(np.frombuffer(b, np.uint8).copy()).cuda() for b in blobs]
+    back, res = batch.decompress_tensors(chunks, torch.int16, [a.size for a in arrs], CompressionOptions(True, 2, level, 0), sized=True)
+    torch.cuda.synchronize()
+    assert (res.cpu().numpy().view(np.uint32) == np.array([a.nbytes for a in arrs], np.uint32)).all()
+    for (_, w), b in zip(want, back):
+        assert b.cpu().numpy().tobytes() == w
+
+
 @pytest.mark.parametrize("lookahead", ["0", "1"])
 def test_device_batches_in_waves(lookahead, monkeypatch):
     """A device-resident batch larger than the intermediate budget runs as waves; on the decode side the walker and the sequence kernel of

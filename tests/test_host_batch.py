@@ -222,3 +222,26 @@ def test_pinned_and_pageable_reads_in_one_wave(level):
             assert r2 == a.nbytes and dec == a.tobytes(), i
         assert res_d[i] == a.nbytes
         assert bytes((ctypes.c_uint8 * a.nbytes).from_address(bp[i])) == a.tobytes(), i
+
+
+def test_frames_that_claim_gigabytes_fail_alone(backend):
+    """A chunk whose zstd frame header claims 2 GiB of content must cost the batch nothing: its intermediate slot is bounded by what
+    stage 1 could consume for the caller's output size, the chunk gets its own error, the reads around it decode (the reference fails
+    only the offending read: vbz.cpp:222-236)."""
+    _, batch, _ = backend
+    rng = np.random.default_rng(5)
+    o = Options(True, 2, 1, 0)
+    opts = CompressionOptions(True, 2, 1, 0)
+    good = [data_gen.nanopore_like(n, rng) for n in (30_000, 7, 120_000)]
+    blobs = [port.compress(a, o, sized=True)[1] for a in good]
+    # sized header (40 bytes of samples) + frame header: magic, single-segment with a 4-byte content size of 0x7FFFFFF0, one empty raw last block
+    crafted = (40).to_bytes(4, "little") + bytes([0x28, 0xB5, 0x2F, 0xFD, 0xA0]) + (0x7FFFFFF0).to_bytes(4, "little") + bytes([0x01, 0x00, 0x00])
+    chunks = [blobs[0]] + [crafted] * 200 + blobs[1:]
+    sizes = [good[0].nbytes] + [40] * 200 + [a.nbytes for a in good[1:]]
+    res = batch.decompress(chunks, sizes, opts, sized=True)
+    assert res[0] == (good[0].nbytes, good[0].tobytes())
+    assert res[201] == (good[1].nbytes, good[1].tobytes()) and res[202] == (good[2].nbytes, good[2].tobytes())
+    want, _ = port.decompress(crafted, o, 40, sized=True)
+    assert ol.is_error(want)
+    for code, blob in res[1:201]:
+        assert ol.is_error(code) and blob == b""
