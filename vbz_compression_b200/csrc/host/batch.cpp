@@ -223,7 +223,7 @@ static int enqueue_zstd_decode(vbz_b200_ctx* ctx, const uint8_t* d_src, uint8_t*
     if (!ctx->d_zseqs.ensure((size_t)seq_cap * sizeof(ZstdSeq)) || !ctx->d_zseqframes.ensure((size_t)n * sizeof(ZstdSeqFrame))) return -1;
     if (!ctx->d_zreads.ensure(bytes) || !ctx->d_zcounter.ensure(256) || (phase == 0 && !ctx->d_zlit.ensure(vbzk_zstd_decode_scratch_bytes())) ||
         !ctx->d_zunits.ensure((size_t)unit_cap * sizeof(ZstdUnit)) || !ctx->d_zgroups.ensure((size_t)unit_cap * sizeof(ZstdGroup)) ||
-        !ctx->d_zgeneral.ensure((size_t)n * 4) || !ctx->d_zseqlist.ensure((size_t)unit_cap * 4))
+        !ctx->d_zgeneral.ensure((size_t)n * 4) || !ctx->d_zseqlist.ensure((size_t)unit_cap * 20))  // the executor's list, and behind it the sequence kernel's chains (4 words each)
         return -1;
     if (!upload_descriptors(ctx, ctx->d_zreads.p, reads.data(), bytes, stream) ||
         !zero_device(ctx, ctx->d_zcounter.p, 256, stream))

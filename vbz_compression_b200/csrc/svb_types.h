@@ -102,13 +102,14 @@ struct ZstdDecParams {
     uint32_t* counter;   // 16 words, zeroed before launch: [0] work counter of the general kernel, [1] units listed,
                          // [2] frames left to the general kernel, [3] work counter of the units kernel, [4] groups listed,
                          // [5] sequence records allotted, [6] frames with Seq units, [7] / [8] work counters of the two sequence kernels,
-                         // [9] entries of seq_list
+                         // [9] entries of seq_list, [10] chains listed for the sequence kernel, [11] its second work counter
     ZstdUnit* units;     // unit_cap entries
     ZstdGroup* groups;   // unit_cap entries
     uint32_t* general;   // n_reads entries: the frames the walker left to the general kernel
     ZstdSeq* seqs;       // seq_cap records
     ZstdSeqFrame* seq_frames;  // n_reads entries
-    uint32_t* seq_list;  // unit_cap entries: the Seq units of the frames the sequence kernel vouches for, in block order (the executor's work list)
+    uint32_t* seq_list;  // unit_cap entries: the Seq units of the frames the sequence kernel vouches for, in block order (the executor's work list);
+                         // behind them unit_cap ZstdSeqChain records (csrc/zstd_dec_kernels.cuh): the sequence kernel's own work list
     uint32_t unit_cap;
     uint32_t n_reads;
     uint32_t seq_cap;

@@ -186,7 +186,7 @@ extern "C" int vbzk_zstd_decode_front(const VbzkZstdDecParams* params, void* str
     const uint32_t ssmem = (uint32_t)(sizeof(ZSeqWarp) * kZSeqWarps);
     if (int e = VBZK_SET_SMEM(zstd_seq_kernel, ssmem)) return e;
     static const uint32_t sgrid_max = persistent_grid(zstd_seq_kernel, kZSeqWarps * 32, ssmem, 0xFFFFFFFFu, 0);
-    const uint32_t sneed = (p.n_reads + kZSeqWarps - 1) / kZSeqWarps;
+    const uint32_t sneed = p.n_reads < (1u << 24) ? (p.n_reads * 16u + kZSeqWarps - 1) / kZSeqWarps : 0xFFFFFFFFu;  // a warp per chain: a frame brings a handful (one per block with its own tables)
     VBZ_LAUNCH(zstd_seq_kernel, sneed < sgrid_max ? sneed : sgrid_max, kZSeqWarps * 32, ssmem, (vbz_stream_t)stream, p);
     return VBZK_LAST_ERROR();
 }

@@ -813,9 +813,13 @@ __device__ __forceinline__ bool z_seq_count(const uint8_t* q, uint32_t left, uin
 // One pass over a frame.  emit == nullptr: count.  Returns the number of units, or 0xFFFFFFFF if the frame is not for
 // this path.  *total = content bytes (only meaningful when no block carries sequences); *n_seqs = sequences of all Seq units
 // (their records are numbered from seq_base on, block after block).
-struct ZWalk { uint32_t total, groups, seqs; bool deferred; };
+// A CHAIN = a Seq unit whose block brings all three sequence tables itself (or is the frame's first) and the units up to the next such
+// unit: what one warp of zstd_seq_kernel decodes - the chains of a frame need nothing from each other but the repeat offsets, which
+// are settled when the last of them is done.  The list lives behind the executor's list (ZstdDecParams::seq_list + unit_cap).
+struct ZstdSeqChain { uint32_t frame, first, count, nseq; };  // slot in seq_frames, first unit (relative to the frame's), units, their sequences
+struct ZWalk { uint32_t total, groups, seqs; bool deferred; uint32_t chains; };
 __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_t r, ZstdUnit* emit, ZstdGroup* gemit, uint32_t unit_base,
-                                 uint32_t seq_base, ZWalk* out)
+                                 uint32_t seq_base, ZWalk* out, ZstdSeqChain* cemit = nullptr, uint32_t frame_slot = 0)
 {
     const uint32_t kNo = 0xFFFFFFFFu;
     const uint8_t* p = src + rd.src_off;
@@ -828,7 +832,7 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
     n -= h;
     const uint64_t cap = rd.dst_cap;
     uint64_t op = 0;
-    uint32_t units = 0, groups = 0, seqs = 0;
+    uint32_t units = 0, groups = 0, seqs = 0, chains = 0, chain_first = 0, chain_seqs = 0;
     bool deferred = false;         // a block with sequences came by: positions from here on are known after zstd_seq_kernel only
     const uint8_t* tab = nullptr;  // the last literals section that carried a tree
     // a GROUP = up to 16 consecutive Huffman units decoded with the same table (the one that carries the tree and the
@@ -882,6 +886,15 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
                 seq_lt = lt;
                 u.nseq = nseq; u.seq_first = seq_base + seqs;
                 seqs += nseq;
+                // the compression modes byte: no Repeat_Mode among the three = the block stands alone (a damaged one: the sequence kernel says so)
+                const uint32_t modes = sec + sh < bs ? p[sec + sh] : 0u;
+                const bool alone = ((modes >> 6) & 3u) != 3u && ((modes >> 4) & 3u) != 3u && ((modes >> 2) & 3u) != 3u;
+                if (!deferred || alone) {
+                    if (deferred) { if (cemit) cemit[chains] = ZstdSeqChain{frame_slot, chain_first, units - chain_first, chain_seqs}; ++chains; }
+                    chain_first = units;
+                    chain_seqs = 0;
+                }
+                chain_seqs += nseq;
                 deferred = true;
             }
             adv = bs;
@@ -913,10 +926,12 @@ __device__ uint32_t z_walk_frame(const uint8_t* src, const ZstdRead& rd, uint32_
     if (n != 0 || op > 0xFFFFFFF0ull) return kNo;
     if (!deferred && has && op != fcs) return kNo;
     if (g_count) { if (gemit) gemit[groups] = ZstdGroup{unit_base + g_first, g_count}; ++groups; }
+    if (deferred) { if (cemit) cemit[chains] = ZstdSeqChain{frame_slot, chain_first, units - chain_first, chain_seqs}; ++chains; }
     out->total = (uint32_t)op;
     out->groups = groups;
     out->seqs = seqs;
     out->deferred = deferred;
+    out->chains = chains;
     return units;
 }
 
@@ -926,7 +941,7 @@ __global__ void zstd_walk_kernel(ZstdDecParams p)
     if (r >= p.n_reads) return;
     const ZstdRead rd = p.reads[r];
     if (rd.rejected) { p.results[r] = rd.preset; return; }
-    ZWalk w = {0, 0, 0, false};
+    ZWalk w = {0, 0, 0, false, 0};
     const uint32_t cnt = z_walk_frame(p.src, rd, r, nullptr, nullptr, 0, 0, &w);
     bool mine = cnt != 0xFFFFFFFFu;
     if (mine && cnt != 0) {
@@ -934,14 +949,18 @@ __global__ void zstd_walk_kernel(ZstdDecParams p)
         const uint32_t gbase = w.groups ? atomicAdd(p.counter + 4, w.groups) : 0u;
         const uint32_t sbase = w.seqs ? atomicAdd(p.counter + 5, w.seqs) : 0u;
         const uint32_t gcnt = w.groups;
+        const uint32_t cbase = w.chains ? atomicAdd(p.counter + 10, w.chains) : 0u;
         if (base >= p.unit_cap || cnt > p.unit_cap - base || (gcnt && (gbase >= p.unit_cap || gcnt > p.unit_cap - gbase)) ||
-            (w.seqs && (sbase >= p.seq_cap || w.seqs > p.seq_cap - sbase))) {
+            (w.seqs && (sbase >= p.seq_cap || w.seqs > p.seq_cap - sbase)) || (w.chains && (cbase >= p.unit_cap || w.chains > p.unit_cap - cbase))) {
             // out of slots: the units kernel stops at unit_cap; what was allotted here stays empty
             for (uint32_t k = gbase; gcnt && k < p.unit_cap && k - gbase < gcnt; ++k) p.groups[k] = ZstdGroup{0, 0};
+            for (uint32_t k = cbase; w.chains && k < p.unit_cap && k - cbase < w.chains; ++k)
+                reinterpret_cast<ZstdSeqChain*>(p.seq_list + p.unit_cap)[k] = ZstdSeqChain{0xFFFFFFFFu, 0, 0, 0};
             mine = false;
         } else {
-            z_walk_frame(p.src, rd, r, p.units + base, p.groups + gbase, base, sbase, &w);
-            if (w.deferred) p.seq_frames[atomicAdd(p.counter + 6, 1u)] = ZstdSeqFrame{r, base, cnt, 0};
+            const uint32_t slot = w.deferred ? atomicAdd(p.counter + 6, 1u) : 0u;
+            if (w.deferred) p.seq_frames[slot] = ZstdSeqFrame{r, base, cnt, w.chains};  // (pad: chains still to be decoded; top bit: one of them failed)
+            z_walk_frame(p.src, rd, r, p.units + base, p.groups + gbase, base, sbase, &w, reinterpret_cast<ZstdSeqChain*>(p.seq_list + p.unit_cap) + cbase, slot);
         }
     }
     if (mine) { if (!w.deferred) p.results[r] = w.total; }
@@ -1337,60 +1356,95 @@ __device__ uint32_t z_lane_sequences(const ZSeqWarp* zw, int al_ll, int al_of, i
     *back = reach;
     return regen;
 }
-// the repeat codes a lane left in the records of a block, resolved in order from the offsets the block starts with (one lane)
-__device__ void z_resolve_repeats(ZstdSeq* sq, uint32_t nseq, uint32_t* rep)
+__device__ __forceinline__ uint32_t z_ld_cg(const uint32_t* p)
+{
+#ifdef VBZ_CPUSIM
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
+// The repeat codes the lanes left in the records of a block, resolved in order from the offsets the block starts with - by the whole
+// warp: 32 records per round are loaded side by side (ld.cg: they may have been written by a warp of another SM), then walked in
+// order with their fields broadcast by shuffles, so no load sits in the serial chain.  rep[] is the same in all lanes.
+__device__ void z_resolve_repeats(ZstdSeq* sq, uint32_t nseq, uint32_t* rep, uint32_t lane)
 {
     uint32_t rep0 = rep[0], rep1 = rep[1], rep2 = rep[2];
-    for (uint32_t i = 0; i < nseq; ++i) {
-        uint32_t offset = sq[i].offset;
-        if (!(offset & 0x80000000u)) { rep2 = rep1; rep1 = rep0; rep0 = offset; continue; }
-        const uint32_t kk = (offset & 3u) + (sq[i].ll == 0 ? 1u : 0u);
-        if (kk == 1) offset = rep0;
-        else {
-            offset = (kk == 4) ? rep0 - 1 : (kk == 2 ? rep1 : rep2);
-            if (offset == 0) offset = 1;
-            if (kk != 2) rep2 = rep1;
-            rep1 = rep0;
-            rep0 = offset;
+    for (uint32_t base = 0; base < nseq; base += 32) {
+        const uint32_t i = base + lane, cnt = nseq - base < 32u ? nseq - base : 32u;
+        const uint32_t off = i < nseq ? z_ld_cg(&sq[i].offset) : 0u;
+        const uint32_t ll = i < nseq ? z_ld_cg(&sq[i].ll) : 1u;
+        if (!__ballot_sync(0xffffffffu, (off & 0x80000000u) != 0)) {  // explicit offsets only: the last three are what is left behind
+            const uint32_t a = __shfl_sync(0xffffffffu, off, (int)cnt - 1), b = __shfl_sync(0xffffffffu, off, cnt >= 2 ? (int)cnt - 2 : 0),
+                           c = __shfl_sync(0xffffffffu, off, cnt >= 3 ? (int)cnt - 3 : 0);
+            if (cnt >= 3) { rep2 = c; rep1 = b; rep0 = a; }
+            else if (cnt == 2) { rep2 = rep0; rep1 = b; rep0 = a; }
+            else { rep2 = rep1; rep1 = rep0; rep0 = a; }
+            continue;
         }
-        sq[i].offset = offset;
+        uint32_t mine = off;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            uint32_t offset = __shfl_sync(0xffffffffu, off, (int)j);
+            if (!(offset & 0x80000000u)) { rep2 = rep1; rep1 = rep0; rep0 = offset; continue; }
+            const uint32_t kk = (offset & 3u) + (__shfl_sync(0xffffffffu, ll, (int)j) == 0 ? 1u : 0u);
+            if (kk == 1) offset = rep0;
+            else {
+                offset = (kk == 4) ? rep0 - 1 : (kk == 2 ? rep1 : rep2);
+                if (offset == 0) offset = 1;  // libzstd: "0 is not valid; input is corrupted; force offset to 1"
+                if (kk != 2) rep2 = rep1;
+                rep1 = rep0;
+                rep0 = offset;
+            }
+            if (lane == j) mine = offset;
+        }
+        if (i < nseq && mine != off) sq[i].offset = mine;
     }
     rep[0] = rep0; rep[1] = rep1; rep[2] = rep2;
 }
 
-// zstd_seq_kernel: a WARP per frame with Seq units.  Its Seq units are taken in SETS: a unit whose block brings tables (or names the
-// predefined / RLE ones) and the units after it that repeat all three (Repeat_Mode x 3: what the writer of csrc/zstd_match_kernels.cuh
-// gives every block of a group but the first).  Lanes 0 - 2 build the set's tables, then every unit of the set is decoded by a lane of
-// its own - sequences are serial work per block, not per frame.  libzstd's frames have sets of one.
+// zstd_seq_kernel: a WARP per CHAIN of a frame's Seq units (zstd_walk_kernel lists them).  The chain's Seq units are taken in SETS: a
+// unit whose block brings tables (or names the predefined / RLE ones) and the units after it that repeat all three (Repeat_Mode x 3:
+// what the writer of csrc/zstd_match_kernels.cuh gives every block of a group but the first).  Lanes 0 - 2 build the set's tables,
+// then every unit of the set is decoded by a lane of its own - sequences are serial work per block, not per frame.  libzstd's sets are
+// single blocks, so its frames are decoded a warp per block (the blocks that repeat a table ride with the one before them).
+// No lane knows the repeat offsets its block starts with: repeat codes stay in the records, and the warp that finishes a frame's LAST
+// chain walks the frame's units once - resolves the codes in order, gives every unit its place in the output and lists the executor's
+// chains.  (What other warps wrote is read with ld.cg there: their lines may sit stale in this SM's L1.)
 constexpr int kZSeqWarps = 4;
 __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams p)
 {
     VBZ_DYN_SMEM(smem);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     ZSeqWarp* zw = reinterpret_cast<ZSeqWarp*>(smem) + wid;
-    const uint32_t n_frames = p.counter[6];
+    const ZstdSeqChain* chains = reinterpret_cast<const ZstdSeqChain*>(p.seq_list + p.unit_cap);
+    const uint32_t n_chains = p.counter[10] < p.unit_cap ? p.counter[10] : p.unit_cap;
     const uint32_t kBad = 0xFFFFFFFFu;
-    for (;;) {
+    // the list is walked twice: the long chains first (a block of control bytes written by libzstd holds 19 k sequences, serial work for one
+    // lane: started last, it would run alone at the end), then the rest
+    constexpr uint32_t kLong = 2048;
+    for (uint32_t round = 0;;) {
         uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(p.counter + 7, 1u);
+        if (lane == 0) k = atomicAdd(p.counter + (round == 0 ? 7 : 11), 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= n_frames) break;
-        const ZstdSeqFrame sf = p.seq_frames[k];
-        const ZstdRead rd = p.reads[sf.read];
-        uint64_t fcs = 0;
-        bool has = false, ck = false;
-        z_frame_header(p.src + rd.src_off, rd.src_bytes, &fcs, &has, &ck);  // (the walker accepted it)
+        if (k >= n_chains) {
+            if (round == 0) { round = 1; continue; }
+            break;
+        }
+        const ZstdSeqChain ch = chains[k];
+        if (ch.frame == 0xFFFFFFFFu) continue;  // (slots of a frame that found no room for its units)
+        if ((ch.nseq >= kLong) != (round == 0)) continue;
+        const ZstdSeqFrame sf = p.seq_frames[ch.frame];
         int al[3] = {0, 0, 0};  // literal lengths, offsets, match lengths
         bool tables_valid = false;
-        uint32_t rep[3] = {1, 4, 8};  // the repeat offsets before the next Seq unit (all lanes hold them)
         bool ok = true;
-        uint32_t ui = 0, n_seq_units = 0;
-        while (ui < sf.unit_count && ok) {
+        const uint32_t ch_end = ch.first + ch.count;
+        uint32_t ui = ch.first;
+        while (ui < ch_end && ok) {
             // ---- the next 32 units: which are Seq, what their blocks say ---------------------------------------------------------------
             const uint32_t mine = ui + lane;
             ZstdUnit u = {};
             u.kind = kZUnitNop;
-            if (mine < sf.unit_count) u = p.units[sf.unit_first + mine];
+            if (mine < ch_end) u = p.units[sf.unit_first + mine];
             const bool is_seq = u.kind == kZUnitSeq;
             const uint32_t seqmask = __ballot_sync(0xffffffffu, is_seq);
             if (!seqmask) { ui += 32; continue; }
@@ -1456,8 +1510,8 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                 if (((hmodes >> 2) & 3) != 3) z_seq_pack(zw->ml, al[2], 2, lane);
             }
             __syncwarp();
-            // ---- every member decodes its block.  The head knows the repeat offsets it starts with; the others leave repeat codes raw ------
-            uint32_t regen = 0, my_rep[3] = {rep[0], rep[1], rep[2]};
+            // ---- every member decodes its block; repeat codes stay in the records ------------------------------------------------------------------
+            uint32_t regen = 0, my_rep[3] = {1, 4, 8};
             bool raw = false, back = false;
             if (member) {
                 const bool is_head = lane == head_lane;
@@ -1465,47 +1519,57 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                 const uint32_t nbits = is_head ? (h.n >= 1 + used_all ? h.n - 1 - used_all : 0u) : h.n - 1;
                 regen = (u.seq_first >= p.seq_cap || u.nseq > p.seq_cap - u.seq_first)
                             ? kBad
-                            : z_lane_sequences(zw, al[0], al[1], al[2], bits, nbits, h.nseq, h.lit_n, p.seqs + u.seq_first, is_head, my_rep, &raw, &back);
+                            : z_lane_sequences(zw, al[0], al[1], al[2], bits, nbits, h.nseq, h.lit_n, p.seqs + u.seq_first, false, my_rep, &raw, &back);
             }
             if (__ballot_sync(0xffffffffu, member && regen == kBad)) { ok = false; break; }
-            // ---- the repeat offsets behind the set: member after member (what a block without repeat codes leaves behind is its last three
-            // offsets; one with codes is walked by a lane) ----------------------------------------------------------------------------------------
-            {
-                uint32_t mm = members;
-                while (mm) {
-                    const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
-                    mm &= mm - 1;
-                    if (m == head_lane) {
-                        rep[0] = __shfl_sync(0xffffffffu, my_rep[0], m); rep[1] = __shfl_sync(0xffffffffu, my_rep[1], m); rep[2] = __shfl_sync(0xffffffffu, my_rep[2], m);
-                        continue;
-                    }
-                    const bool m_raw = __shfl_sync(0xffffffffu, raw ? 1u : 0u, m) != 0;
-                    const uint32_t m_nseq = __shfl_sync(0xffffffffu, h.nseq, m), m_first = __shfl_sync(0xffffffffu, u.seq_first, m);
-                    if (m_raw) {
-                        if (lane == 0) z_resolve_repeats(p.seqs + m_first, m_nseq, rep);
-                        rep[0] = __shfl_sync(0xffffffffu, rep[0], 0); rep[1] = __shfl_sync(0xffffffffu, rep[1], 0); rep[2] = __shfl_sync(0xffffffffu, rep[2], 0);
-                    } else {  // the lane started from the wrong offsets but pushed only explicit ones: its last min(nseq, 3) are right
-                        const uint32_t r0 = __shfl_sync(0xffffffffu, my_rep[0], m), r1 = __shfl_sync(0xffffffffu, my_rep[1], m), r2 = __shfl_sync(0xffffffffu, my_rep[2], m);
-                        if (m_nseq >= 3) { rep[0] = r0; rep[1] = r1; rep[2] = r2; }
-                        else if (m_nseq == 2) { rep[2] = rep[0]; rep[0] = r0; rep[1] = r1; }
-                        else { rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = r0; }
-                    }
-                }
-            }
             if (member) {
                 ZstdUnit* up = p.units + sf.unit_first + mine;
                 up->regen = regen;
-                up->pad = back || raw ? 1u : 0u;  // a match may reach back beyond the block: the executor waits for the units before it
+                up->pad = (back || raw ? 1u : 0u) | (raw ? 2u : 0u);  // 1: a match may reach back beyond the block (the executor waits for the units before it); 2: repeat codes to resolve
             }
             __syncwarp();
-            n_seq_units += (uint32_t)__popc((int)members);
             ui += upto;  // (upto >= head_lane + 1: the units before the head are not Seq)
         }
+        // ---- report; the warp that finishes the frame's last chain goes on --------------------------------------------------------------------
+        __threadfence();
+        __syncwarp();
+        uint32_t old = 0;
+        if (lane == 0) {
+            if (!ok) atomicOr(&p.seq_frames[ch.frame].pad, 0x80000000u);
+            old = atomicAdd(&p.seq_frames[ch.frame].pad, 0xFFFFFFFFu);  // (minus one)
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if ((old & 0x7FFFFFFFu) != 1u) continue;
+        __threadfence();
+        ok = !(old & 0x80000000u);
+        const ZstdRead rd = p.reads[sf.read];
+        uint64_t fcs = 0;
+        bool has = false, ck = false;
+        z_frame_header(p.src + rd.src_off, rd.src_bytes, &fcs, &has, &ck);  // (the walker accepted it)
+        // ---- the repeat offsets, unit after unit (all lanes alike): a block without codes leaves its last three offsets behind, one with codes is walked ----
+        if (ok) {
+            uint32_t rep[3] = {1, 4, 8};
+            for (uint32_t i = 0; i < sf.unit_count; ++i) {
+                const ZstdUnit* up = p.units + sf.unit_first + i;
+                if (up->kind != kZUnitSeq) continue;  // (kind, nseq, seq_first: the walker's, read-only here)
+                ZstdSeq* sq = p.seqs + up->seq_first;
+                const uint32_t nseq = up->nseq;
+                if (z_ld_cg(&up->pad) & 2u) z_resolve_repeats(sq, nseq, rep, lane);
+                else {
+                    const uint32_t r0 = z_ld_cg(&sq[nseq - 1].offset);
+                    if (nseq >= 3) { rep[2] = z_ld_cg(&sq[nseq - 3].offset); rep[1] = z_ld_cg(&sq[nseq - 2].offset); rep[0] = r0; }
+                    else if (nseq == 2) { rep[2] = rep[0]; rep[1] = z_ld_cg(&sq[0].offset); rep[0] = r0; }
+                    else { rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = r0; }
+                }
+            }
+            __threadfence();
+        }
+        __syncwarp();
         // ---- positions: every unit of the frame, 32 at a time ----------------------------------------------------------------------------
         uint64_t op = 0;
         for (uint32_t u0 = 0; u0 < sf.unit_count && ok; u0 += 32) {
             const uint32_t mine = u0 + lane;
-            const uint32_t regen = mine < sf.unit_count ? p.units[sf.unit_first + mine].regen : 0u;
+            const uint32_t regen = mine < sf.unit_count ? z_ld_cg(&p.units[sf.unit_first + mine].regen) : 0u;
             const uint32_t incl = warp_incl_scan(regen, lane);
             if (mine < sf.unit_count) p.units[sf.unit_first + mine].dst_off = rd.dst_off + op + incl - regen;
             op += __shfl_sync(0xffffffffu, incl, 31);
@@ -1522,7 +1586,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                 const uint32_t mine = u0 + lane;
                 const bool is_seq = mine < sf.unit_count && p.units[sf.unit_first + mine].kind == kZUnitSeq;
                 const uint32_t m = __ballot_sync(0xffffffffu, is_seq);
-                const bool head = is_seq && ((heads == 0 && !(m & ((1u << lane) - 1u))) || !(p.units[sf.unit_first + mine].pad & 1u));
+                const bool head = is_seq && ((heads == 0 && !(m & ((1u << lane) - 1u))) || !(z_ld_cg(&p.units[sf.unit_first + mine].pad) & 1u));
                 heads += (uint32_t)__popc((int)__ballot_sync(0xffffffffu, head));
             }
             uint32_t base = 0;
@@ -1533,7 +1597,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                 const uint32_t mine = u0 + lane;
                 const bool is_seq = mine < sf.unit_count && p.units[sf.unit_first + mine].kind == kZUnitSeq;
                 const uint32_t m = __ballot_sync(0xffffffffu, is_seq);
-                const bool head = is_seq && ((done == 0 && !(m & ((1u << lane) - 1u))) || !(p.units[sf.unit_first + mine].pad & 1u));
+                const bool head = is_seq && ((done == 0 && !(m & ((1u << lane) - 1u))) || !(z_ld_cg(&p.units[sf.unit_first + mine].pad) & 1u));
                 const uint32_t hm = __ballot_sync(0xffffffffu, head);
                 const uint32_t rank = done + (uint32_t)__popc((int)(hm & ((1u << lane) - 1u)));
                 if (head) p.seq_list[base + rank] = (sf.unit_first + mine) | (rank == 0 ? kZListFirst : 0u);
@@ -1543,7 +1607,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
             // not for this path after all: its units do nothing, the general kernel decides the frame's result
             for (uint32_t ui2 = lane; ui2 < sf.unit_count; ui2 += 32) p.units[sf.unit_first + ui2].kind = kZUnitNop;
             if (lane == 0) {
-                p.seq_frames[k].unit_count = 0;
+                p.seq_frames[ch.frame].unit_count = 0;
                 p.general[atomicAdd(p.counter + 2, 1u)] = sf.read;
             }
         }
