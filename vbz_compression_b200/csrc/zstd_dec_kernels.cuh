@@ -1646,6 +1646,41 @@ __device__ __forceinline__ void z_exec_wait(const uint32_t* list, uint32_t k, ui
     }
     __syncwarp();
 }
+// A short match copied by its own lane.  Byte after byte every load would wait for the store before it (the compiler must assume they
+// meet), and that wait was half of the executor's time on libzstd's frames.  So: a source eight or more bytes behind is copied in chunks
+// whose loads are all issued before their stores; a nearer one (the match repeats the `offset` bytes before it) is loaded once into a
+// register and written out of it.
+__device__ __forceinline__ void z_lane_match(uint8_t* out, uint64_t dst, uint32_t offset, uint32_t n)
+{
+    const uint8_t* from = out + dst - offset;
+    uint8_t* to = out + dst;
+    if (offset >= 8) {
+        uint32_t q = 0;
+        for (; q + 8 <= n; q += 8) {
+            uint8_t b[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b[k] = from[q + k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) to[q + k] = b[k];
+        }
+        const uint32_t r = n - q;
+        uint8_t b[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) b[k] = (uint32_t)k < r ? from[q + k] : (uint8_t)0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+            if ((uint32_t)k < r) to[q + k] = b[k];
+        return;
+    }
+    uint64_t pat = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if ((uint32_t)k < offset) pat |= (uint64_t)from[k] << (8 * k);
+    for (uint32_t q = 0, ph = 0; q < n; ++q) {
+        to[q] = (uint8_t)(pat >> (8u * ph));
+        ph = ph + 1 == offset ? 0u : ph + 1;
+    }
+}
 // the records of one Seq unit (all lanes); false: the block is damaged
 __device__ bool z_exec_unit(const ZstdDecParams& p, const ZstdUnit& u, uint64_t frame_off, uint32_t lane)
 {
@@ -1687,26 +1722,54 @@ __device__ bool z_exec_unit(const ZstdDecParams& p, const ZstdUnit& u, uint64_t 
             if (o < total) out[(((uint64_t)oj_hi << 32) | oj_lo) + (o - ej)] = v;
         }
         __syncwarp();
-        // ---- matches: short and independent of this round's other sequences -> the lane itself; the others by the whole warp, in order
+        // ---- matches: short and independent of this round's other sequences -> the lane itself
         const bool dep = msrc < my_out && msrc + rec.ml > op;
-        const bool self = rec.ml != 0 && rec.ml <= 48 && !dep;
+        // (a run - offset 1 - of any reasonable length too: libzstd turns the zero runs among control bytes into matches of hundreds of bytes, and
+        // a lane that fills 16 bytes per store is done long before the warp has made its round trip through memory for it)
+        const bool self = rec.ml != 0 && !dep && (rec.ml <= 48 || (rec.offset == 1 && rec.ml <= 4096));
         if (self) {
             if (rec.offset == 1) {
-                const uint8_t v = out[mdst - 1];
-                for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = v;
+                const uint32_t v = out[mdst - 1];
+                uint8_t* a = out + mdst;
+                uint8_t* const e = a + rec.ml;
+                while (a < e && ((uintptr_t)a & 15u)) *a++ = (uint8_t)v;
+                const uint32_t w = v * 0x01010101u;
+                for (; a + 16 <= e; a += 16) *reinterpret_cast<uint4*>(a) = make_uint4(w, w, w, w);
+                while (a < e) *a++ = (uint8_t)v;
             } else {
-                for (uint32_t q = 0; q < rec.ml; ++q) out[mdst + q] = out[msrc + q];
+                z_lane_match(out, mdst, rec.offset, rec.ml);
             }
         }
-        uint32_t rest = __ballot_sync(0xffffffffu, rec.ml != 0 && !self);
+        // ---- the others (libzstd's control bytes: eight or nine of a round's 32, nearly all short and fed by bytes this round writes): what is
+        // final now are the literals and the matches above.  A waiting match is READY when its source meets no destination of a waiting match
+        // before it; the ready ones run side by side (the short ones in their lanes, the long ones by the warp), then the test is made
+        // again - a round trip through memory per level of dependence instead of one per match.  (A later destination never reaches down
+        // into an earlier source, so nothing is overwritten before it is read.)
+        uint32_t waiting = __ballot_sync(0xffffffffu, rec.ml != 0 && !self);
+        const uint32_t d_lo = (uint32_t)(mdst - op), d_hi = d_lo + rec.ml;  // relative to the round's first byte
+        const uint32_t s_hi = msrc + rec.ml > op ? (uint32_t)(msrc + rec.ml - op) : 0u, s_lo = msrc > op ? (uint32_t)(msrc - op) : 0u;
         __syncwarp();
-        while (rest) {
-            const uint32_t fl = (uint32_t)__ffs((int)rest) - 1;
-            rest &= rest - 1;
-            const uint32_t n = __shfl_sync(0xffffffffu, rec.ml, fl), fo = __shfl_sync(0xffffffffu, rec.offset, fl);
-            const uint32_t fd_lo = __shfl_sync(0xffffffffu, (uint32_t)mdst, fl), fd_hi = __shfl_sync(0xffffffffu, (uint32_t)(mdst >> 32), fl);
-            z_warp_match(out, ((uint64_t)fd_hi << 32) | fd_lo, fo, n, lane);
+        while (waiting) {
+            bool blocked = false;
+            for (uint32_t scan = waiting; scan; scan &= scan - 1) {
+                const uint32_t f = (uint32_t)__ffs((int)scan) - 1;
+                const uint32_t f_lo = __shfl_sync(0xffffffffu, d_lo, f), f_hi = __shfl_sync(0xffffffffu, d_hi, f);
+                if (lane > f && s_lo < f_hi && s_hi > f_lo) blocked = true;
+            }
+            const bool go = ((waiting >> lane) & 1u) && !blocked;
+            const uint32_t ready = __ballot_sync(0xffffffffu, go);
+            if (go && rec.ml <= 48) z_lane_match(out, mdst, rec.offset, rec.ml);
+            uint32_t longs = __ballot_sync(0xffffffffu, go && rec.ml > 48);
             __syncwarp();
+            while (longs) {
+                const uint32_t fl = (uint32_t)__ffs((int)longs) - 1;
+                longs &= longs - 1;
+                const uint32_t n = __shfl_sync(0xffffffffu, rec.ml, fl), fo = __shfl_sync(0xffffffffu, rec.offset, fl);
+                const uint32_t fd_lo = __shfl_sync(0xffffffffu, (uint32_t)mdst, fl), fd_hi = __shfl_sync(0xffffffffu, (uint32_t)(mdst >> 32), fl);
+                z_warp_match(out, ((uint64_t)fd_hi << 32) | fd_lo, fo, n, lane);
+                __syncwarp();
+            }
+            waiting &= ~ready;
         }
         op += __shfl_sync(0xffffffffu, incl, 31);
         lp += total;
