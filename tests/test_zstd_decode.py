@@ -217,3 +217,56 @@ def test_pool_overflow_and_damage_fall_back_to_the_general_kernel(backend):
     want = [port.decompress(f, Options(False, 0, 1, 0), s, sized=False) for f, s in zip(frames, sizes)]
     for (code, blob), (wc, wb) in zip(res, want):
         assert code == wc and (ol.is_error(wc) or blob == wb)
+
+
+def test_blocks_that_repeat_tables_ride_with_the_block_before_them(backend):
+    """The sequence kernel takes a warp per CHAIN: a block that brings all three tables and the blocks behind it that repeat any of them
+    (Repeat_Mode, what libzstd's lazy strategies - level 6 and up - choose block after block); repeat-offset codes cross the chains and
+    are settled by whoever finishes the frame's last one.  Frames with every mix of both, several per batch, next to own frames."""
+    _, batch, _ = backend
+    small = backend[0].path.endswith("cpusim.so")
+    rng = np.random.default_rng(12)
+    buf = bytearray(rng.integers(0, 256, 400_000 if small else 900_000, dtype=np.uint8).tobytes())
+    pos = 3000
+    while pos < len(buf) - 400:  # copies of what lies a little further back, at random distances: a few hundred sequences per block
+        n = int(rng.integers(8, 200))
+        back = int(rng.integers(n, 2500))
+        buf[pos:pos + n] = buf[pos - back:pos - back + n]
+        pos += n + int(rng.integers(20, 600))
+    data = bytes(buf)
+    sig = ol.stage1_encode(data_gen.nanopore_like(150_000 if small else 600_000, rng), 2, True)
+    frames, sizes, want = [], [], []
+    for level in (1, 7, 19):
+        for d in (data, sig, data[:150_000]):
+            frames.append(ol.zstd_compress_lib(d, level))
+            sizes.append(len(d))
+            want.append(d)
+    modes = set()
+    for f in frames:  # (the scenario is there: some block repeats one table, some block all three, some none)
+        p = 4 + 1 + (0, 1, 2, 4)[f[4] & 3] + ((1 if (f[4] >> 5) & 1 else 0, 2, 4, 8)[f[4] >> 6]) + (0 if (f[4] >> 5) & 1 else 1)
+        while True:
+            bh = int.from_bytes(f[p:p + 3], "little")
+            p += 3
+            if (bh >> 1) & 3 == 2:
+                b0 = f[p]
+                lt, sf = b0 & 3, (b0 >> 2) & 3
+                if lt < 2:
+                    hdr, regen = (1, b0 >> 3) if sf in (0, 2) else ((2, int.from_bytes(f[p:p + 2], "little") >> 4) if sf == 1 else (3, int.from_bytes(f[p:p + 3], "little") >> 4))
+                    sec = hdr + (regen if lt == 0 else 1)
+                else:
+                    v = int.from_bytes(f[p:p + 5], "little")
+                    hdr, comp = ((3, (v >> 14) & 0x3FF) if sf in (0, 1) else ((4, (v >> 18) & 0x3FFF) if sf == 2 else (5, (v >> 22) & 0x3FFFF)))
+                    sec = hdr + comp
+                n0 = f[p + sec]
+                if n0:
+                    modes.add(f[p + sec + (1 if n0 < 128 else 2 if n0 < 255 else 3)])
+            p += 1 if (bh >> 1) & 3 == 1 else bh >> 3
+            if bh & 1:
+                break
+    rep = lambda m: [(m >> s) & 3 == 3 for s in (6, 4, 2)]
+    assert any(all(rep(m)) for m in modes) and any(any(rep(m)) and not all(rep(m)) for m in modes) and any(not any(rep(m)) for m in modes), modes
+    res = batch.decompress(frames, sizes, Options(False, 0, 1, 0), sized=False)
+    for i, (d, (code, blob)) in enumerate(zip(want, res)):
+        assert code == len(d) and blob == d, (i, code, len(d))
+    st = _decode_stats(backend)
+    assert st["general"] == 0 and st["seq_frames"] == len(frames), st
