@@ -1163,16 +1163,17 @@ __global__ void __launch_bounds__(kZUnitThreads) zstd_units_kernel(ZstdDecParams
 // ---- frames with sequences: the two sequence kernels ------------------------------------------------------------------------
 // A block with sequences regenerates lit_n + sum(match lengths) bytes - known only once its sequences have been decoded, and
 // the FSE states make that a serial walk.  So the work is split by what it depends on:
-//   zstd_seq_kernel      a WARP per frame with Seq units, its blocks in order: lane 0 builds the sequence tables (they and the three
-//                        repeat offsets persist from block to block) and decodes the sequences into RECORDS {offset, ll, ml} with the
-//                        repeat-offset codes resolved; the block's size follows, and with it the position of every unit of the frame
-//                        (dst_off of ALL its units is written here).  Nothing is copied yet.
-//   zstd_units_kernel    then decodes every block WITHOUT sequences of every frame, as before - including the 20 of 21 blocks of a
-//                        libzstd-written signal frame that follow its one block with sequences.
-//   zstd_seqexec_kernel  a warp per frame again, its Seq units in order: Huffman literals (4 lanes, one per stream) into the warp's
-//                        scratch, then the records: literal runs and matches are warp-wide copies.  Matches may reach back into
-//                        earlier blocks: those are complete (the units kernel ran before; earlier Seq units of the frame were
-//                        executed by this same warp).
+//   zstd_seq_kernel      a WARP per CHAIN of a frame's Seq units (a block that brings its own sequence tables and the blocks that repeat
+//                        them; the walker lists the chains): lanes 0 - 2 build the tables, a lane per block decodes the sequences into
+//                        RECORDS {offset, ll, ml}.  The warp that finishes a frame's last chain resolves the repeat-offset codes,
+//                        derives every unit's position from the block sizes (dst_off of ALL the frame's units is written here) and
+//                        lists the executor's work.  Nothing is copied yet.
+//   zstd_units_kernel    then decodes every block WITHOUT sequences of every frame, as before - including the blocks of a
+//                        libzstd-written signal frame that follow its one or two blocks with sequences - and the LITERALS of the
+//                        blocks with sequences, right-aligned in the block's place in the output.
+//   zstd_seqexec_kernel  a warp per executor chain (a Seq unit whose matches stay inside its block, and the units behind it whose matches
+//                        do not): the records expand the block in place, 32 per round.  Matches may reach back into earlier blocks:
+//                        those are complete (the units kernel ran before; earlier chains of the frame report done, release/acquire).
 // A frame the sequence kernel cannot vouch for (damaged, more records than the pool holds) goes to the general kernel.
 // entries of ZstdDecParams::seq_list: a unit index, whether the unit is the first Seq unit of its frame, and - set by the executor - done
 constexpr uint32_t kZListIndexMask = 0x3FFFFFFFu, kZListFirst = 0x40000000u, kZListDone = 0x80000000u;
