@@ -176,3 +176,47 @@ def test_fast5compress_command_line(tmp_path, capsys):
     fast5compress.main([printed, "-d", "-s", ".gz"])
     back = _zip_signals(printed + ".gz")
     assert all(np.array_equal(back[k], want[k]) for k in want)
+
+
+def test_types_that_hold_addresses_are_recognised():
+    """`compact` moves bytes: data whose elements are file addresses (variable-length values = global heap IDs, references) must be found
+    wherever a datatype can hide them - or the file refused."""
+    import struct
+    i16 = bytes([0x10, 0x08, 0, 0]) + struct.pack("<I", 2) + bytes([0, 0, 16, 0])
+    fstr = bytes([0x13, 0, 0, 0]) + struct.pack("<I", 7)
+    f64 = bytes([0x11, 0x20, 0x3F, 0]) + struct.pack("<I", 8) + bytes(12)
+    vlen = bytes([0x19, 0x01, 0, 0]) + struct.pack("<I", 16) + fstr
+    ref = bytes([0x17, 0, 0, 0]) + struct.pack("<I", 8)
+
+    def member_v1(name, off, dt):
+        nm = name + b"\0"
+        return nm + bytes(-len(nm) % 8) + struct.pack("<I", off) + bytes(28) + dt
+
+    def compound_v1(members, size):
+        return bytes([0x16, len(members), 0, 0]) + struct.pack("<I", size) + b"".join(member_v1(n, o, d) for n, o, d in members)
+
+    plain = compound_v1([(b"start", 0, i16), (b"a_name_longer_than_eight", 2, f64), (b"s", 10, fstr)], 17)
+    hiding = compound_v1([(b"start", 0, i16), (b"label", 2, vlen)], 18)
+    nested = compound_v1([(b"inner", 0, compound_v1([(b"r", 0, ref)], 8))], 8)
+    array_v2 = bytes([0x2A, 0, 0, 0]) + struct.pack("<I", 6) + bytes([1, 0, 0, 0]) + struct.pack("<II", 3, 0) + i16
+    array_of_vlen = bytes([0x3A, 0, 0, 0]) + struct.pack("<I", 32) + bytes([1]) + struct.pack("<I", 2) + vlen
+    compound_v3 = bytes([0x36, 2, 0, 0]) + struct.pack("<I", 10) + b"x\0" + bytes([0]) + i16 + b"yy\0" + bytes([2]) + fstr
+    for msg, want in ((i16, False), (fstr, False), (f64, False), (vlen, True), (ref, True), (plain, False), (hiding, True), (nested, True),
+                      (array_v2, False), (array_of_vlen, True), (compound_v3, False)):
+        holds, used = fast5._datatype_span(msg + b"\xEE" * 8, 0)
+        assert holds == want and used == len(msg), (msg.hex(), holds, used, len(msg))
+    # the datatype messages libhdf5 wrote into the fixture are walked to their exact ends too
+    f = fast5.Fast5File.open(os.path.join(DATA, "multi_fast5_zip.fast5"))
+    seen = 0
+    for hdr in f.objects().values():
+        for mtype, d, size in f._messages(hdr):
+            if mtype == 0x0003:
+                holds, used = fast5._datatype_span(f.b, d)
+                assert not holds and used <= size and size - used < 8
+                seen += 1
+            elif mtype == 0x000C:
+                name, tp, tlen, sp, slen, dp = f._attribute_parts(d)
+                holds, used = fast5._datatype_span(f.b, tp)
+                assert used == tlen, (name, used, tlen)
+                seen += 1
+    assert seen > 700

@@ -597,6 +597,62 @@ def _read_raw(f, targets, batch):
             t.raw[c.offset[0]:c.offset[0] + n] = np.frombuffer(blob, t.raw.dtype, n)
 
 
+def _datatype_span(b, p):
+    """(holds_addresses, bytes) of the datatype message that starts at b[p]: variable-length and reference types store file addresses
+    (global heap IDs, object addresses) in the data; compound, array, enumeration and variable-length types nest other datatypes."""
+    u = lambda q, n: int.from_bytes(b[q:q + n], "little")
+    cls, ver = b[p] & 15, b[p] >> 4
+    bits = u(p + 1, 3)
+    size = u(p + 4, 4)
+    q = p + 8
+    if cls in (0, 4):
+        return False, 12
+    if cls == 1:
+        return False, 20
+    if cls == 2:
+        return False, 10
+    if cls == 3:
+        return False, 8
+    if cls == 5:
+        return False, 8 + ((bits & 0xFF) + 7) // 8 * 8
+    if cls == 7:
+        return True, 8
+    if cls == 9:
+        return True, 8 + _datatype_span(b, q)[1]
+    if cls == 6:
+        holds = False
+        for _ in range(bits & 0xFFFF):
+            e = q
+            while b[e] != 0:
+                e += 1
+            q = q + (e - q) // 8 * 8 + 8 if ver < 3 else e + 1  # the name, NUL-padded to a multiple of eight before version 3
+            if ver == 1:
+                q += 4 + 1 + 3 + 4 + 4 + 16  # offset, dimensionality, reserved, permutation, reserved, four dimension sizes
+            elif ver == 2:
+                q += 4
+            else:
+                q += max(1, (max(size, 1).bit_length() + 7) // 8)  # the offset takes as many bytes as the compound's size needs
+            h, n = _datatype_span(b, q)
+            holds = holds or h
+            q += n
+        return holds, q - p
+    if cls == 8:
+        h, n = _datatype_span(b, q)
+        q += n
+        for _ in range(bits & 0xFFFF):
+            e = q
+            while b[e] != 0:
+                e += 1
+            q = q + (e - q) // 8 * 8 + 8 if ver < 3 else e + 1
+        return h, q - p + (bits & 0xFFFF) * u(p + 8 + 4, 4)
+    if cls == 10:
+        rank = b[q]
+        q += 4 + 8 * rank if ver < 3 else 1 + 4 * rank
+        h, n = _datatype_span(b, q)
+        return h, q - p + n
+    raise Fast5FormatError("datatype class %d" % cls)
+
+
 def _address_sites(f):
     """Position of every file address stored in the metadata reachable from the superblock (undefined addresses left
     out).  Anything that may hold an address this walk does not understand raises Fast5FormatError - `compact` must never
@@ -668,10 +724,10 @@ def _address_sites(f):
     def attribute(d):
         name, tp, tlen, sp, slen, dp = f._attribute_parts(d)
         cls = b[tp] & 15
-        if cls in (6, 7, 10):
-            raise Fast5FormatError("attribute %s: compound, reference and array types may hold addresses" % name)
+        if cls != 9 and _datatype_span(b, tp)[0]:
+            raise Fast5FormatError("attribute %s: its type holds file addresses inside a compound, array or reference" % name)
         if cls == 9:
-            if b[tp + 8] & 15 in (6, 7, 9, 10):
+            if _datatype_span(b, tp + 8)[0]:
                 raise Fast5FormatError("attribute %s: nested variable-length type" % name)
             for k in range(f._elements(sp)):
                 q = dp + k * (8 + so)
@@ -687,7 +743,12 @@ def _address_sites(f):
         if hdr in seen:
             continue
         seen.add(hdr)
-        for mtype, d, size in f._messages(hdr):
+        msgs = f._messages(hdr)
+        if any(m[0] == 0x0008 for m in msgs):  # a dataset: its elements must not be addresses (variable-length data, references)
+            for mtype, d, size in msgs:
+                if mtype == 0x0003 and not b[d - 4] & 2 and _datatype_span(b, d)[0]:
+                    raise Fast5FormatError("a dataset of variable-length or reference type stores file addresses in its data")
+        for mtype, d, size in msgs:
             if mtype != 0 and b[d - 4] & 2:
                 raise Fast5FormatError("shared header message")
             if mtype == 0x0010:
