@@ -220,3 +220,18 @@ def test_types_that_hold_addresses_are_recognised():
                 assert used == tlen, (name, used, tlen)
                 seen += 1
     assert seen > 700
+
+
+@pytest.mark.parametrize("backend", product.BACKENDS)
+def test_transcode_between_vbz_versions_is_stable(backend):
+    """VBZ v0 -> v1 keeps the samples, doing it again changes nothing (same frames, same layout), and a file with nothing to replace comes
+    back byte for byte."""
+    _, batch, _ = product.get(backend)
+    v0 = open(os.path.join(DATA, "multi_fast5_vbz.fast5"), "rb").read()
+    want = fast5.read_vbz_signals(v0, batch)
+    a = fast5.transcode(v0, batch, vbz_version=1)
+    got = fast5.read_vbz_signals(a, batch)
+    assert set(got) == set(want) and all(np.array_equal(got[k], want[k]) for k in want)
+    assert all(d.vbz_cd_values == [1, 2, 1, 1] for d in fast5.Fast5File(a).datasets())
+    assert fast5.transcode(a, batch, vbz_version=1) == a
+    assert fast5.transcode(v0, batch, name_filter=lambda name: False) == v0
