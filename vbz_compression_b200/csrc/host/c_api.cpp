@@ -32,6 +32,13 @@ int default_device()
     return e ? atoi(e) : 0;
 }
 
+// VBZ_B200_QUIET=1: a library should not write to its host's stderr unasked; the text stays available through vbz_b200_last_error()
+bool quiet()
+{
+    const char* e = getenv("VBZ_B200_QUIET");
+    return e && *e && *e != '0';
+}
+
 struct Lease {
     vbz_b200_ctx* ctx = nullptr;
     Lease()
@@ -43,7 +50,7 @@ struct Lease {
         if (!ctx) ctx = vbz_b200_create(default_device());
         if (!ctx) {
             static bool warned = false;
-            if (!warned) {
+            if (!warned && !quiet()) {
                 warned = true;
                 fprintf(stderr, "libvbz_b200: cannot run on a GPU (%s). This library has no CPU implementation.\n", vbz_b200_last_error());
             }
@@ -67,7 +74,7 @@ vbz_size_t run_one(bool compress, bool sized, const void* src, vbz_size_t n, voi
     int rc = compress ? vbz_b200_compress_batch(lease.ctx, srcs, &n, dsts, &cap, &result, 1, o, sized)
                       : vbz_b200_decompress_batch(lease.ctx, srcs, &n, dsts, &cap, &result, 1, o, sized);
     if (rc != 0) {
-        fprintf(stderr, "libvbz_b200: %s\n", vbz_b200_last_error());
+        if (!quiet()) fprintf(stderr, "libvbz_b200: %s\n", vbz_b200_last_error());
         return VBZ_OUT_OF_MEMORY_ERROR;
     }
     return result;
