@@ -235,3 +235,50 @@ def test_transcode_between_vbz_versions_is_stable(backend):
     assert all(d.vbz_cd_values == [1, 2, 1, 1] for d in fast5.Fast5File(a).datasets())
     assert fast5.transcode(a, batch, vbz_version=1) == a
     assert fast5.transcode(v0, batch, name_filter=lambda name: False) == v0
+
+
+@pytest.mark.parametrize("backend", product.BACKENDS)
+def test_transcode_into_several_chunks(backend):
+    """chunk_elems: datasets of several chunks, edge chunks stored whole - written, read back (the VBZ batch path and the zlib path both
+    walk multi-chunk datasets), and every chunk decoded by the unmodified reference."""
+    _, batch, _ = product.get(backend)
+    src = open(os.path.join(DATA, "multi_fast5_zip.fast5"), "rb").read()
+    want = _zip_signals(os.path.join(DATA, "multi_fast5_zip.fast5"))
+    out = fast5.transcode(src, batch, vbz_version=0, chunk_elems=20_000)
+    g = fast5.Fast5File(out)
+    ref = product.oracle_lib.ref() or product.oracle_lib.port()
+    opts = product.oracle_lib.Options(True, 2, 1, 0)
+    for d in g.datasets():
+        n = d.shape[0]
+        assert d.chunk_shape == (20_000,) and len(d.chunks) == (n + 19_999) // 20_000 and [c.offset[0] for c in d.chunks] == list(range(0, n, 20_000))
+        for c in d.chunks:
+            code, raw = ref.decompress(np.frombuffer(g.chunk_bytes(c), np.uint8), opts, 40_000, sized=True)
+            part = want[d.name][c.offset[0]:c.offset[0] + 20_000]
+            assert code == 40_000 and np.array_equal(np.frombuffer(raw, np.int16)[:part.size], part) and not np.frombuffer(raw, np.int16)[part.size:].any()
+    got = fast5.read_vbz_signals(out, batch)
+    assert all(np.array_equal(got[k], want[k]) for k in want) and len(got) == 10
+    back = fast5.transcode(out, batch, decompress=True, chunk_elems=30_000)  # several VBZ chunks in, several gzip chunks out
+    b = fast5.Fast5File(back)
+    for d in b.datasets():
+        parts = [np.frombuffer(zlib.decompress(bytes(b.chunk_bytes(c))), np.int16) for c in d.chunks]
+        assert all(p.size == 30_000 for p in parts) and np.array_equal(np.concatenate(parts)[:d.shape[0]], want[d.name])
+    again = fast5.transcode(back, batch, vbz_version=1)  # and several gzip chunks in
+    got = fast5.read_vbz_signals(again, batch)
+    assert all(np.array_equal(got[k], want[k]) for k in want)
+    with pytest.raises(fast5.Fast5FormatError):
+        fast5.transcode(src, batch, chunk_elems=1000)  # 506 chunks for the longest read: more than one B-tree node holds
+
+
+def test_libhdf5_filters_are_undone_in_reverse_order():
+    """shuffle, deflate, fletcher32 - the other filters a fast5 Signal may carry - and the filter mask that says which were skipped."""
+    rng = np.random.default_rng(4)
+    arr = rng.integers(-500, 500, 1001).astype("<i2")
+    raw = arr.tobytes()
+    shuffled = np.frombuffer(raw, np.uint8).reshape(-1, 2).T.tobytes()
+    ds = fast5.Dataset("/x", (1001,), 2, [(2, [2]), (1, [4]), (3, [])], (1001,), [])
+    payload = zlib.compress(shuffled, 4) + bytes([0x12, 0x34, 0x56, 0x78])
+    assert fast5._unfilter(ds, fast5.Chunk((0,), 0, 0, len(payload)), payload) == raw
+    assert fast5._unfilter(ds, fast5.Chunk((0,), 0b010, 0, 0), shuffled + b"abcd") == raw          # deflate skipped for this chunk
+    assert fast5._unfilter(ds, fast5.Chunk((0,), 0b101, 0, 0), zlib.compress(raw, 1)) == raw      # shuffle and checksum skipped
+    with pytest.raises(fast5.Fast5FormatError):
+        fast5._unfilter(fast5.Dataset("/x", (4,), 2, [(32015, [])], (4,), []), fast5.Chunk((0,), 0, 0, 0), b"12345678")

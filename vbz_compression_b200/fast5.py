@@ -798,7 +798,7 @@ def compact(data, holes):
     return bytes(out)
 
 
-def transcode(data, batch, decompress=False, vbz_version=1, zstd_level=1, name_filter=is_read_signal, compact_file=True):
+def transcode(data, batch, decompress=False, vbz_version=1, zstd_level=1, name_filter=is_read_signal, compact_file=True, chunk_elems=None):
     """bytes of a fast5 file -> bytes of the same file with every read's Raw/Signal stored as ONE chunk, VBZ-compressed
     (cd_values (vbz_version, element size, zigzag for signed samples, zstd_level)) or, with `decompress`, gzip level 1 -
     the two directions of python/fast5compress/fast5vbz.py:17-55.  All reads are decoded as one batch and encoded as one
@@ -807,23 +807,37 @@ def transcode(data, batch, decompress=False, vbz_version=1, zstd_level=1, name_f
     one link that pointed at it is re-aimed.  With `compact_file` the space that stays unused is then cut out and every
     address in the file's metadata moved along (`compact`), so the file shrinks by what the new compression saves - a file
     with structures `compact` does not know raises Fast5FormatError; pass compact_file=False to keep such a file's holes
-    (what the reference's script leaves too).  Empty datasets are left alone (h5py cannot chunk them either)."""
+    (what the reference's script leaves too).  Empty datasets are left alone (h5py cannot chunk them either).
+    `chunk_elems` cuts every dataset into chunks of that many samples instead of one (the last chunk is stored whole, padded with
+    zeros, as HDF5 stores edge chunks); up to 2K = 64 chunks fit the single B-tree node written here."""
     f = Fast5File(memoryview(bytes(data)))
     targets = [t for t in _targets(f, name_filter) if t.ds.shape[0] > 0]
     _read_raw(f, targets, batch)
+    pieces = []  # (target index, first sample, samples of one chunk)
+    for i, t in enumerate(targets):
+        n = t.ds.shape[0]
+        c = n if chunk_elems is None else int(chunk_elems)
+        if c <= 0 or (n + c - 1) // c > 2 * f.chunk_k:
+            raise Fast5FormatError("%s: %d samples do not fit %d chunks of %d" % (t.ds.name, n, 2 * f.chunk_k, c))
+        t.chunk_len = c
+        for a in range(0, n, c):
+            part = t.raw[a:a + c]
+            if part.size < c:
+                part = np.concatenate([part, np.zeros(c - part.size, part.dtype)])
+            pieces.append((i, a, part))
+    payloads = [None] * len(pieces)
     if decompress:
-        payloads = [zlib.compress(t.raw.tobytes(), 1) for t in targets]
+        payloads = [zlib.compress(part.tobytes(), 1) for _, _, part in pieces]
     else:
-        payloads = [None] * len(targets)
         groups = {}
-        for i, t in enumerate(targets):
-            groups.setdefault((t.ds.itemsize, t.ds.signed), []).append(i)
+        for k, (i, _, _) in enumerate(pieces):
+            groups.setdefault((targets[i].ds.itemsize, targets[i].ds.signed), []).append(k)
         for (itemsize, signed), idx in groups.items():
             opts = CompressionOptions(bool(signed), itemsize, int(zstd_level), int(vbz_version))
-            for i, (code, blob) in zip(idx, batch.compress([targets[i].raw for i in idx], opts, sized=True)):
+            for k, (code, blob) in zip(idx, batch.compress([pieces[k][2] for k in idx], opts, sized=True)):
                 if code >= 0xFFFFFFF9 or code != len(blob):
-                    raise Fast5FormatError("%s failed to compress: 0x%08X" % (targets[i].ds.name, code))
-                payloads[i] = blob
+                    raise Fast5FormatError("%s failed to compress: 0x%08X" % (targets[pieces[k][0]].ds.name, code))
+                payloads[k] = blob
     out = bytearray(f.b)
     space = _Space(len(out))
     for t in targets:
@@ -838,12 +852,14 @@ def transcode(data, batch, decompress=False, vbz_version=1, zstd_level=1, name_f
         out[pos:pos + len(blob)] = blob
         return pos - f.base_address
 
-    for t, payload in zip(targets, payloads):  # big pieces first, so that they get the low, big holes
-        t.chunk_at = put(payload)
-    for t, payload in zip(targets, payloads):
+    for t in targets:
+        t.entries = []
+    for (i, a, _), payload in zip(pieces, payloads):  # big pieces first, so that they get the low, big holes
+        targets[i].entries.append((len(payload), 0, a, put(payload)))
+    for t in targets:
         ds = t.ds
-        n = ds.shape[0]
-        tree = put(chunk_btree_node(f, [(len(payload), 0, 0, t.chunk_at)], n, ds.itemsize))
+        n = t.chunk_len
+        tree = put(chunk_btree_node(f, t.entries, len(t.entries) * n, ds.itemsize))
         pipeline = gzip_pipeline(1) if decompress else vbz_pipeline(vbz_version, ds.itemsize, ds.signed, zstd_level)
         msgs, placed = [], False
         for mtype, flags, body in t.messages:
@@ -865,7 +881,7 @@ def transcode(data, batch, decompress=False, vbz_version=1, zstd_level=1, name_f
     return bytes(out)
 
 
-def compress_fast5(filename, output_suffix, batch, vbz_version=0, decompress=False, compact_file=True):
+def compress_fast5(filename, output_suffix, batch, vbz_version=0, decompress=False, compact_file=True, chunk_elems=None):
     """python/fast5compress/fast5vbz.py:17-55 with a batch handle in place of h5py: writes filename + output_suffix and
     returns its name."""
     import os
@@ -873,7 +889,7 @@ def compress_fast5(filename, output_suffix, batch, vbz_version=0, decompress=Fal
     out_filename = filename + output_suffix
     with open(filename, "rb") as fh:
         data = fh.read()
-    result = transcode(data, batch, decompress=decompress, vbz_version=vbz_version, compact_file=compact_file)
+    result = transcode(data, batch, decompress=decompress, vbz_version=vbz_version, compact_file=compact_file, chunk_elems=chunk_elems)
     with open(out_filename, "wb") as fh:
         fh.write(result)
     return out_filename
