@@ -818,7 +818,7 @@ extern "C" int vbz_b200_stage_times(vbz_b200_ctx* ctx, float* stage1_ms, float* 
 }
 
 // ---- host-pointer batches -------------------------------------------------------------------------------------
-// A batch of host reads runs as WAVES (16 .. 256 MiB of input + output) through kWaveSlots slots (device in/out buffers, pinned staging,
+// A batch of host reads runs as WAVES (64 .. 768 MiB of input + output) through kWaveSlots slots (device in/out buffers, pinned staging,
 // events).  The host enqueues the upload, the kernels and the download of wave w, then turns to wave w-D
 // (D = kWaveSlots - 2), whose kernels have long finished, reads its per-read results, and finally hands wave w-D-1 to
 // the caller.  The upload queue therefore always holds D waves and the PCIe link (both directions) and the SMs work at
