@@ -270,3 +270,46 @@ def test_blocks_that_repeat_tables_ride_with_the_block_before_them(backend):
         assert code == len(d) and blob == d, (i, code, len(d))
     st = _decode_stats(backend)
     assert st["general"] == 0 and st["seq_frames"] == len(frames), st
+
+
+def test_frames_that_run_the_pool_dry_leave_nothing_behind_for_their_neighbours(backend):
+    """Unit slots are allotted before the walker knows whether a frame's records fit the pool; a frame that does not fit leaves its slots
+    unwritten.  They must not keep what an earlier batch of the same context left there: the executor follows a frame's Seq units by
+    their read index, and a valid frame in front of such slots was decoded into the error code (found by a fuzz run over batches)."""
+    _, batch, _ = backend
+    rng = np.random.default_rng(31)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(200)]
+
+    def text(n):  # a sequence every few bytes: more records than the pool holds for a frame (one per 32 bytes)
+        out, tot = [], 0
+        while tot < n:
+            w = words[int(rng.integers(0, 200))]
+            out.append(w + b" ")
+            tot += len(w) + 1
+        return b"".join(out)[:n]
+
+    def copies(n):  # noise with a copy of 100 - 250 bytes every few hundred: a sequence per ~400 bytes
+        buf = bytearray(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        pos = 3000
+        while pos < n - 600:
+            m = int(rng.integers(100, 250))
+            back = int(rng.integers(m, 2500))
+            buf[pos:pos + m] = buf[pos - back:pos - back + m]
+            pos += m + int(rng.integers(100, 400))
+        return bytes(buf)
+
+    o = Options(False, 0, 1, 0)
+    # batch A: six frames of five blocks with sequences each - the unit slots now hold Seq units of reads 0 .. 5
+    a = [copies(600_000) for _ in range(6)]
+    res = batch.decompress([ol.zstd_compress_lib(d, 3) for d in a], [len(d) for d in a], o, sized=False)
+    assert all(code == len(d) and blob == d for d, (code, blob) in zip(a, res))
+    st = _decode_stats(backend)
+    assert st["general"] == 0 and st["seq_frames"] == 6, st
+    # batch B: a short frame that fits, in front of one that runs the pool dry (45 k sequences, 14 k records for the two)
+    b = [copies(100_000), text(350_000)]
+    for _ in range(2):
+        res = batch.decompress([ol.zstd_compress_lib(d, 1) for d in b], [len(d) for d in b], o, sized=False)
+        for i, (d, (code, blob)) in enumerate(zip(b, res)):
+            assert code == len(d) and blob == d, (i, hex(code))
+        st = _decode_stats(backend)
+        assert st["general"] >= 1 and st["seq_frames"] >= 1, st  # (the scenario: some frames ran the pool dry, the first did not)

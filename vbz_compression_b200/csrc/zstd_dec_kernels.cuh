@@ -952,7 +952,9 @@ __global__ void zstd_walk_kernel(ZstdDecParams p)
         const uint32_t cbase = w.chains ? atomicAdd(p.counter + 10, w.chains) : 0u;
         if (base >= p.unit_cap || cnt > p.unit_cap - base || (gcnt && (gbase >= p.unit_cap || gcnt > p.unit_cap - gbase)) ||
             (w.seqs && (sbase >= p.seq_cap || w.seqs > p.seq_cap - sbase)) || (w.chains && (cbase >= p.unit_cap || w.chains > p.unit_cap - cbase))) {
-            // out of slots: the units kernel stops at unit_cap; what was allotted here stays empty
+            // out of slots: the units kernel stops at unit_cap; what was allotted here stays empty - and must say so: the executor walks from a
+            // Seq unit to the units behind it for as long as they name the same read, and what an earlier batch left in these slots may
+            for (uint32_t k = base; k < p.unit_cap && k - base < cnt; ++k) { p.units[k].kind = kZUnitNop; p.units[k].read = 0xFFFFFFFFu; }
             for (uint32_t k = gbase; gcnt && k < p.unit_cap && k - gbase < gcnt; ++k) p.groups[k] = ZstdGroup{0, 0};
             for (uint32_t k = cbase; w.chains && k < p.unit_cap && k - cbase < w.chains; ++k)
                 reinterpret_cast<ZstdSeqChain*>(p.seq_list + p.unit_cap)[k] = ZstdSeqChain{0xFFFFFFFFu, 0, 0, 0};
@@ -1412,6 +1414,11 @@ __device__ void z_resolve_repeats(ZstdSeq* sq, uint32_t nseq, uint32_t* rep, uin
 // chain walks the frame's units once - resolves the codes in order, gives every unit its place in the output and lists the executor's
 // chains.  (What other warps wrote is read with ld.cg there: their lines may sit stale in this SM's L1.)
 constexpr int kZSeqWarps = 4;
+#ifdef VBZ_CPUSIM
+#define Z_SEQ_TRACE(...) do { if (lane == 0 && getenv("VBZ_B200_TRACE_SEQ")) fprintf(stderr, __VA_ARGS__); } while (0)
+#else
+#define Z_SEQ_TRACE(...) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams p)
 {
     VBZ_DYN_SMEM(smem);
@@ -1452,7 +1459,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
             const uint32_t head_lane = (uint32_t)__ffs((int)seqmask) - 1;
             ZSeqHead h = {nullptr, 0, 0, 0, -1};
             if (is_seq) h = z_seq_head(p.src + u.src_off, u.n, u.nseq);
-            if (__ballot_sync(0xffffffffu, is_seq && h.modes < 0)) { ok = false; break; }
+            if (__ballot_sync(0xffffffffu, is_seq && h.modes < 0)) { Z_SEQ_TRACE("seq: chain %u of read %u: a block's sequences section is damaged\n", k, sf.read); ok = false; break; }
             // the set: the head and the Seq units behind it (among these 32) that repeat all three tables
             const uint32_t stop = __ballot_sync(0xffffffffu, is_seq && lane > head_lane && h.modes != 0xFC);
             const uint32_t upto = stop ? (uint32_t)__ffs((int)stop) - 1 : 32u;
@@ -1484,7 +1491,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                     used_all = at;
                 }
                 bad = __shfl_sync(0xffffffffu, bad, 0);
-                if (bad) { ok = false; break; }
+                if (bad) { Z_SEQ_TRACE("seq: chain %u of read %u: table descriptions\n", k, sf.read); ok = false; break; }
                 used_all = __shfl_sync(0xffffffffu, used_all, 0);
                 const uint32_t o0 = __shfl_sync(0xffffffffu, off3[0], 0), o1 = __shfl_sync(0xffffffffu, off3[1], 0), o2 = __shfl_sync(0xffffffffu, off3[2], 0);
                 uint32_t tbad = 0;
@@ -1499,7 +1506,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                                                     lane == 0 ? 36 : (lane == 1 ? 29 : 53), lane == 1 ? 5 : 6, tables_valid);
                     if (r == kBad) tbad = 1;
                 }
-                if (__ballot_sync(0xffffffffu, tbad != 0)) { ok = false; break; }
+                if (__ballot_sync(0xffffffffu, tbad != 0)) { Z_SEQ_TRACE("seq: chain %u of read %u: table build\n", k, sf.read); ok = false; break; }
                 al[0] = __shfl_sync(0xffffffffu, my_al, 0);
                 al[1] = __shfl_sync(0xffffffffu, my_al, 1);
                 al[2] = __shfl_sync(0xffffffffu, my_al, 2);
@@ -1522,7 +1529,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
                             ? kBad
                             : z_lane_sequences(zw, al[0], al[1], al[2], bits, nbits, h.nseq, h.lit_n, p.seqs + u.seq_first, false, my_rep, &raw, &back);
             }
-            if (__ballot_sync(0xffffffffu, member && regen == kBad)) { ok = false; break; }
+            if (__ballot_sync(0xffffffffu, member && regen == kBad)) { Z_SEQ_TRACE("seq: chain %u of read %u: a block's sequences (or no room for its records)\n", k, sf.read); ok = false; break; }
             if (member) {
                 ZstdUnit* up = p.units + sf.unit_first + mine;
                 up->regen = regen;
@@ -1543,6 +1550,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
         if ((old & 0x7FFFFFFFu) != 1u) continue;
         __threadfence();
         ok = !(old & 0x80000000u);
+        Z_SEQ_TRACE("seq: read %u: last chain done, %s\n", sf.read, ok ? "all good" : "a chain failed");
         const ZstdRead rd = p.reads[sf.read];
         uint64_t fcs = 0;
         bool has = false, ck = false;
@@ -1578,6 +1586,7 @@ __global__ void __launch_bounds__(kZSeqWarps * 32) zstd_seq_kernel(ZstdDecParams
         }
         if (ok && has && op != fcs) ok = false;
         if (ok && (uint64_t)sf.unit_first + sf.unit_count >= kZListIndexMask) ok = false;
+        Z_SEQ_TRACE("seq: read %u: %llu bytes, content size %llu -> %s\n", sf.read, (unsigned long long)op, (unsigned long long)fcs, ok ? "executor" : "general kernel");
         if (ok) {
             if (lane == 0) p.results[sf.read] = (uint32_t)op;
             // the executor's work list: the frame's CHAINS in block order, side by side.  A chain = a Seq unit that needs nothing from the
