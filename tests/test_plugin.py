@@ -126,3 +126,51 @@ def test_pyvbz_style_calls(plugin):
             m = lib.vbz_decompress_sized(out.ctypes.data, n, back.ctypes.data, back.nbytes, ctypes.byref(o))
             assert m == arr.nbytes and (back == arr).all()
     del saved
+
+
+@pytest.mark.parametrize("backend", product.BACKENDS)
+def test_batch_form_of_the_filter_callback(backend):
+    """vbz_b200_h5z_filter_batch (include/vbz_b200.h): many chunks of one dataset per call, results[i] = what the reference's sized call
+    returns for chunk i (vbz_plugin.cpp:136-229 per chunk).  Both directions, three and four cd_values, chunks written by the reference,
+    a damaged chunk among good ones, and fewer than three cd_values refused."""
+    capi, batch, lib = product.get(backend)
+    ref = ol.ref() or ol.port()
+    rng = np.random.default_rng(17)
+    reads = [data_gen.nanopore_like(int(n), rng) for n in (1, 777, 40_000, 0, 123_456, 9)]
+    vp = ctypes.c_void_p
+
+    def call(flags, cd, srcs, caps):
+        n = len(srcs)
+        arrs = [np.frombuffer(bytes(s), np.uint8) for s in srcs]
+        outs = [np.full(max(c, 1), 0xEE, np.uint8) for c in caps]
+        res = (ctypes.c_uint32 * n)()
+        rc = lib.vbz_b200_h5z_filter_batch(batch.ctx, flags, len(cd), (ctypes.c_uint * max(len(cd), 1))(*cd), n, (vp * n)(*[a.ctypes.data if a.size else None for a in arrs]),
+                                           (ctypes.c_uint32 * n)(*[a.size for a in arrs]), (vp * n)(*[o.ctypes.data for o in outs]), (ctypes.c_uint32 * n)(*caps), res)
+        return rc, [int(r) for r in res], outs
+
+    for cd in ([1, 2, 1, 1], [0, 2, 1], [1, 2, 1, 3]):
+        o = ol.Options(True, 2, cd[3] if len(cd) > 3 else 1, cd[0])
+        caps = [int(capi.max_compressed_size(r.nbytes, o)) + 4 for r in reads]
+        rc, sizes, outs = call(0, cd, [r.tobytes() for r in reads], caps)
+        assert rc == 0
+        chunks = []
+        for r, z, out in zip(reads, sizes, outs):
+            assert not ol.is_error(z) and z <= out.size
+            code, raw = ref.decompress(out[:z].tobytes(), o, r.nbytes, sized=True)  # the reference reads what the batch call wrote
+            assert code == r.nbytes and raw == r.tobytes()
+            chunks.append(out[:z].tobytes())
+        theirs = [ref.compress(r, o, sized=True)[1] for r in reads]  # and the batch call reads what the reference wrote
+        for written in (chunks, theirs):
+            rc, sizes, outs = call(REVERSE, cd, written, [r.nbytes for r in reads])
+            assert rc == 0
+            for r, z, out in zip(reads, sizes, outs):
+                assert z == r.nbytes and out[:z].tobytes() == r.tobytes()
+        broken = list(theirs)
+        broken[2] = broken[2][:len(broken[2]) // 2]
+        rc, sizes, outs = call(REVERSE, cd, broken, [r.nbytes for r in reads])
+        assert rc == 0
+        for i, (r, z, out) in enumerate(zip(reads, sizes, outs)):
+            want, _ = ref.decompress(broken[i], o, r.nbytes, sized=True)
+            assert z == want and (ol.is_error(z) or out[:z].tobytes() == r.tobytes()), i
+    rc, _, _ = call(REVERSE, [1, 2], [b"\0" * 8], [8])
+    assert rc == -1
